@@ -1,0 +1,141 @@
+/* circuitmap_b200 -- C ABI of the B200-native hot paths of marcustriplett/circuitmap.
+ *
+ * The reference has no FFI of its own: its boundary is the Python call surface
+ *   circuitmap.NeuralDemixer(path)(traces)                   circuitmap/neural_waveform_demixing.py:17-54
+ *   circuitmap.Model(N).fit(psc, stim, 'caviar', fit_options) circuitmap/model.py:36-44,104-162
+ *                                      -> optimise.caviar(...) circuitmap/optimise/caviar.py:20-100
+ * circuitmap_b200/{neural_waveform_demixing,model}.py keep that surface and marshal to the entry
+ * points below (ctypes; see INTEGRATION.md for the binding a reference maintainer would add).
+ *
+ * Conventions
+ *   - plain C types only; every *_dev pointer is DEVICE memory owned by the caller;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); calls are
+ *     stream-ordered and return without synchronising unless stated otherwise;
+ *   - return 0 on success, a CM_E* code otherwise; cm_last_error() gives the thread-local text;
+ *   - re-entrant: no global state besides the per-handle weights.
+ */
+#ifndef CIRCUITMAP_B200_H
+#define CIRCUITMAP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CM_VERSION 100
+#if defined(__GNUC__)
+#define CM_API __attribute__((visibility("default")))
+#else
+#define CM_API
+#endif
+
+enum { CM_OK = 0, CM_EINVAL = 1, CM_ESHAPE = 2, CM_EUNSUPPORTED = 3, CM_ECUDA = 4, CM_EWORKSPACE = 5 };
+enum { CM_F32 = 0, CM_F64 = 1 };
+
+CM_API int cm_version(void);
+CM_API const char* cm_last_error(void);
+/* number of SMs / device ordinal of the current CUDA device (diagnostics for the host layer) */
+CM_API int cm_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------------------------
+ * NWD demixer forward  (replaces NeuralDemixer.__call__ / NWDUNet.forward,
+ *                       neural_waveform_demixing.py:36-54,204-287,337-348)
+ * ------------------------------------------------------------------------------------------ */
+typedef struct cm_nwd cm_nwd_t;
+
+/* CM_NWD_NUM_TENSORS host float32 tensors in state_dict order (neural_waveform_demixing.py:259-269):
+ * for each of dblock1..4, ublock1..4, conv: {conv|deconv}.weight, .bias, bn.weight, bn.bias,
+ * bn.running_mean, bn.running_var.  BatchNorm (eval) is folded into the convolutions inside. */
+#define CM_NWD_NUM_TENSORS 54
+#define CM_NWD_T 900
+CM_API int  cm_nwd_create(const float* const* tensors, int n_tensors, cm_nwd_t** out);
+CM_API void cm_nwd_destroy(cm_nwd_t* h);
+
+/* traces_dev: K x T row-major (in_dtype), out_dev: K x T row-major (out_dtype).
+ * Per trace: x = trace / max_t(trace); net(x) in fp32; out = net * max; running minimum from
+ * column monotone_start (nwd.py:337-343; monotone_start >= T or < 1 disables it).
+ * y_dev / ss_dev (optional, may be NULL): per-trace trapz(out) and sum(out^2) in fp64 -- the
+ * CAVIaR prologue statistics (caviar.py:28,30), so a following cm_caviar_fit need not re-read
+ * the K x T array.  T must be CM_NWD_T. */
+CM_API int  cm_nwd_forward(cm_nwd_t* h, const void* traces_dev, int in_dtype, void* out_dev, int out_dtype,
+                    int K, int T, int monotone_start, double* y_dev, double* ss_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * CAVIaR fit  (replaces optimise.caviar, caviar.py:20-316 + pava.py:9-88)
+ * B independent fits of identical (N, K) per call; B = 1 for Model.fit.
+ * ------------------------------------------------------------------------------------------ */
+#define CM_CAVIAR_MAX_POWERS 16
+
+typedef struct cm_caviar_options {      /* keyword arguments of caviar(), caviar.py:21-23 */
+    int    iters;                /* 50   */
+    int    num_mc_samples;       /* 100  */
+    double y_xcorr_thresh;       /* 1e-2 */
+    double minimum_spike_count;  /* 3    */
+    int    delay_spont_est;      /* 1    */
+    double msrmp;                /* 0.3  */
+    double scale_factor;         /* 0.75 */
+    double penalty;              /* 5.0  */
+    int    max_backtrack_iters;  /* 20 (soft-threshold passes, caviar.py:86) */
+    double tol;                  /* 0.05 */
+    double spont_orthogonality;  /* 0.1  */
+    int    fn_scan;              /* 1    */
+    int    save_histories;       /* 0    */
+} cm_caviar_options;
+
+typedef struct cm_caviar_args {
+    int B, N, K, T;              /* fits, neurons, trials, samples per trace (T ignored if psc_dev==NULL) */
+    /* inputs ------------------------------------------------------------------------------ */
+    const void*   psc_dev;       /* B x K x T (psc_dtype) or NULL when y_dev/ss_dev are given      */
+    int           psc_dtype;
+    const double* y_dev;         /* B x K  trapz(psc)   (used when psc_dev == NULL)                */
+    const double* ss_dev;        /* B x K  sum_t psc^2  (used when psc_dev == NULL)                */
+    const void*   stim_dev;      /* B x N x K, neuron-major rows, K contiguous (stim_dtype)        */
+    int           stim_dtype;
+    int           n_powers;      /* P = number of distinct non-zero powers (<= CM_CAVIAR_MAX_POWERS) */
+    const double* powers;        /* HOST array, ascending: np.unique(stim)[1:] (caviar.py:42)      */
+    const uint64_t* seeds;       /* HOST array, B seeds (caviar.py:76)                             */
+    /* priors, B x ... fp64 (model.py:24-31) --------------------------------------------------- */
+    const double* mu0_dev;       /* B x N     */
+    const double* beta0_dev;     /* B x N     */
+    const double* phi0_dev;      /* B x N x 2 */
+    const double* phi_cov0_dev;  /* B x N x 2 x 2 */
+    const double* shape0;        /* HOST, B   */
+    const double* rate0;         /* HOST, B   */
+    cm_caviar_options opt;
+    /* outputs, fp64 --------------------------------------------------------------------------- */
+    double* mu_dev;              /* B x N */
+    double* beta_dev;            /* B x N */
+    double* lam_dev;             /* B x N x K dense, or NULL to skip densification */
+    double* shape_dev;           /* B */
+    double* rate_dev;            /* B */
+    double* phi_dev;             /* B x N x 2 */
+    double* phi_cov_dev;         /* B x N x 2 x 2 */
+    double* z_dev;               /* B x K */
+    /* optional per-iteration histories (opt.save_histories); NULL to skip individual ones ------ */
+    double* mu_hist_dev;         /* B x iters x N */
+    double* beta_hist_dev;       /* B x iters x N */
+    double* lam_hist_dev;        /* B x iters x N x K */
+    double* shape_hist_dev;      /* B x iters */
+    double* rate_hist_dev;       /* B x iters */
+    double* phi_hist_dev;        /* B x iters x N x 2 */
+    double* phi_cov_hist_dev;    /* B x iters x N x 2 x 2 */
+    double* z_hist_dev;          /* B x iters x K */
+    /* workspace -------------------------------------------------------------------------------- */
+    int64_t nnz_cap;             /* upper bound on non-zeros of stim PER FIT */
+    void*   workspace_dev;
+    size_t  workspace_bytes;     /* >= cm_caviar_workspace_bytes(B, N, K, nnz_cap, flags) */
+    int*    status_dev;          /* B ints: 0 ok, else CM_E* detected on device (e.g. nnz overflow) */
+} cm_caviar_args;
+
+CM_API size_t cm_caviar_workspace_bytes(int B, int N, int K, int64_t nnz_cap, int save_histories);
+CM_API int    cm_caviar_fit(const cm_caviar_args* a, void* stream);
+
+/* number of kernel launches issued by the last cm_* call on this thread (for bench accounting) */
+CM_API int cm_last_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,73 @@
+"""GPU parity: cm_nwd_forward (through the C ABI / NeuralDemixer) vs the oracle and the reference golden vectors."""
+import os
+
+import numpy as np
+import pytest
+
+from tests.conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+# fp32 CUDA-core path: differs from the reference's fp32 oneDNN path only by summation order and BN folding.
+# torch fp32 vs fp64 of the same network is 2.6e-5 max-abs on unit-normalised traces.
+TOL_UNIT = 2e-4   # max-abs on unit-normalised traces
+
+
+@pytest.fixture(scope="module")
+def demixer():
+    from circuitmap_b200 import NeuralDemixer
+    return NeuralDemixer(path=os.path.join(GOLDEN, "nwd_ie_ChroME2f_weights.npz"))
+
+
+def test_golden_reference_vectors(demixer):
+    g = np.load(os.path.join(GOLDEN, "nwd_golden.npz"))
+    traces = g["traces"]
+    tmax = traces.max(1)[:, None]
+    out = demixer(traces.copy(), verbose=False)
+    assert out.dtype == np.float64 and out.shape == traces.shape
+    assert np.max(np.abs(out - g["out"]) / tmax) < TOL_UNIT
+    out_nf = demixer(traces.copy(), monotone_filter_start=900, verbose=False)
+    assert np.max(np.abs(out_nf - g["out_nofilt"]) / tmax) < TOL_UNIT
+    # against the fp64 network: bounded by fp32 rounding of the whole net
+    assert np.max(np.abs(out_nf / tmax - g["net_out_f64"])) < TOL_UNIT
+
+
+def test_vs_oracle_seeded(demixer):
+    from oracle import nwd as onwd
+    from oracle.make_golden import synth_traces
+    sd = dict(np.load(os.path.join(GOLDEN, "nwd_ie_ChroME2f_weights.npz")))
+    folded = onwd.fold_bn(sd)
+    traces = synth_traces(300, seed=11)
+    ref = onwd.demix_np(traces.copy(), folded)
+    out = demixer(traces.copy(), verbose=False)
+    tmax = traces.max(1)[:, None]
+    assert np.max(np.abs(out - ref) / tmax) < TOL_UNIT
+    # monotone property beyond sample 500 and idempotence of the filter
+    assert np.all(np.diff(out[:, 499:], axis=1) <= 0)
+
+
+def test_fp32_io_and_stats(demixer):
+    import torch
+    from oracle.make_golden import synth_traces
+    traces = synth_traces(64, seed=5)
+    x64 = torch.from_numpy(traces).cuda()
+    o64, y, ss = demixer.forward_device(x64, stats=True)
+    o32 = demixer.forward_device(x64.float())
+    tmax = torch.from_numpy(traces.max(1)[:, None]).cuda()
+    assert torch.max(torch.abs(o32.double() - o64) / tmax).item() < TOL_UNIT
+    ref_y = o64.sum(1) - 0.5 * (o64[:, 0] + o64[:, -1])
+    assert torch.allclose(y, ref_y, rtol=1e-12, atol=1e-12)
+    assert torch.allclose(ss, (o64 * o64).sum(1), rtol=1e-12, atol=1e-14)
+
+
+def test_ragged_and_edge_batches(demixer):
+    from oracle.make_golden import synth_traces
+    traces = synth_traces(3, seed=2)
+    full = demixer(traces.copy(), verbose=False)
+    one = demixer(traces[:1].copy(), verbose=False)
+    assert one.shape == (1, 900)
+    assert np.array_equal(one[0], full[0])              # batch-size independence, bit exact
+    empty = demixer(np.zeros((0, 900)), verbose=False)
+    assert empty.shape == (0, 900)
+    with pytest.raises(RuntimeError):
+        demixer(np.ones((2, 800)), verbose=False)       # T != 900 is rejected loudly
