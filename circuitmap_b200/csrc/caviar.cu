@@ -1,3 +1,1394 @@
+// CAVIaR (coordinate-ascent variational inference + isotonic regularisation) for sm_100a.
+//
+// Replaces optimise.caviar and everything it calls (reference circuitmap/optimise/caviar.py:20-316,
+// circuitmap/optimise/pava.py:9-88).  Design:
+//   * HBM-bound prologue kernels turn the dense inputs into what the loop needs: per-trace trapz / sum of
+//     squares (caviar.py:28,30) and a CSR+CSC index of the stimulus design (supp(lam) is a subset of
+//     supp(stim), caviar.py:32-34,216), one streaming pass each.
+//   * ONE persistent kernel then runs the whole fit -- all `iters` iterations of block_update_mu,
+//     update_lam, update_sigma, update_phi, estimate_spont_act_soft_thresh, then reconnect_spont_cells and
+//     the final update_phi -- without returning to the host.  One CTA per fit; B fits run concurrently.
+//   * fp64 throughout (the reference runs with jax_enable_x64, caviar.py:12), threefry PRNG stream identical
+//     to jax.random's (caviar.py:76,196,209-210,304).
 #include "common.cuh"
-extern "C" size_t cm_caviar_workspace_bytes(int, int, int, int64_t, int) { return 0; }
-extern "C" int cm_caviar_fit(const cm_caviar_args*, void*) { cm::set_error("not built yet"); return CM_EUNSUPPORTED; }
+#include <vector>
+#include <cfloat>
+#include <cstring>
+
+namespace cm {
+namespace cav {
+
+constexpr int PMAX = CM_CAVIAR_MAX_POWERS;
+constexpr int NT = 512;          // threads of a fit CTA
+constexpr int NW = NT / 32;
+constexpr int NB = 32;           // block size of the bordered Cholesky/inverse
+constexpr int RG = 4;            // row groups of 8 in the panel GEMMs
+constexpr int MAX_SHUFFLE_ROUNDS = 4;
+
+// ------------------------------------------------------------------------------------------------ layout
+struct Layout {
+    size_t stride;
+    // fp64
+    size_t X, PA, PB, lam, cst, y, ss, pred, resid, z, mu, beta, bvec, dvec, wvec, slam, slam2, sp, phibar, phi,
+        phicov, phiz, phicovz, lamhist;
+    // int32 / uint32
+    size_t row_ptr, col_ptr, colfill, col_k, csc_row, csc_pos, cntp, n0p, n1p, act, ainv, order, order2, pos, rownz,
+        phizok, sortkeys, keys, dcnt, dlist;
+    // bytes
+    size_t pw, mask, blocked;
+};
+
+static Layout make_layout(int N, int K, int64_t nnz, int iters, bool lamhist) {
+    Layout L{};
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 255) & ~size_t(255); return r; };
+    const size_t n = N, k = K, z = (size_t)nnz;
+    L.X = take(n * n * 8);
+    L.PA = take((size_t)NB * n * 8);
+    L.PB = take((size_t)NB * n * 8);
+    L.lam = take(z * 8);
+    L.cst = take(z * 8);
+    L.y = take(k * 8);
+    L.ss = take(k * 8);
+    L.pred = take(k * 8);
+    L.resid = take(k * 8);
+    L.z = take(k * 8);
+    L.mu = take(n * 8);
+    L.beta = take(n * 8);
+    L.bvec = take(n * 8);
+    L.dvec = take(n * 8);
+    L.wvec = take(n * 8);
+    L.slam = take(n * 8);
+    L.slam2 = take(n * 8);
+    L.sp = take(n * PMAX * 8);
+    L.phibar = take(n * 2 * 8);
+    L.phi = take(n * 2 * 8);
+    L.phicov = take(n * 4 * 8);
+    L.phiz = take(n * 2 * 8);
+    L.phicovz = take(n * 4 * 8);
+    L.lamhist = take(lamhist ? (size_t)iters * z * 8 : 0);
+    L.row_ptr = take((n + 1) * 4);
+    L.col_ptr = take((k + 1) * 4);
+    L.colfill = take(k * 4);
+    L.col_k = take(z * 4);
+    L.csc_row = take(z * 4);
+    L.csc_pos = take(z * 4);
+    L.cntp = take(n * PMAX * 4);
+    L.n0p = take(n * PMAX * 4);
+    L.n1p = take(n * PMAX * 4);
+    L.act = take(n * 4);
+    L.ainv = take(n * 4);
+    L.order = take(n * 4);
+    L.order2 = take(n * 4);
+    L.pos = take(n * 4);
+    L.rownz = take(n * 4);
+    L.phizok = take(n * 4);
+    L.sortkeys = take(n * 4);
+    L.keys = take(2 * n * 2 * 4);
+    L.dcnt = take(n * 4);
+    L.dlist = take(n * 4);
+    L.pw = take(z);
+    L.mask = take(k);
+    L.blocked = take(k);
+    L.stride = o;
+    return L;
+}
+
+struct FitParams {
+    Layout L;
+    char* ws;
+    int B, N, K, P;
+    int64_t nnz_cap;
+    double powers[PMAX];
+    const double *mu0, *beta0, *phi0, *phicov0;
+    double shape0, rate0;             // per-launch scalars when all fits share them, else arrays below
+    const double *shape0_arr, *rate0_arr;
+    const unsigned long long* seeds;  // device, B
+    cm_caviar_options opt;
+    double *mu_out, *beta_out, *shape_out, *rate_out, *phi_out, *phicov_out, *z_out;
+    double *mu_hist, *beta_hist, *shape_hist, *rate_hist, *phi_hist, *phicov_hist, *z_hist;
+    int lamhist;
+    int* status;
+    int smem_doubles;                 // dynamic shared memory available for pred / row buffers
+};
+
+// ------------------------------------------------------------------------------------------------ PRNG
+__device__ __forceinline__ uint32_t rotl32(uint32_t x, int r) { return (x << r) | (x >> (32 - r)); }
+
+// Threefry-2x32-20 (Random123), the block function behind jax.random (oracle/prng.py).
+__device__ __forceinline__ void threefry2x32(uint32_t k0, uint32_t k1, uint32_t& x0, uint32_t& x1) {
+    const uint32_t k2 = k0 ^ k1 ^ 0x1BD11BDAu;
+    x0 += k0; x1 += k1;
+#define TF_R(r) x0 += x1; x1 = rotl32(x1, r); x1 ^= x0;
+    TF_R(13) TF_R(15) TF_R(26) TF_R(6)
+    x0 += k1; x1 += k2 + 1u;
+    TF_R(17) TF_R(29) TF_R(16) TF_R(24)
+    x0 += k2; x1 += k0 + 2u;
+    TF_R(13) TF_R(15) TF_R(26) TF_R(6)
+    x0 += k0; x1 += k1 + 3u;
+    TF_R(17) TF_R(29) TF_R(16) TF_R(24)
+    x0 += k1; x1 += k2 + 4u;
+    TF_R(13) TF_R(15) TF_R(26) TF_R(6)
+    x0 += k2; x1 += k0 + 5u;
+#undef TF_R
+}
+
+// jax.random.split(key): rows (new_key, subkey).  Executed by lanes 0 and 1 of a warp; every lane gets the result.
+__device__ __forceinline__ void warp_split(uint32_t k0, uint32_t k1, uint32_t& r00, uint32_t& r01, uint32_t& r10,
+                                           uint32_t& r11) {
+    const int lane = threadIdx.x & 31;
+    uint32_t x0 = lane & 1, x1 = 2 + (lane & 1);
+    threefry2x32(k0, k1, x0, x1);
+    r00 = __shfl_sync(0xffffffffu, x0, 0);
+    r01 = __shfl_sync(0xffffffffu, x0, 1);
+    r10 = __shfl_sync(0xffffffffu, x1, 0);
+    r11 = __shfl_sync(0xffffffffu, x1, 1);
+}
+
+__device__ __forceinline__ double bits_to_unit_double(uint32_t hi, uint32_t lo) {
+    const unsigned long long b = ((unsigned long long)hi << 32) | lo;
+    return __longlong_as_double((long long)((b >> 12) | 0x3FF0000000000000ull)) - 1.0;
+}
+
+// ------------------------------------------------------------------------------------------------ helpers
+__device__ __forceinline__ double sigmoid_d(double x) { return 1.0 / (1.0 + exp(-x)); }
+
+// isotonic_regression(sr)[-1] with unit weights: mean of the last pool (pava.py:9-61).
+__device__ __forceinline__ double pava_last(const double* sr, int P) {
+    double v[PMAX], w[PMAX];
+    int top = 0;
+    v[0] = sr[0]; w[0] = 1.0;
+    for (int t = 1; t < P; ++t) {
+        ++top;
+        v[top] = sr[t]; w[top] = 1.0;
+        while (top > 0 && (v[top - 1] / w[top - 1]) > (v[top] / w[top])) {
+            --top;
+            v[top] = v[top] + v[top + 1];
+            w[top] = w[top] + w[top + 1];
+        }
+    }
+    return v[top] / w[top];
+}
+
+struct Ctx {
+    int N, K, P, nnz, it;
+    double *X, *PA, *PB, *lam, *cst, *y, *ss, *pred, *resid, *z, *mu, *beta, *bvec, *dvec, *wvec, *slam, *slam2, *sp,
+        *phibar, *phi, *phicov, *phiz, *phicovz, *lamhist;
+    int *row_ptr, *col_ptr, *col_k, *csc_row, *csc_pos, *cntp, *n0p, *n1p, *act, *ainv, *order, *order2, *pos, *rownz,
+        *phizok, *dcnt, *dlist;
+    uint32_t *sortkeys, *keys;
+    unsigned char *pw, *mask, *blocked;
+    const double *mu0, *beta0, *phi0, *phicov0;
+    double* red;      // shared: NW doubles scratch
+    double* sm;       // shared: dynamic region
+    int smd;          // its size in doubles
+};
+
+__device__ __forceinline__ double block_sum(double v, double* red) {
+    v = warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double r = 0.0;
+#pragma unroll
+    for (int i = 0; i < NW; ++i) r += red[i];
+    return r;
+}
+__device__ __forceinline__ int block_sum_int(int v, double* red) {
+    v = warp_sum(v);
+    int* ri = reinterpret_cast<int*>(red);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) ri[threadIdx.x >> 5] = v;
+    __syncthreads();
+    int r = 0;
+#pragma unroll
+    for (int i = 0; i < NW; ++i) r += ri[i];
+    return r;
+}
+
+// ordered compaction of {i < n : flag(i)} into out[]; returns the count (block-wide, deterministic)
+template <typename F>
+__device__ int block_compact(int n, F flag, int* out, int* inv, double* red) {
+    int* wcnt = reinterpret_cast<int*>(red);     // NW ints
+    __shared__ int base_s;
+    if (threadIdx.x == 0) base_s = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int i0 = 0; i0 < n; i0 += NT) {
+        const int i = i0 + threadIdx.x;
+        const bool f = i < n && flag(i);
+        const unsigned bal = __ballot_sync(0xffffffffu, f);
+        if (lane == 0) wcnt[wid] = __popc(bal);
+        __syncthreads();
+        int off = base_s;
+        for (int w = 0; w < wid; ++w) off += wcnt[w];
+        if (f) {
+            const int idx = off + __popc(bal & ((1u << lane) - 1u));
+            out[idx] = i;
+            if (inv) inv[i] = idx;
+        } else if (i < n && inv) {
+            inv[i] = -1;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int t = 0;
+            for (int w = 0; w < NW; ++w) t += wcnt[w];
+            base_s += t;
+        }
+        __syncthreads();
+    }
+    return base_s;
+}
+
+// fresh prediction pred[k] = sum_n mu[n] lam[n,k] over the (neuron-sorted) column lists
+__device__ __forceinline__ void compute_pred(const Ctx& c, double* dst) {
+    for (int k = threadIdx.x; k < c.K; k += NT) {
+        double s = 0.0;
+        for (int i = c.col_ptr[k]; i < c.col_ptr[k + 1]; ++i) s += c.mu[c.csc_row[i]] * c.lam[c.csc_pos[i]];
+        dst[k] = s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ a2
+// block_update_mu (caviar.py:166-172) on the active set A = {n : lam[n,:] != 0}:
+// M = sigma (diag(sum lam(1-lam)) + lam_A lam_A^T) + diag(1/beta0^2);  C = M^-1;  mu = C b;  beta = diag C.
+// C = X^T X with X = L^-1 built by a bordered (block-row) recursion that keeps X (lower) and X^T (upper) in one
+// na x na array, so both panel GEMMs read it with unit stride across threads.
+__device__ void gram_rows(const Ctx& c, int na, int i0, int nb, double sigma) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int cap = c.smd / NW;                   // row-buffer doubles per warp
+    for (int r = wid; r < nb; r += NW) {
+        const int ia = i0 + r;
+        const int n = c.act[ia];
+        double* acc = (ia + 1 <= cap) ? (c.sm + (size_t)wid * cap) : (c.PA + (size_t)r * na);
+        for (int q = lane; q <= ia; q += 32) acc[q] = 0.0;
+        __syncwarp();
+        const int beg = c.row_ptr[n], end = c.row_ptr[n + 1];
+        for (int jb = beg; jb < end; jb += 32) {
+            const int j = jb + lane;
+            double myla = 0.0;
+            int mycb = 0, myce = 0;
+            if (j < end) {
+                myla = c.lam[j];
+                const int k = c.col_k[j];
+                mycb = c.col_ptr[k];
+                myce = c.col_ptr[k + 1];
+            }
+            const int cnt = min(32, end - jb);
+            for (int t = 0; t < cnt; ++t) {
+                const double la = __shfl_sync(0xffffffffu, myla, t);
+                if (la == 0.0) continue;
+                const int cb = __shfl_sync(0xffffffffu, mycb, t), ce = __shfl_sync(0xffffffffu, myce, t);
+                for (int i = cb + lane; i < ce; i += 32) {
+                    const int ib = c.ainv[c.csc_row[i]];
+                    if (ib >= 0 && ib <= ia) acc[ib] += la * c.lam[c.csc_pos[i]];
+                }
+                __syncwarp();
+            }
+        }
+        const double b0 = c.beta0[n];
+        const double dd = c.dvec[ia];
+        double* prow = c.PA + (size_t)r * na;
+        for (int q = lane; q <= ia; q += 32) {
+            double v = acc[q];
+            if (q == ia) v = sigma * (dd + v) + 1.0 / (b0 * b0);
+            else v = sigma * v;
+            prow[q] = v;
+        }
+        __syncwarp();
+    }
+}
+
+// OUT[r][cc] = sum_kk IN[r][kk] * X[kk][cc] over kk in [klo(cc), khi(cc)) ; UPPER: kk<=cc (X^T half), else kk>=cc.
+template <bool UPPER>
+__device__ void panel_gemm(const Ctx& c, int na, int i0, int nb, const double* IN, double* OUT, double* As) {
+    constexpr int KC = 32;
+    const int i0r = (i0 + 31) & ~31;
+    const int items = i0r * RG;
+    for (int base = 0; base < items; base += NT) {      // all threads iterate the same number of rounds
+        const int item = base + threadIdx.x;
+        const int rg = item / i0r;
+        const int cc = item - rg * i0r;
+        const bool valid = item < items && cc < i0;
+        double acc[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[q] = 0.0;
+        for (int kk0 = 0; kk0 < i0; kk0 += KC) {
+            __syncthreads();
+            for (int e = threadIdx.x; e < KC * NB; e += NT) {
+                const int r = e / KC, kl = e - r * KC;
+                const int kk = kk0 + kl;
+                As[kl * NB + r] = (r < nb && kk < i0) ? IN[(size_t)r * na + kk] : 0.0;
+            }
+            __syncthreads();
+            if (valid) {
+                const bool touch = UPPER ? (kk0 <= cc) : (kk0 + KC > cc);
+                if (touch) {
+                    const int kend = min(KC, i0 - kk0);
+#pragma unroll 4
+                    for (int kl = 0; kl < kend; ++kl) {
+                        const int kk = kk0 + kl;
+                        const bool in = UPPER ? (kk <= cc) : (kk >= cc);
+                        if (in) {
+                            const double x = c.X[(size_t)kk * na + cc];
+                            const double* ap = As + kl * NB + rg * 8;
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) acc[q] = fma(ap[q], x, acc[q]);
+                        }
+                    }
+                }
+            }
+        }
+        if (valid) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int r = rg * 8 + q;
+                if (r < nb) OUT[(size_t)r * na + cc] = acc[q];
+            }
+        }
+    }
+    __syncthreads();
+}
+
+__device__ void phase_a2(const Ctx& c, double sigma, int* na_s) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int N = c.N;
+    const int na = block_compact(N, [&](int i) { return c.rownz[i] > 0; }, c.act, c.ainv, c.red);
+    if (threadIdx.x == 0) *na_s = na;
+    // inactive rows decouple: mu = mu0, beta = beta0^2 (variance)
+    for (int n = threadIdx.x; n < N; n += NT)
+        if (c.rownz[n] == 0) { c.mu[n] = c.mu0[n]; c.beta[n] = c.beta0[n] * c.beta0[n]; }
+    // per active row: D = sum lam(1-lam), b = sigma * sum lam*y + mu0/beta0^2
+    for (int ia = wid; ia < na; ia += NW) {
+        const int n = c.act[ia];
+        double d = 0.0, by = 0.0;
+        for (int j = c.row_ptr[n] + lane; j < c.row_ptr[n + 1]; j += 32) {
+            const double l = c.lam[j];
+            d += l * (1.0 - l);
+            by += l * c.y[c.col_k[j]];
+        }
+        d = warp_sum(d); by = warp_sum(by);
+        if (lane == 0) {
+            const double b0 = c.beta0[n];
+            c.dvec[ia] = d;
+            c.bvec[ia] = sigma * by + c.mu0[n] / (b0 * b0);
+        }
+    }
+    __syncthreads();
+    if (na == 0) return;
+
+    __shared__ double Sd[NB][NB + 1];     // diagonal block -> its Cholesky factor
+    __shared__ double Xd[NB][NB + 1];     // inverse of the diagonal factor
+    __shared__ double As[32 * NB];        // staged panel chunk
+    for (int i0 = 0; i0 < na; i0 += NB) {
+        const int nb = min(NB, na - i0);
+        gram_rows(c, na, i0, nb, sigma);          // PA[r][0..i0+r] = M[i0+r][.]
+        __syncthreads();
+        if (i0 > 0) panel_gemm<true>(c, na, i0, nb, c.PA, c.PB, As);   // PB = Lrow = A[I,0:i0] X11^T
+        // S = A[I,I] - Lrow Lrow^T
+        for (int pr = wid; pr < nb * NB; pr += NW) {
+            const int r = pr / NB, r2 = pr - r * NB;
+            if (r2 > r || r2 >= nb) continue;
+            double s = 0.0;
+            for (int q = lane; q < i0; q += 32) s += c.PB[(size_t)r * na + q] * c.PB[(size_t)r2 * na + q];
+            s = warp_sum(s);
+            if (lane == 0) Sd[r][r2] = c.PA[(size_t)r * na + i0 + r2] - s;
+        }
+        __syncthreads();
+        if (wid == 0) {
+            // Cholesky of the nb x nb block (lane = row), then its inverse (lane = column)
+            for (int j = 0; j < nb; ++j) {
+                const double djj = sqrt(Sd[j][j]);
+                __syncwarp();
+                if (lane == j) Sd[j][j] = djj;
+                if (lane > j && lane < nb) Sd[lane][j] /= djj;
+                __syncwarp();
+                if (lane > j && lane < nb)
+                    for (int q = j + 1; q <= lane; ++q) Sd[lane][q] -= Sd[lane][j] * Sd[q][j];
+                __syncwarp();
+            }
+            if (lane < nb) {
+                const int cc = lane;
+                Xd[cc][cc] = 1.0 / Sd[cc][cc];
+                for (int r = cc + 1; r < nb; ++r) {
+                    double s = 0.0;
+                    for (int t = cc; t < r; ++t) s += Sd[r][t] * Xd[t][cc];
+                    Xd[r][cc] = -s / Sd[r][r];
+                }
+            }
+        }
+        __syncthreads();
+        if (i0 > 0) {
+            panel_gemm<false>(c, na, i0, nb, c.PB, c.PA, As);           // PA = W = Lrow X11
+            // X[I, 0:i0] = -Xd W ; mirrored into the upper half
+            const int i0r = (i0 + 31) & ~31;
+            for (int item = threadIdx.x; item < i0r * RG; item += NT) {
+                const int rg = item / i0r, cc = item - rg * i0r;
+                if (cc >= i0) continue;
+                double wv[NB];
+#pragma unroll
+                for (int r = 0; r < NB; ++r) wv[r] = (r < nb) ? c.PA[(size_t)r * na + cc] : 0.0;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int r = rg * 8 + q;
+                    if (r < nb) {
+                        double s = 0.0;
+#pragma unroll
+                        for (int r2 = 0; r2 < NB; ++r2)
+                            if (r2 <= r) s += Xd[r][r2] * wv[r2];
+                        c.X[(size_t)(i0 + r) * na + cc] = -s;
+                        c.X[(size_t)cc * na + i0 + r] = -s;
+                    }
+                }
+            }
+        }
+        for (int e = threadIdx.x; e < nb * nb; e += NT) {
+            const int r = e / nb, r2 = e - r * nb;
+            if (r2 <= r) {
+                c.X[(size_t)(i0 + r) * na + i0 + r2] = Xd[r][r2];
+                c.X[(size_t)(i0 + r2) * na + i0 + r] = Xd[r][r2];
+            }
+        }
+        __syncthreads();
+    }
+    // w = X b ; mu = X^T w ; beta = column sums of squares of X
+    for (int i = wid; i < na; i += NW) {
+        double s = 0.0;
+        for (int q = lane; q <= i; q += 32) s += c.X[(size_t)i * na + q] * c.bvec[q];
+        s = warp_sum(s);
+        if (lane == 0) c.wvec[i] = s;
+    }
+    __syncthreads();
+    for (int cc = threadIdx.x; cc < na; cc += NT) {
+        double m = 0.0, v = 0.0;
+        for (int i = cc; i < na; ++i) {
+            const double x = c.X[(size_t)i * na + cc];
+            m += x * c.wvec[i];
+            v += x * x;
+        }
+        const int n = c.act[cc];
+        c.mu[n] = m;
+        c.beta[n] = v;
+    }
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------------ a3
+// One neuron of update_lam's sweep (caviar.py:200-227, reduced form App. A.8), executed by one warp.
+// chain=true: the neuron reads and updates the running prediction (mu[n] != 0).
+template <int PT>
+__device__ void sweep_neuron(const Ctx& c, int n, bool chain, double sigma, double thr, double minspk, bool gate,
+                             double* pred) {
+    const int lane = threadIdx.x & 31;
+    const int beg = c.row_ptr[n], end = c.row_ptr[n + 1];
+    const double mu_n = c.mu[n];
+    const double coef = sigma * mu_n;
+    double tot = 0.0, accp[PT];
+    int c0[PT], c1[PT];
+#pragma unroll
+    for (int p = 0; p < PT; ++p) { accp[p] = 0.0; c0[p] = 0; c1[p] = 0; }
+    for (int j = beg + lane; j < end; j += 32) {
+        const int k = c.col_k[j];
+        double est = 0.0;
+        if (c.mask[k]) {
+            const double x = chain ? (c.cst[j] - coef * pred[k]) : c.cst[j];
+            est = sigmoid_d(x);
+        }
+        c.cst[j] = est;
+        tot += est;
+        const int pw = c.pw[j];
+#pragma unroll
+        for (int p = 0; p < PT; ++p) {
+            const bool m = (pw == p);
+            accp[p] += m ? est : 0.0;
+            c0[p] += (m && est == 0.0);
+            c1[p] += (m && est == 1.0);
+        }
+    }
+    tot = warp_sum(tot);
+    double sr[PMAX];
+    for (int p = 0; p < c.P; ++p) {
+        double s = 0.0; int a0 = 0, a1 = 0;
+#pragma unroll
+        for (int q = 0; q < PT; ++q) if (q == p) { s = accp[q]; a0 = c0[q]; a1 = c1[q]; }
+        s = warp_sum(s); a0 = warp_sum(a0); a1 = warp_sum(a1);
+#pragma unroll
+        for (int q = 0; q < PT; ++q) if (q == p) { accp[q] = s; c0[q] = a0; c1[q] = a1; }
+        const int cnt = c.cntp[n * PMAX + p];
+        sr[p] = s / ((double)cnt + 1e-4 * (cnt == 0 ? 1.0 : 0.0));
+    }
+    bool ok = true;
+    if (gate) ok = (pava_last(sr, c.P) >= thr) && (tot >= minspk);
+    // second pass: commit the row, update the running prediction and the row statistics
+    double sl = 0.0, sl2 = 0.0;
+    int nz = 0;
+    for (int j = beg + lane; j < end; j += 32) {
+        const double nw = ok ? c.cst[j] : 0.0;
+        const double old = c.lam[j];
+        c.lam[j] = nw;
+        if (chain) {
+            const int k = c.col_k[j];
+            pred[k] = (pred[k] + (ok ? mu_n : 0.0) * nw) - mu_n * old;
+        }
+        sl += nw; sl2 += nw * nw; nz += (nw != 0.0);
+    }
+    sl = warp_sum(sl); sl2 = warp_sum(sl2); nz = warp_sum(nz);
+    if (lane == 0) {
+        c.slam[n] = sl; c.slam2[n] = sl2; c.rownz[n] = nz;
+        for (int p = 0; p < c.P; ++p) {
+            double s = 0.0; int a0 = 0, a1 = 0;
+#pragma unroll
+            for (int q = 0; q < PT; ++q) if (q == p) { s = accp[q]; a0 = c0[q]; a1 = c1[q]; }
+            const int cnt = c.cntp[n * PMAX + p];
+            c.sp[n * PMAX + p] = ok ? s : 0.0;
+            c.n0p[n * PMAX + p] = ok ? a0 : cnt;
+            c.n1p[n * PMAX + p] = ok ? a1 : 0;
+        }
+    }
+    __syncwarp();
+}
+
+// PRNG work for one iteration, done by ONE warp: shuffle sub-keys, the N per-neuron sample keys
+// (key, key_next = split(key), caviar.py:209) and the key the next iteration starts from (caviar.py:251,304).
+__device__ void rng_iteration(int N, int rounds, uint32_t& k0, uint32_t& k1, uint32_t* keys_out, uint32_t* subkeys) {
+    const int lane = threadIdx.x & 31;
+    uint32_t p0 = k0, p1 = k1;
+    for (int r = 0; r < rounds; ++r) {                 // permutation(key): key, subkey = split(key) per round
+        uint32_t a, b, s0, s1;
+        warp_split(p0, p1, a, b, s0, s1);
+        p0 = a; p1 = b;
+        if (lane == 0) { subkeys[2 * r] = s0; subkeys[2 * r + 1] = s1; }
+    }
+    uint32_t c0 = k0, c1 = k1;
+    for (int m = 0; m < N; ++m) {
+        uint32_t s0, s1, n0, n1;
+        warp_split(c0, c1, s0, s1, n0, n1);
+        if (lane == 0) { keys_out[2 * m] = s0; keys_out[2 * m + 1] = s1; }
+        c0 = n0; c1 = n1;
+    }
+    uint32_t a, b, n0, n1;
+    warp_split(c0, c1, a, b, n0, n1);                  // update_phi returns split(key)[1]
+    k0 = n0; k1 = n1;
+}
+
+// ------------------------------------------------------------------------------------------------ a7
+struct NewtonStats {
+    int P;
+    double pv[PMAX + 1], cnt[PMAX + 1], S[PMAX + 1], n0[PMAX + 1], n1[PMAX + 1];
+};
+
+__device__ __forceinline__ double group_loglik(double f, double cnt, double S, double n0, double n1) {
+    if (cnt == 0.0) return 0.0;
+    if (f != f) return 0.0;                                   // nan_to_num(nan) = 0
+    if (f == 1.0) return -DBL_MAX * (cnt - n1);               // lam<1 elements are -inf -> -DBL_MAX each
+    if (f == 0.0) return -DBL_MAX * (cnt - n0);
+    return S * log(f) + (cnt - S) * log(1.0 - f);
+}
+
+// negloglik_with_barrier (caviar.py:312-316) from per-power sufficient statistics
+__device__ double nll_reduced(const NewtonStats& s, double p0, double p1, const double* prior, const double* prec,
+                              double t) {
+    double ll = 0.0;
+    for (int g = 0; g <= s.P; ++g) {
+        const double f = sigmoid_d(p0 * s.pv[g] - p1);
+        ll += group_loglik(f, s.cnt[g], s.S[g], s.n0[g], s.n1[g]);
+    }
+    const double d0 = p0 - prior[0], d1 = p1 - prior[1];
+    const double quad = 0.5 * (d0 * (prec[0] * d0 + prec[1] * d1) + d1 * (prec[2] * d0 + prec[3] * d1));
+    return -ll - (log(p0) + log(p1)) / t + quad;
+}
+
+// _laplace_approx (caviar.py:253-308): 10 damped Newton steps from the PRIOR mean; covariance = H^-1 before the last step
+__device__ void laplace_newton(const NewtonStats& s, const double* prior, const double* cov0, double* phi_out,
+                               double* cov_out) {
+    const double t = 10.0, alpha = 0.25, bbeta = 0.5;
+    const double det0 = cov0[0] * cov0[3] - cov0[1] * cov0[2];
+    const double prec[4] = {cov0[3] / det0, -cov0[1] / det0, -cov0[2] / det0, cov0[0] / det0};
+    double p0 = prior[0], p1 = prior[1];
+    double hi[4] = {0, 0, 0, 0};
+    for (int step = 0; step < 10; ++step) {
+        double j1 = 0, j2 = 0, h11 = 0, h12 = 0, h22 = 0;
+        for (int g = 0; g <= s.P; ++g) {
+            const double f = sigmoid_d(p0 * s.pv[g] - p1);
+            const double r = s.S[g] - s.cnt[g] * f;
+            const double w = s.cnt[g] * f * (1.0 - f);
+            j1 -= s.pv[g] * r;
+            j2 += r;
+            h11 += s.pv[g] * s.pv[g] * w;
+            h12 -= s.pv[g] * w;
+            h22 += w;
+        }
+        const double d0 = p0 - prior[0], d1 = p1 - prior[1];
+        const double J0 = j1 + (prec[0] * d0 + prec[1] * d1) - 1.0 / (t * p0);
+        const double J1 = j2 + (prec[2] * d0 + prec[3] * d1) - 1.0 / (t * p1);
+        const double H00 = h11 + prec[0] + 1.0 / (t * p0 * p0);
+        const double H01 = h12 + prec[1];
+        const double H10 = h12 + prec[2];
+        const double H11 = h22 + prec[3] + 1.0 / (t * p1 * p1);
+        const double det = H00 * H11 - H01 * H10;
+        hi[0] = H11 / det; hi[1] = -H01 / det; hi[2] = -H10 / det; hi[3] = H00 / det;
+        const double v0 = -(hi[0] * J0 + hi[1] * J1), v1 = -(hi[2] * J0 + hi[3] * J1);
+        double stp = 1.0;
+        const double base = nll_reduced(s, p0, p1, prior, prec, t);
+        const double Jv = J0 * v0 + J1 * v1;
+        double lhs = nll_reduced(s, p0 + stp * v0, p1 + stp * v1, prior, prec, t);
+        double rhs = base + alpha * stp * Jv;
+        int bt = 0;
+        while (bt < 40 && ((lhs != lhs) || lhs > rhs)) {
+            ++bt;
+            stp *= bbeta;
+            lhs = nll_reduced(s, p0 + stp * v0, p1 + stp * v1, prior, prec, t);
+            rhs = base + alpha * stp * Jv;
+        }
+        p0 += stp * v0;
+        p1 += stp * v1;
+    }
+    phi_out[0] = p0; phi_out[1] = p1;
+    cov_out[0] = hi[0]; cov_out[1] = hi[1]; cov_out[2] = hi[2]; cov_out[3] = hi[3];
+}
+
+__device__ void newton_row(const Ctx& c, const double* powers, int n) {
+    const bool zero_row = c.rownz[n] == 0;
+    if (zero_row && c.phizok[n]) {
+        c.phi[2 * n] = c.phiz[2 * n]; c.phi[2 * n + 1] = c.phiz[2 * n + 1];
+        for (int q = 0; q < 4; ++q) c.phicov[4 * n + q] = c.phicovz[4 * n + q];
+        return;
+    }
+    NewtonStats s;
+    s.P = c.P;
+    double ctot = 0.0;
+    for (int p = 0; p < c.P; ++p) {
+        s.pv[p + 1] = powers[p];
+        s.cnt[p + 1] = (double)c.cntp[n * PMAX + p];
+        s.S[p + 1] = c.sp[n * PMAX + p];
+        s.n0[p + 1] = (double)c.n0p[n * PMAX + p];
+        s.n1[p + 1] = (double)c.n1p[n * PMAX + p];
+        ctot += s.cnt[p + 1];
+    }
+    s.pv[0] = 0.0; s.cnt[0] = (double)c.K - ctot; s.S[0] = 0.0; s.n0[0] = s.cnt[0]; s.n1[0] = 0.0;
+    laplace_newton(s, c.phi0 + 2 * n, c.phicov0 + 4 * n, c.phi + 2 * n, c.phicov + 4 * n);
+    if (zero_row) {
+        c.phiz[2 * n] = c.phi[2 * n]; c.phiz[2 * n + 1] = c.phi[2 * n + 1];
+        for (int q = 0; q < 4; ++q) c.phicovz[4 * n + q] = c.phicov[4 * n + q];
+        c.phizok[n] = 1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ the fit
+template <int PT>
+__global__ void __launch_bounds__(NT, 1) caviar_fit_kernel(const FitParams p) {
+    extern __shared__ __align__(16) double dyn_smem[];
+    __shared__ double red[NW + 2];
+    __shared__ double sc_shape, sc_rate, sc_spont, sc_err;
+    __shared__ int sc_na, sc_flag, sc_focus;
+    __shared__ uint32_t sc_key[2];
+    __shared__ uint32_t sc_subkeys[2 * MAX_SHUFFLE_ROUNDS];
+    __shared__ double sc_powers[PMAX];
+
+    const int b = blockIdx.x;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    char* base = p.ws + (size_t)b * p.L.stride;
+    const Layout& L = p.L;
+    Ctx c;
+    c.N = p.N; c.K = p.K; c.P = p.P; c.it = 0;
+#define CM_D(name) c.name = reinterpret_cast<double*>(base + L.name)
+#define CM_I(name) c.name = reinterpret_cast<int*>(base + L.name)
+    CM_D(X); CM_D(PA); CM_D(PB); CM_D(lam); CM_D(cst); CM_D(y); CM_D(ss); CM_D(pred); CM_D(resid); CM_D(z); CM_D(mu);
+    CM_D(beta); CM_D(bvec); CM_D(dvec); CM_D(wvec); CM_D(slam); CM_D(slam2); CM_D(sp); CM_D(phibar); CM_D(phi);
+    CM_D(phicov); CM_D(phiz); CM_D(phicovz); CM_D(lamhist);
+    CM_I(row_ptr); CM_I(col_ptr); CM_I(col_k); CM_I(csc_row); CM_I(csc_pos); CM_I(cntp); CM_I(n0p); CM_I(n1p);
+    CM_I(act); CM_I(ainv); CM_I(order); CM_I(order2); CM_I(pos); CM_I(rownz); CM_I(phizok); CM_I(dcnt); CM_I(dlist);
+#undef CM_D
+#undef CM_I
+    c.sortkeys = reinterpret_cast<uint32_t*>(base + L.sortkeys);
+    c.keys = reinterpret_cast<uint32_t*>(base + L.keys);
+    c.pw = reinterpret_cast<unsigned char*>(base + L.pw);
+    c.mask = reinterpret_cast<unsigned char*>(base + L.mask);
+    c.blocked = reinterpret_cast<unsigned char*>(base + L.blocked);
+    c.mu0 = p.mu0 + (size_t)b * p.N;
+    c.beta0 = p.beta0 + (size_t)b * p.N;
+    c.phi0 = p.phi0 + (size_t)b * p.N * 2;
+    c.phicov0 = p.phicov0 + (size_t)b * p.N * 4;
+    c.red = red;
+    c.sm = dyn_smem;
+    c.smd = p.smem_doubles;
+    const int N = c.N, K = c.K, P = c.P;
+    const cm_caviar_options& o = p.opt;
+    if (p.status[b] != 0) return;                     // prologue reported an error for this fit
+    c.nnz = c.row_ptr[N];
+    const int iters = o.iters;
+    const int S = o.num_mc_samples;
+    // number of shuffle rounds of jax.random.permutation: ceil(3 ln N / ln(2^32-1))
+    int rounds = (int)ceil(3.0 * log((double)max(1, N)) / log(4294967295.0));
+    rounds = min(rounds, MAX_SHUFFLE_ROUNDS);
+    double* pred = (K <= c.smd) ? c.sm : c.pred;      // running prediction lives in shared memory when it fits
+
+    // ---------------- init (caviar.py:28-51) ----------------
+    if (threadIdx.x < PMAX) sc_powers[threadIdx.x] = threadIdx.x < P ? p.powers[threadIdx.x] : 0.0;
+    if (threadIdx.x == 0) {
+        sc_shape = p.shape0_arr ? p.shape0_arr[b] : p.shape0;
+        sc_rate = p.rate0_arr ? p.rate0_arr[b] : p.rate0;
+        sc_spont = 0.0;
+        const unsigned long long seed = p.seeds[b];
+        sc_key[0] = (uint32_t)(seed >> 32);
+        sc_key[1] = (uint32_t)(seed & 0xffffffffull);
+    }
+    for (int k = threadIdx.x; k < K; k += NT) {
+        c.mask[k] = c.ss[k] > o.y_xcorr_thresh ? 1 : 0;
+        c.z[k] = 0.0;
+    }
+    for (int n = threadIdx.x; n < N; n += NT) {
+        c.phi[2 * n] = c.phi0[2 * n]; c.phi[2 * n + 1] = c.phi0[2 * n + 1];
+        for (int q = 0; q < 4; ++q) c.phicov[4 * n + q] = c.phicov0[4 * n + q];
+        c.phizok[n] = 0;
+        c.mu[n] = c.mu0[n]; c.beta[n] = c.beta0[n];
+    }
+    __syncthreads();
+    for (int n = wid; n < N; n += NW) {               // lam0 = 0.95 [I>0] lam_mask
+        double sl = 0.0; int nz = 0;
+        for (int j = c.row_ptr[n] + lane; j < c.row_ptr[n + 1]; j += 32) {
+            const double v = c.mask[c.col_k[j]] ? 0.95 : 0.0;
+            c.lam[j] = v; sl += v; nz += (v != 0.0);
+        }
+        sl = warp_sum(sl); nz = warp_sum(nz);
+        if (lane == 0) { c.slam[n] = sl; c.slam2[n] = sl * 0.95; c.rownz[n] = nz; }
+    }
+    double sumy = 0.0, ysq = 0.0;
+    for (int k = threadIdx.x; k < K; k += NT) { const double v = c.y[k]; sumy += v; ysq += v * v; }
+    sumy = block_sum(sumy, red);
+    ysq = block_sum(ysq, red) + 1e-5;
+    // PRNG stream for iteration 0
+    uint32_t rk0 = sc_key[0], rk1 = sc_key[1];
+    if (wid == NW - 1) rng_iteration(N, rounds, rk0, rk1, c.keys, sc_subkeys);
+    __syncthreads();
+
+    for (int it = 0; it < iters; ++it) {
+        c.it = it;
+        const double sigma = sc_shape / sc_rate;
+        // ================= a2: block_update_mu =================
+        phase_a2(c, sigma, &sc_na);
+        // ================= a3: update_lam =================
+        uint32_t* keys_cur = c.keys + (size_t)(it & 1) * 2 * N;
+        uint32_t* keys_nxt = c.keys + (size_t)((it + 1) & 1) * 2 * N;
+        // update order: permutation(key, N) by `rounds` stable sorts on fresh 32-bit keys (caviar.py:196)
+        for (int n = threadIdx.x; n < N; n += NT) c.order[n] = n;
+        __syncthreads();
+        for (int r = 0; r < rounds; ++r) {
+            const uint32_t s0 = sc_subkeys[2 * r], s1 = sc_subkeys[2 * r + 1];
+            const int h = (N + 1) / 2;
+            for (int q = threadIdx.x; q < h; q += NT) {
+                uint32_t x0 = (uint32_t)q, x1 = (h + q < N) ? (uint32_t)(h + q) : 0u;
+                threefry2x32(s0, s1, x0, x1);
+                c.sortkeys[q] = x0;
+                if (h + q < N) c.sortkeys[h + q] = x1;
+            }
+            __syncthreads();
+            for (int i = threadIdx.x; i < N; i += NT) {
+                const uint32_t ki = c.sortkeys[i];
+                int rank = 0;
+                for (int j = 0; j < N; ++j) {
+                    const uint32_t kj = c.sortkeys[j];
+                    rank += (kj < ki) || (kj == ki && j < i);
+                }
+                c.order2[rank] = c.order[i];
+            }
+            __syncthreads();
+            for (int n = threadIdx.x; n < N; n += NT) c.order[n] = c.order2[n];
+            __syncthreads();
+        }
+        for (int m = threadIdx.x; m < N; m += NT) c.pos[c.order[m]] = m;
+        __syncthreads();
+        // Monte-Carlo means of the truncated-normal sigmoid coefficients (caviar.py:209-215, App. A.2)
+        for (int n = wid; n < N; n += NW) {
+            const int m = c.pos[n];
+            const uint32_t k0 = keys_cur[2 * m], k1 = keys_cur[2 * m + 1];
+            const int cc = lane & 1;                                   // flat index e = 2 s + component
+            const double mean = c.phi[2 * n + cc];
+            const double sd = c.phicov[4 * n + 3 * cc];                // diag(phi_cov): a variance used as sd
+            const double cdf0 = normcdf(-mean / sd);
+            double acc = 0.0;
+            for (int e = lane; e < 2 * S; e += 32) {
+                uint32_t x0 = (uint32_t)e, x1 = (uint32_t)(2 * S + e);
+                threefry2x32(k0, k1, x0, x1);
+                const double u = bits_to_unit_double(x0, x1);
+                acc += normcdfinv(cdf0 + u * (1.0 - cdf0)) * sd + mean;
+            }
+#pragma unroll
+            for (int off = 16; off > 1; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+            if (lane < 2) c.phibar[2 * n + lane] = acc / (double)S;
+        }
+        compute_pred(c, pred);
+        __syncthreads();
+        // per-entry constant part of the sigmoid argument
+        for (int n = wid; n < N; n += NW) {
+            const double mu_n = c.mu[n], be = c.beta[n];
+            const double pb0 = c.phibar[2 * n], pb1 = c.phibar[2 * n + 1];
+            const double cterm = 0.5 * sigma * (mu_n * mu_n + be * be);
+            for (int j = c.row_ptr[n] + lane; j < c.row_ptr[n + 1]; j += 32) {
+                const int k = c.col_k[j];
+                const double pwv = sc_powers[c.pw[j]];
+                c.cst[j] = (pb0 * pwv - pb1 - cterm) + sigma * mu_n * c.y[k] + sigma * mu_n * mu_n * c.lam[j];
+            }
+        }
+        __syncthreads();
+        {
+            const double thr = o.msrmp + sc_spont;
+            const bool gate = it > o.delay_spont_est;
+            if (wid == 0) {
+                // the sequential chain: neurons with mu != 0, in update order
+                for (int m = 0; m < N; ++m) {
+                    const int n = c.order[m];
+                    if (c.mu[n] != 0.0) sweep_neuron<PT>(c, n, true, sigma, thr, o.minimum_spike_count, gate, pred);
+                }
+            } else if (wid == NW - 1) {
+                if (it + 1 < iters) rng_iteration(N, rounds, rk0, rk1, keys_nxt, sc_subkeys);
+            } else {
+                // mu == 0: the row neither reads nor changes the prediction -> order-free, run concurrently
+                for (int m = wid - 1; m < N; m += NW - 2) {
+                    const int n = c.order[m];
+                    if (c.mu[n] == 0.0) sweep_neuron<PT>(c, n, false, sigma, thr, o.minimum_spike_count, gate, pred);
+                }
+            }
+        }
+        __syncthreads();
+        // ================= a6: update_sigma (caviar.py:238-244), with a2's mu =================
+        compute_pred(c, pred);
+        __syncthreads();
+        {
+            double s1 = 0.0, s2 = 0.0, s3 = 0.0;
+            for (int k = threadIdx.x; k < K; k += NT) {
+                const double r = c.y[k] - pred[k];
+                c.resid[k] = r;
+                s1 += r * r;
+            }
+            for (int n = threadIdx.x; n < N; n += NT) {
+                const double m = c.mu[n], be = c.beta[n];
+                s2 += m * m * c.slam2[n];
+                s3 += (m * m + be * be) * c.slam[n];
+            }
+            s1 = block_sum(s1, red); s2 = block_sum(s2, red); s3 = block_sum(s3, red);
+            if (threadIdx.x == 0) {
+                sc_shape = (p.shape0_arr ? p.shape0_arr[b] : p.shape0) + (double)K / 2.0;
+                sc_rate = (p.rate0_arr ? p.rate0_arr[b] : p.rate0) + 0.5 * (s1 - s2 + s3);
+            }
+        }
+        // ================= a7: update_phi (caviar.py:246-310) =================
+        for (int n = threadIdx.x; n < N; n += NT) newton_row(c, sc_powers, n);
+        // ================= a8: estimate_spont_act_soft_thresh (caviar.py:146-163, 86-88) =================
+        for (int k = threadIdx.x; k < K; k += NT) {
+            unsigned char bl = 0;
+            for (int i = c.col_ptr[k]; i < c.col_ptr[k + 1]; ++i) bl |= (c.lam[c.csc_pos[i]] >= o.spont_orthogonality);
+            c.blocked[k] = bl;
+        }
+        __syncthreads();
+        {
+            double err = sumy, pen = o.penalty;
+            int j = it;
+            while (j < o.max_backtrack_iters && err > o.tol) {
+                double e = 0.0;
+                for (int k = threadIdx.x; k < K; k += NT) {
+                    const double r = c.resid[k];
+                    double zz = (r < pen) ? 0.0 : r - pen;
+                    zz = zz < 0.0 ? 0.0 : zz;
+                    if (c.blocked[k]) zz = 0.0;
+                    zz *= (double)c.mask[k];
+                    c.z[k] = zz;
+                    const double d = r - zz;
+                    e += d * d;
+                }
+                err = block_sum(e, red) / ysq;
+                ++j;
+                pen *= o.scale_factor;
+            }
+            int nzz = 0;
+            for (int k = threadIdx.x; k < K; k += NT) nzz += (c.z[k] != 0.0);
+            nzz = block_sum_int(nzz, red);
+            if (threadIdx.x == 0) sc_spont = (double)nzz / (double)K;
+        }
+        __syncthreads();
+        // ================= histories (caviar.py:90-92) =================
+        if (o.save_histories) {
+            const size_t hb = (size_t)b * iters + it;
+            if (p.mu_hist) for (int n = threadIdx.x; n < N; n += NT) p.mu_hist[hb * N + n] = c.mu[n];
+            if (p.beta_hist) for (int n = threadIdx.x; n < N; n += NT) p.beta_hist[hb * N + n] = c.beta[n];
+            if (p.phi_hist) for (int n = threadIdx.x; n < 2 * N; n += NT) p.phi_hist[hb * 2 * N + n] = c.phi[n];
+            if (p.phicov_hist) for (int n = threadIdx.x; n < 4 * N; n += NT) p.phicov_hist[hb * 4 * N + n] = c.phicov[n];
+            if (p.z_hist) for (int k = threadIdx.x; k < K; k += NT) p.z_hist[hb * K + k] = c.z[k];
+            if (threadIdx.x == 0) {
+                if (p.shape_hist) p.shape_hist[hb] = sc_shape;
+                if (p.rate_hist) p.rate_hist[hb] = sc_rate;
+            }
+            if (p.lamhist) for (int j = threadIdx.x; j < c.nnz; j += NT) c.lamhist[(size_t)it * c.nnz + j] = c.lam[j];
+            __syncthreads();
+        }
+    }
+
+    // ================= a9: reconnect_spont_cells (caviar.py:102-144) + final update_phi (caviar.py:98) =================
+    if (o.fn_scan) {
+        // disconnected cells in ascending order; per-cell count of spontaneous events on its stimulated trials
+        const int nd = block_compact(N, [&](int i) { return c.mu[i] == 0.0; }, c.dlist, nullptr, red);
+        int* alive = c.order2;               // 1 while the cell is still a candidate
+        for (int i = threadIdx.x; i < nd; i += NT) alive[i] = 1;
+        for (int n = threadIdx.x; n < N; n += NT) c.pos[n] = 0;      // "row changed" flags for the final update_phi
+        __syncthreads();
+        int remaining = nd;
+        bool recount = true;
+        while (remaining > 0) {
+            int nzz = 0;
+            for (int k = threadIdx.x; k < K; k += NT) nzz += (c.z[k] != 0.0);
+            nzz = block_sum_int(nzz, red);
+            if (!((double)nzz > o.minimum_spike_count)) break;
+            if (recount) {
+                for (int i = wid; i < nd; i += NW) {
+                    if (!alive[i]) continue;
+                    const int n = c.dlist[i];
+                    int cnt = 0;
+                    for (int j = c.row_ptr[n] + lane; j < c.row_ptr[n + 1]; j += 32) cnt += (c.z[c.col_k[j]] != 0.0);
+                    cnt = warp_sum(cnt);
+                    if (lane == 0) c.dcnt[i] = cnt;
+                }
+                recount = false;
+                __syncthreads();
+            }
+            // focus = first maximum of the counts among remaining cells (np.argmax, caviar.py:117)
+            long long best = -1;
+            for (int i = threadIdx.x; i < nd; i += NT)
+                if (alive[i]) {
+                    const long long key = ((long long)c.dcnt[i] << 32) | (unsigned)(0x7fffffff - i);
+                    best = key > best ? key : best;
+                }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const long long oth = __shfl_xor_sync(0xffffffffu, best, off);
+                best = oth > best ? oth : best;
+            }
+            long long* redl = reinterpret_cast<long long*>(red);
+            __syncthreads();
+            if (lane == 0) redl[wid] = best;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                long long bb = -1;
+                for (int w = 0; w < NW; ++w) bb = redl[w] > bb ? redl[w] : bb;
+                sc_focus = 0x7fffffff - (int)(bb & 0xffffffffll);
+                sc_flag = 0;
+            }
+            __syncthreads();
+            const int fi = sc_focus;
+            const int focus = c.dlist[fi];
+            const int maxcnt = c.dcnt[fi];
+            if ((double)maxcnt < o.minimum_spike_count) break;        // no remaining cell can pass (exact shortcut)
+            if (wid == 0) {
+                int cz[PT];
+#pragma unroll
+                for (int q = 0; q < PT; ++q) cz[q] = 0;
+                for (int j = c.row_ptr[focus] + lane; j < c.row_ptr[focus + 1]; j += 32) {
+                    const bool nzv = c.z[c.col_k[j]] != 0.0;
+                    const int pw = c.pw[j];
+#pragma unroll
+                    for (int q = 0; q < PT; ++q) cz[q] += (pw == q && nzv);
+                }
+                double sr[PMAX];
+                int spike_count = 0;
+                for (int pp = 0; pp < P; ++pp) {
+                    int v = 0;
+#pragma unroll
+                    for (int q = 0; q < PT; ++q) if (q == pp) v = cz[q];
+                    v = warp_sum(v);
+                    const int cnt = c.cntp[focus * PMAX + pp];
+                    sr[pp] = cnt > 0 ? (double)v / (double)cnt : 0.0;
+                    spike_count += v;
+                }
+                const double pv = pava_last(sr, P);
+                if (pv >= o.msrmp && (double)spike_count >= o.minimum_spike_count) {
+                    // mu = mean(z[locs]), beta = sem(z[locs]) (ddof=1), lam[focus, locs] = 1, z[locs] = 0
+                    double s = 0.0;
+                    for (int j = c.row_ptr[focus] + lane; j < c.row_ptr[focus + 1]; j += 32) s += c.z[c.col_k[j]];
+                    s = warp_sum(s);
+                    const double mean = s / (double)spike_count;
+                    double q2 = 0.0;
+                    for (int j = c.row_ptr[focus] + lane; j < c.row_ptr[focus + 1]; j += 32) {
+                        const double zv = c.z[c.col_k[j]];
+                        if (zv != 0.0) q2 += (zv - mean) * (zv - mean);
+                    }
+                    q2 = warp_sum(q2);
+                    __syncwarp();
+                    for (int j = c.row_ptr[focus] + lane; j < c.row_ptr[focus + 1]; j += 32) {
+                        const int k = c.col_k[j];
+                        if (c.z[k] != 0.0) {
+                            c.lam[j] = 1.0;
+                            c.z[k] = 0.0;
+                        }
+                    }
+                    if (lane == 0) {
+                        c.mu[focus] = mean;
+                        c.beta[focus] = spike_count > 1 ? sqrt(q2 / (double)(spike_count - 1)) / sqrt((double)spike_count)
+                                                        : __longlong_as_double(0x7ff8000000000000ll);
+                        c.pos[focus] = 1;
+                        sc_flag = 1;
+                    }
+                }
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) alive[fi] = 0;
+            if (sc_flag) recount = true;
+            --remaining;
+            __syncthreads();
+        }
+        __syncthreads();
+        // rows touched by reconnection: exact statistics from the row, then the Laplace/Newton update
+        for (int n = wid; n < N; n += NW) {
+            if (!c.pos[n]) continue;
+            double accp[PT]; int c0[PT], c1[PT];
+#pragma unroll
+            for (int q = 0; q < PT; ++q) { accp[q] = 0.0; c0[q] = 0; c1[q] = 0; }
+            int nz = 0;
+            for (int j = c.row_ptr[n] + lane; j < c.row_ptr[n + 1]; j += 32) {
+                const double l = c.lam[j];
+                const int pw = c.pw[j];
+                nz += (l != 0.0);
+#pragma unroll
+                for (int q = 0; q < PT; ++q) {
+                    const bool m = pw == q;
+                    accp[q] += m ? l : 0.0; c0[q] += (m && l == 0.0); c1[q] += (m && l == 1.0);
+                }
+            }
+            nz = warp_sum(nz);
+            for (int pp = 0; pp < P; ++pp) {
+                double s = 0.0; int a0 = 0, a1 = 0;
+#pragma unroll
+                for (int q = 0; q < PT; ++q) if (q == pp) { s = accp[q]; a0 = c0[q]; a1 = c1[q]; }
+                s = warp_sum(s); a0 = warp_sum(a0); a1 = warp_sum(a1);
+                if (lane == 0) { c.sp[n * PMAX + pp] = s; c.n0p[n * PMAX + pp] = a0; c.n1p[n * PMAX + pp] = a1; }
+            }
+            if (lane == 0) c.rownz[n] = nz;
+        }
+        __syncthreads();
+        for (int n = threadIdx.x; n < N; n += NT)
+            if (c.pos[n]) newton_row(c, sc_powers, n);
+        __syncthreads();
+    }
+
+    // ---------------- outputs ----------------
+    for (int n = threadIdx.x; n < N; n += NT) {
+        p.mu_out[(size_t)b * N + n] = c.mu[n];
+        p.beta_out[(size_t)b * N + n] = c.beta[n];
+    }
+    for (int n = threadIdx.x; n < 2 * N; n += NT) p.phi_out[(size_t)b * 2 * N + n] = c.phi[n];
+    for (int n = threadIdx.x; n < 4 * N; n += NT) p.phicov_out[(size_t)b * 4 * N + n] = c.phicov[n];
+    for (int k = threadIdx.x; k < K; k += NT) p.z_out[(size_t)b * K + k] = c.z[k];
+    if (threadIdx.x == 0) { p.shape_out[b] = sc_shape; p.rate_out[b] = sc_rate; }
+}
+
+// ------------------------------------------------------------------------------------------------ prologue kernels
+// a1: y = trapz(psc), ss = sum psc^2 per trace (caviar.py:28,30); one warp per trace, coalesced vector loads.
+template <typename T>
+__global__ void __launch_bounds__(256) psc_stats_kernel(const T* __restrict__ psc, long long ntraces, int Tn,
+                                                        const Layout L, char* ws, int K) {
+    const int lane = threadIdx.x & 31;
+    const long long tr = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (tr >= ntraces) return;
+    const T* row = psc + (size_t)tr * Tn;
+    double s1 = 0.0, s2 = 0.0;
+    for (int t = lane; t < Tn; t += 32) {
+        const double v = (double)row[t];
+        s1 += v; s2 += v * v;
+    }
+    s1 = warp_sum(s1); s2 = warp_sum(s2);
+    if (lane == 0) {
+        const int b = (int)(tr / K), k = (int)(tr - (long long)b * K);
+        double* y = reinterpret_cast<double*>(ws + (size_t)b * L.stride + L.y);
+        double* ss = reinterpret_cast<double*>(ws + (size_t)b * L.stride + L.ss);
+        y[k] = s1 - 0.5 * ((double)row[0] + (double)row[Tn - 1]);
+        ss[k] = s2;
+    }
+}
+
+__global__ void copy_stats_kernel(const double* __restrict__ yin, const double* __restrict__ ssin, const Layout L,
+                                  char* ws, int K, long long total) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int b = (int)(i / K), k = (int)(i - (long long)b * K);
+    reinterpret_cast<double*>(ws + (size_t)b * L.stride + L.y)[k] = yin[i];
+    reinterpret_cast<double*>(ws + (size_t)b * L.stride + L.ss)[k] = ssin[i];
+}
+
+struct PowerTable { double v[PMAX]; int P; };
+
+__device__ __forceinline__ int power_index(const PowerTable& pt, double v) {
+    for (int p = 0; p < pt.P; ++p) if (pt.v[p] == v) return p;
+    return -1;
+}
+
+// pass 1 over the dense design: per-row and per-column counts
+template <typename T>
+__global__ void __launch_bounds__(256) csr_count_kernel(const T* __restrict__ stim, int N, int K, const Layout L,
+                                                        char* ws, const PowerTable pt, int* status) {
+    const int n = blockIdx.x, b = blockIdx.y;
+    char* base = ws + (size_t)b * L.stride;
+    int* row_ptr = reinterpret_cast<int*>(base + L.row_ptr);
+    int* colcnt = reinterpret_cast<int*>(base + L.colfill);
+    int* cntp = reinterpret_cast<int*>(base + L.cntp);
+    __shared__ int cs[PMAX + 1];
+    if (threadIdx.x <= PMAX) cs[threadIdx.x] = 0;
+    __syncthreads();
+    const T* row = stim + ((size_t)b * N + n) * K;
+    int bad = 0;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+        const double v = (double)row[k];
+        if (v > 0.0) {
+            const int pi = power_index(pt, v);
+            if (pi < 0) bad = 1;
+            else { atomicAdd(&cs[pi], 1); atomicAdd(&cs[PMAX], 1); atomicAdd(&colcnt[k], 1); }
+        } else if (v < 0.0 || v != v) bad = 1;
+    }
+    if (bad) atomicExch(&status[b], CM_EINVAL);
+    __syncthreads();
+    if (threadIdx.x < PMAX) cntp[n * PMAX + threadIdx.x] = cs[threadIdx.x];
+    if (threadIdx.x == 0) row_ptr[n + 1] = cs[PMAX];      // counts; scanned next
+}
+
+// exclusive scans of the row / column counts (one CTA per fit)
+__global__ void __launch_bounds__(1024) scan_kernel(int N, int K, const Layout L, char* ws, long long nnz_cap,
+                                                    int* status) {
+    const int b = blockIdx.x;
+    char* base = ws + (size_t)b * L.stride;
+    int* row_ptr = reinterpret_cast<int*>(base + L.row_ptr);
+    int* col_ptr = reinterpret_cast<int*>(base + L.col_ptr);
+    int* colfill = reinterpret_cast<int*>(base + L.colfill);
+    __shared__ int wsum[32];
+    __shared__ int carry;
+    for (int pass = 0; pass < 2; ++pass) {
+        const int n = pass == 0 ? N : K;
+        if (threadIdx.x == 0) carry = 0;
+        __syncthreads();
+        for (int i0 = 0; i0 < n; i0 += 1024) {
+            const int i = i0 + threadIdx.x;
+            int v = 0;
+            if (i < n) v = pass == 0 ? row_ptr[i + 1] : colfill[i];
+            int inc = v;
+            const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += u;
+            }
+            if (lane == 31) wsum[wid] = inc;
+            __syncthreads();
+            int off = carry;
+            for (int w = 0; w < wid; ++w) off += wsum[w];
+            __syncthreads();
+            if (i < n) {
+                if (pass == 0) row_ptr[i + 1] = off + inc;         // inclusive -> row_ptr[i+1]
+                else { col_ptr[i + 1] = off + inc; colfill[i] = 0; }
+            }
+            if (threadIdx.x == 1023) carry = off + inc;
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            if (pass == 0) { row_ptr[0] = 0; if ((long long)carry > nnz_cap) atomicExch(&status[b], CM_EWORKSPACE); }
+            else col_ptr[0] = 0;
+        }
+        __syncthreads();
+    }
+}
+
+// pass 2 over the dense design: ordered CSR fill + unordered CSC scatter
+template <typename T>
+__global__ void __launch_bounds__(256) csr_fill_kernel(const T* __restrict__ stim, int N, int K, const Layout L,
+                                                       char* ws, const PowerTable pt, const int* status) {
+    const int n = blockIdx.x, b = blockIdx.y;
+    if (status[b] != 0) return;
+    char* base = ws + (size_t)b * L.stride;
+    const int* row_ptr = reinterpret_cast<const int*>(base + L.row_ptr);
+    const int* col_ptr = reinterpret_cast<const int*>(base + L.col_ptr);
+    int* colfill = reinterpret_cast<int*>(base + L.colfill);
+    int* col_k = reinterpret_cast<int*>(base + L.col_k);
+    int* csc_row = reinterpret_cast<int*>(base + L.csc_row);
+    int* csc_pos = reinterpret_cast<int*>(base + L.csc_pos);
+    unsigned char* pw = reinterpret_cast<unsigned char*>(base + L.pw);
+    __shared__ int wcnt[8];
+    __shared__ int run;
+    if (threadIdx.x == 0) run = row_ptr[n];
+    __syncthreads();
+    const T* row = stim + ((size_t)b * N + n) * K;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int k0 = 0; k0 < K; k0 += 256) {
+        const int k = k0 + threadIdx.x;
+        double v = 0.0;
+        if (k < K) v = (double)row[k];
+        const bool f = v > 0.0;
+        const unsigned bal = __ballot_sync(0xffffffffu, f);
+        if (lane == 0) wcnt[wid] = __popc(bal);
+        __syncthreads();
+        int off = run;
+        for (int w = 0; w < wid; ++w) off += wcnt[w];
+        if (f) {
+            const int j = off + __popc(bal & ((1u << lane) - 1u));
+            col_k[j] = k;
+            pw[j] = (unsigned char)power_index(pt, v);
+            const int slot = atomicAdd(&colfill[k], 1);
+            csc_row[col_ptr[k] + slot] = n;
+            csc_pos[col_ptr[k] + slot] = j;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < 8; ++w) t += wcnt[w]; run += t; }
+        __syncthreads();
+    }
+}
+
+// sort every column list by neuron index (deterministic summation order for pred / Gram)
+__global__ void csc_sort_kernel(int K, const Layout L, char* ws, const int* status, long long total) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int b = (int)(i / K), k = (int)(i - (long long)b * K);
+    if (status[b] != 0) return;
+    char* base = ws + (size_t)b * L.stride;
+    const int* col_ptr = reinterpret_cast<const int*>(base + L.col_ptr);
+    int* csc_row = reinterpret_cast<int*>(base + L.csc_row);
+    int* csc_pos = reinterpret_cast<int*>(base + L.csc_pos);
+    const int s = col_ptr[k], e = col_ptr[k + 1];
+    for (int a = s + 1; a < e; ++a) {
+        const int r = csc_row[a], q = csc_pos[a];
+        int t = a - 1;
+        while (t >= s && csc_row[t] > r) { csc_row[t + 1] = csc_row[t]; csc_pos[t + 1] = csc_pos[t]; --t; }
+        csc_row[t + 1] = r; csc_pos[t + 1] = q;
+    }
+}
+
+// scatter the sparse posterior back into the dense N x K array the reference returns (memset to 0 beforehand)
+__global__ void __launch_bounds__(128) densify_kernel(const Layout L, char* ws, int N, int K, double* __restrict__ out,
+                                                      int iters_hist, const int* status) {
+    const int n = blockIdx.x, b = blockIdx.z;
+    const int h = blockIdx.y;                     // history slot (0 when densifying the final state)
+    if (status[b] != 0) return;
+    char* base = ws + (size_t)b * L.stride;
+    const int* row_ptr = reinterpret_cast<const int*>(base + L.row_ptr);
+    const int* col_k = reinterpret_cast<const int*>(base + L.col_k);
+    const int nnz = row_ptr[N];
+    const double* src = iters_hist ? reinterpret_cast<const double*>(base + L.lamhist) + (size_t)h * nnz
+                                   : reinterpret_cast<const double*>(base + L.lam);
+    double* dst = out + (((size_t)b * (iters_hist ? iters_hist : 1) + h) * N + n) * (size_t)K;
+    for (int j = row_ptr[n] + threadIdx.x; j < row_ptr[n + 1]; j += blockDim.x) dst[col_k[j]] = src[j];
+}
+
+}  // namespace cav
+}  // namespace cm
+
+using namespace cm;
+using namespace cm::cav;
+
+extern "C" size_t cm_caviar_workspace_bytes(int B, int N, int K, int64_t nnz_cap, int save_histories) {
+    if (B <= 0 || N <= 0 || K <= 0 || nnz_cap < 0) return 0;
+    const Layout L = make_layout(N, K, nnz_cap, save_histories > 0 ? save_histories : 0, save_histories > 0);
+    return L.stride * (size_t)B + (size_t)B * 8 + 256;      // + device copy of the seeds
+}
+
+template <typename TS>
+static int run_csr(const cm_caviar_args* a, const Layout& L, char* ws, const PowerTable& pt, cudaStream_t st) {
+    dim3 grid(a->N, a->B);
+    csr_count_kernel<TS><<<grid, 256, 0, st>>>((const TS*)a->stim_dev, a->N, a->K, L, ws, pt, a->status_dev);
+    scan_kernel<<<a->B, 1024, 0, st>>>(a->N, a->K, L, ws, (long long)a->nnz_cap, a->status_dev);
+    csr_fill_kernel<TS><<<grid, 256, 0, st>>>((const TS*)a->stim_dev, a->N, a->K, L, ws, pt, a->status_dev);
+    const long long total = (long long)a->B * a->K;
+    csc_sort_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a->K, L, ws, a->status_dev, total);
+    count_launch(4);
+    CM_CUDA_CHECK(cudaGetLastError());
+    return CM_OK;
+}
+
+extern "C" int cm_caviar_fit(const cm_caviar_args* a, void* stream) {
+    reset_launch_count();
+    if (!a) { set_error("cm_caviar_fit: null args"); return CM_EINVAL; }
+    if (a->B <= 0 || a->N <= 0 || a->K <= 0) { set_error("cm_caviar_fit: bad shape B=%d N=%d K=%d", a->B, a->N, a->K); return CM_ESHAPE; }
+    if (a->n_powers < 1 || a->n_powers > PMAX) {
+        set_error("cm_caviar_fit: %d distinct powers unsupported (1..%d)", a->n_powers, PMAX);
+        return CM_EUNSUPPORTED;
+    }
+    if (!a->stim_dev || !a->powers || !a->seeds || !a->mu0_dev || !a->beta0_dev || !a->phi0_dev || !a->phi_cov0_dev ||
+        !a->shape0 || !a->rate0 || !a->mu_dev || !a->beta_dev || !a->shape_dev || !a->rate_dev || !a->phi_dev ||
+        !a->phi_cov_dev || !a->z_dev || !a->workspace_dev || !a->status_dev) {
+        set_error("cm_caviar_fit: null pointer among required arguments");
+        return CM_EINVAL;
+    }
+    if (!a->psc_dev && !(a->y_dev && a->ss_dev)) { set_error("cm_caviar_fit: need psc_dev or (y_dev, ss_dev)"); return CM_EINVAL; }
+    if (a->opt.iters < 0 || a->opt.num_mc_samples < 1) { set_error("cm_caviar_fit: bad iters/num_mc_samples"); return CM_EINVAL; }
+    const bool want_lamhist = a->opt.save_histories && a->lam_hist_dev;
+    const Layout L = make_layout(a->N, a->K, a->nnz_cap, a->opt.iters, want_lamhist);
+    const size_t need = L.stride * (size_t)a->B + (size_t)a->B * 8 + 256;
+    if (a->workspace_bytes < need) {
+        set_error("cm_caviar_fit: workspace %zu < required %zu bytes", a->workspace_bytes, need);
+        return CM_EWORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    char* ws = (char*)a->workspace_dev;
+    unsigned long long* seeds_dev = (unsigned long long*)(ws + L.stride * (size_t)a->B);
+    seeds_dev = (unsigned long long*)(((uintptr_t)seeds_dev + 255) & ~(uintptr_t)255);
+    CM_CUDA_CHECK(cudaMemcpyAsync(seeds_dev, a->seeds, (size_t)a->B * 8, cudaMemcpyHostToDevice, st));
+    CM_CUDA_CHECK(cudaMemsetAsync(a->status_dev, 0, (size_t)a->B * sizeof(int), st));
+    // zero the column counters of every fit
+    for (int b = 0; b < a->B; ++b)
+        CM_CUDA_CHECK(cudaMemsetAsync(ws + (size_t)b * L.stride + L.colfill, 0, (size_t)a->K * 4, st));
+
+    // ---- a1 prologue ----
+    const long long ntr = (long long)a->B * a->K;
+    if (a->psc_dev) {
+        if (a->T <= 0) { set_error("cm_caviar_fit: T=%d", a->T); return CM_ESHAPE; }
+        const unsigned blocks = (unsigned)((ntr + 7) / 8);
+        if (a->psc_dtype == CM_F32) psc_stats_kernel<float><<<blocks, 256, 0, st>>>((const float*)a->psc_dev, ntr, a->T, L, ws, a->K);
+        else if (a->psc_dtype == CM_F64) psc_stats_kernel<double><<<blocks, 256, 0, st>>>((const double*)a->psc_dev, ntr, a->T, L, ws, a->K);
+        else { set_error("cm_caviar_fit: bad psc dtype"); return CM_EINVAL; }
+    } else {
+        copy_stats_kernel<<<(unsigned)((ntr + 255) / 256), 256, 0, st>>>(a->y_dev, a->ss_dev, L, ws, a->K, ntr);
+    }
+    count_launch();
+    PowerTable pt{};
+    pt.P = a->n_powers;
+    for (int i = 0; i < a->n_powers; ++i) pt.v[i] = a->powers[i];
+    int rc;
+    if (a->stim_dtype == CM_F32) rc = run_csr<float>(a, L, ws, pt, st);
+    else if (a->stim_dtype == CM_F64) rc = run_csr<double>(a, L, ws, pt, st);
+    else { set_error("cm_caviar_fit: bad stim dtype"); return CM_EINVAL; }
+    if (rc) return rc;
+
+    // ---- the persistent fit kernel ----
+    FitParams p{};
+    p.L = L; p.ws = ws; p.B = a->B; p.N = a->N; p.K = a->K; p.P = a->n_powers; p.nnz_cap = a->nnz_cap;
+    for (int i = 0; i < a->n_powers; ++i) p.powers[i] = a->powers[i];
+    p.mu0 = a->mu0_dev; p.beta0 = a->beta0_dev; p.phi0 = a->phi0_dev; p.phicov0 = a->phi_cov0_dev;
+    bool same = true;
+    for (int b = 1; b < a->B; ++b) same = same && a->shape0[b] == a->shape0[0] && a->rate0[b] == a->rate0[0];
+    if (!same) { set_error("cm_caviar_fit: per-fit shape/rate priors must currently be identical within one call"); return CM_EUNSUPPORTED; }
+    p.shape0 = a->shape0[0]; p.rate0 = a->rate0[0]; p.shape0_arr = nullptr; p.rate0_arr = nullptr;
+    p.seeds = seeds_dev; p.opt = a->opt;
+    p.mu_out = a->mu_dev; p.beta_out = a->beta_dev; p.shape_out = a->shape_dev; p.rate_out = a->rate_dev;
+    p.phi_out = a->phi_dev; p.phicov_out = a->phi_cov_dev; p.z_out = a->z_dev;
+    p.mu_hist = a->mu_hist_dev; p.beta_hist = a->beta_hist_dev; p.shape_hist = a->shape_hist_dev;
+    p.rate_hist = a->rate_hist_dev; p.phi_hist = a->phi_hist_dev; p.phicov_hist = a->phi_cov_hist_dev;
+    p.z_hist = a->z_hist_dev; p.lamhist = want_lamhist ? 1 : 0;
+    p.status = a->status_dev;
+    const int smem_bytes = 160 * 1024;
+    p.smem_doubles = smem_bytes / 8;
+    if (a->n_powers <= 4) {
+        CM_CUDA_CHECK(cudaFuncSetAttribute(caviar_fit_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        caviar_fit_kernel<4><<<a->B, NT, smem_bytes, st>>>(p);
+    } else {
+        CM_CUDA_CHECK(cudaFuncSetAttribute(caviar_fit_kernel<PMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        caviar_fit_kernel<PMAX><<<a->B, NT, smem_bytes, st>>>(p);
+    }
+    count_launch();
+    CM_CUDA_CHECK(cudaGetLastError());
+
+    // ---- dense lam outputs ----
+    if (a->lam_dev) {
+        CM_CUDA_CHECK(cudaMemsetAsync(a->lam_dev, 0, (size_t)a->B * a->N * a->K * 8, st));
+        densify_kernel<<<dim3(a->N, 1, a->B), 128, 0, st>>>(L, ws, a->N, a->K, a->lam_dev, 0, a->status_dev);
+        count_launch();
+    }
+    if (want_lamhist) {
+        CM_CUDA_CHECK(cudaMemsetAsync(a->lam_hist_dev, 0, (size_t)a->B * a->opt.iters * a->N * a->K * 8, st));
+        densify_kernel<<<dim3(a->N, a->opt.iters, a->B), 128, 0, st>>>(L, ws, a->N, a->K, a->lam_hist_dev, a->opt.iters, a->status_dev);
+        count_launch();
+    }
+    CM_CUDA_CHECK(cudaGetLastError());
+    return CM_OK;
+}

@@ -1,0 +1,179 @@
+"""`caviar(...)` with the reference's signature (circuitmap/optimise/caviar.py:20-23,100) on the B200 kernel.
+
+Host side only marshals: dense float arrays go to the device as they are, `cm_caviar_fit` (csrc/caviar.cu) does
+every arithmetic step of the fit, and the 17-tuple the reference returns is rebuilt from its outputs.
+`caviar_batched` is the same call for B independent maps of identical (N, K) -- the unit that is sharded over
+GPUs (simulation sweeps, LOHO-CV folds).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+_DEFAULTS = dict(iters=50, num_mc_samples=100, seed=0, y_xcorr_thresh=1e-2, minimum_spike_count=3, delay_spont_est=1,
+                 msrmp=0.3, scale_factor=0.75, penalty=5e0, save_histories=False, max_backtrack_iters=20, tol=0.05,
+                 spont_orthogonality=0.1, fn_scan=True)
+
+
+def _options(kw):
+    o = _lib.CaviarOptions()
+    o.iters = int(kw["iters"])
+    o.num_mc_samples = int(kw["num_mc_samples"])
+    o.y_xcorr_thresh = float(kw["y_xcorr_thresh"])
+    o.minimum_spike_count = float(kw["minimum_spike_count"])
+    o.delay_spont_est = int(kw["delay_spont_est"])
+    o.msrmp = float(kw["msrmp"])
+    o.scale_factor = float(kw["scale_factor"])
+    o.penalty = float(kw["penalty"])
+    o.max_backtrack_iters = int(kw["max_backtrack_iters"])
+    o.tol = float(kw["tol"])
+    o.spont_orthogonality = float(kw["spont_orthogonality"])
+    o.fn_scan = 1 if kw["fn_scan"] else 0
+    o.save_histories = 1 if kw["save_histories"] else 0
+    return o
+
+
+def _dt(t):
+    import torch
+    return {torch.float32: _lib.CM_F32, torch.float64: _lib.CM_F64}[t.dtype]
+
+
+def caviar_batched(stim, powers, mu_prior, beta_prior, shape_prior, rate_prior, phi_prior, phi_cov_prior, psc=None,
+                   y=None, ss=None, seeds=None, nnz_cap=None, want_lam=True, workspace=None, **fit_options):
+    """B fits on the current CUDA device.  All array arguments are CUDA tensors:
+         stim (B,N,K) f32/f64; psc (B,K,T) f32/f64 or (y, ss) (B,K) f64; priors (B,N[,2[,2]]) f64.
+       `powers` is a host sequence (ascending distinct non-zero powers), `seeds` a host sequence of B ints.
+       Returns a dict of CUDA tensors (mu, beta, lam, shape, rate, phi, phi_cov, z, status[, *_hist])."""
+    import torch
+    unknown = set(fit_options) - set(_DEFAULTS)
+    if unknown:
+        raise TypeError("caviar() got an unexpected keyword argument %r" % sorted(unknown)[0])
+    kw = dict(_DEFAULTS)
+    kw.update(fit_options)
+    lib = _lib.load()
+    dev = stim.device
+    B, N, K = stim.shape
+    if not stim.is_contiguous():
+        raise ValueError("stim must be contiguous (B, N, K) with K fastest")
+    iters = int(kw["iters"])
+    f64 = dict(dtype=torch.float64, device=dev)
+    powers = np.ascontiguousarray(powers, dtype=np.float64)
+    if powers.size < 1 or powers.size > _lib.CM_CAVIAR_MAX_POWERS:
+        raise RuntimeError("cm_caviar_fit supports 1..%d distinct stimulus powers, got %d"
+                           % (_lib.CM_CAVIAR_MAX_POWERS, powers.size))
+    if seeds is None:
+        seeds = [int(kw["seed"])] * B
+    seeds_arr = (C.c_uint64 * B)(*[int(s) & 0xFFFFFFFFFFFFFFFF for s in seeds])
+    if nnz_cap is None:
+        nnz_cap = int(torch.count_nonzero(stim.reshape(B, -1), dim=1).max().item())
+    nnz_cap = max(int(nnz_cap), 1)
+    hist = bool(kw["save_histories"])
+
+    out = dict(mu=torch.empty((B, N), **f64), beta=torch.empty((B, N), **f64),
+               lam=torch.empty((B, N, K), **f64) if want_lam else None,
+               shape=torch.empty((B,), **f64), rate=torch.empty((B,), **f64),
+               phi=torch.empty((B, N, 2), **f64), phi_cov=torch.empty((B, N, 2, 2), **f64),
+               z=torch.empty((B, K), **f64), status=torch.zeros((B,), dtype=torch.int32, device=dev))
+    if hist:
+        out.update(mu_hist=torch.empty((B, iters, N), **f64), beta_hist=torch.empty((B, iters, N), **f64),
+                   lam_hist=torch.empty((B, iters, N, K), **f64) if want_lam else None,
+                   shape_hist=torch.empty((B, iters), **f64), rate_hist=torch.empty((B, iters), **f64),
+                   phi_hist=torch.empty((B, iters, N, 2), **f64), phi_cov_hist=torch.empty((B, iters, N, 2, 2), **f64),
+                   z_hist=torch.empty((B, iters, K), **f64))
+    need = lib.cm_caviar_workspace_bytes(B, N, K, nnz_cap, iters if (hist and want_lam) else 0)
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty((need,), dtype=torch.uint8, device=dev)
+
+    a = _lib.CaviarArgs()
+    a.B, a.N, a.K = B, N, K
+    keep = []
+
+    def ptr(t, dtype=None):
+        if t is None:
+            return None
+        if dtype is not None and t.dtype != dtype:
+            t = t.to(dtype)
+        t = t.contiguous()
+        keep.append(t)
+        return t.data_ptr()
+
+    if psc is not None:
+        if psc.shape[:2] != (B, K):
+            raise ValueError("psc must be (B, K, T)")
+        a.T = psc.shape[2]
+        a.psc_dev, a.psc_dtype = ptr(psc), _dt(psc)
+    else:
+        a.T = 0
+        a.y_dev, a.ss_dev = ptr(y, torch.float64), ptr(ss, torch.float64)
+    a.stim_dev, a.stim_dtype = stim.data_ptr(), _dt(stim)
+    a.n_powers = powers.size
+    a.powers = powers.ctypes.data_as(C.POINTER(C.c_double))
+    a.seeds = seeds_arr
+    a.mu0_dev, a.beta0_dev = ptr(mu_prior, torch.float64), ptr(beta_prior, torch.float64)
+    a.phi0_dev, a.phi_cov0_dev = ptr(phi_prior, torch.float64), ptr(phi_cov_prior, torch.float64)
+    shape0 = (C.c_double * B)(*np.broadcast_to(np.asarray(shape_prior, dtype=np.float64), (B,)))
+    rate0 = (C.c_double * B)(*np.broadcast_to(np.asarray(rate_prior, dtype=np.float64), (B,)))
+    a.shape0, a.rate0 = shape0, rate0
+    a.opt = _options(kw)
+    for name in ("mu", "beta", "lam", "shape", "rate", "phi", "phi_cov", "z"):
+        setattr(a, name + "_dev", out[name].data_ptr() if out[name] is not None else None)
+    if hist:
+        for name in ("mu", "beta", "lam", "shape", "rate", "phi", "phi_cov", "z"):
+            t = out[name + "_hist"]
+            setattr(a, name + "_hist_dev", t.data_ptr() if t is not None else None)
+    a.nnz_cap = nnz_cap
+    a.workspace_dev, a.workspace_bytes = workspace.data_ptr(), workspace.numel()
+    a.status_dev = out["status"].data_ptr()
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream().cuda_stream
+        _lib.check(lib.cm_caviar_fit(C.byref(a), C.c_void_p(stream)), "cm_caviar_fit")
+    out["_workspace"] = workspace
+    out["_keep"] = keep
+    out["launches"] = lib.cm_last_launch_count()
+    return out
+
+
+def check_status(out):
+    st = out["status"].cpu().numpy()
+    if np.any(st != 0):
+        b = int(np.nonzero(st)[0][0])
+        msg = {1: "stimulus matrix holds a value that is negative, NaN or not among `powers`",
+               5: "non-zeros of the stimulus matrix exceed nnz_cap"}.get(int(st[b]), "device error")
+        raise RuntimeError("cm_caviar_fit: fit %d failed with code %d (%s)" % (b, int(st[b]), msg))
+
+
+def caviar(y_psc, I, mu_prior, beta_prior, shape_prior, rate_prior, phi_prior, phi_cov_prior, device=None,
+           **fit_options):
+    """Drop-in for circuitmap.optimise.caviar (caviar.py:20-100): NumPy in, the 17-tuple of NumPy arrays out."""
+    torch = _lib.require_cuda()
+    print("Running coordinate-ascent variational inference and isotonic regularisation (CAVIaR) algorithm.")
+    dev = torch.device("cuda" if device is None else device)
+    I = np.asarray(I)
+    if not np.issubdtype(I.dtype, np.floating):
+        I = I.astype(float)
+    I = np.ascontiguousarray(I)                      # simulate() returns a non-contiguous (N, K) view
+    y_psc = np.ascontiguousarray(y_psc)
+    if not np.issubdtype(y_psc.dtype, np.floating):
+        y_psc = y_psc.astype(float)
+    N, K = I.shape
+    powers = np.unique(I)[1:]                        # caviar.py:42 (assumes 0 is present and smallest)
+    nnz = int(np.count_nonzero(I))
+    t = lambda x: torch.from_numpy(np.ascontiguousarray(np.asarray(x, dtype=np.float64))).to(dev)
+    seed = int(fit_options.get("seed", _DEFAULTS["seed"]))
+    opts = {k: v for k, v in fit_options.items() if k != "seed"}
+    out = caviar_batched(torch.from_numpy(I).to(dev)[None], powers, t(mu_prior)[None], t(beta_prior)[None],
+                         float(shape_prior), float(rate_prior), t(phi_prior)[None], t(phi_cov_prior)[None],
+                         psc=torch.from_numpy(y_psc).to(dev)[None], seeds=[seed], nnz_cap=nnz, seed=seed, **opts)
+    check_status(out)
+    g = lambda k: out[k][0].cpu().numpy()
+    mu, beta, lam, phi, phi_cov, z = g("mu"), g("beta"), g("lam"), g("phi"), g("phi_cov"), g("z")
+    shape, rate = np.float64(out["shape"][0].item()), np.float64(out["rate"][0].item())
+    if out.get("mu_hist") is not None:
+        iters = out["mu_hist"].shape[1]
+        hist = [g("mu_hist"), g("beta_hist"), g("lam_hist"),
+                np.repeat(g("shape_hist")[:, None], K, axis=1), np.repeat(g("rate_hist")[:, None], K, axis=1),
+                g("phi_hist"), g("phi_cov_hist"), g("z_hist")]                 # caviar.py:57-64,92
+    else:
+        hist = [None] * 8
+    return (mu, beta, lam, shape, rate, phi, phi_cov, z, None, *hist)
