@@ -1,0 +1,463 @@
+#!/usr/bin/env python
+"""Benchmark of the two B200 hot paths (BASELINE.json metric: CAVIaR fits/s & iters/s at N=1k,K=10k; NWD traces/s).
+
+    python bench.py --gpus N --steps K --warmup W            # own arm (torchrun launches N>1)
+    python bench.py --impl reference ...                     # reference arm: the CPU oracle on the host cores
+
+A step = one pass of the CAVIaR hot path over one batch of B independent synthetic maps of the C3 shape
+(N=1000 neurons, K=10000 trials x 900 samples, 10-target holograms, 3 powers, 50 iterations) per GPU, inputs
+resident in HBM.  Prints ONE JSON line (rank 0).  The NWD path (C2: 20000 traces) is measured in the same run
+and reported under "nwd".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+ALGO_NOTE = "iters*(16NK+8N^2+12K)+3600K+8NK bytes per fit (SURVEY.md 8(d), dense fp32 accounting)"
+
+
+def algorithmic_bytes_per_fit(N, K, iters):
+    return iters * (16.0 * N * K + 8.0 * N * N + 12.0 * K) + 3600.0 * K + 8.0 * N * K
+
+
+# ----------------------------------------------------------------------------------------- synthetic data
+def synth_map(N, K, H, seed, T=900, powers=(45.0, 55.0, 65.0), connection_prob=0.1):
+    """Synthetic compressive-mapping experiment with circuitmap.simulation's distributions (blockwise design):
+    stim (N,K) f64 with exactly H targets per trial, psc (K,T) f64 = evoked + spontaneous PSCs + GP + iid noise."""
+    rng = np.random.default_rng(seed)
+    pw = np.sort(np.asarray(powers))[::-1]
+    nh = int(np.ceil(N / H))
+    tars = np.zeros((K, H), dtype=np.int64)
+    pcol = np.zeros(K)
+    k = 0
+    while k < K:
+        order = rng.permutation(N)
+        for p in pw:
+            for h in range(nh):
+                if k >= K:
+                    break
+                sl = order[h * H:(h + 1) * H]
+                tars[k, :len(sl)] = sl
+                tars[k, len(sl):] = sl[0]
+                pcol[k] = p
+                k += 1
+    perm = rng.permutation(K)
+    tars, pcol = tars[perm], pcol[perm]
+    stim = np.zeros((N, K))
+    stim[tars, np.arange(K)[:, None]] = pcol[:, None]
+    tau_r = rng.uniform(25, 60, N)
+    tau_d = tau_r + rng.uniform(75, 250, N)
+    phi0, phi1 = rng.uniform(0.2, 0.25, N), rng.uniform(10, 15, N)
+    ncon = int(connection_prob * N)
+    conn = rng.choice(N, ncon, replace=False)
+    ns = int(np.ceil(0.2 * ncon))
+    w = np.zeros(N)
+    w[conn[:ns]] = rng.uniform(20, 40, ns)
+    w[conn[ns:]] = rng.exponential(4, ncon - ns) + 9
+    t = np.arange(T)
+    psc = np.zeros((K, T))
+    for n in conn:
+        ks = np.nonzero(stim[n])[0]
+        fr = 1 / (1 + np.exp(-(phi0[n] * stim[n, ks] - phi1[n])))
+        sp = rng.random(ks.size) <= fr
+        top = stim[n, ks] == pw[0]
+        if top.any() and sp[top].mean() < 0.4:
+            idx = np.nonzero(top & ~sp)[0]
+            need = int(np.ceil((0.4 - sp[top].mean()) * top.sum()))
+            sp[rng.choice(idx, min(need, idx.size), replace=False)] = True
+        kern = np.exp(-t / tau_d[n]) - np.exp(-t / tau_r[n])
+        kern = kern / (kern.sum() - 0.5 * (kern[0] + kern[-1]) + 1e-5)
+        for kk in ks[sp]:
+            s = int(160 + rng.gamma(1e4 / stim[n, kk] ** 2, 15.0))
+            if s < T:
+                ke = np.zeros(T)
+                ke[s:] = kern[:T - s]
+                psc[kk] += ke / (ke.sum() + 1e-5) * rng.lognormal(0, 0.01) * w[n]
+    for kk in np.nonzero(rng.random(K) <= 0.05)[0]:
+        tr = rng.uniform(25, 60)
+        td = tr + rng.uniform(75, 250)
+        st = rng.integers(1, T)
+        ke = (np.exp(-(t - st) / td) - np.exp(-(t - st) / tr)) * (t > st)
+        psc[kk] += rng.uniform(w[conn].min(), w[conn].max()) * ke / (ke.sum() + 1e-5)
+    D = t[None, :] - t[:, None]
+    Lc = np.linalg.cholesky(np.exp(-D ** 2 / (2 * 50.0 ** 2)) + 1e-6 * np.eye(T))
+    psc += 4e-3 * (rng.standard_normal((K, T)) @ Lc.T)
+    psc += rng.normal(0, 6e-4, (K, T))
+    return stim, psc, w
+
+
+def synth_traces(K, seed, T=900):
+    rng = np.random.default_rng(seed)
+    t = np.arange(T)[None, :]
+    tr = rng.uniform(25, 60, (K, 1))
+    td = tr + rng.uniform(75, 250, (K, 1))
+    d = rng.uniform(100, 400, (K, 1))
+    with np.errstate(over="ignore"):
+        ev = (np.exp(-(t - d) / td) - np.exp(-(t - d) / tr)) * (t > d)
+    ev = ev / (ev.sum(1, keepdims=True) + 1e-5) * rng.uniform(5, 40, (K, 1))
+    return ev + np.cumsum(rng.normal(0, 2e-4, (K, T)), axis=1) + rng.normal(0, 6e-4, (K, T))
+
+
+# ----------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 8:
+                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d["hbm_gbs"], d["bf16_tflops"], d.get("bf16_tflops_sustained", d["bf16_tflops"]), "measured"
+    return 6650.0, 1590.0, 1400.0, "fallback"
+
+
+def read_traffic(name):
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get(name)
+    return None
+
+
+# ----------------------------------------------------------------------------------------- CPU legs (oracle)
+def cpu_caviar_sample(N, K, H, iters_total, sample_iters, seed=0):
+    """The reference CPU path: NumPy fp64 restatement (oracle, reduced O(nnz) form) of caviar.py, timed on
+    `sample_iters` iterations of one map and scaled to a full `iters_total`-iteration fit."""
+    from oracle import caviar as oc
+    stim, psc, _ = synth_map(N, K, H, seed)
+    pr = oc.default_priors(N)
+    t0 = time.time()
+    oc.caviar(psc, stim, pr["mu"], pr["beta"], pr["shape"], pr["rate"], pr["phi"], pr["phi_cov"], iters=sample_iters,
+              seed=1, msrmp=0.4, fn_scan=False)
+    dt = time.time() - t0
+    return dt, 1.0 / (dt / sample_iters * iters_total)
+
+
+def cpu_nwd_sample(Ktr, seed=0):
+    """The reference CPU path of the demixer: the torch module restated from the reference (bit-identical to it on
+    the golden vectors), whole batch at once as nwd.py:44-46, all host threads."""
+    import torch
+    from oracle import nwd as onwd
+    net = onwd.TorchNWD(dict(np.load(os.path.join(GOLD, "nwd_ie_ChroME2f_weights.npz"))))
+    tr = synth_traces(Ktr, seed)
+    net.demix(tr[:64].copy())
+    t0 = time.time()
+    net.demix(tr.copy())
+    dt = time.time() - t0
+    return dt, Ktr / dt, torch.get_num_threads()
+
+
+def reference_arm(args, rank):
+    if rank != 0:
+        return
+    import torch
+    cores = os.cpu_count()
+    times = []
+    for i in range(args.warmup + args.steps):
+        dt, fps = cpu_caviar_sample(args.N, args.K, args.H, args.iters, args.ref_iters, seed=i % 2)
+        if i >= args.warmup:
+            times.append(dt)
+    ms = 1e3 * float(np.mean(times))
+    fits_per_s = 1.0 / (ms / 1e3 / args.ref_iters * args.iters)
+    ndt, ntps, nthr = cpu_nwd_sample(2000)
+    sample = "%d of %d iterations of one N=%d,K=%d map per step, scaled linearly to a full fit" % (
+        args.ref_iters, args.iters, args.N, args.K)
+    line = {"impl": "reference", "metric": "caviar_fits_per_s", "value": fits_per_s, "unit": "fits/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, None),
+            "iters_per_s": fits_per_s * args.iters,
+            "cpu_baseline": {"value": fits_per_s, "unit": "fits/s", "cores": int(torch.get_num_threads()),
+                             "host_cores": cores, "kind": "port", "sample": sample,
+                             "note": "JAX is not installable here; NumPy fp64 restatement of caviar.py (oracle, reduced form)"},
+            "e2e": {"value": fits_per_s, "unit": "fits/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "nwd": {"metric": "nwd_traces_per_s", "value": ntps, "unit": "traces/s", "kind": "port",
+                    "cores": nthr, "sample": "2000 traces in one batch (torch CPU restatement of NWDUNet)"}}
+    print(json.dumps(line))
+
+
+def workload_config(args, B):
+    return {"workload": "C3 compressive ensemble map: N=%d neurons, K=%d trials x 900 samples, H=%d targets, P=3 powers, "
+                        "caviar %d iters%s" % (args.N, args.K, args.H, args.iters,
+                                               "" if B is None else ", %d independent maps per GPU per step" % B),
+            "fits_per_gpu_per_step": B, "distinct_maps": args.maps,
+            "l2_hygiene": "inputs larger than L2 (each fit reads its own 152 MB of psc+stim; >20 GB per step)",
+            "parallelism": "independent fits sharded over GPUs, no data-path collective"}
+
+
+# ----------------------------------------------------------------------------------------- own arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--N", type=int, default=1000)
+    ap.add_argument("--K", type=int, default=10000)
+    ap.add_argument("--H", type=int, default=10)
+    ap.add_argument("--iters", type=int, default=50)
+    ap.add_argument("--fits-per-gpu", type=int, default=0, help="B; default = number of SMs")
+    ap.add_argument("--maps", type=int, default=2, help="distinct synthetic maps tiled to B")
+    ap.add_argument("--nwd-traces", type=int, default=20000)
+    ap.add_argument("--ref-iters", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-nwd", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        reference_arm(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from circuitmap_b200 import NeuralDemixer, optimise, _lib
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (own arm) needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    B = args.fits_per_gpu or sms
+    N, K, H, iters = args.N, args.K, args.H, args.iters
+    hbm_peak, bf16_burst, bf16_sust, peak_kind = measured_peaks()
+
+    # ---- synthetic inputs: `maps` distinct maps (seeded per rank), tiled to B fits, pinned on the host ----
+    host_stim, host_psc = [], []
+    for i in range(args.maps):
+        s, p, _ = synth_map(N, K, H, seed=1000 * rank + i)
+        host_stim.append(torch.from_numpy(s).pin_memory())
+        host_psc.append(torch.from_numpy(p).pin_memory())
+    powers = np.array([45.0, 55.0, 65.0])
+    nnz = int(max(np.count_nonzero(s.numpy()) for s in host_stim))
+    f64 = dict(dtype=torch.float64, device=dev)
+    stim = torch.empty((B, N, K), **f64)
+    psc = torch.empty((B, K, 900), **f64)
+    for b in range(B):
+        stim[b].copy_(host_stim[b % args.maps], non_blocking=True)
+        psc[b].copy_(host_psc[b % args.maps], non_blocking=True)
+    cov = torch.zeros(B, N, 2, 2, **f64)
+    cov[..., 0, 0] = 0.1
+    cov[..., 1, 1] = 1.0
+    phi = torch.stack([0.1 * torch.ones(B, N, **f64), 5 * torch.ones(B, N, **f64)], -1).contiguous()
+    pri = (torch.zeros(B, N, **f64), 10 * torch.ones(B, N, **f64), 1.0, 0.1, phi, cov)
+    seeds = [1 + b + 100000 * rank for b in range(B)]
+    opts = dict(iters=iters, msrmp=0.4)
+    ws = [None]
+
+    def step():
+        out = optimise.caviar_batched(stim, powers, *pri, psc=psc, seeds=seeds, nnz_cap=nnz, want_lam=True,
+                                      workspace=ws[0], **opts)
+        ws[0] = out["_workspace"]
+        return out
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        out = step()
+    torch.cuda.synchronize()
+    assert int(out["status"].sum().item()) == 0, "device status reported an error"
+    launches_per_step = out["launches"]
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kern_ms = []
+    e0.record()
+    for _ in range(args.steps):
+        out = step()
+        kern_ms.append(lib.cm_last_main_kernel_ms())        # waits for this step's fit kernel (same stream)
+    e1.record()
+    sync_all()
+    clocks = sampler.stop()
+    ms_total = e0.elapsed_time(e1)
+    tms = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms_step = float(tms.item()) / args.steps
+    fits_per_s = world * B / (ms_step / 1e3)
+    kms = float(np.mean(kern_ms))
+    algo = algorithmic_bytes_per_fit(N, K, iters) * B
+    achieved = algo / (kms / 1e3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "caviar_fit_kernel", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                "frac": achieved / hbm_peak, "traffic": read_traffic("caviar_fit_kernel"),
+                "peak_kind": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback",
+                "kernel_ms_per_launch": kms, "algorithmic_bytes_per_launch": algo, "algorithmic_model": ALGO_NOTE,
+                "note": "kernel works on a CSR/CSC index of the design (supp(lam) within supp(stim)); achieved is the "
+                        "DENSE algorithmic byte count over time, traffic is what DRAM actually moved"}
+    connected = int((out["mu"][0] != 0).sum().item())
+
+    # ---- end-to-end through host buffers: H2D of every fit's psc+stim (pinned), fit, D2H of the full state ----
+    e2e = None
+    if not args.no_e2e:
+        slab = max(1, min(B, 16))
+        pin = {k: torch.empty(out[k].shape, dtype=out[k].dtype).pin_memory()
+               for k in ["mu", "beta", "shape", "rate", "phi", "phi_cov", "z"]}
+        pin_lam = torch.empty((slab, N, K), dtype=torch.float64).pin_memory()
+        h2d = B * (N * K * 8 + K * 900 * 8)
+        d2h = sum(v.numel() * 8 for v in pin.values()) + B * N * K * 8
+
+        def e2e_step():
+            for b in range(B):
+                stim[b].copy_(host_stim[b % args.maps], non_blocking=True)
+                psc[b].copy_(host_psc[b % args.maps], non_blocking=True)
+            o = step()
+            for k in pin:
+                pin[k].copy_(o[k], non_blocking=True)
+            for b0 in range(0, B, slab):
+                n = min(slab, B - b0)
+                pin_lam[:n].copy_(o["lam"][b0:b0 + n], non_blocking=True)
+            torch.cuda.synchronize()
+
+        e2e_step()
+        sync_all()
+        t0 = time.time()
+        n_e2e = max(1, min(args.steps, 2))
+        for _ in range(n_e2e):
+            e2e_step()
+        sync_all()
+        dt = torch.tensor([(time.time() - t0) / n_e2e], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * B / float(dt.item()), "unit": "fits/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * float(dt.item()),
+               "note": "NumPy-compatible fp64 host buffers (pinned) -> cm_caviar_fit -> full state incl. dense lam back"}
+    del stim, psc, out
+    ws[0] = None
+    torch.cuda.empty_cache()
+
+    # ---- NWD (C2): K traces through cm_nwd_forward ----
+    nwd = None
+    if not args.no_nwd:
+        Kt = args.nwd_traces
+        dem = NeuralDemixer(path=os.path.join(GOLD, "nwd_ie_ChroME2f_weights.npz"), device=dev)
+        htr = torch.from_numpy(synth_traces(Kt, seed=rank)).pin_memory()
+        x32 = htr.to(dev).float()
+        o32 = torch.empty_like(x32)
+        for _ in range(3):
+            dem.forward_device(x32, out=o32)
+        sync_all()
+        n_it = 5
+        kms_n = []
+        n0, n1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0.record()
+        for _ in range(n_it):
+            dem.forward_device(x32, out=o32)
+            kms_n.append(lib.cm_last_main_kernel_ms())
+        n1.record()
+        sync_all()
+        nms = torch.tensor([n0.elapsed_time(n1) / n_it], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(nms, op=dist.ReduceOp.MAX)
+        tps = world * Kt / (float(nms.item()) / 1e3)
+        flops = 2 * 8435200.0 * Kt
+        ach = flops / (float(np.mean(kms_n)) / 1e3) / 1e12
+        hout = torch.empty((Kt, 900), dtype=torch.float64).pin_memory()
+        x64 = torch.empty((Kt, 900), **f64)
+        o64 = torch.empty((Kt, 900), **f64)
+
+        def nwd_e2e():
+            x64.copy_(htr, non_blocking=True)
+            dem.forward_device(x64, out=o64)
+            hout.copy_(o64, non_blocking=True)
+            torch.cuda.synchronize()
+
+        nwd_e2e()
+        sync_all()
+        t0 = time.time()
+        for _ in range(3):
+            nwd_e2e()
+        sync_all()
+        edt = torch.tensor([(time.time() - t0) / 3], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(edt, op=dist.ReduceOp.MAX)
+        nwd = {"metric": "nwd_traces_per_s", "value": tps, "unit": "traces/s", "dtype": "f32",
+               "config": {"workload": "C2: NeuralDemixer nwd_ie_ChroME2f forward on %d x 900 traces per GPU" % Kt,
+                          "l2_hygiene": "in+out = %.0f MB > L2" % (2 * Kt * 3600 / 1e6)},
+               "ms_per_step": float(nms.item()),
+               "roofline": {"bound": "tensor", "kernel": "nwd_forward", "achieved": ach, "peak": bf16_burst,
+                            "unit": "TFLOP/s", "frac": ach / bf16_burst, "traffic": read_traffic("nwd_forward"),
+                            "peak_kind": peak_kind + " bf16 burst; the kernel computes in fp32 on CUDA cores "
+                                                     "(16.87 MFLOP/trace, SURVEY.md App. C)"},
+               "e2e": {"value": world * Kt / float(edt.item()), "unit": "traces/s", "h2d_bytes_per_step": Kt * 7200,
+                       "d2h_bytes_per_step": Kt * 7200}}
+
+    # ---- CPU baseline on the host cores (rank 0, N=1 only) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        dt, fps = cpu_caviar_sample(N, K, H, iters, args.ref_iters)
+        cpu = {"value": fps, "unit": "fits/s", "cores": int(torch.get_num_threads()), "host_cores": os.cpu_count(),
+               "kind": "port",
+               "sample": "%d of %d iterations of one N=%d,K=%d map (%.1f s), scaled linearly to a full fit" % (
+                   args.ref_iters, iters, N, K, dt)}
+        if nwd is not None:
+            ndt, ntps, nthr = cpu_nwd_sample(2000)
+            nwd["cpu_baseline"] = {"value": ntps, "unit": "traces/s", "cores": nthr, "kind": "port",
+                                   "sample": "2000 traces in one batch (%.2f s)" % ndt}
+
+    if rank == 0:
+        line = {"metric": "caviar_fits_per_s", "value": fits_per_s, "unit": "fits/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": workload_config(args, B), "iters_per_s": fits_per_s * iters,
+                "connected_in_fit0": connected, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+                "gpu_launches": int(launches_per_step * args.steps), "clocks": clocks, "nwd": nwd}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -45,7 +45,7 @@ class CaviarArgs(C.Structure):
 
 # every symbol include/circuitmap_b200.h declares
 EXPORTS = ["cm_version", "cm_last_error", "cm_device_info", "cm_nwd_create", "cm_nwd_destroy", "cm_nwd_forward",
-           "cm_caviar_workspace_bytes", "cm_caviar_fit", "cm_last_launch_count"]
+           "cm_caviar_workspace_bytes", "cm_caviar_fit", "cm_last_launch_count", "cm_last_main_kernel_ms"]
 
 _lib = None
 
@@ -63,6 +63,7 @@ def load():
     lib.cm_version.restype = C.c_int
     lib.cm_last_error.restype = C.c_char_p
     lib.cm_last_launch_count.restype = C.c_int
+    lib.cm_last_main_kernel_ms.restype = C.c_float
     lib.cm_device_info.argtypes = [C.POINTER(C.c_int)] * 3
     lib.cm_nwd_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_void_p)]
     lib.cm_nwd_destroy.argtypes = [C.c_void_p]

@@ -1368,6 +1368,7 @@ extern "C" int cm_caviar_fit(const cm_caviar_args* a, void* stream) {
     p.status = a->status_dev;
     const int smem_bytes = 160 * 1024;
     p.smem_doubles = smem_bytes / 8;
+    main_kernel_begin(st);
     if (a->n_powers <= 4) {
         CM_CUDA_CHECK(cudaFuncSetAttribute(caviar_fit_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
         caviar_fit_kernel<4><<<a->B, NT, smem_bytes, st>>>(p);
@@ -1375,6 +1376,7 @@ extern "C" int cm_caviar_fit(const cm_caviar_args* a, void* stream) {
         CM_CUDA_CHECK(cudaFuncSetAttribute(caviar_fit_kernel<PMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
         caviar_fit_kernel<PMAX><<<a->B, NT, smem_bytes, st>>>(p);
     }
+    main_kernel_end(st);
     count_launch();
     CM_CUDA_CHECK(cudaGetLastError());
 

@@ -11,6 +11,8 @@ namespace cm {
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 void reset_launch_count();
+void main_kernel_begin(cudaStream_t st);
+void main_kernel_end(cudaStream_t st);
 
 #define CM_CUDA_CHECK(expr)                                                                  \
     do {                                                                                     \

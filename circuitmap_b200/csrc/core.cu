@@ -12,12 +12,26 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 void count_launch(int n) { g_launches += n; }
+static thread_local cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
+static thread_local bool g_timed = false;
+void main_kernel_begin(cudaStream_t st) {
+    if (!g_ev0) { cudaEventCreate(&g_ev0); cudaEventCreate(&g_ev1); }
+    cudaEventRecord(g_ev0, st);
+}
+void main_kernel_end(cudaStream_t st) { cudaEventRecord(g_ev1, st); g_timed = true; }
 void reset_launch_count() { g_launches = 0; }
 }  // namespace cm
 
 extern "C" int cm_version(void) { return CM_VERSION; }
 extern "C" const char* cm_last_error(void) { return cm::g_err; }
 extern "C" int cm_last_launch_count(void) { return cm::g_launches; }
+extern "C" float cm_last_main_kernel_ms(void) {
+    if (!cm::g_timed) return -1.f;
+    float ms = -1.f;
+    if (cudaEventSynchronize(cm::g_ev1) != cudaSuccess) return -1.f;
+    if (cudaEventElapsedTime(&ms, cm::g_ev0, cm::g_ev1) != cudaSuccess) return -1.f;
+    return ms;
+}
 extern "C" int cm_device_info(int* sm_count, int* cc_major, int* cc_minor) {
     int dev = 0;
     CM_CUDA_CHECK(cudaGetDevice(&dev));

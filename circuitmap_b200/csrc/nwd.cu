@@ -347,7 +347,9 @@ static int launch_fp32(cm_nwd_t* h, const void* in, void* out, int K, int ms, do
     auto kern = nwd_forward_fp32_kernel<TIn, TOut>;
     CM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     const int grid = K < h->sm_count ? K : h->sm_count;
+    main_kernel_begin(st);
     kern<<<grid, THREADS, SMEM_BYTES, st>>>(h->w_dev, (const TIn*)in, (TOut*)out, K, ms, y, ss);
+    main_kernel_end(st);
     count_launch();
     CM_CUDA_CHECK(cudaGetLastError());
     return CM_OK;

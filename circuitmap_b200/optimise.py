@@ -34,6 +34,16 @@ def _options(kw):
     return o
 
 
+def _validate_options(fit_options):
+    """Unknown keyword -> TypeError, exactly like splatting into caviar(**fit_options) (model.py:107-110)."""
+    unknown = set(fit_options) - set(_DEFAULTS)
+    if unknown:
+        raise TypeError("caviar() got an unexpected keyword argument %r" % sorted(unknown)[0])
+    kw = dict(_DEFAULTS)
+    kw.update(fit_options)
+    return kw
+
+
 def _dt(t):
     import torch
     return {torch.float32: _lib.CM_F32, torch.float64: _lib.CM_F64}[t.dtype]
@@ -46,11 +56,7 @@ def caviar_batched(stim, powers, mu_prior, beta_prior, shape_prior, rate_prior, 
        `powers` is a host sequence (ascending distinct non-zero powers), `seeds` a host sequence of B ints.
        Returns a dict of CUDA tensors (mu, beta, lam, shape, rate, phi, phi_cov, z, status[, *_hist])."""
     import torch
-    unknown = set(fit_options) - set(_DEFAULTS)
-    if unknown:
-        raise TypeError("caviar() got an unexpected keyword argument %r" % sorted(unknown)[0])
-    kw = dict(_DEFAULTS)
-    kw.update(fit_options)
+    kw = _validate_options(fit_options)
     lib = _lib.load()
     dev = stim.device
     B, N, K = stim.shape
@@ -146,6 +152,7 @@ def check_status(out):
 def caviar(y_psc, I, mu_prior, beta_prior, shape_prior, rate_prior, phi_prior, phi_cov_prior, device=None,
            **fit_options):
     """Drop-in for circuitmap.optimise.caviar (caviar.py:20-100): NumPy in, the 17-tuple of NumPy arrays out."""
+    _validate_options(fit_options)
     torch = _lib.require_cuda()
     print("Running coordinate-ascent variational inference and isotonic regularisation (CAVIaR) algorithm.")
     dev = torch.device("cuda" if device is None else device)

@@ -134,6 +134,10 @@ CM_API int    cm_caviar_fit(const cm_caviar_args* a, void* stream);
 
 /* number of kernel launches issued by the last cm_* call on this thread (for bench accounting) */
 CM_API int cm_last_launch_count(void);
+/* device time (ms, CUDA events on the caller's stream) of the dominant kernel of the last cm_nwd_forward /
+ * cm_caviar_fit call on this thread: the U-Net kernel, resp. the persistent fit kernel.  Synchronises on the
+ * kernel's end event.  Returns a negative value if no timed kernel was launched. */
+CM_API float cm_last_main_kernel_ms(void);
 
 #ifdef __cplusplus
 }

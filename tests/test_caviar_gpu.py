@@ -1,0 +1,198 @@
+"""GPU parity: cm_caviar_fit (through Model.fit / optimise.caviar, i.e. the C ABI) vs the NumPy fp64 oracle.
+
+Tolerance (BASELINE.json north_star): connected set and accept/reject pattern IDENTICAL; mu/beta/lam/phi/phi_cov/
+shape/rate/z within 1e-4 relative.  The kernel computes in fp64 and lands around 1e-8.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-4
+NAMES = ["mu", "beta", "lam", "shape", "rate", "phi", "phi_cov", "z"]
+
+
+def close(a, b, rtol=RTOL):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    scale = max(float(np.max(np.abs(b))) if b.size else 0.0, 1e-300)
+    return np.allclose(a, b, rtol=rtol, atol=1e-7 * scale, equal_nan=True)
+
+
+def oracle_fit(psc, stim, trace=None, **opts):
+    from oracle import caviar as oc
+    pr = oc.default_priors(stim.shape[0])
+    return oc.caviar(psc, stim, pr["mu"], pr["beta"], pr["shape"], pr["rate"], pr["phi"], pr["phi_cov"],
+                     form="reduced", trace=trace, **opts)
+
+
+def gpu_fit(psc, stim, **opts):
+    from circuitmap_b200 import Model
+    m = Model(stim.shape[0])
+    m.fit(psc, stim, method="caviar", fit_options=opts)
+    return m
+
+
+@pytest.fixture(scope="module")
+def tiny():
+    from oracle import simulate as osim
+    np.random.seed(3)
+    return osim.simulate(N=32, trials=300, H=4, connection_prob=0.15)
+
+
+def test_tiny_map_matches_oracle_every_iteration(tiny):
+    opts = dict(iters=30, seed=1, msrmp=0.4)
+    tr = {"decisions": []}
+    ref = oracle_fit(tiny["psc"], tiny["stim_matrix"], trace=tr, **opts)
+    m = gpu_fit(tiny["psc"], tiny["stim_matrix"], save_histories=True, **opts)
+    for i, nm in enumerate(NAMES):
+        assert close(m.state[nm], ref[i], 1e-6), nm
+    assert np.array_equal(m.state["mu"] != 0, ref[0] != 0)
+    assert np.array_equal(np.nonzero(m.state["mu"])[0], np.nonzero(tiny["weights"])[0])
+    for it, o in enumerate(tr["iters"]):                        # accept/reject pattern of every sweep is identical
+        assert np.array_equal(m.history["lam"][it].sum(1) > 0, o["lam_sum"] > 0), it
+        assert close(m.history["mu"][it], o["mu"], 1e-6) and close(m.history["rate"][it][0], o["rate"], 1e-6)
+    K = tiny["psc"].shape[0]
+    assert m.history["shape"].shape == (30, K) and m.history["lam"].shape == (30, 32, K)    # caviar.py:57-64
+    assert m.state["receptive_fields"].shape == () and m.trial_count == K and m.time > 0
+    assert m.state["lam"].dtype == np.float64 and m.state["phi_cov"].shape == (32, 2, 2)
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_c1_map_matches_oracle(seed):
+    """BASELINE.json configs[0]: N=100, K=2000 trials x 900 samples, 50 iterations."""
+    from oracle import simulate as osim
+    np.random.seed(seed)
+    sim = osim.simulate(N=100, trials=2000, H=10, connection_prob=0.1)
+    opts = dict(iters=50, seed=1, msrmp=0.4)
+    ref = oracle_fit(sim["psc"], sim["stim_matrix"], **opts)
+    m = gpu_fit(sim["psc"], sim["stim_matrix"], **opts)
+    assert np.array_equal(m.state["mu"] != 0, ref[0] != 0)
+    for i, nm in enumerate(NAMES):
+        assert close(m.state[nm], ref[i]), nm
+    assert np.all(m.state["lam"][sim["stim_matrix"] == 0] == 0)
+
+
+def test_batched_fits_equal_single_fits_bitwise():
+    import torch
+    from oracle import simulate as osim
+    from circuitmap_b200 import optimise
+    sims = [osim.simulate_fast(N=48, K=400, H=6, seed=s) for s in range(3)]
+    powers = np.unique(sims[0]["stim_matrix"])[1:]
+    dev = "cuda"
+    f64 = dict(dtype=torch.float64, device=dev)
+
+    def priors(B, N):
+        cov = torch.zeros(B, N, 2, 2, **f64); cov[..., 0, 0] = 0.1; cov[..., 1, 1] = 1.0
+        phi = torch.stack([0.1 * torch.ones(B, N, **f64), 5 * torch.ones(B, N, **f64)], -1).contiguous()
+        return torch.zeros(B, N, **f64), 10 * torch.ones(B, N, **f64), 1.0, 0.1, phi, cov
+
+    stim = torch.from_numpy(np.stack([s["stim_matrix"] for s in sims])).to(dev)
+    psc = torch.from_numpy(np.stack([s["psc"] for s in sims])).to(dev)
+    both = optimise.caviar_batched(stim, powers, *priors(3, 48), psc=psc, seeds=[5, 6, 7], iters=12)
+    optimise.check_status(both)
+    for b in range(3):
+        one = optimise.caviar_batched(stim[b:b + 1].contiguous(), powers, *priors(1, 48), psc=psc[b:b + 1].contiguous(),
+                                      seeds=[5 + b], iters=12)
+        for nm in NAMES:
+            assert torch.equal(one[nm][0], both[nm][b]), (b, nm)
+    again = optimise.caviar_batched(stim, powers, *priors(3, 48), psc=psc, seeds=[5, 6, 7], iters=12)
+    for nm in NAMES:
+        assert torch.equal(again[nm], both[nm]), nm                 # run-to-run determinism
+
+
+def test_edge_cases_against_oracle():
+    """Never-stimulated neuron, all-masked trials, single power, N and K not multiples of 32, fp32 inputs."""
+    from oracle import simulate as osim
+    sim = osim.simulate_fast(N=37, K=333, H=5, seed=4, powers=(50,))
+    stim, psc = sim["stim_matrix"].copy(), sim["psc"].copy()
+    stim[5, :] = 0.0                                              # neuron 5 is never targeted
+    psc[::7] *= 1e-4                                              # these trials fall under y_xcorr_thresh (lam_mask = 0)
+    assert np.unique(stim).size == 2
+    opts = dict(iters=10, seed=2, msrmp=0.3, minimum_spike_count=2)
+    ref = oracle_fit(psc, stim, **opts)
+    m = gpu_fit(psc, stim, **opts)
+    for i, nm in enumerate(NAMES):
+        assert close(m.state[nm], ref[i], 1e-6), nm
+    assert m.state["mu"][5] == 0 and np.all(m.state["lam"][5] == 0)
+    assert np.all(m.state["lam"][:, ::7] == 0)
+    m32 = gpu_fit(psc.astype(np.float32), stim.astype(np.float32), **opts)
+    ref32 = oracle_fit(psc.astype(np.float32), stim.astype(np.float32), **opts)
+    for i, nm in enumerate(NAMES):
+        assert close(m32.state[nm], ref32[i], 1e-6), nm
+
+
+def test_many_powers_and_reconnection():
+    """Five distinct powers (templated P>4 path); fn_scan on/off."""
+    from oracle import simulate as osim
+    sim = osim.simulate_fast(N=40, K=600, H=4, seed=9, powers=(30, 40, 50, 60, 70))
+    for fn_scan in (True, False):
+        opts = dict(iters=25, seed=3, msrmp=0.4, fn_scan=fn_scan)
+        tr = {"decisions": []}
+        ref = oracle_fit(sim["psc"], sim["stim_matrix"], trace=tr, **opts)
+        m = gpu_fit(sim["psc"], sim["stim_matrix"], **opts)
+        assert np.array_equal(m.state["mu"] != 0, ref[0] != 0)
+        for i, nm in enumerate(NAMES):
+            assert close(m.state[nm], ref[i], 1e-6), (fn_scan, nm)
+
+
+def test_errors_are_loud():
+    from circuitmap_b200 import Model
+    stim = np.zeros((4, 50)); stim[0, :10] = 45.0
+    psc = np.random.default_rng(0).random((50, 900))
+    with pytest.raises(TypeError):
+        Model(4).fit(psc, stim, fit_options={"minimax_spk_prob": 0.3})
+    stim17 = np.zeros((20, 60))
+    for p in range(17):
+        stim17[p, p] = 10.0 + p
+    with pytest.raises(RuntimeError, match="distinct stimulus powers"):
+        Model(20).fit(np.ones((60, 900)), stim17)
+    bad = stim.copy(); bad[1, 3] = -5.0
+    with pytest.raises(RuntimeError, match="negative"):
+        Model(4).fit(psc, bad)
+
+
+def test_demix_to_fit_handoff_matches_two_step():
+    """cm_nwd_forward's (y, ss) epilogue feeds cm_caviar_fit without re-reading the K x 900 array."""
+    import os
+    import torch
+    from oracle import simulate as osim
+    from circuitmap_b200 import NeuralDemixer, optimise
+    from tests.conftest import GOLDEN
+    sim = osim.simulate_fast(N=40, K=500, H=5, seed=12)
+    dem = NeuralDemixer(path=os.path.join(GOLDEN, "nwd_ie_ChroME2f_weights.npz"))
+    psc = torch.from_numpy(sim["psc"]).cuda()
+    out, y, ss = dem.forward_device(psc, stats=True)
+    stim = torch.from_numpy(sim["stim_matrix"]).cuda()[None].contiguous()
+    f64 = dict(dtype=torch.float64, device="cuda")
+    cov = torch.zeros(1, 40, 2, 2, **f64); cov[..., 0, 0] = 0.1; cov[..., 1, 1] = 1.0
+    phi = torch.stack([0.1 * torch.ones(1, 40, **f64), 5 * torch.ones(1, 40, **f64)], -1).contiguous()
+    pri = (torch.zeros(1, 40, **f64), 10 * torch.ones(1, 40, **f64), 1.0, 0.1, phi, cov)
+    powers = np.unique(sim["stim_matrix"])[1:]
+    a = optimise.caviar_batched(stim, powers, *pri, psc=out[None].contiguous(), seeds=[1], iters=15, msrmp=0.4)
+    b = optimise.caviar_batched(stim, powers, *pri, y=y[None], ss=ss[None], seeds=[1], iters=15, msrmp=0.4)
+    for nm in NAMES:
+        assert torch.allclose(a[nm], b[nm], rtol=1e-9, atol=1e-12), nm
+
+
+def test_full_size_single_fit_properties():
+    """BASELINE.json configs[2] shape (N=1000, K=10000, H=10, 50 iters): size-independent properties."""
+    import torch
+    from oracle import simulate as osim
+    from circuitmap_b200 import optimise
+    N, K = 1000, 10000
+    sim = osim.simulate_fast(N=N, K=K, H=10, seed=0, dtype=np.float32)
+    f64 = dict(dtype=torch.float64, device="cuda")
+    cov = torch.zeros(1, N, 2, 2, **f64); cov[..., 0, 0] = 0.1; cov[..., 1, 1] = 1.0
+    phi = torch.stack([0.1 * torch.ones(1, N, **f64), 5 * torch.ones(1, N, **f64)], -1).contiguous()
+    stim = torch.from_numpy(sim["stim_matrix"]).cuda()[None].contiguous()
+    out = optimise.caviar_batched(stim, np.unique(sim["stim_matrix"])[1:], torch.zeros(1, N, **f64),
+                                  10 * torch.ones(1, N, **f64), 1.0, 0.1, phi, cov,
+                                  psc=torch.from_numpy(sim["psc"]).cuda()[None].contiguous(), seeds=[1], iters=50, msrmp=0.4)
+    optimise.check_status(out)
+    lam, mu = out["lam"][0], out["mu"][0]
+    assert torch.all(lam[stim[0] == 0] == 0)                       # supp(lam) within supp(stim)
+    assert out["shape"][0].item() == 1.0 + K / 2                   # caviar.py:241
+    assert torch.all((lam.sum(1) > 0) == (mu != 0)) or torch.all(lam.sum(1)[mu != 0] > 0)
+    assert torch.all((lam >= 0) & (lam <= 1)) and torch.isfinite(out["phi"]).all()
+    truth = set(np.nonzero(sim["weights"])[0]); got = set(np.nonzero(mu.cpu().numpy())[0])
+    assert len(got - truth) <= 2 and len(truth & got) >= 0.75 * len(truth)     # recovers the planted connectivity

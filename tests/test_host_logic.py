@@ -1,0 +1,61 @@
+"""Host-side behaviour of the drop-in classes that does not need a GPU."""
+import numpy as np
+import pytest
+import torch
+
+from circuitmap_b200 import Model, NeuralDemixer, optimise
+from circuitmap_b200.neural_waveform_demixing import state_dict_keys, load_weights, random_weights
+from tests.conftest import GOLDEN
+import os
+
+no_gpu = not torch.cuda.is_available()
+
+
+def test_model_default_priors_match_reference():
+    m = Model(5)                                                      # model.py:24-34
+    assert np.array_equal(m.state["alpha"], 0.25 * np.ones(5))
+    assert np.array_equal(m.state["phi"], np.c_[0.1 * np.ones(5), 5.0 * np.ones(5)])
+    assert m.state["phi_cov"].shape == (5, 2, 2) and m.state["phi_cov"][0].tolist() == [[0.1, 0], [0, 1.0]]
+    assert np.array_equal(m.state["mu"], np.zeros(5)) and np.array_equal(m.state["beta"], 10 * np.ones(5))
+    assert m.state["shape"] == 1.0 and m.state["rate"] == 0.1
+    pri = {"beta": 3 * np.ones(5)}
+    m2 = Model(5, priors=pri)
+    assert "mu" in pri and m2.state["beta"][0] == 3                  # caller's dict is filled by setdefault
+
+
+def test_unknown_method_raises_bare_exception():
+    with pytest.raises(Exception):
+        Model(3).fit(np.zeros((4, 900)), np.zeros((3, 4)), method="nope")
+
+
+def test_unknown_fit_option_is_a_typeerror():
+    # the live spelling is `msrmp`; stale scripts pass `minimax_spk_prob` and get a TypeError (caviar.py:21-23)
+    with pytest.raises(TypeError):
+        optimise._validate_options({"minimax_spk_prob": 0.3})
+    assert optimise._validate_options({"iters": 3})["iters"] == 3
+
+
+@pytest.mark.skipif(not no_gpu, reason="checks the no-GPU failure mode")
+def test_product_fails_loudly_without_cuda():
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        NeuralDemixer(path=os.path.join(GOLDEN, "nwd_ie_ChroME2f_weights.npz"))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        Model(3).fit(np.ones((4, 900)), np.ones((3, 4)))
+
+
+def test_weight_loading_and_key_order():
+    keys = state_dict_keys()
+    assert len(keys) == 54 and keys[0] == "dblock1.conv.weight" and keys[-1] == "conv.bn.running_var"
+    w = load_weights(os.path.join(GOLDEN, "nwd_ie_ChroME2f_weights.npz"))
+    assert w["ublock4.deconv.weight"].shape == (32, 4, 32) and w["conv.conv.weight"].dtype == np.float32
+    r = random_weights()
+    assert all(r[k].shape == w[k].shape for k in keys)
+    # 76,018 checkpoint elements = these 54 tensors + 9 num_batches_tracked scalars
+    assert sum(v.size for v in w.values()) + 9 == 76018
+
+
+def test_product_never_imports_the_oracle():
+    import circuitmap_b200, pathlib
+    for f in pathlib.Path(circuitmap_b200.__file__).parent.rglob("*.py"):
+        src = f.read_text()
+        assert "import oracle" not in src and "from oracle" not in src, f
