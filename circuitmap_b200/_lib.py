@@ -45,7 +45,8 @@ class CaviarArgs(C.Structure):
 
 # every symbol include/circuitmap_b200.h declares
 EXPORTS = ["cm_version", "cm_last_error", "cm_device_info", "cm_nwd_create", "cm_nwd_destroy", "cm_nwd_forward",
-           "cm_caviar_workspace_bytes", "cm_caviar_fit", "cm_last_launch_count", "cm_last_main_kernel_ms"]
+           "cm_caviar_workspace_bytes", "cm_caviar_fit", "cm_last_launch_count", "cm_last_main_kernel_ms",
+           "cm_caviar_debug_phase_cycles"]
 
 _lib = None
 

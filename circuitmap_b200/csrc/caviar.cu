@@ -13,6 +13,7 @@
 #include "common.cuh"
 #include <vector>
 #include <cfloat>
+#include <math_constants.h>
 #include <cstring>
 
 namespace cm {
@@ -24,16 +25,19 @@ constexpr int NW = NT / 32;
 constexpr int NB = 32;           // block size of the bordered Cholesky/inverse
 constexpr int RG = 4;            // row groups of 8 in the panel GEMMs
 constexpr int MAX_SHUFFLE_ROUNDS = 4;
+constexpr int GK = 32, GCT = 256, AS_LD = 34;                    // panel GEMM tiles
+constexpr int GEMM_SMEM_DOUBLES = 2 * GK * AS_LD + 2 * GK * GCT; // 18560 doubles = 145 KB
+constexpr int FIT_SMEM_BYTES = 200 * 1024;
 
 // ------------------------------------------------------------------------------------------------ layout
 struct Layout {
     size_t stride;
     // fp64
     size_t X, PA, PB, lam, cst, y, ss, pred, resid, z, mu, beta, bvec, dvec, wvec, slam, slam2, sp, phibar, phi,
-        phicov, phiz, phicovz, lamhist;
+        phicov, phiz, phicovz, lamhist, lamT;
     // int32 / uint32
     size_t row_ptr, col_ptr, colfill, col_k, csc_row, csc_pos, cntp, n0p, n1p, act, ainv, order, order2, pos, rownz,
-        phizok, sortkeys, keys, dcnt, dlist;
+        phizok, sortkeys, keys, dcnt, dlist, colpw, nmask, chinfo;
     // bytes
     size_t pw, mask, blocked;
 };
@@ -67,6 +71,7 @@ static Layout make_layout(int N, int K, int64_t nnz, int iters, bool lamhist) {
     L.phiz = take(n * 2 * 8);
     L.phicovz = take(n * 4 * 8);
     L.lamhist = take(lamhist ? (size_t)iters * z * 8 : 0);
+    L.lamT = take(z * 8);
     L.row_ptr = take((n + 1) * 4);
     L.col_ptr = take((k + 1) * 4);
     L.colfill = take(k * 4);
@@ -87,6 +92,9 @@ static Layout make_layout(int N, int K, int64_t nnz, int iters, bool lamhist) {
     L.keys = take(2 * n * 2 * 4);
     L.dcnt = take(n * 4);
     L.dlist = take(n * 4);
+    L.colpw = take(z * 4);
+    L.nmask = take(n * PMAX * 4);
+    L.chinfo = take(n * 16);
     L.pw = take(z);
     L.mask = take(k);
     L.blocked = take(k);
@@ -161,21 +169,28 @@ __device__ __forceinline__ double pava_last(const double* sr, int P) {
     for (int t = 1; t < P; ++t) {
         ++top;
         v[top] = sr[t]; w[top] = 1.0;
-        while (top > 0 && (v[top - 1] / w[top - 1]) > (v[top] / w[top])) {
+        // x / 1.0 == x exactly, so singleton pools skip the division
+        while (top > 0 && ((w[top - 1] == 1.0 ? v[top - 1] : v[top - 1] / w[top - 1]) >
+                           (w[top] == 1.0 ? v[top] : v[top] / w[top]))) {
             --top;
             v[top] = v[top] + v[top + 1];
             w[top] = w[top] + w[top + 1];
         }
     }
-    return v[top] / w[top];
+    return w[top] == 1.0 ? v[top] : v[top] / w[top];
 }
 
+__device__ long long g_phase_cycles[32];
+__device__ int g_phase_enable = 0;
+
 struct Ctx {
+    long long* tlast;   // shared: last phase timestamp (block 0 / thread 0 only)
     int N, K, P, nnz, it;
     double *X, *PA, *PB, *lam, *cst, *y, *ss, *pred, *resid, *z, *mu, *beta, *bvec, *dvec, *wvec, *slam, *slam2, *sp,
-        *phibar, *phi, *phicov, *phiz, *phicovz, *lamhist;
+        *phibar, *phi, *phicov, *phiz, *phicovz, *lamhist, *lamT;
     int *row_ptr, *col_ptr, *col_k, *csc_row, *csc_pos, *cntp, *n0p, *n1p, *act, *ainv, *order, *order2, *pos, *rownz,
-        *phizok, *dcnt, *dlist;
+        *phizok, *dcnt, *dlist, *colpw, *nmask;
+    int4* chinfo;
     uint32_t *sortkeys, *keys;
     unsigned char *pw, *mask, *blocked;
     const double *mu0, *beta0, *phi0, *phicov0;
@@ -183,6 +198,15 @@ struct Ctx {
     double* sm;       // shared: dynamic region
     int smd;          // its size in doubles
 };
+
+// phase accounting for cm_caviar_debug_phase_cycles (block 0, thread 0; enabled on request only)
+__device__ __forceinline__ void phase_mark(const Ctx& c, int id) {
+    if (g_phase_enable && blockIdx.x == 0 && threadIdx.x == 0) {
+        const long long t = clock64();
+        g_phase_cycles[id] += t - *c.tlast;
+        *c.tlast = t;
+    }
+}
 
 __device__ __forceinline__ double block_sum(double v, double* red) {
     v = warp_sum(v);
@@ -244,7 +268,7 @@ __device__ int block_compact(int n, F flag, int* out, int* inv, double* red) {
 __device__ __forceinline__ void compute_pred(const Ctx& c, double* dst) {
     for (int k = threadIdx.x; k < c.K; k += NT) {
         double s = 0.0;
-        for (int i = c.col_ptr[k]; i < c.col_ptr[k + 1]; ++i) s += c.mu[c.csc_row[i]] * c.lam[c.csc_pos[i]];
+        for (int i = c.col_ptr[k]; i < c.col_ptr[k + 1]; ++i) s += c.mu[c.csc_row[i]] * c.lamT[i];
         dst[k] = s;
     }
 }
@@ -254,9 +278,25 @@ __device__ __forceinline__ void compute_pred(const Ctx& c, double* dst) {
 // M = sigma (diag(sum lam(1-lam)) + lam_A lam_A^T) + diag(1/beta0^2);  C = M^-1;  mu = C b;  beta = diag C.
 // C = X^T X with X = L^-1 built by a bordered (block-row) recursion that keeps X (lower) and X^T (upper) in one
 // na x na array, so both panel GEMMs read it with unit stride across threads.
+// ---- async copy helpers (LDGSTS) ----
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+    const unsigned sdst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sdst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+    const unsigned sdst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sdst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N_>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N_) : "memory"); }
+
+// Gram rows of one 32-row block of M into PA (lower part incl. the diagonal block).
+// One warp per row; 32 entries of the row are expanded at once (each lane walks the column list of its own
+// trial), lanes that hit the same target column in the same step are combined in lane order -> deterministic.
 __device__ void gram_rows(const Ctx& c, int na, int i0, int nb, double sigma) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int cap = c.smd / NW;                   // row-buffer doubles per warp
+    const int cap = GEMM_SMEM_DOUBLES / NW;       // row-buffer doubles per warp
     for (int r = wid; r < nb; r += NW) {
         const int ia = i0 + r;
         const int n = c.act[ia];
@@ -266,22 +306,40 @@ __device__ void gram_rows(const Ctx& c, int na, int i0, int nb, double sigma) {
         const int beg = c.row_ptr[n], end = c.row_ptr[n + 1];
         for (int jb = beg; jb < end; jb += 32) {
             const int j = jb + lane;
-            double myla = 0.0;
-            int mycb = 0, myce = 0;
+            double la = 0.0;
+            int cb = 0, len = 0;
             if (j < end) {
-                myla = c.lam[j];
-                const int k = c.col_k[j];
-                mycb = c.col_ptr[k];
-                myce = c.col_ptr[k + 1];
+                la = c.lam[j];
+                if (la != 0.0) {
+                    const int k = c.col_k[j];
+                    cb = c.col_ptr[k];
+                    len = c.col_ptr[k + 1] - cb;
+                }
             }
-            const int cnt = min(32, end - jb);
-            for (int t = 0; t < cnt; ++t) {
-                const double la = __shfl_sync(0xffffffffu, myla, t);
-                if (la == 0.0) continue;
-                const int cb = __shfl_sync(0xffffffffu, mycb, t), ce = __shfl_sync(0xffffffffu, myce, t);
-                for (int i = cb + lane; i < ce; i += 32) {
-                    const int ib = c.ainv[c.csc_row[i]];
-                    if (ib >= 0 && ib <= ia) acc[ib] += la * c.lam[c.csc_pos[i]];
+            int maxlen = len;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, o));
+            for (int t = 0; t < maxlen; ++t) {
+                int ib = -1;
+                double v = 0.0;
+                if (t < len) {
+                    const int i = cb + t;
+                    ib = c.ainv[c.csc_row[i]];
+                    if (ib > ia) ib = -1;
+                    v = la * c.lamT[i];
+                }
+                const unsigned amask = __ballot_sync(0xffffffffu, ib >= 0);
+                if (ib >= 0) {
+                    const unsigned grp = __match_any_sync(amask, ib);
+                    const int leader = __ffs(grp) - 1;
+                    unsigned rest = grp & ~(1u << leader);
+                    double ssum = __shfl_sync(amask, v, leader);
+                    while (__any_sync(amask, rest != 0)) {
+                        const int src = rest ? (__ffs(rest) - 1) : lane;
+                        const double ov = __shfl_sync(amask, v, src);
+                        if (rest) { ssum += ov; rest &= rest - 1; }
+                    }
+                    if (lane == leader) acc[ib] += ssum;
                 }
                 __syncwarp();
             }
@@ -299,51 +357,80 @@ __device__ void gram_rows(const Ctx& c, int na, int i0, int nb, double sigma) {
     }
 }
 
-// OUT[r][cc] = sum_kk IN[r][kk] * X[kk][cc] over kk in [klo(cc), khi(cc)) ; UPPER: kk<=cc (X^T half), else kk>=cc.
+// OUT[r][cc] = sum_kk IN[r][kk] * X[kk][cc] ; UPPER: kk <= cc (the X^T half), else kk >= cc (the X half).
+// Classic smem-tiled GEMM: 32 x 32 chunk of IN and 32 x 256 chunk of X staged by cp.async (double buffered),
+// each thread owns 8 rows x 2 columns of the 32 x 256 output tile (16 fp64 accumulators).
 template <bool UPPER>
-__device__ void panel_gemm(const Ctx& c, int na, int i0, int nb, const double* IN, double* OUT, double* As) {
-    constexpr int KC = 32;
-    const int i0r = (i0 + 31) & ~31;
-    const int items = i0r * RG;
-    for (int base = 0; base < items; base += NT) {      // all threads iterate the same number of rounds
-        const int item = base + threadIdx.x;
-        const int rg = item / i0r;
-        const int cc = item - rg * i0r;
-        const bool valid = item < items && cc < i0;
-        double acc[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) acc[q] = 0.0;
-        for (int kk0 = 0; kk0 < i0; kk0 += KC) {
-            __syncthreads();
-            for (int e = threadIdx.x; e < KC * NB; e += NT) {
-                const int r = e / KC, kl = e - r * KC;
+__device__ void panel_gemm(const Ctx& c, int na, int i0, int nb, const double* IN, double* OUT) {
+    double* As = c.sm;                              // [2][GK][AS_LD]
+    double* Xs = c.sm + 2 * GK * AS_LD;             // [2][GK][GCT]
+    const int ccl = threadIdx.x & 127, rg = threadIdx.x >> 7;
+    for (int ct0 = 0; ct0 < i0; ct0 += GCT) {
+        const int cA = ct0 + ccl, cB = cA + 128;
+        const bool vA = cA < i0, vB = cB < i0;
+        const int tile_end = min(i0, ct0 + GCT);
+        const int kfirst = UPPER ? 0 : ct0;
+        const int klast = UPPER ? tile_end : i0;
+        const int nc = (klast - kfirst + GK - 1) / GK;
+        auto issue = [&](int ci, int buf) {
+            const int kk0 = kfirst + ci * GK;
+            for (int e = threadIdx.x; e < GK * NB; e += NT) {
+                const int kl = e & (GK - 1), r = e / GK;
                 const int kk = kk0 + kl;
-                As[kl * NB + r] = (r < nb && kk < i0) ? IN[(size_t)r * na + kk] : 0.0;
+                double* dst = As + (size_t)buf * GK * AS_LD + kl * AS_LD + r;
+                if (r < nb && kk < i0) cp_async8(dst, IN + (size_t)r * na + kk);
+                else *dst = 0.0;
             }
-            __syncthreads();
-            if (valid) {
-                const bool touch = UPPER ? (kk0 <= cc) : (kk0 + KC > cc);
-                if (touch) {
-                    const int kend = min(KC, i0 - kk0);
-#pragma unroll 4
-                    for (int kl = 0; kl < kend; ++kl) {
-                        const int kk = kk0 + kl;
-                        const bool in = UPPER ? (kk <= cc) : (kk >= cc);
-                        if (in) {
-                            const double x = c.X[(size_t)kk * na + cc];
-                            const double* ap = As + kl * NB + rg * 8;
+            for (int e = threadIdx.x; e < GK * GCT; e += NT) {
+                const int kl = e / GCT, cl = e - kl * GCT;
+                const int kk = kk0 + kl, cc = ct0 + cl;
+                if (kk < i0 && cc < i0) cp_async8(Xs + (size_t)buf * GK * GCT + kl * GCT + cl, c.X + (size_t)kk * na + cc);
+            }
+            cp_async_commit();
+        };
+        double acc[16];
 #pragma unroll
-                            for (int q = 0; q < 8; ++q) acc[q] = fma(ap[q], x, acc[q]);
-                        }
-                    }
+        for (int q = 0; q < 16; ++q) acc[q] = 0.0;
+        issue(0, 0);
+        for (int ci = 0; ci < nc; ++ci) {
+            if (ci + 1 < nc) { issue(ci + 1, (ci + 1) & 1); cp_async_wait<1>(); }
+            else cp_async_wait<0>();
+            __syncthreads();
+            const int kk0 = kfirst + ci * GK, buf = ci & 1;
+            const int klim = min(GK, i0 - kk0);
+            int a0, a1, b0, b1;
+            if (UPPER) {
+                a0 = 0; a1 = vA ? min(klim, cA - kk0 + 1) : 0;
+                b0 = 0; b1 = vB ? min(klim, cB - kk0 + 1) : 0;
+            } else {
+                a0 = vA ? max(0, cA - kk0) : klim; a1 = klim;
+                b0 = vB ? max(0, cB - kk0) : klim; b1 = klim;
+            }
+            const int lo = min(a0, b0), hi = max(a1, b1);
+            const double* ab = As + (size_t)buf * GK * AS_LD + rg * 8;
+            const double* xb = Xs + (size_t)buf * GK * GCT + ccl;
+#pragma unroll 4
+            for (int kl = lo; kl < hi; ++kl) {
+                const double xa = (kl >= a0 && kl < a1) ? xb[kl * GCT] : 0.0;
+                const double xv = (kl >= b0 && kl < b1) ? xb[kl * GCT + 128] : 0.0;
+                const double2* ap = reinterpret_cast<const double2*>(ab + kl * AS_LD);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const double2 av = ap[q];
+                    acc[2 * q] = fma(av.x, xa, acc[2 * q]);
+                    acc[2 * q + 1] = fma(av.y, xa, acc[2 * q + 1]);
+                    acc[8 + 2 * q] = fma(av.x, xv, acc[8 + 2 * q]);
+                    acc[8 + 2 * q + 1] = fma(av.y, xv, acc[8 + 2 * q + 1]);
                 }
             }
+            __syncthreads();
         }
-        if (valid) {
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const int r = rg * 8 + q;
-                if (r < nb) OUT[(size_t)r * na + cc] = acc[q];
+        for (int q = 0; q < 8; ++q) {
+            const int r = rg * 8 + q;
+            if (r < nb) {
+                if (vA) OUT[(size_t)r * na + cA] = acc[q];
+                if (vB) OUT[(size_t)r * na + cB] = acc[8 + q];
             }
         }
     }
@@ -375,24 +462,55 @@ __device__ void phase_a2(const Ctx& c, double sigma, int* na_s) {
         }
     }
     __syncthreads();
+    phase_mark(c, 0);
     if (na == 0) return;
 
     __shared__ double Sd[NB][NB + 1];     // diagonal block -> its Cholesky factor
     __shared__ double Xd[NB][NB + 1];     // inverse of the diagonal factor
-    __shared__ double As[32 * NB];        // staged panel chunk
     for (int i0 = 0; i0 < na; i0 += NB) {
         const int nb = min(NB, na - i0);
         gram_rows(c, na, i0, nb, sigma);          // PA[r][0..i0+r] = M[i0+r][.]
         __syncthreads();
-        if (i0 > 0) panel_gemm<true>(c, na, i0, nb, c.PA, c.PB, As);   // PB = Lrow = A[I,0:i0] X11^T
-        // S = A[I,I] - Lrow Lrow^T
-        for (int pr = wid; pr < nb * NB; pr += NW) {
-            const int r = pr / NB, r2 = pr - r * NB;
-            if (r2 > r || r2 >= nb) continue;
-            double s = 0.0;
-            for (int q = lane; q < i0; q += 32) s += c.PB[(size_t)r * na + q] * c.PB[(size_t)r2 * na + q];
-            s = warp_sum(s);
-            if (lane == 0) Sd[r][r2] = c.PA[(size_t)r * na + i0 + r2] - s;
+        phase_mark(c, 1);
+        if (i0 > 0) panel_gemm<true>(c, na, i0, nb, c.PA, c.PB);       // PB = Lrow = A[I,0:i0] X11^T
+        phase_mark(c, 2);
+        // S = A[I,I] - Lrow Lrow^T : Lrow staged through shared memory in 256-column tiles, thread per (r, r2)
+        {
+            constexpr int ST = 256, SLD = ST + 1;
+            double* Ps = c.sm;                    // [NB][SLD]
+            int pr = -1, pr2 = -1;
+            if (threadIdx.x < NB * (NB + 1) / 2) {          // 528 pairs > 512 threads: the last 16 pairs go to a 2nd round
+                int t = threadIdx.x, rr = 0;
+                while (t >= rr + 1) { t -= rr + 1; ++rr; }
+                pr = rr; pr2 = t;
+            }
+            double s0 = 0.0, s1 = 0.0;            // s1: pair index 512 + threadIdx.x (threads 0..15)
+            int qr = -1, qr2 = -1;
+            if (threadIdx.x < NB * (NB + 1) / 2 - NT) {
+                int t = NT + threadIdx.x, rr = 0;
+                while (t >= rr + 1) { t -= rr + 1; ++rr; }
+                qr = rr; qr2 = t;
+            }
+            for (int c0 = 0; c0 < i0; c0 += ST) {
+                const int w = min(ST, i0 - c0);
+                __syncthreads();
+                for (int e = threadIdx.x; e < NB * ST; e += NT) {
+                    const int r = e / ST, cl = e - r * ST;
+                    Ps[r * SLD + cl] = (r < nb && cl < w) ? c.PB[(size_t)r * na + c0 + cl] : 0.0;
+                }
+                __syncthreads();
+                if (pr >= 0) {
+                    const double *pa = Ps + pr * SLD, *pb = Ps + pr2 * SLD;
+#pragma unroll 8
+                    for (int q = 0; q < w; ++q) s0 = fma(pa[q], pb[q], s0);
+                }
+                if (qr >= 0) {
+                    const double *pa = Ps + qr * SLD, *pb = Ps + qr2 * SLD;
+                    for (int q = 0; q < w; ++q) s1 = fma(pa[q], pb[q], s1);
+                }
+            }
+            if (pr >= 0 && pr < nb) Sd[pr][pr2] = c.PA[(size_t)pr * na + i0 + pr2] - s0;
+            if (qr >= 0 && qr < nb) Sd[qr][qr2] = c.PA[(size_t)qr * na + i0 + qr2] - s1;
         }
         __syncthreads();
         if (wid == 0) {
@@ -418,8 +536,10 @@ __device__ void phase_a2(const Ctx& c, double sigma, int* na_s) {
             }
         }
         __syncthreads();
+        phase_mark(c, 3);
         if (i0 > 0) {
-            panel_gemm<false>(c, na, i0, nb, c.PB, c.PA, As);           // PA = W = Lrow X11
+            panel_gemm<false>(c, na, i0, nb, c.PB, c.PA);               // PA = W = Lrow X11
+            phase_mark(c, 4);
             // X[I, 0:i0] = -Xd W ; mirrored into the upper half
             const int i0r = (i0 + 31) & ~31;
             for (int item = threadIdx.x; item < i0r * RG; item += NT) {
@@ -450,6 +570,7 @@ __device__ void phase_a2(const Ctx& c, double sigma, int* na_s) {
             }
         }
         __syncthreads();
+        phase_mark(c, 5);
     }
     // w = X b ; mu = X^T w ; beta = column sums of squares of X
     for (int i = wid; i < na; i += NW) {
@@ -471,81 +592,175 @@ __device__ void phase_a2(const Ctx& c, double sigma, int* na_s) {
         c.beta[n] = v;
     }
     __syncthreads();
+    phase_mark(c, 6);
 }
 
 // ------------------------------------------------------------------------------------------------ a3
 // One neuron of update_lam's sweep (caviar.py:200-227, reduced form App. A.8), executed by one warp.
+// cp/cs/lo: the row's packed (trial | power<<27) entries, sigmoid-argument constants (in) / new posteriors (out),
+// and old posteriors -- either staged in shared memory (chain) or the global arrays themselves.
 // chain=true: the neuron reads and updates the running prediction (mu[n] != 0).
+#define NEG_INF (-CUDART_INF)
+
 template <int PT>
-__device__ void sweep_neuron(const Ctx& c, int n, bool chain, double sigma, double thr, double minspk, bool gate,
-                             double* pred) {
+__device__ __forceinline__ void sweep_row(const Ctx& c, int n, int beg, int len, bool chain, double mu_n,
+                                          const int* cntp, const int* nmask, const int* __restrict__ cp, double* cs,
+                                          const double* lo, double sigma, double thr, double minspk, bool gate,
+                                          double* pred) {
     const int lane = threadIdx.x & 31;
-    const int beg = c.row_ptr[n], end = c.row_ptr[n + 1];
-    const double mu_n = c.mu[n];
     const double coef = sigma * mu_n;
     double tot = 0.0, accp[PT];
-    int c0[PT], c1[PT];
 #pragma unroll
-    for (int p = 0; p < PT; ++p) { accp[p] = 0.0; c0[p] = 0; c1[p] = 0; }
-    for (int j = beg + lane; j < end; j += 32) {
-        const int k = c.col_k[j];
-        double est = 0.0;
-        if (c.mask[k]) {
-            const double x = chain ? (c.cst[j] - coef * pred[k]) : c.cst[j];
-            est = sigmoid_d(x);
-        }
-        c.cst[j] = est;
+    for (int p = 0; p < PT; ++p) accp[p] = 0.0;
+    bool rare = false;
+    int q = lane;
+    for (; q + 32 < len; q += 64) {                      // two independent entries per trip (ILP across the exp/div chains)
+        const int pk0 = cp[q], pk1 = cp[q + 32];
+        const double cj0 = cs[q], cj1 = cs[q + 32];
+        const double x0 = chain ? (cj0 - coef * pred[pk0 & 0x7ffffff]) : cj0;
+        const double x1 = chain ? (cj1 - coef * pred[pk1 & 0x7ffffff]) : cj1;
+        const double e0 = sigmoid_d(x0), e1 = sigmoid_d(x1);
+        cs[q] = e0; cs[q + 32] = e1;
+        tot += e0; tot += e1;
+        const int pw0 = pk0 >> 27, pw1 = pk1 >> 27;
+#pragma unroll
+        for (int p = 0; p < PT; ++p) { accp[p] += (pw0 == p) ? e0 : 0.0; accp[p] += (pw1 == p) ? e1 : 0.0; }
+        rare |= (e0 == 1.0) || (e0 == 0.0) || (e1 == 1.0) || (e1 == 0.0);
+    }
+    if (q < len) {
+        const int pk = cp[q];
+        const double cj = cs[q];
+        const double x = chain ? (cj - coef * pred[pk & 0x7ffffff]) : cj;
+        const double est = sigmoid_d(x);
+        cs[q] = est;
         tot += est;
-        const int pw = c.pw[j];
+        const int pw = pk >> 27;
 #pragma unroll
-        for (int p = 0; p < PT; ++p) {
-            const bool m = (pw == p);
-            accp[p] += m ? est : 0.0;
-            c0[p] += (m && est == 0.0);
-            c1[p] += (m && est == 1.0);
-        }
+        for (int p = 0; p < PT; ++p) accp[p] += (pw == p) ? est : 0.0;
+        rare |= (est == 1.0) || (est == 0.0);
     }
     tot = warp_sum(tot);
-    double sr[PMAX];
-    for (int p = 0; p < c.P; ++p) {
-        double s = 0.0; int a0 = 0, a1 = 0;
 #pragma unroll
-        for (int q = 0; q < PT; ++q) if (q == p) { s = accp[q]; a0 = c0[q]; a1 = c1[q]; }
-        s = warp_sum(s); a0 = warp_sum(a0); a1 = warp_sum(a1);
+    for (int p = 0; p < PT; ++p) accp[p] = warp_sum(accp[p]);
+    int c0[PT], c1[PT];
 #pragma unroll
-        for (int q = 0; q < PT; ++q) if (q == p) { accp[q] = s; c0[q] = a0; c1[q] = a1; }
-        const int cnt = c.cntp[n * PMAX + p];
-        sr[p] = s / ((double)cnt + 1e-4 * (cnt == 0 ? 1.0 : 0.0));
+    for (int p = 0; p < PT; ++p) { c0[p] = (p < c.P) ? nmask[p] : 0; c1[p] = 0; }
+    if (__any_sync(0xffffffffu, rare)) {                 // exact zero / one counts (needed by update_phi's nan_to_num)
+        int z0[PT];
+#pragma unroll
+        for (int p = 0; p < PT; ++p) z0[p] = 0;
+        for (int q = lane; q < len; q += 32) {
+            const int pw = cp[q] >> 27;
+            const double est = cs[q];
+#pragma unroll
+            for (int p = 0; p < PT; ++p) { z0[p] += (pw == p && est == 0.0); c1[p] += (pw == p && est == 1.0); }
+        }
+#pragma unroll
+        for (int p = 0; p < PT; ++p) { c0[p] += warp_sum(z0[p]); c1[p] = warp_sum(c1[p]); }
     }
     bool ok = true;
-    if (gate) ok = (pava_last(sr, c.P) >= thr) && (tot >= minspk);
-    // second pass: commit the row, update the running prediction and the row statistics
-    double sl = 0.0, sl2 = 0.0;
-    int nz = 0;
-    for (int j = beg + lane; j < end; j += 32) {
-        const double nw = ok ? c.cst[j] : 0.0;
-        const double old = c.lam[j];
-        c.lam[j] = nw;
-        if (chain) {
-            const int k = c.col_k[j];
-            pred[k] = (pred[k] + (ok ? mu_n : 0.0) * nw) - mu_n * old;
-        }
-        sl += nw; sl2 += nw * nw; nz += (nw != 0.0);
-    }
-    sl = warp_sum(sl); sl2 = warp_sum(sl2); nz = warp_sum(nz);
-    if (lane == 0) {
-        c.slam[n] = sl; c.slam2[n] = sl2; c.rownz[n] = nz;
-        for (int p = 0; p < c.P; ++p) {
-            double s = 0.0; int a0 = 0, a1 = 0;
+    if (gate) {
+        double sr[PMAX];
 #pragma unroll
-            for (int q = 0; q < PT; ++q) if (q == p) { s = accp[q]; a0 = c0[q]; a1 = c1[q]; }
-            const int cnt = c.cntp[n * PMAX + p];
-            c.sp[n * PMAX + p] = ok ? s : 0.0;
-            c.n0p[n * PMAX + p] = ok ? a0 : cnt;
-            c.n1p[n * PMAX + p] = ok ? a1 : 0;
+        for (int p = 0; p < PT; ++p)
+            if (p < c.P) {
+                const int cnt = cntp[p];
+                sr[p] = accp[p] / ((double)cnt + 1e-4 * (cnt == 0 ? 1.0 : 0.0));
+            }
+        ok = (pava_last(sr, c.P) >= thr) && (tot >= minspk);
+    }
+    // second pass: commit the row, update the running prediction
+    const double muok = ok ? mu_n : 0.0;
+    double sl2 = 0.0;
+    double* lam_row = c.lam + beg;
+    for (int q = lane; q < len; q += 32) {
+        const double nw = ok ? cs[q] : 0.0;
+        const double old = lo[q];
+        lam_row[q] = nw;
+        if (chain) {
+            const int k = cp[q] & 0x7ffffff;
+            pred[k] = (pred[k] + muok * nw) - mu_n * old;
         }
+        sl2 += nw * nw;
+    }
+    sl2 = warp_sum(sl2);
+    if (lane == 0) {
+        int zeros = 0;
+#pragma unroll
+        for (int p = 0; p < PT; ++p)
+            if (p < c.P) {
+                zeros += c0[p];
+                c.sp[n * PMAX + p] = ok ? accp[p] : 0.0;
+                c.n0p[n * PMAX + p] = ok ? c0[p] : cntp[p];
+                c.n1p[n * PMAX + p] = ok ? c1[p] : 0;
+            }
+        c.slam[n] = ok ? tot : 0.0;
+        c.slam2[n] = sl2;
+        int masked = 0;
+#pragma unroll
+        for (int p = 0; p < PT; ++p) if (p < c.P) masked += nmask[p];
+        c.rownz[n] = ok ? (len - (zeros - masked)) : 0;
     }
     __syncwarp();
+}
+
+constexpr int RC = 512;          // staged row capacity (entries) of the chain warp's prefetch buffers
+constexpr int NSTAGE = 3;
+constexpr int HD = 18;           // header doubles per stage: mu, then 2*PT ints (cntp, nmask)
+constexpr int STAGE_DOUBLES = NSTAGE * (RC + RC + RC / 2 + HD);   // cs, lo, cp (ints), header
+
+// The sequential part of the sweep: neurons with mu != 0, in update order, by ONE warp.  Rows are prefetched two
+// neurons ahead into shared memory with cp.async so that the chain only waits on shared-memory latency.
+template <int PT>
+__device__ void sweep_chain(const Ctx& c, int nchain, double sigma, double thr, double minspk, bool gate, double* pred,
+                            double* stage_base) {
+    const int lane = threadIdx.x & 31;
+    double* scs = stage_base;                                   // [NSTAGE][RC]
+    double* slo = scs + NSTAGE * RC;                            // [NSTAGE][RC]
+    int* scp = reinterpret_cast<int*>(slo + NSTAGE * RC);       // [NSTAGE][RC]
+    double* shd = reinterpret_cast<double*>(scp + NSTAGE * RC); // [NSTAGE][HD]: mu, then ints cntp[PT], nmask[PT]
+    auto stage = [&](int4 inf, int buf) {
+        const int n = inf.x, beg = inf.y, len = inf.z;
+        if (len <= RC) {
+            for (int q = lane; q < len; q += 32) {
+                cp_async4(scp + buf * RC + q, c.colpw + beg + q);
+                cp_async8(scs + buf * RC + q, c.cst + beg + q);
+                cp_async8(slo + buf * RC + q, c.lam + beg + q);
+            }
+        }
+        if (lane == 0) cp_async8(shd + buf * HD, c.mu + n);
+        int* hi = reinterpret_cast<int*>(shd + buf * HD + 1);
+        for (int q = lane; q < 2 * PT; q += 32)
+            cp_async4(hi + q, (q < PT) ? (c.cntp + n * PMAX + q) : (c.nmask + n * PMAX + (q - PT)));
+        cp_async_commit();
+    };
+    int4 infA = make_int4(0, 0, 0, 0), infB = infA;
+    if (nchain > 0) stage(c.chinfo[0], 0);
+    if (nchain > 1) stage(c.chinfo[1], 1);
+    if (nchain > 2) infA = c.chinfo[2];
+    if (nchain > 3) infB = c.chinfo[3];
+    int4 cur = nchain > 0 ? c.chinfo[0] : infA, nxt = nchain > 1 ? c.chinfo[1] : infA;
+    for (int i = 0; i < nchain; ++i) {
+        if (i + 2 < nchain) { stage(infA, (i + 2) % NSTAGE); cp_async_wait<2>(); }
+        else if (i + 1 < nchain) cp_async_wait<1>();
+        else cp_async_wait<0>();
+        __syncwarp();
+        const int4 after = infA;
+        infA = infB;
+        if (i + 4 < nchain) infB = c.chinfo[i + 4];
+        const int buf = i % NSTAGE;
+        const int n = cur.x, beg = cur.y, len = cur.z;
+        const double mu_n = shd[buf * HD];
+        const int* hi = reinterpret_cast<const int*>(shd + buf * HD + 1);
+        if (len <= RC)
+            sweep_row<PT>(c, n, beg, len, true, mu_n, hi, hi + PT, scp + buf * RC, scs + buf * RC, slo + buf * RC, sigma,
+                          thr, minspk, gate, pred);
+        else
+            sweep_row<PT>(c, n, beg, len, true, mu_n, hi, hi + PT, c.colpw + beg, c.cst + beg, c.lam + beg, sigma, thr,
+                          minspk, gate, pred);
+        cur = nxt;
+        nxt = after;
+    }
 }
 
 // PRNG work for one iteration, done by ONE warp: shuffle sub-keys, the N per-neuron sample keys
@@ -679,11 +894,12 @@ template <int PT>
 __global__ void __launch_bounds__(NT, 1) caviar_fit_kernel(const FitParams p) {
     extern __shared__ __align__(16) double dyn_smem[];
     __shared__ double red[NW + 2];
-    __shared__ double sc_shape, sc_rate, sc_spont, sc_err;
+    __shared__ double sc_shape, sc_rate, sc_spont;
     __shared__ int sc_na, sc_flag, sc_focus;
     __shared__ uint32_t sc_key[2];
     __shared__ uint32_t sc_subkeys[2 * MAX_SHUFFLE_ROUNDS];
     __shared__ double sc_powers[PMAX];
+    __shared__ long long sc_tlast;
 
     const int b = blockIdx.x;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -695,11 +911,12 @@ __global__ void __launch_bounds__(NT, 1) caviar_fit_kernel(const FitParams p) {
 #define CM_I(name) c.name = reinterpret_cast<int*>(base + L.name)
     CM_D(X); CM_D(PA); CM_D(PB); CM_D(lam); CM_D(cst); CM_D(y); CM_D(ss); CM_D(pred); CM_D(resid); CM_D(z); CM_D(mu);
     CM_D(beta); CM_D(bvec); CM_D(dvec); CM_D(wvec); CM_D(slam); CM_D(slam2); CM_D(sp); CM_D(phibar); CM_D(phi);
-    CM_D(phicov); CM_D(phiz); CM_D(phicovz); CM_D(lamhist);
+    CM_D(phicov); CM_D(phiz); CM_D(phicovz); CM_D(lamhist); CM_D(lamT);
     CM_I(row_ptr); CM_I(col_ptr); CM_I(col_k); CM_I(csc_row); CM_I(csc_pos); CM_I(cntp); CM_I(n0p); CM_I(n1p);
-    CM_I(act); CM_I(ainv); CM_I(order); CM_I(order2); CM_I(pos); CM_I(rownz); CM_I(phizok); CM_I(dcnt); CM_I(dlist);
+    CM_I(act); CM_I(ainv); CM_I(order); CM_I(order2); CM_I(pos); CM_I(rownz); CM_I(phizok); CM_I(dcnt); CM_I(dlist); CM_I(colpw); CM_I(nmask);
 #undef CM_D
 #undef CM_I
+    c.chinfo = reinterpret_cast<int4*>(base + L.chinfo);
     c.sortkeys = reinterpret_cast<uint32_t*>(base + L.sortkeys);
     c.keys = reinterpret_cast<uint32_t*>(base + L.keys);
     c.pw = reinterpret_cast<unsigned char*>(base + L.pw);
@@ -710,6 +927,8 @@ __global__ void __launch_bounds__(NT, 1) caviar_fit_kernel(const FitParams p) {
     c.phi0 = p.phi0 + (size_t)b * p.N * 2;
     c.phicov0 = p.phicov0 + (size_t)b * p.N * 4;
     c.red = red;
+    c.tlast = &sc_tlast;
+    if (threadIdx.x == 0) sc_tlast = clock64();
     c.sm = dyn_smem;
     c.smd = p.smem_doubles;
     const int N = c.N, K = c.K, P = c.P;
@@ -721,7 +940,11 @@ __global__ void __launch_bounds__(NT, 1) caviar_fit_kernel(const FitParams p) {
     // number of shuffle rounds of jax.random.permutation: ceil(3 ln N / ln(2^32-1))
     int rounds = (int)ceil(3.0 * log((double)max(1, N)) / log(4294967295.0));
     rounds = min(rounds, MAX_SHUFFLE_ROUNDS);
-    double* pred = (K <= c.smd) ? c.sm : c.pred;      // running prediction lives in shared memory when it fits
+    // a3 shared-memory plan: [pred (K doubles, when it fits)] [row staging of the chain warp]
+    const int kpad = (K + 1) & ~1;
+    const bool pred_smem = kpad + STAGE_DOUBLES <= c.smd;
+    double* pred = pred_smem ? c.sm : c.pred;
+    double* stage_base = pred_smem ? c.sm + kpad : c.sm;
 
     // ---------------- init (caviar.py:28-51) ----------------
     if (threadIdx.x < PMAX) sc_powers[threadIdx.x] = threadIdx.x < P ? p.powers[threadIdx.x] : 0.0;
@@ -744,15 +967,13 @@ __global__ void __launch_bounds__(NT, 1) caviar_fit_kernel(const FitParams p) {
         c.mu[n] = c.mu0[n]; c.beta[n] = c.beta0[n];
     }
     __syncthreads();
-    for (int n = wid; n < N; n += NW) {               // lam0 = 0.95 [I>0] lam_mask
-        double sl = 0.0; int nz = 0;
-        for (int j = c.row_ptr[n] + lane; j < c.row_ptr[n + 1]; j += 32) {
-            const double v = c.mask[c.col_k[j]] ? 0.95 : 0.0;
-            c.lam[j] = v; sl += v; nz += (v != 0.0);
-        }
-        sl = warp_sum(sl); nz = warp_sum(nz);
-        if (lane == 0) { c.slam[n] = sl; c.slam2[n] = sl * 0.95; c.rownz[n] = nz; }
+    for (int n = threadIdx.x; n < N; n += NT) {       // lam0 = 0.95 [I>0] lam_mask: every indexed entry is unmasked
+        const int len = c.row_ptr[n + 1] - c.row_ptr[n];
+        c.slam[n] = 0.95 * len; c.slam2[n] = 0.95 * 0.95 * len; c.rownz[n] = len;
     }
+    for (int j = threadIdx.x; j < c.nnz; j += NT) c.lam[j] = 0.95;
+    __syncthreads();
+    for (int i = threadIdx.x; i < c.nnz; i += NT) c.lamT[i] = c.lam[c.csc_pos[i]];
     double sumy = 0.0, ysq = 0.0;
     for (int k = threadIdx.x; k < K; k += NT) { const double v = c.y[k]; sumy += v; ysq += v * v; }
     sumy = block_sum(sumy, red);
@@ -761,6 +982,7 @@ __global__ void __launch_bounds__(NT, 1) caviar_fit_kernel(const FitParams p) {
     uint32_t rk0 = sc_key[0], rk1 = sc_key[1];
     if (wid == NW - 1) rng_iteration(N, rounds, rk0, rk1, c.keys, sc_subkeys);
     __syncthreads();
+    phase_mark(c, 15);
 
     for (int it = 0; it < iters; ++it) {
         c.it = it;
@@ -798,8 +1020,32 @@ __global__ void __launch_bounds__(NT, 1) caviar_fit_kernel(const FitParams p) {
         }
         for (int m = threadIdx.x; m < N; m += NT) c.pos[c.order[m]] = m;
         __syncthreads();
+        phase_mark(c, 7);
+        // Rows that are all-zero with mu == 0 and cannot reach minimum_spike_count are rejected again whatever the
+        // samples are: est_k <= sigmoid((m0 + 8.3 s0) Imax - sigma beta^2 / 2) because the truncated-normal samples
+        // obey phi_0 <= m0 + ndtri(1 - 2^-53) s0 and phi_1 >= 0.  Their row stays zero -> no work at all (exact).
+        {
+            const bool gate_on = it > o.delay_spont_est;
+            const double imax = sc_powers[P - 1];
+            for (int n = threadIdx.x; n < N; n += NT) {
+                int skip = 0;
+                if (gate_on && c.rownz[n] == 0 && c.mu[n] == 0.0) {
+                    const double m0 = c.phi[2 * n], s0 = c.phicov[4 * n], be = c.beta[n];
+                    const double len = (double)(c.row_ptr[n + 1] - c.row_ptr[n]);
+                    if (s0 > 0.0 && m0 == m0) {
+                        const double xmax = (m0 + 8.3 * s0) * imax - 0.5 * sigma * be * be;
+                        const double ub = len * sigmoid_d(xmax) * (1.0 + 1e-9);
+                        skip = (ub < o.minimum_spike_count) ? 1 : 0;
+                    }
+                    if (len == 0.0) skip = 1;
+                }
+                c.dcnt[n] = skip;
+            }
+        }
+        __syncthreads();
         // Monte-Carlo means of the truncated-normal sigmoid coefficients (caviar.py:209-215, App. A.2)
         for (int n = wid; n < N; n += NW) {
+            if (c.dcnt[n]) continue;
             const int m = c.pos[n];
             const uint32_t k0 = keys_cur[2 * m], k1 = keys_cur[2 * m + 1];
             const int cc = lane & 1;                                   // flat index e = 2 s + component
@@ -817,10 +1063,13 @@ __global__ void __launch_bounds__(NT, 1) caviar_fit_kernel(const FitParams p) {
             for (int off = 16; off > 1; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
             if (lane < 2) c.phibar[2 * n + lane] = acc / (double)S;
         }
+        __syncthreads();
+        phase_mark(c, 8);
         compute_pred(c, pred);
         __syncthreads();
         // per-entry constant part of the sigmoid argument
         for (int n = wid; n < N; n += NW) {
+            if (c.dcnt[n]) continue;
             const double mu_n = c.mu[n], be = c.beta[n];
             const double pb0 = c.phibar[2 * n], pb1 = c.phibar[2 * n + 1];
             const double cterm = 0.5 * sigma * (mu_n * mu_n + be * be);
@@ -831,26 +1080,41 @@ __global__ void __launch_bounds__(NT, 1) caviar_fit_kernel(const FitParams p) {
             }
         }
         __syncthreads();
+        phase_mark(c, 9);
+        // chain = neurons with mu != 0 in update order; (n, row begin, row length) table for the prefetching warp
+        const int nchain = block_compact(N, [&](int m) { return c.mu[c.order[m]] != 0.0; }, c.dlist, nullptr, red);
+        for (int i = threadIdx.x; i < nchain; i += NT) {
+            const int n = c.order[c.dlist[i]];
+            c.chinfo[i] = make_int4(n, c.row_ptr[n], c.row_ptr[n + 1] - c.row_ptr[n], 0);
+        }
+        __syncthreads();
         {
             const double thr = o.msrmp + sc_spont;
             const bool gate = it > o.delay_spont_est;
+            const long long role_t0 = clock64();
             if (wid == 0) {
-                // the sequential chain: neurons with mu != 0, in update order
-                for (int m = 0; m < N; ++m) {
-                    const int n = c.order[m];
-                    if (c.mu[n] != 0.0) sweep_neuron<PT>(c, n, true, sigma, thr, o.minimum_spike_count, gate, pred);
-                }
+                sweep_chain<PT>(c, nchain, sigma, thr, o.minimum_spike_count, gate, pred, stage_base);
+                if (g_phase_enable && blockIdx.x == 0 && lane == 0) g_phase_cycles[16] += clock64() - role_t0;
             } else if (wid == NW - 1) {
                 if (it + 1 < iters) rng_iteration(N, rounds, rk0, rk1, keys_nxt, sc_subkeys);
+                if (g_phase_enable && blockIdx.x == 0 && lane == 0) g_phase_cycles[17] += clock64() - role_t0;
             } else {
                 // mu == 0: the row neither reads nor changes the prediction -> order-free, run concurrently
                 for (int m = wid - 1; m < N; m += NW - 2) {
                     const int n = c.order[m];
-                    if (c.mu[n] == 0.0) sweep_neuron<PT>(c, n, false, sigma, thr, o.minimum_spike_count, gate, pred);
+                    if (c.mu[n] == 0.0 && !c.dcnt[n]) {
+                        const int beg = c.row_ptr[n], len = c.row_ptr[n + 1] - beg;
+                        sweep_row<PT>(c, n, beg, len, false, 0.0, c.cntp + n * PMAX, c.nmask + n * PMAX, c.colpw + beg,
+                                      c.cst + beg, c.lam + beg, sigma, thr, o.minimum_spike_count, gate, pred);
+                    }
                 }
+                if (g_phase_enable && blockIdx.x == 0 && wid == 1 && lane == 0) g_phase_cycles[18] += clock64() - role_t0;
             }
         }
         __syncthreads();
+        for (int i = threadIdx.x; i < c.nnz; i += NT) c.lamT[i] = c.lam[c.csc_pos[i]];   // CSC-ordered copy of the new lam
+        __syncthreads();
+        phase_mark(c, 10);
         // ================= a6: update_sigma (caviar.py:238-244), with a2's mu =================
         compute_pred(c, pred);
         __syncthreads();
@@ -872,12 +1136,16 @@ __global__ void __launch_bounds__(NT, 1) caviar_fit_kernel(const FitParams p) {
                 sc_rate = (p.rate0_arr ? p.rate0_arr[b] : p.rate0) + 0.5 * (s1 - s2 + s3);
             }
         }
+        __syncthreads();
+        phase_mark(c, 11);
         // ================= a7: update_phi (caviar.py:246-310) =================
         for (int n = threadIdx.x; n < N; n += NT) newton_row(c, sc_powers, n);
+        __syncthreads();
+        phase_mark(c, 12);
         // ================= a8: estimate_spont_act_soft_thresh (caviar.py:146-163, 86-88) =================
         for (int k = threadIdx.x; k < K; k += NT) {
             unsigned char bl = 0;
-            for (int i = c.col_ptr[k]; i < c.col_ptr[k + 1]; ++i) bl |= (c.lam[c.csc_pos[i]] >= o.spont_orthogonality);
+            for (int i = c.col_ptr[k]; i < c.col_ptr[k + 1]; ++i) bl |= (c.lamT[i] >= o.spont_orthogonality);
             c.blocked[k] = bl;
         }
         __syncthreads();
@@ -906,6 +1174,7 @@ __global__ void __launch_bounds__(NT, 1) caviar_fit_kernel(const FitParams p) {
             if (threadIdx.x == 0) sc_spont = (double)nzz / (double)K;
         }
         __syncthreads();
+        phase_mark(c, 13);
         // ================= histories (caviar.py:90-92) =================
         if (o.save_histories) {
             const size_t hb = (size_t)b * iters + it;
@@ -1058,7 +1327,7 @@ __global__ void __launch_bounds__(NT, 1) caviar_fit_kernel(const FitParams p) {
 #pragma unroll
                 for (int q = 0; q < PT; ++q) if (q == pp) { s = accp[q]; a0 = c0[q]; a1 = c1[q]; }
                 s = warp_sum(s); a0 = warp_sum(a0); a1 = warp_sum(a1);
-                if (lane == 0) { c.sp[n * PMAX + pp] = s; c.n0p[n * PMAX + pp] = a0; c.n1p[n * PMAX + pp] = a1; }
+                if (lane == 0) { c.sp[n * PMAX + pp] = s; c.n0p[n * PMAX + pp] = a0 + c.nmask[n * PMAX + pp]; c.n1p[n * PMAX + pp] = a1; }
             }
             if (lane == 0) c.rownz[n] = nz;
         }
@@ -1068,6 +1337,7 @@ __global__ void __launch_bounds__(NT, 1) caviar_fit_kernel(const FitParams p) {
         __syncthreads();
     }
 
+    phase_mark(c, 14);
     // ---------------- outputs ----------------
     for (int n = threadIdx.x; n < N; n += NT) {
         p.mu_out[(size_t)b * N + n] = c.mu[n];
@@ -1119,17 +1389,22 @@ __device__ __forceinline__ int power_index(const PowerTable& pt, double v) {
     return -1;
 }
 
-// pass 1 over the dense design: per-row and per-column counts
+// pass 1 over the dense design: per-row and per-column counts.  Only trials that pass the lam_mask
+// (sum psc^2 > y_xcorr_thresh, caviar.py:30) enter the CSR/CSC index -- lam is identically zero on the others
+// (caviar.py:34,216); the per-power trial counts (spike-rate denominators, caviar.py:183) count every trial.
 template <typename T>
 __global__ void __launch_bounds__(256) csr_count_kernel(const T* __restrict__ stim, int N, int K, const Layout L,
-                                                        char* ws, const PowerTable pt, int* status) {
+                                                        char* ws, const PowerTable pt, int* status, double thresh) {
     const int n = blockIdx.x, b = blockIdx.y;
     char* base = ws + (size_t)b * L.stride;
     int* row_ptr = reinterpret_cast<int*>(base + L.row_ptr);
     int* colcnt = reinterpret_cast<int*>(base + L.colfill);
     int* cntp = reinterpret_cast<int*>(base + L.cntp);
-    __shared__ int cs[PMAX + 1];
+    int* nmask = reinterpret_cast<int*>(base + L.nmask);
+    const double* ss = reinterpret_cast<const double*>(base + L.ss);
+    __shared__ int cs[PMAX + 1], cm[PMAX];
     if (threadIdx.x <= PMAX) cs[threadIdx.x] = 0;
+    if (threadIdx.x < PMAX) cm[threadIdx.x] = 0;
     __syncthreads();
     const T* row = stim + ((size_t)b * N + n) * K;
     int bad = 0;
@@ -1138,12 +1413,16 @@ __global__ void __launch_bounds__(256) csr_count_kernel(const T* __restrict__ st
         if (v > 0.0) {
             const int pi = power_index(pt, v);
             if (pi < 0) bad = 1;
-            else { atomicAdd(&cs[pi], 1); atomicAdd(&cs[PMAX], 1); atomicAdd(&colcnt[k], 1); }
+            else {
+                atomicAdd(&cs[pi], 1);
+                if (ss[k] > thresh) { atomicAdd(&cs[PMAX], 1); atomicAdd(&colcnt[k], 1); }
+                else atomicAdd(&cm[pi], 1);
+            }
         } else if (v < 0.0 || v != v) bad = 1;
     }
     if (bad) atomicExch(&status[b], CM_EINVAL);
     __syncthreads();
-    if (threadIdx.x < PMAX) cntp[n * PMAX + threadIdx.x] = cs[threadIdx.x];
+    if (threadIdx.x < PMAX) { cntp[n * PMAX + threadIdx.x] = cs[threadIdx.x]; nmask[n * PMAX + threadIdx.x] = cm[threadIdx.x]; }
     if (threadIdx.x == 0) row_ptr[n + 1] = cs[PMAX];      // counts; scanned next
 }
 
@@ -1195,7 +1474,7 @@ __global__ void __launch_bounds__(1024) scan_kernel(int N, int K, const Layout L
 // pass 2 over the dense design: ordered CSR fill + unordered CSC scatter
 template <typename T>
 __global__ void __launch_bounds__(256) csr_fill_kernel(const T* __restrict__ stim, int N, int K, const Layout L,
-                                                       char* ws, const PowerTable pt, const int* status) {
+                                                       char* ws, const PowerTable pt, const int* status, double thresh) {
     const int n = blockIdx.x, b = blockIdx.y;
     if (status[b] != 0) return;
     char* base = ws + (size_t)b * L.stride;
@@ -1206,6 +1485,8 @@ __global__ void __launch_bounds__(256) csr_fill_kernel(const T* __restrict__ sti
     int* csc_row = reinterpret_cast<int*>(base + L.csc_row);
     int* csc_pos = reinterpret_cast<int*>(base + L.csc_pos);
     unsigned char* pw = reinterpret_cast<unsigned char*>(base + L.pw);
+    int* colpw = reinterpret_cast<int*>(base + L.colpw);
+    const double* ss = reinterpret_cast<const double*>(base + L.ss);
     __shared__ int wcnt[8];
     __shared__ int run;
     if (threadIdx.x == 0) run = row_ptr[n];
@@ -1216,7 +1497,7 @@ __global__ void __launch_bounds__(256) csr_fill_kernel(const T* __restrict__ sti
         const int k = k0 + threadIdx.x;
         double v = 0.0;
         if (k < K) v = (double)row[k];
-        const bool f = v > 0.0;
+        const bool f = v > 0.0 && ss[k < K ? k : 0] > thresh;
         const unsigned bal = __ballot_sync(0xffffffffu, f);
         if (lane == 0) wcnt[wid] = __popc(bal);
         __syncthreads();
@@ -1225,7 +1506,9 @@ __global__ void __launch_bounds__(256) csr_fill_kernel(const T* __restrict__ sti
         if (f) {
             const int j = off + __popc(bal & ((1u << lane) - 1u));
             col_k[j] = k;
-            pw[j] = (unsigned char)power_index(pt, v);
+            const int pi = power_index(pt, v);
+            pw[j] = (unsigned char)pi;
+            colpw[j] = k | (pi << 27);            // packed (trial, power) for the sweep
             const int slot = atomicAdd(&colfill[k], 1);
             csc_row[col_ptr[k] + slot] = n;
             csc_pos[col_ptr[k] + slot] = j;
@@ -1277,6 +1560,18 @@ __global__ void __launch_bounds__(128) densify_kernel(const Layout L, char* ws, 
 using namespace cm;
 using namespace cm::cav;
 
+extern "C" int cm_caviar_debug_phase_cycles(long long* out, int n, int enable) {
+    if (out && n > 0) {
+        long long h[32];
+        CM_CUDA_CHECK(cudaMemcpyFromSymbol(h, g_phase_cycles, sizeof(h)));
+        for (int i = 0; i < n && i < 32; ++i) out[i] = h[i];
+    }
+    long long z[32] = {0};
+    CM_CUDA_CHECK(cudaMemcpyToSymbol(g_phase_cycles, z, sizeof(z)));
+    CM_CUDA_CHECK(cudaMemcpyToSymbol(g_phase_enable, &enable, sizeof(int)));
+    return CM_OK;
+}
+
 extern "C" size_t cm_caviar_workspace_bytes(int B, int N, int K, int64_t nnz_cap, int save_histories) {
     if (B <= 0 || N <= 0 || K <= 0 || nnz_cap < 0) return 0;
     const Layout L = make_layout(N, K, nnz_cap, save_histories > 0 ? save_histories : 0, save_histories > 0);
@@ -1286,9 +1581,11 @@ extern "C" size_t cm_caviar_workspace_bytes(int B, int N, int K, int64_t nnz_cap
 template <typename TS>
 static int run_csr(const cm_caviar_args* a, const Layout& L, char* ws, const PowerTable& pt, cudaStream_t st) {
     dim3 grid(a->N, a->B);
-    csr_count_kernel<TS><<<grid, 256, 0, st>>>((const TS*)a->stim_dev, a->N, a->K, L, ws, pt, a->status_dev);
+    csr_count_kernel<TS><<<grid, 256, 0, st>>>((const TS*)a->stim_dev, a->N, a->K, L, ws, pt, a->status_dev,
+                                               a->opt.y_xcorr_thresh);
     scan_kernel<<<a->B, 1024, 0, st>>>(a->N, a->K, L, ws, (long long)a->nnz_cap, a->status_dev);
-    csr_fill_kernel<TS><<<grid, 256, 0, st>>>((const TS*)a->stim_dev, a->N, a->K, L, ws, pt, a->status_dev);
+    csr_fill_kernel<TS><<<grid, 256, 0, st>>>((const TS*)a->stim_dev, a->N, a->K, L, ws, pt, a->status_dev,
+                                              a->opt.y_xcorr_thresh);
     const long long total = (long long)a->B * a->K;
     csc_sort_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a->K, L, ws, a->status_dev, total);
     count_launch(4);
@@ -1366,7 +1663,7 @@ extern "C" int cm_caviar_fit(const cm_caviar_args* a, void* stream) {
     p.rate_hist = a->rate_hist_dev; p.phi_hist = a->phi_hist_dev; p.phicov_hist = a->phi_cov_hist_dev;
     p.z_hist = a->z_hist_dev; p.lamhist = want_lamhist ? 1 : 0;
     p.status = a->status_dev;
-    const int smem_bytes = 160 * 1024;
+    const int smem_bytes = FIT_SMEM_BYTES;
     p.smem_doubles = smem_bytes / 8;
     main_kernel_begin(st);
     if (a->n_powers <= 4) {

@@ -132,6 +132,10 @@ typedef struct cm_caviar_args {
 CM_API size_t cm_caviar_workspace_bytes(int B, int N, int K, int64_t nnz_cap, int save_histories);
 CM_API int    cm_caviar_fit(const cm_caviar_args* a, void* stream);
 
+/* diagnostics: per-phase SM cycle counters of fit 0 of the persistent kernel (see csrc/caviar.cu phase_mark ids);
+ * copies up to n counters to `out` (may be NULL), then clears them and sets the enable flag (synchronises). */
+CM_API int cm_caviar_debug_phase_cycles(long long* out, int n, int enable);
+
 /* number of kernel launches issued by the last cm_* call on this thread (for bench accounting) */
 CM_API int cm_last_launch_count(void);
 /* device time (ms, CUDA events on the caller's stream) of the dominant kernel of the last cm_nwd_forward /

@@ -31,3 +31,22 @@ for rep in range(3):
         int((out["mu"][0] != 0).sum()), int((sim["weights"] != 0).sum())))
 tw = set(np.nonzero(sim["weights"])[0]); gw = set(np.nonzero(out["mu"][0].cpu().numpy())[0])
 print("TP %d FP %d FN %d" % (len(tw & gw), len(gw - tw), len(tw - gw)))
+
+# ---- phase breakdown of fit 0 ----
+import ctypes as C
+from circuitmap_b200 import _lib
+lib = _lib.load()
+lib.cm_caviar_debug_phase_cycles(None, 0, 1)
+out = optimise.caviar_batched(stim, powers, mu0, beta0, 1.0, 0.1, phi0, cov0, psc=psc, seeds=list(range(1, B + 1)),
+                              nnz_cap=int(np.count_nonzero(sim["stim_matrix"])), want_lam=False, workspace=ws, iters=iters, msrmp=0.4)
+torch.cuda.synchronize()
+buf = (C.c_longlong * 32)()
+lib.cm_caviar_debug_phase_cycles(buf, 32, 0)
+names = ["a2.compact+rows", "a2.gram", "a2.gemm1", "a2.S+chol", "a2.gemm2", "a2.Xupd", "a2.mu/beta", "a3.order", "a3.mc",
+         "a3.pred+cst", "a3.sweep", "a6", "a7.newton", "a8", "hist+recon", "init"]
+tot = sum(buf[:16])
+for i, nm in enumerate(names):
+    print("  %-16s %10.3f ms  %5.1f%%" % (nm, buf[i] / 1.9e6, 100.0 * buf[i] / max(tot, 1)))
+print("  total %.2f ms (at 1.9 GHz)" % (tot / 1.9e6))
+for i, nm in [(16, "sweep.chain warp"), (17, "sweep.rng warp"), (18, "sweep.inactive warp1")]:
+    print("  %-22s %10.3f ms" % (nm, buf[i] / 1.9e6))
