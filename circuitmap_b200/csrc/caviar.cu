@@ -25,8 +25,22 @@ constexpr int NW = NT / 32;
 constexpr int NB = 32;           // block size of the bordered Cholesky/inverse
 constexpr int RG = 4;            // row groups of 8 in the panel GEMMs
 constexpr int MAX_SHUFFLE_ROUNDS = 4;
-constexpr int GK = 32, GCT = 256, AS_LD = 34;                    // panel GEMM tiles
-constexpr int GEMM_SMEM_DOUBLES = 2 * GK * AS_LD + 2 * GK * GCT; // 18560 doubles = 145 KB
+constexpr int GK = 16, GCT = 256, NST = 4;                        // panel GEMM: k-chunk, column tile, pipeline stages
+constexpr int XD_LD = NB + 4;
+constexpr int STAGE_GEMM_DOUBLES = GK * NB + GK * GCT;            // A chunk [GK][32] + X chunk [GK][256] = 4608 doubles
+constexpr int GEMM_SMEM_DOUBLES = NST * STAGE_GEMM_DOUBLES;       // 18432 doubles = 144 KB
+constexpr int ROWPAD = 2 + GK;                                    // slack rows so that whole chunks can be copied
+
+// X = L^-1 (lower) with X^T mirrored in the upper half is stored in 256-column tiles, each tile row-major with 256
+// doubles per row, so that a GK x 256 chunk is ONE contiguous block (one bulk copy).  Odd rows have bit 3 of the
+// in-tile column flipped: with this swizzle the DMMA B-fragment loads from the dense shared-memory copy hit every
+// 8-byte bank exactly twice (the minimum for 32 lanes).
+__device__ __forceinline__ size_t xidx(int kk, int cc, int ldr) {
+    return ((size_t)(cc >> 8) * ldr + kk) * GCT + ((cc & (GCT - 1)) ^ ((kk & 1) << 3));
+}
+// The 32-row panels (A block row, Lrow, W) are stored transposed, [column][32 rows], same bit-3 swizzle on odd columns.
+__device__ __forceinline__ size_t pidx(int r, int cc) { return (size_t)cc * NB + (r ^ ((cc & 1) << 3)); }
+
 constexpr int FIT_SMEM_BYTES = 200 * 1024;
 
 // ------------------------------------------------------------------------------------------------ layout
@@ -34,7 +48,7 @@ struct Layout {
     size_t stride;
     // fp64
     size_t X, PA, PB, lam, cst, y, ss, pred, resid, z, mu, beta, bvec, dvec, wvec, slam, slam2, sp, phibar, phi,
-        phicov, phiz, phicovz, lamhist, lamT;
+        phicov, phiz, phicovz, lamhist, lamT, growbuf;
     // int32 / uint32
     size_t row_ptr, col_ptr, colfill, col_k, csc_row, csc_pos, cntp, n0p, n1p, act, ainv, order, order2, pos, rownz,
         phizok, sortkeys, keys, dcnt, dlist, colpw, nmask, chinfo;
@@ -47,9 +61,10 @@ static Layout make_layout(int N, int K, int64_t nnz, int iters, bool lamhist) {
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 255) & ~size_t(255); return r; };
     const size_t n = N, k = K, z = (size_t)nnz;
-    L.X = take(n * n * 8);
-    L.PA = take((size_t)NB * n * 8);
-    L.PB = take((size_t)NB * n * 8);
+    L.X = take(((n + GCT - 1) / GCT) * (size_t)GCT * (n + ROWPAD) * 8);
+    L.PA = take((size_t)NB * (n + ROWPAD) * 8);
+    L.PB = take((size_t)NB * (n + ROWPAD) * 8);
+    L.growbuf = take((size_t)NW * (n + 2) * 8);
     L.lam = take(z * 8);
     L.cst = take(z * 8);
     L.y = take(k * 8);
@@ -183,11 +198,53 @@ __device__ __forceinline__ double pava_last(const double* sr, int P) {
 __device__ long long g_phase_cycles[32];
 __device__ int g_phase_enable = 0;
 
+// register-resident variant for the sweep's critical path: every array index is static after unrolling
+template <int PT>
+__device__ __forceinline__ double rget(const double (&a)[PT], int i) {
+    double r = a[0];
+#pragma unroll
+    for (int p = 1; p < PT; ++p) r = (i == p) ? a[p] : r;
+    return r;
+}
+template <int PT>
+__device__ __forceinline__ void rset(double (&a)[PT], int i, double x) {
+#pragma unroll
+    for (int p = 0; p < PT; ++p) a[p] = (i == p) ? x : a[p];
+}
+template <int PT>
+__device__ __forceinline__ double pava_last_reg(const double (&sr)[PT], int P) {
+    double v[PT], w[PT];
+#pragma unroll
+    for (int p = 0; p < PT; ++p) { v[p] = 0.0; w[p] = 1.0; }
+    int top = 0;
+    v[0] = sr[0];
+#pragma unroll
+    for (int t = 1; t < PT; ++t) {
+        if (t < P) {
+            ++top;
+            rset<PT>(v, top, sr[t]);
+            rset<PT>(w, top, 1.0);
+            while (top > 0) {
+                const double vb = rget<PT>(v, top - 1), wb = rget<PT>(w, top - 1);
+                const double vt = rget<PT>(v, top), wt = rget<PT>(w, top);
+                const double mb = (wb == 1.0) ? vb : vb / wb;      // x / 1.0 == x exactly
+                const double mt = (wt == 1.0) ? vt : vt / wt;
+                if (!(mb > mt)) break;
+                --top;
+                rset<PT>(v, top, vb + vt);
+                rset<PT>(w, top, wb + wt);
+            }
+        }
+    }
+    const double vt = rget<PT>(v, top), wt = rget<PT>(w, top);
+    return (wt == 1.0) ? vt : vt / wt;
+}
+
 struct Ctx {
     long long* tlast;   // shared: last phase timestamp (block 0 / thread 0 only)
     int N, K, P, nnz, it;
     double *X, *PA, *PB, *lam, *cst, *y, *ss, *pred, *resid, *z, *mu, *beta, *bvec, *dvec, *wvec, *slam, *slam2, *sp,
-        *phibar, *phi, *phicov, *phiz, *phicovz, *lamhist, *lamT;
+        *phibar, *phi, *phicov, *phiz, *phicovz, *lamhist, *lamT, *growbuf;
     int *row_ptr, *col_ptr, *col_k, *csc_row, *csc_pos, *cntp, *n0p, *n1p, *act, *ainv, *order, *order2, *pos, *rownz,
         *phizok, *dcnt, *dlist, *colpw, *nmask;
     int4* chinfo;
@@ -201,7 +258,7 @@ struct Ctx {
 
 // phase accounting for cm_caviar_debug_phase_cycles (block 0, thread 0; enabled on request only)
 __device__ __forceinline__ void phase_mark(const Ctx& c, int id) {
-    if (g_phase_enable && blockIdx.x == 0 && threadIdx.x == 0) {
+    if ((g_phase_enable & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
         const long long t = clock64();
         g_phase_cycles[id] += t - *c.tlast;
         *c.tlast = t;
@@ -291,16 +348,46 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N_>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N_) : "memory"); }
 
+// ---- mbarrier / bulk-copy helpers (UBLKCP + SYNCS in SASS) ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {}
+}
+// global -> shared bulk copy (bytes % 16 == 0, both addresses 16-byte aligned), completion on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
 // Gram rows of one 32-row block of M into PA (lower part incl. the diagonal block).
 // One warp per row; 32 entries of the row are expanded at once (each lane walks the column list of its own
-// trial), lanes that hit the same target column in the same step are combined in lane order -> deterministic.
-__device__ void gram_rows(const Ctx& c, int na, int i0, int nb, double sigma) {
+// trial, 8 list entries prefetched per round), lanes that hit the same target column in the same step are
+// combined in lane order -> deterministic.
+__device__ void gram_rows(const Ctx& c, int i0, int nb, double sigma) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int cap = GEMM_SMEM_DOUBLES / NW;       // row-buffer doubles per warp
+    const int* __restrict__ ainv = c.ainv;
+    const int* __restrict__ csc_row = c.csc_row;
+    const double* __restrict__ lamT = c.lamT;
     for (int r = wid; r < nb; r += NW) {
         const int ia = i0 + r;
         const int n = c.act[ia];
-        double* acc = (ia + 1 <= cap) ? (c.sm + (size_t)wid * cap) : (c.PA + (size_t)r * na);
+        double* acc = (ia + 1 <= cap) ? (c.sm + (size_t)wid * cap) : (c.growbuf + (size_t)wid * (c.N + 2));
         for (int q = lane; q <= ia; q += 32) acc[q] = 0.0;
         __syncwarp();
         const int beg = c.row_ptr[n], end = c.row_ptr[n + 1];
@@ -319,128 +406,179 @@ __device__ void gram_rows(const Ctx& c, int na, int i0, int nb, double sigma) {
             int maxlen = len;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, o));
-            for (int t = 0; t < maxlen; ++t) {
-                int ib = -1;
-                double v = 0.0;
-                if (t < len) {
-                    const int i = cb + t;
-                    ib = c.ainv[c.csc_row[i]];
+            for (int t0 = 0; t0 < maxlen; t0 += 8) {
+                int ibs[8];
+                double vs[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {                  // independent loads first (memory-level parallelism)
+                    const int t = t0 + u;
+                    int rw = -1;
+                    double lv = 0.0;
+                    if (t < len) { rw = csc_row[cb + t]; lv = lamT[cb + t]; }
+                    ibs[u] = rw;
+                    vs[u] = la * lv;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    int ib = ibs[u] >= 0 ? ainv[ibs[u]] : -1;
                     if (ib > ia) ib = -1;
-                    v = la * c.lamT[i];
+                    ibs[u] = ib;
                 }
-                const unsigned amask = __ballot_sync(0xffffffffu, ib >= 0);
-                if (ib >= 0) {
-                    const unsigned grp = __match_any_sync(amask, ib);
-                    const int leader = __ffs(grp) - 1;
-                    unsigned rest = grp & ~(1u << leader);
-                    double ssum = __shfl_sync(amask, v, leader);
-                    while (__any_sync(amask, rest != 0)) {
-                        const int src = rest ? (__ffs(rest) - 1) : lane;
-                        const double ov = __shfl_sync(amask, v, src);
-                        if (rest) { ssum += ov; rest &= rest - 1; }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    if (t0 + u >= maxlen) break;               // warp-uniform
+                    const int ib = ibs[u];
+                    const double v = vs[u];
+                    const unsigned amask = __ballot_sync(0xffffffffu, ib >= 0);
+                    if (ib >= 0) {
+                        const unsigned grp = __match_any_sync(amask, ib);
+                        const int leader = __ffs(grp) - 1;
+                        unsigned rest = grp & ~(1u << leader);
+                        double ssum = __shfl_sync(amask, v, leader);
+                        while (__any_sync(amask, rest != 0)) {
+                            const int src = rest ? (__ffs(rest) - 1) : lane;
+                            const double ov = __shfl_sync(amask, v, src);
+                            if (rest) { ssum += ov; rest &= rest - 1; }
+                        }
+                        if (lane == leader) acc[ib] += ssum;
                     }
-                    if (lane == leader) acc[ib] += ssum;
+                    __syncwarp();
                 }
-                __syncwarp();
             }
         }
         const double b0 = c.beta0[n];
         const double dd = c.dvec[ia];
-        double* prow = c.PA + (size_t)r * na;
         for (int q = lane; q <= ia; q += 32) {
             double v = acc[q];
             if (q == ia) v = sigma * (dd + v) + 1.0 / (b0 * b0);
             else v = sigma * v;
-            prow[q] = v;
+            c.PA[pidx(r, q)] = v;
         }
         __syncwarp();
     }
 }
 
+// D(8x8) += A(8x4, row) * B(4x8, col): the fp64 tensor-core path (SASS DMMA.8x8x4); operands in registers.
+__device__ __forceinline__ void dmma8x8x4(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+// Pipeline state of the panel GEMMs: NST-stage ring of (A chunk, X chunk) filled by bulk copies, one "full" and one
+// "empty" mbarrier per stage.  `seq` counts chunks since kernel start (stage = seq % NST, parity = seq / NST & 1).
+struct GemmPipe {
+    uint64_t* full;      // [NST]
+    uint64_t* empty;     // [NST]
+    unsigned seq;
+};
+
 // OUT[r][cc] = sum_kk IN[r][kk] * X[kk][cc] ; UPPER: kk <= cc (the X^T half), else kk >= cc (the X half).
-// Classic smem-tiled GEMM: 32 x 32 chunk of IN and 32 x 256 chunk of X staged by cp.async (double buffered),
-// each thread owns 8 rows x 2 columns of the 32 x 256 output tile (16 fp64 accumulators).
+// 32 x GK chunks of IN and GK x 256 chunks of X are streamed through shared memory by cp.async.bulk (issued by warp
+// 0, completion on mbarriers, 4 stages in flight); each warp owns the 32 x 16 slice of the 32 x 256 output tile as
+// 4 x 2 DMMA tiles.  Row strides = 4 (mod 16) doubles keep the fragment loads bank-conflict free.
 template <bool UPPER>
-__device__ void panel_gemm(const Ctx& c, int na, int i0, int nb, const double* IN, double* OUT) {
-    double* As = c.sm;                              // [2][GK][AS_LD]
-    double* Xs = c.sm + 2 * GK * AS_LD;             // [2][GK][GCT]
-    const int ccl = threadIdx.x & 127, rg = threadIdx.x >> 7;
+__device__ void panel_gemm(const Ctx& c, int ldr, int i0, int nb, const double* IN, double* OUT, GemmPipe& gp) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int lq = lane >> 2, lr = lane & 3;
+    const int sw = (lr & 1) << 3;                 // swizzle term of this lane's k rows (k = 4*ks + lr)
+    const int wc = wid * 16;
+    double* stage0 = c.sm;
+    const double* Xg = c.X;
+    // the staging ring was last written through the generic proxy (row buffers, pred): order those writes before
+    // the async-proxy bulk copies that reuse the same shared memory
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    __syncthreads();
     for (int ct0 = 0; ct0 < i0; ct0 += GCT) {
-        const int cA = ct0 + ccl, cB = cA + 128;
-        const bool vA = cA < i0, vB = cB < i0;
         const int tile_end = min(i0, ct0 + GCT);
         const int kfirst = UPPER ? 0 : ct0;
         const int klast = UPPER ? tile_end : i0;
         const int nc = (klast - kfirst + GK - 1) / GK;
-        auto issue = [&](int ci, int buf) {
-            const int kk0 = kfirst + ci * GK;
-            for (int e = threadIdx.x; e < GK * NB; e += NT) {
-                const int kl = e & (GK - 1), r = e / GK;
-                const int kk = kk0 + kl;
-                double* dst = As + (size_t)buf * GK * AS_LD + kl * AS_LD + r;
-                if (r < nb && kk < i0) cp_async8(dst, IN + (size_t)r * na + kk);
-                else *dst = 0.0;
-            }
-            for (int e = threadIdx.x; e < GK * GCT; e += NT) {
-                const int kl = e / GCT, cl = e - kl * GCT;
-                const int kk = kk0 + kl, cc = ct0 + cl;
-                if (kk < i0 && cc < i0) cp_async8(Xs + (size_t)buf * GK * GCT + kl * GCT + cl, c.X + (size_t)kk * na + cc);
-            }
-            cp_async_commit();
-        };
-        double acc[16];
-#pragma unroll
-        for (int q = 0; q < 16; ++q) acc[q] = 0.0;
-        issue(0, 0);
-        for (int ci = 0; ci < nc; ++ci) {
-            if (ci + 1 < nc) { issue(ci + 1, (ci + 1) & 1); cp_async_wait<1>(); }
-            else cp_async_wait<0>();
-            __syncthreads();
-            const int kk0 = kfirst + ci * GK, buf = ci & 1;
-            const int klim = min(GK, i0 - kk0);
-            int a0, a1, b0, b1;
-            if (UPPER) {
-                a0 = 0; a1 = vA ? min(klim, cA - kk0 + 1) : 0;
-                b0 = 0; b1 = vB ? min(klim, cB - kk0 + 1) : 0;
-            } else {
-                a0 = vA ? max(0, cA - kk0) : klim; a1 = klim;
-                b0 = vB ? max(0, cB - kk0) : klim; b1 = klim;
-            }
-            const int lo = min(a0, b0), hi = max(a1, b1);
-            const double* ab = As + (size_t)buf * GK * AS_LD + rg * 8;
-            const double* xb = Xs + (size_t)buf * GK * GCT + ccl;
-#pragma unroll 4
-            for (int kl = lo; kl < hi; ++kl) {
-                const double xa = (kl >= a0 && kl < a1) ? xb[kl * GCT] : 0.0;
-                const double xv = (kl >= b0 && kl < b1) ? xb[kl * GCT + 128] : 0.0;
-                const double2* ap = reinterpret_cast<const double2*>(ab + kl * AS_LD);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const double2 av = ap[q];
-                    acc[2 * q] = fma(av.x, xa, acc[2 * q]);
-                    acc[2 * q + 1] = fma(av.y, xa, acc[2 * q + 1]);
-                    acc[8 + 2 * q] = fma(av.x, xv, acc[8 + 2 * q]);
-                    acc[8 + 2 * q + 1] = fma(av.y, xv, acc[8 + 2 * q + 1]);
+        const unsigned seq0 = gp.seq;
+        const double* Xtile = Xg + (size_t)(ct0 >> 8) * ldr * GCT;
+        auto fill = [&](int ci) {                             // warp 0 only: two bulk copies per chunk
+            const unsigned g = seq0 + ci;
+            const int st = g % NST;
+            if (g >= NST) mbar_wait(&gp.empty[st], ((g / NST) - 1) & 1);
+            if (lane == 0) {
+                double* As = stage0 + (size_t)st * STAGE_GEMM_DOUBLES;
+                double* Xs = As + GK * NB;
+                const int kk0 = kfirst + ci * GK;
+                if (g_phase_enable & 4) mbar_arrive(&gp.full[st]);          // debug: no copies
+                else {
+                    mbar_expect_tx(&gp.full[st], (uint32_t)(GK * NB * 8 + GK * GCT * 8));
+                    bulk_g2s(As, IN + (size_t)kk0 * NB, GK * NB * 8, &gp.full[st]);
+                    bulk_g2s(Xs, Xtile + (size_t)kk0 * GCT, GK * GCT * 8, &gp.full[st]);
                 }
             }
-            __syncthreads();
-        }
+            __syncwarp();
+        };
+        if (wid == 0)
+            for (int ci = 0; ci < min(nc, NST); ++ci) fill(ci);
+        double acc[4][2][2];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const int r = rg * 8 + q;
+        for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) { acc[mt][nt][0] = 0.0; acc[mt][nt][1] = 0.0; }
+        const int cmin = ct0 + wc, cmax = cmin + 15;
+        for (int ci = 0; ci < nc; ++ci) {
+            const unsigned g = seq0 + ci;
+            const int st = g % NST;
+            mbar_wait(&gp.full[st], (g / NST) & 1);
+            const int kk0 = kfirst + ci * GK;
+            if (cmin < i0 && !(g_phase_enable & 2)) {                       // debug bit 2: no math
+                const double* ab = stage0 + (size_t)st * STAGE_GEMM_DOUBLES;
+                const double* xb = ab + GK * NB;
+#pragma unroll
+                for (int ks = 0; ks < GK / 4; ++ks) {
+                    const int kbase = kk0 + 4 * ks;
+                    const bool skip = UPPER ? (kbase > cmax) : (kbase + 3 < cmin);
+                    if (skip || kbase >= i0) continue;                   // warp-uniform
+                    const int kk = kbase + lr;
+                    double af[4];
+#pragma unroll
+                    for (int mt = 0; mt < 4; ++mt) {
+                        const double av = ab[(4 * ks + lr) * NB + ((8 * mt + lq) ^ sw)];
+                        af[mt] = (8 * mt + lq < nb && kk < i0) ? av : 0.0;
+                    }
+#pragma unroll
+                    for (int nt = 0; nt < 2; ++nt) {
+                        const int cl = wc + 8 * nt + lq;
+                        const int cc = ct0 + cl;
+                        const bool in = (kk < i0) && (cc < i0) && (UPPER ? (kk <= cc) : (kk >= cc));
+                        const double xv = xb[(4 * ks + lr) * GCT + (cl ^ sw)];
+                        const double bv = in ? xv : 0.0;
+#pragma unroll
+                        for (int mt = 0; mt < 4; ++mt) dmma8x8x4(acc[mt][nt][0], acc[mt][nt][1], af[mt], bv);
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&gp.empty[st]);
+            if (wid == 0 && ci + NST < nc) fill(ci + NST);
+        }
+        gp.seq = seq0 + nc;
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) {
+            const int r = 8 * mt + lq;
             if (r < nb) {
-                if (vA) OUT[(size_t)r * na + cA] = acc[q];
-                if (vB) OUT[(size_t)r * na + cB] = acc[8 + q];
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt) {
+                    const int cc = cmin + 8 * nt + 2 * lr;
+                    if (cc < i0) OUT[pidx(r, cc)] = acc[mt][nt][0];
+                    if (cc + 1 < i0) OUT[pidx(r, cc + 1)] = acc[mt][nt][1];
+                }
             }
         }
     }
     __syncthreads();
 }
 
-__device__ void phase_a2(const Ctx& c, double sigma, int* na_s) {
+__device__ __noinline__ void phase_a2(const Ctx& c, double sigma, int* na_s, GemmPipe& gp) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int lq = lane >> 2, lr = lane & 3;
     const int N = c.N;
     const int na = block_compact(N, [&](int i) { return c.rownz[i] > 0; }, c.act, c.ainv, c.red);
+    const int ldr = N + ROWPAD;                   // rows per 256-column tile of X
     if (threadIdx.x == 0) *na_s = na;
     // inactive rows decouple: mu = mu0, beta = beta0^2 (variance)
     for (int n = threadIdx.x; n < N; n += NT)
@@ -466,51 +604,46 @@ __device__ void phase_a2(const Ctx& c, double sigma, int* na_s) {
     if (na == 0) return;
 
     __shared__ double Sd[NB][NB + 1];     // diagonal block -> its Cholesky factor
-    __shared__ double Xd[NB][NB + 1];     // inverse of the diagonal factor
+    __shared__ double Xd[NB][XD_LD];      // inverse of the diagonal factor, strict upper part zeroed
+    double* X = c.X;
+    double* PA = c.PA;
+    double* PB = c.PB;
     for (int i0 = 0; i0 < na; i0 += NB) {
         const int nb = min(NB, na - i0);
-        gram_rows(c, na, i0, nb, sigma);          // PA[r][0..i0+r] = M[i0+r][.]
+        gram_rows(c, i0, nb, sigma);              // PA[r][0..i0+r] = M[i0+r][.]
         __syncthreads();
         phase_mark(c, 1);
-        if (i0 > 0) panel_gemm<true>(c, na, i0, nb, c.PA, c.PB);       // PB = Lrow = A[I,0:i0] X11^T
+        if (i0 > 0) panel_gemm<true>(c, ldr, i0, nb, PA, PB, gp);      // PB = Lrow = A[I,0:i0] X11^T
         phase_mark(c, 2);
-        // S = A[I,I] - Lrow Lrow^T : Lrow staged through shared memory in 256-column tiles, thread per (r, r2)
+        // S = A[I,I] - Lrow Lrow^T : warp w owns the 8x8 tile (w/4, w%4) and runs the whole k range with DMMA,
+        // four independent accumulator pairs hide the dependent-issue latency.
         {
-            constexpr int ST = 256, SLD = ST + 1;
-            double* Ps = c.sm;                    // [NB][SLD]
-            int pr = -1, pr2 = -1;
-            if (threadIdx.x < NB * (NB + 1) / 2) {          // 528 pairs > 512 threads: the last 16 pairs go to a 2nd round
-                int t = threadIdx.x, rr = 0;
-                while (t >= rr + 1) { t -= rr + 1; ++rr; }
-                pr = rr; pr2 = t;
-            }
-            double s0 = 0.0, s1 = 0.0;            // s1: pair index 512 + threadIdx.x (threads 0..15)
-            int qr = -1, qr2 = -1;
-            if (threadIdx.x < NB * (NB + 1) / 2 - NT) {
-                int t = NT + threadIdx.x, rr = 0;
-                while (t >= rr + 1) { t -= rr + 1; ++rr; }
-                qr = rr; qr2 = t;
-            }
-            for (int c0 = 0; c0 < i0; c0 += ST) {
-                const int w = min(ST, i0 - c0);
-                __syncthreads();
-                for (int e = threadIdx.x; e < NB * ST; e += NT) {
-                    const int r = e / ST, cl = e - r * ST;
-                    Ps[r * SLD + cl] = (r < nb && cl < w) ? c.PB[(size_t)r * na + c0 + cl] : 0.0;
-                }
-                __syncthreads();
-                if (pr >= 0) {
-                    const double *pa = Ps + pr * SLD, *pb = Ps + pr2 * SLD;
-#pragma unroll 8
-                    for (int q = 0; q < w; ++q) s0 = fma(pa[q], pb[q], s0);
-                }
-                if (qr >= 0) {
-                    const double *pa = Ps + qr * SLD, *pb = Ps + qr2 * SLD;
-                    for (int q = 0; q < w; ++q) s1 = fma(pa[q], pb[q], s1);
+            const int mt = wid >> 2, nt = wid & 3;
+            double d[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
+            if (nt <= mt && i0 > 0) {
+                const int ra = 8 * mt + lq, rb = 8 * nt + lq;
+                const bool va = ra < nb, vb = rb < nb;
+                for (int k0 = 0; k0 < i0; k0 += 16) {
+                    double av[4], bv[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int k = k0 + 4 * u + lr;
+                        av[u] = (va && k < i0) ? PB[pidx(ra, k)] : 0.0;
+                        bv[u] = (vb && k < i0) ? PB[pidx(rb, k)] : 0.0;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) dmma8x8x4(d[u][0], d[u][1], av[u], bv[u]);
                 }
             }
-            if (pr >= 0 && pr < nb) Sd[pr][pr2] = c.PA[(size_t)pr * na + i0 + pr2] - s0;
-            if (qr >= 0 && qr < nb) Sd[qr][qr2] = c.PA[(size_t)qr * na + i0 + qr2] - s1;
+            if (nt <= mt) {
+                const double s0 = (d[0][0] + d[1][0]) + (d[2][0] + d[3][0]);
+                const double s1 = (d[0][1] + d[1][1]) + (d[2][1] + d[3][1]);
+                const int r = 8 * mt + lq, cc = 8 * nt + 2 * lr;
+                if (r < nb) {
+                    Sd[r][cc] = PA[pidx(r, i0 + cc)] - s0;
+                    Sd[r][cc + 1] = PA[pidx(r, i0 + cc + 1)] - s1;
+                }
+            }
         }
         __syncthreads();
         if (wid == 0) {
@@ -525,6 +658,8 @@ __device__ void phase_a2(const Ctx& c, double sigma, int* na_s) {
                     for (int q = j + 1; q <= lane; ++q) Sd[lane][q] -= Sd[lane][j] * Sd[q][j];
                 __syncwarp();
             }
+            for (int r = 0; r < NB; ++r) Xd[r][lane] = 0.0;       // column `lane`
+            __syncwarp();
             if (lane < nb) {
                 const int cc = lane;
                 Xd[cc][cc] = 1.0 / Sd[cc][cc];
@@ -538,35 +673,58 @@ __device__ void phase_a2(const Ctx& c, double sigma, int* na_s) {
         __syncthreads();
         phase_mark(c, 3);
         if (i0 > 0) {
-            panel_gemm<false>(c, na, i0, nb, c.PB, c.PA);               // PA = W = Lrow X11
+            panel_gemm<false>(c, ldr, i0, nb, PB, PA, gp);              // PA = W = Lrow X11
             phase_mark(c, 4);
-            // X[I, 0:i0] = -Xd W ; mirrored into the upper half
-            const int i0r = (i0 + 31) & ~31;
-            for (int item = threadIdx.x; item < i0r * RG; item += NT) {
-                const int rg = item / i0r, cc = item - rg * i0r;
-                if (cc >= i0) continue;
-                double wv[NB];
+            // X[I, 0:i0] = -Xd W (32x32 lower-triangular times 32 x i0, DMMA), mirrored into the upper half
+            const int nsl = (i0 + 15) / 16;
+            for (int sl = wid; sl < nsl; sl += NW) {
+                const int cb0 = sl * 16;
+                double acc[4][2][2];
 #pragma unroll
-                for (int r = 0; r < NB; ++r) wv[r] = (r < nb) ? c.PA[(size_t)r * na + cc] : 0.0;
+                for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const int r = rg * 8 + q;
-                    if (r < nb) {
-                        double s = 0.0;
+                    for (int nt = 0; nt < 2; ++nt) { acc[mt][nt][0] = 0.0; acc[mt][nt][1] = 0.0; }
+                double bvv[8][2];
 #pragma unroll
-                        for (int r2 = 0; r2 < NB; ++r2)
-                            if (r2 <= r) s += Xd[r][r2] * wv[r2];
-                        c.X[(size_t)(i0 + r) * na + cc] = -s;
-                        c.X[(size_t)cc * na + i0 + r] = -s;
+                for (int ks = 0; ks < 8; ++ks)
+#pragma unroll
+                    for (int nt = 0; nt < 2; ++nt) {
+                        const int r2 = 4 * ks + lr, cc = cb0 + 8 * nt + lq;
+                        bvv[ks][nt] = (r2 < nb && cc < i0) ? PA[pidx(r2, cc)] : 0.0;
                     }
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) {
+                    double af[4];
+#pragma unroll
+                    for (int mt = 0; mt < 4; ++mt) af[mt] = Xd[8 * mt + lq][4 * ks + lr];
+#pragma unroll
+                    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                        for (int mt = 0; mt < 4; ++mt) dmma8x8x4(acc[mt][nt][0], acc[mt][nt][1], af[mt], bvv[ks][nt]);
+                }
+#pragma unroll
+                for (int mt = 0; mt < 4; ++mt) {
+                    const int r = 8 * mt + lq;
+                    if (r >= nb) continue;
+#pragma unroll
+                    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int cc = cb0 + 8 * nt + 2 * lr + e;
+                            if (cc < i0) {
+                                const double v = -acc[mt][nt][e];
+                                X[xidx(i0 + r, cc, ldr)] = v;
+                                X[xidx(cc, i0 + r, ldr)] = v;
+                            }
+                        }
                 }
             }
         }
         for (int e = threadIdx.x; e < nb * nb; e += NT) {
             const int r = e / nb, r2 = e - r * nb;
             if (r2 <= r) {
-                c.X[(size_t)(i0 + r) * na + i0 + r2] = Xd[r][r2];
-                c.X[(size_t)(i0 + r2) * na + i0 + r] = Xd[r][r2];
+                X[xidx(i0 + r, i0 + r2, ldr)] = Xd[r][r2];
+                X[xidx(i0 + r2, i0 + r, ldr)] = Xd[r][r2];
             }
         }
         __syncthreads();
@@ -575,7 +733,7 @@ __device__ void phase_a2(const Ctx& c, double sigma, int* na_s) {
     // w = X b ; mu = X^T w ; beta = column sums of squares of X
     for (int i = wid; i < na; i += NW) {
         double s = 0.0;
-        for (int q = lane; q <= i; q += 32) s += c.X[(size_t)i * na + q] * c.bvec[q];
+        for (int q = lane; q <= i; q += 32) s += X[xidx(i, q, ldr)] * c.bvec[q];
         s = warp_sum(s);
         if (lane == 0) c.wvec[i] = s;
     }
@@ -583,7 +741,7 @@ __device__ void phase_a2(const Ctx& c, double sigma, int* na_s) {
     for (int cc = threadIdx.x; cc < na; cc += NT) {
         double m = 0.0, v = 0.0;
         for (int i = cc; i < na; ++i) {
-            const double x = c.X[(size_t)i * na + cc];
+            const double x = X[xidx(i, cc, ldr)];
             m += x * c.wvec[i];
             v += x * x;
         }
@@ -602,14 +760,30 @@ __device__ void phase_a2(const Ctx& c, double sigma, int* na_s) {
 // chain=true: the neuron reads and updates the running prediction (mu[n] != 0).
 #define NEG_INF (-CUDART_INF)
 
+// what a sweep step needs, held in registers (the big Ctx lives in local memory; keep it off the critical path)
+struct RowCtx {
+    double *lam, *sp, *slam, *slam2;
+    int *n0p, *n1p, *rownz;
+    int P;
+};
+__device__ __forceinline__ RowCtx make_rowctx(const Ctx& c) {
+    RowCtx r;
+    r.lam = c.lam; r.sp = c.sp; r.slam = c.slam; r.slam2 = c.slam2;
+    r.n0p = c.n0p; r.n1p = c.n1p; r.rownz = c.rownz; r.P = c.P;
+    return r;
+}
+
 template <int PT>
-__device__ __forceinline__ void sweep_row(const Ctx& c, int n, int beg, int len, bool chain, double mu_n,
+__device__ __forceinline__ void sweep_row(const RowCtx c, int n, int beg, int len, bool chain, double mu_n,
                                           const int* cntp, const int* nmask, const int* __restrict__ cp, double* cs,
                                           const double* lo, double sigma, double thr, double minspk, bool gate,
                                           double* pred) {
     const int lane = threadIdx.x & 31;
+    const bool prof = chain && g_phase_enable && blockIdx.x == 0 && lane == 0;
+    long long tp0 = 0;
+    if (prof) tp0 = clock64();
     const double coef = sigma * mu_n;
-    double tot = 0.0, accp[PT];
+    double tot, accp[PT];
 #pragma unroll
     for (int p = 0; p < PT; ++p) accp[p] = 0.0;
     bool rare = false;
@@ -621,7 +795,6 @@ __device__ __forceinline__ void sweep_row(const Ctx& c, int n, int beg, int len,
         const double x1 = chain ? (cj1 - coef * pred[pk1 & 0x7ffffff]) : cj1;
         const double e0 = sigmoid_d(x0), e1 = sigmoid_d(x1);
         cs[q] = e0; cs[q + 32] = e1;
-        tot += e0; tot += e1;
         const int pw0 = pk0 >> 27, pw1 = pk1 >> 27;
 #pragma unroll
         for (int p = 0; p < PT; ++p) { accp[p] += (pw0 == p) ? e0 : 0.0; accp[p] += (pw1 == p) ? e1 : 0.0; }
@@ -633,15 +806,28 @@ __device__ __forceinline__ void sweep_row(const Ctx& c, int n, int beg, int len,
         const double x = chain ? (cj - coef * pred[pk & 0x7ffffff]) : cj;
         const double est = sigmoid_d(x);
         cs[q] = est;
-        tot += est;
         const int pw = pk >> 27;
 #pragma unroll
         for (int p = 0; p < PT; ++p) accp[p] += (pw == p) ? est : 0.0;
         rare |= (est == 1.0) || (est == 0.0);
     }
-    tot = warp_sum(tot);
+    if (prof) { const long long t = clock64(); g_phase_cycles[20] += t - tp0; tp0 = t; }
+    // per-power sums (warp-uniform guard skips unused slots); the row total is their sum
 #pragma unroll
-    for (int p = 0; p < PT; ++p) accp[p] = warp_sum(accp[p]);
+    for (int o = 16; o > 0; o >>= 1) {                   // P butterflies interleaved level by level
+        double tmpv[PT];
+#pragma unroll
+        for (int p = 0; p < PT; ++p)
+            if (p < c.P) tmpv[p] = __shfl_xor_sync(0xffffffffu, accp[p], o);
+#pragma unroll
+        for (int p = 0; p < PT; ++p)
+            if (p < c.P) accp[p] += tmpv[p];
+    }
+    tot = 0.0;
+#pragma unroll
+    for (int p = 0; p < PT; ++p)
+        if (p < c.P) tot += accp[p];
+    if (prof) { const long long t = clock64(); g_phase_cycles[21] += t - tp0; tp0 = t; }
     int c0[PT], c1[PT];
 #pragma unroll
     for (int p = 0; p < PT; ++p) { c0[p] = (p < c.P) ? nmask[p] : 0; c1[p] = 0; }
@@ -660,15 +846,22 @@ __device__ __forceinline__ void sweep_row(const Ctx& c, int n, int beg, int len,
     }
     bool ok = true;
     if (gate) {
-        double sr[PMAX];
+        // spike rate of power p is computed by lane p (one division latency instead of P), then broadcast
+        double mine = 0.0;
+        {
+            const int pl = lane < c.P ? lane : 0;
+            const int cnt = cntp[pl];
+            double num = accp[0];
 #pragma unroll
-        for (int p = 0; p < PT; ++p)
-            if (p < c.P) {
-                const int cnt = cntp[p];
-                sr[p] = accp[p] / ((double)cnt + 1e-4 * (cnt == 0 ? 1.0 : 0.0));
-            }
-        ok = (pava_last(sr, c.P) >= thr) && (tot >= minspk);
+            for (int p = 1; p < PT; ++p) num = (pl == p) ? accp[p] : num;
+            mine = num / ((double)cnt + 1e-4 * (cnt == 0 ? 1.0 : 0.0));
+        }
+        double sr[PT];
+#pragma unroll
+        for (int p = 0; p < PT; ++p) sr[p] = __shfl_sync(0xffffffffu, mine, p);
+        ok = (pava_last_reg<PT>(sr, c.P) >= thr) && (tot >= minspk);
     }
+    if (prof) { const long long t = clock64(); g_phase_cycles[22] += t - tp0; tp0 = t; }
     // second pass: commit the row, update the running prediction
     const double muok = ok ? mu_n : 0.0;
     double sl2 = 0.0;
@@ -702,6 +895,7 @@ __device__ __forceinline__ void sweep_row(const Ctx& c, int n, int beg, int len,
         c.rownz[n] = ok ? (len - (zeros - masked)) : 0;
     }
     __syncwarp();
+    if (prof) { const long long t = clock64(); g_phase_cycles[23] += t - tp0; g_phase_cycles[19] += 1; g_phase_cycles[24] += len; }
 }
 
 constexpr int RC = 512;          // staged row capacity (entries) of the chain warp's prefetch buffers
@@ -712,9 +906,12 @@ constexpr int STAGE_DOUBLES = NSTAGE * (RC + RC + RC / 2 + HD);   // cs, lo, cp 
 // The sequential part of the sweep: neurons with mu != 0, in update order, by ONE warp.  Rows are prefetched two
 // neurons ahead into shared memory with cp.async so that the chain only waits on shared-memory latency.
 template <int PT>
-__device__ void sweep_chain(const Ctx& c, int nchain, double sigma, double thr, double minspk, bool gate, double* pred,
+__device__ __noinline__ void sweep_chain(const Ctx& c, int nchain, double sigma, double thr, double minspk, bool gate, double* pred,
                             double* stage_base) {
     const int lane = threadIdx.x & 31;
+    const RowCtx rc = make_rowctx(c);
+    const int* g_colpw = c.colpw; const double* g_cst = c.cst; const double* g_lam = c.lam; const double* g_mu = c.mu;
+    const int* g_cntp = c.cntp; const int* g_nmask = c.nmask; const int4* g_chinfo = c.chinfo;
     double* scs = stage_base;                                   // [NSTAGE][RC]
     double* slo = scs + NSTAGE * RC;                            // [NSTAGE][RC]
     int* scp = reinterpret_cast<int*>(slo + NSTAGE * RC);       // [NSTAGE][RC]
@@ -723,23 +920,23 @@ __device__ void sweep_chain(const Ctx& c, int nchain, double sigma, double thr, 
         const int n = inf.x, beg = inf.y, len = inf.z;
         if (len <= RC) {
             for (int q = lane; q < len; q += 32) {
-                cp_async4(scp + buf * RC + q, c.colpw + beg + q);
-                cp_async8(scs + buf * RC + q, c.cst + beg + q);
-                cp_async8(slo + buf * RC + q, c.lam + beg + q);
+                cp_async4(scp + buf * RC + q, g_colpw + beg + q);
+                cp_async8(scs + buf * RC + q, g_cst + beg + q);
+                cp_async8(slo + buf * RC + q, g_lam + beg + q);
             }
         }
-        if (lane == 0) cp_async8(shd + buf * HD, c.mu + n);
+        if (lane == 0) cp_async8(shd + buf * HD, g_mu + n);
         int* hi = reinterpret_cast<int*>(shd + buf * HD + 1);
         for (int q = lane; q < 2 * PT; q += 32)
-            cp_async4(hi + q, (q < PT) ? (c.cntp + n * PMAX + q) : (c.nmask + n * PMAX + (q - PT)));
+            cp_async4(hi + q, (q < PT) ? (g_cntp + n * PMAX + q) : (g_nmask + n * PMAX + (q - PT)));
         cp_async_commit();
     };
     int4 infA = make_int4(0, 0, 0, 0), infB = infA;
-    if (nchain > 0) stage(c.chinfo[0], 0);
-    if (nchain > 1) stage(c.chinfo[1], 1);
-    if (nchain > 2) infA = c.chinfo[2];
-    if (nchain > 3) infB = c.chinfo[3];
-    int4 cur = nchain > 0 ? c.chinfo[0] : infA, nxt = nchain > 1 ? c.chinfo[1] : infA;
+    if (nchain > 0) stage(g_chinfo[0], 0);
+    if (nchain > 1) stage(g_chinfo[1], 1);
+    if (nchain > 2) infA = g_chinfo[2];
+    if (nchain > 3) infB = g_chinfo[3];
+    int4 cur = nchain > 0 ? g_chinfo[0] : infA, nxt = nchain > 1 ? g_chinfo[1] : infA;
     for (int i = 0; i < nchain; ++i) {
         if (i + 2 < nchain) { stage(infA, (i + 2) % NSTAGE); cp_async_wait<2>(); }
         else if (i + 1 < nchain) cp_async_wait<1>();
@@ -747,17 +944,17 @@ __device__ void sweep_chain(const Ctx& c, int nchain, double sigma, double thr, 
         __syncwarp();
         const int4 after = infA;
         infA = infB;
-        if (i + 4 < nchain) infB = c.chinfo[i + 4];
+        if (i + 4 < nchain) infB = g_chinfo[i + 4];
         const int buf = i % NSTAGE;
         const int n = cur.x, beg = cur.y, len = cur.z;
         const double mu_n = shd[buf * HD];
         const int* hi = reinterpret_cast<const int*>(shd + buf * HD + 1);
         if (len <= RC)
-            sweep_row<PT>(c, n, beg, len, true, mu_n, hi, hi + PT, scp + buf * RC, scs + buf * RC, slo + buf * RC, sigma,
+            sweep_row<PT>(rc, n, beg, len, true, mu_n, hi, hi + PT, scp + buf * RC, scs + buf * RC, slo + buf * RC, sigma,
                           thr, minspk, gate, pred);
         else
-            sweep_row<PT>(c, n, beg, len, true, mu_n, hi, hi + PT, c.colpw + beg, c.cst + beg, c.lam + beg, sigma, thr,
-                          minspk, gate, pred);
+            sweep_row<PT>(rc, n, beg, len, true, mu_n, hi, hi + PT, g_colpw + beg, const_cast<double*>(g_cst) + beg,
+                          g_lam + beg, sigma, thr, minspk, gate, pred);
         cur = nxt;
         nxt = after;
     }
@@ -765,7 +962,7 @@ __device__ void sweep_chain(const Ctx& c, int nchain, double sigma, double thr, 
 
 // PRNG work for one iteration, done by ONE warp: shuffle sub-keys, the N per-neuron sample keys
 // (key, key_next = split(key), caviar.py:209) and the key the next iteration starts from (caviar.py:251,304).
-__device__ void rng_iteration(int N, int rounds, uint32_t& k0, uint32_t& k1, uint32_t* keys_out, uint32_t* subkeys) {
+__device__ __noinline__ void rng_iteration(int N, int rounds, uint32_t& k0, uint32_t& k1, uint32_t* keys_out, uint32_t* subkeys) {
     const int lane = threadIdx.x & 31;
     uint32_t p0 = k0, p1 = k1;
     for (int r = 0; r < rounds; ++r) {                 // permutation(key): key, subkey = split(key) per round
@@ -813,7 +1010,9 @@ __device__ double nll_reduced(const NewtonStats& s, double p0, double p1, const 
     return -ll - (log(p0) + log(p1)) / t + quad;
 }
 
-// _laplace_approx (caviar.py:253-308): 10 damped Newton steps from the PRIOR mean; covariance = H^-1 before the last step
+// _laplace_approx (caviar.py:253-308): 10 damped Newton steps from the PRIOR mean; covariance = H^-1 before the last step.
+// The sigmoids of the gradient pass are reused for the objective at the current point, and the accepted trial value
+// of one step is the base value of the next (identical inputs give identical fp results, so this is exact).
 __device__ void laplace_newton(const NewtonStats& s, const double* prior, const double* cov0, double* phi_out,
                                double* cov_out) {
     const double t = 10.0, alpha = 0.25, bbeta = 0.5;
@@ -822,7 +1021,7 @@ __device__ void laplace_newton(const NewtonStats& s, const double* prior, const 
     double p0 = prior[0], p1 = prior[1];
     double hi[4] = {0, 0, 0, 0};
     for (int step = 0; step < 10; ++step) {
-        double j1 = 0, j2 = 0, h11 = 0, h12 = 0, h22 = 0;
+        double j1 = 0, j2 = 0, h11 = 0, h12 = 0, h22 = 0, ll = 0;
         for (int g = 0; g <= s.P; ++g) {
             const double f = sigmoid_d(p0 * s.pv[g] - p1);
             const double r = s.S[g] - s.cnt[g] * f;
@@ -832,8 +1031,11 @@ __device__ void laplace_newton(const NewtonStats& s, const double* prior, const 
             h11 += s.pv[g] * s.pv[g] * w;
             h12 -= s.pv[g] * w;
             h22 += w;
+            ll += group_loglik(f, s.cnt[g], s.S[g], s.n0[g], s.n1[g]);
         }
         const double d0 = p0 - prior[0], d1 = p1 - prior[1];
+        const double quad = 0.5 * (d0 * (prec[0] * d0 + prec[1] * d1) + d1 * (prec[2] * d0 + prec[3] * d1));
+        const double base = -ll - (log(p0) + log(p1)) / t + quad;
         const double J0 = j1 + (prec[0] * d0 + prec[1] * d1) - 1.0 / (t * p0);
         const double J1 = j2 + (prec[2] * d0 + prec[3] * d1) - 1.0 / (t * p1);
         const double H00 = h11 + prec[0] + 1.0 / (t * p0 * p0);
@@ -844,7 +1046,6 @@ __device__ void laplace_newton(const NewtonStats& s, const double* prior, const 
         hi[0] = H11 / det; hi[1] = -H01 / det; hi[2] = -H10 / det; hi[3] = H00 / det;
         const double v0 = -(hi[0] * J0 + hi[1] * J1), v1 = -(hi[2] * J0 + hi[3] * J1);
         double stp = 1.0;
-        const double base = nll_reduced(s, p0, p1, prior, prec, t);
         const double Jv = J0 * v0 + J1 * v1;
         double lhs = nll_reduced(s, p0 + stp * v0, p1 + stp * v1, prior, prec, t);
         double rhs = base + alpha * stp * Jv;
@@ -862,7 +1063,7 @@ __device__ void laplace_newton(const NewtonStats& s, const double* prior, const 
     cov_out[0] = hi[0]; cov_out[1] = hi[1]; cov_out[2] = hi[2]; cov_out[3] = hi[3];
 }
 
-__device__ void newton_row(const Ctx& c, const double* powers, int n) {
+__device__ __noinline__ void newton_row(const Ctx& c, const double* powers, int n) {
     const bool zero_row = c.rownz[n] == 0;
     if (zero_row && c.phizok[n]) {
         c.phi[2 * n] = c.phiz[2 * n]; c.phi[2 * n + 1] = c.phiz[2 * n + 1];
@@ -900,6 +1101,7 @@ __global__ void __launch_bounds__(NT, 1) caviar_fit_kernel(const FitParams p) {
     __shared__ uint32_t sc_subkeys[2 * MAX_SHUFFLE_ROUNDS];
     __shared__ double sc_powers[PMAX];
     __shared__ long long sc_tlast;
+    __shared__ __align__(8) uint64_t sc_bar[2 * NST];
 
     const int b = blockIdx.x;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -911,7 +1113,7 @@ __global__ void __launch_bounds__(NT, 1) caviar_fit_kernel(const FitParams p) {
 #define CM_I(name) c.name = reinterpret_cast<int*>(base + L.name)
     CM_D(X); CM_D(PA); CM_D(PB); CM_D(lam); CM_D(cst); CM_D(y); CM_D(ss); CM_D(pred); CM_D(resid); CM_D(z); CM_D(mu);
     CM_D(beta); CM_D(bvec); CM_D(dvec); CM_D(wvec); CM_D(slam); CM_D(slam2); CM_D(sp); CM_D(phibar); CM_D(phi);
-    CM_D(phicov); CM_D(phiz); CM_D(phicovz); CM_D(lamhist); CM_D(lamT);
+    CM_D(phicov); CM_D(phiz); CM_D(phicovz); CM_D(lamhist); CM_D(lamT); CM_D(growbuf);
     CM_I(row_ptr); CM_I(col_ptr); CM_I(col_k); CM_I(csc_row); CM_I(csc_pos); CM_I(cntp); CM_I(n0p); CM_I(n1p);
     CM_I(act); CM_I(ainv); CM_I(order); CM_I(order2); CM_I(pos); CM_I(rownz); CM_I(phizok); CM_I(dcnt); CM_I(dlist); CM_I(colpw); CM_I(nmask);
 #undef CM_D
@@ -934,6 +1136,12 @@ __global__ void __launch_bounds__(NT, 1) caviar_fit_kernel(const FitParams p) {
     const int N = c.N, K = c.K, P = c.P;
     const cm_caviar_options& o = p.opt;
     if (p.status[b] != 0) return;                     // prologue reported an error for this fit
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NST; ++i) { mbar_init(&sc_bar[i], 1); mbar_init(&sc_bar[NST + i], NW); }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    GemmPipe gp;
+    gp.full = sc_bar; gp.empty = sc_bar + NST; gp.seq = 0;
     c.nnz = c.row_ptr[N];
     const int iters = o.iters;
     const int S = o.num_mc_samples;
@@ -988,7 +1196,7 @@ __global__ void __launch_bounds__(NT, 1) caviar_fit_kernel(const FitParams p) {
         c.it = it;
         const double sigma = sc_shape / sc_rate;
         // ================= a2: block_update_mu =================
-        phase_a2(c, sigma, &sc_na);
+        phase_a2(c, sigma, &sc_na, gp);
         // ================= a3: update_lam =================
         uint32_t* keys_cur = c.keys + (size_t)(it & 1) * 2 * N;
         uint32_t* keys_nxt = c.keys + (size_t)((it + 1) & 1) * 2 * N;
@@ -1104,8 +1312,8 @@ __global__ void __launch_bounds__(NT, 1) caviar_fit_kernel(const FitParams p) {
                     const int n = c.order[m];
                     if (c.mu[n] == 0.0 && !c.dcnt[n]) {
                         const int beg = c.row_ptr[n], len = c.row_ptr[n + 1] - beg;
-                        sweep_row<PT>(c, n, beg, len, false, 0.0, c.cntp + n * PMAX, c.nmask + n * PMAX, c.colpw + beg,
-                                      c.cst + beg, c.lam + beg, sigma, thr, o.minimum_spike_count, gate, pred);
+                        sweep_row<PT>(make_rowctx(c), n, beg, len, false, 0.0, c.cntp + n * PMAX, c.nmask + n * PMAX,
+                                      c.colpw + beg, c.cst + beg, c.lam + beg, sigma, thr, o.minimum_spike_count, gate, pred);
                     }
                 }
                 if (g_phase_enable && blockIdx.x == 0 && wid == 1 && lane == 0) g_phase_cycles[18] += clock64() - role_t0;

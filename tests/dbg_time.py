@@ -36,7 +36,8 @@ print("TP %d FP %d FN %d" % (len(tw & gw), len(gw - tw), len(tw - gw)))
 import ctypes as C
 from circuitmap_b200 import _lib
 lib = _lib.load()
-lib.cm_caviar_debug_phase_cycles(None, 0, 1)
+import os
+lib.cm_caviar_debug_phase_cycles(None, 0, int(os.environ.get('CM_DBG', '1')))
 out = optimise.caviar_batched(stim, powers, mu0, beta0, 1.0, 0.1, phi0, cov0, psc=psc, seeds=list(range(1, B + 1)),
                               nnz_cap=int(np.count_nonzero(sim["stim_matrix"])), want_lam=False, workspace=ws, iters=iters, msrmp=0.4)
 torch.cuda.synchronize()
@@ -48,5 +49,7 @@ tot = sum(buf[:16])
 for i, nm in enumerate(names):
     print("  %-16s %10.3f ms  %5.1f%%" % (nm, buf[i] / 1.9e6, 100.0 * buf[i] / max(tot, 1)))
 print("  total %.2f ms (at 1.9 GHz)" % (tot / 1.9e6))
+print("  chain steps %d, mean row len %.1f; cycles/step: pass1 %.0f reduce %.0f decide %.0f pass2 %.0f" % (
+    buf[19], buf[24] / max(buf[19], 1), buf[20] / max(buf[19], 1), buf[21] / max(buf[19], 1), buf[22] / max(buf[19], 1), buf[23] / max(buf[19], 1)))
 for i, nm in [(16, "sweep.chain warp"), (17, "sweep.rng warp"), (18, "sweep.inactive warp1")]:
     print("  %-22s %10.3f ms" % (nm, buf[i] / 1.9e6))
