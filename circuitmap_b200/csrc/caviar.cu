@@ -48,7 +48,7 @@ struct Layout {
     size_t stride;
     // fp64
     size_t X, PA, PB, lam, cst, y, ss, pred, resid, z, mu, beta, bvec, dvec, wvec, slam, slam2, sp, phibar, phi,
-        phicov, phiz, phicovz, lamhist, lamT, growbuf;
+        phicov, phiz, phicovz, lamhist, lamT, growbuf, cscq;
     // int32 / uint32
     size_t row_ptr, col_ptr, colfill, col_k, csc_row, csc_pos, cntp, n0p, n1p, act, ainv, order, order2, pos, rownz,
         phizok, sortkeys, keys, dcnt, dlist, colpw, nmask, chinfo;
@@ -65,6 +65,7 @@ static Layout make_layout(int N, int K, int64_t nnz, int iters, bool lamhist) {
     L.PA = take((size_t)NB * (n + ROWPAD) * 8);
     L.PB = take((size_t)NB * (n + ROWPAD) * 8);
     L.growbuf = take((size_t)NW * (n + 2) * 8);
+    L.cscq = take(z * 16);
     L.lam = take(z * 8);
     L.cst = take(z * 8);
     L.y = take(k * 8);
@@ -245,6 +246,7 @@ struct Ctx {
     int N, K, P, nnz, it;
     double *X, *PA, *PB, *lam, *cst, *y, *ss, *pred, *resid, *z, *mu, *beta, *bvec, *dvec, *wvec, *slam, *slam2, *sp,
         *phibar, *phi, *phicov, *phiz, *phicovz, *lamhist, *lamT, *growbuf;
+    double2* cscq;    // per CSC entry: (active index of the row as int bits, lam) -- rebuilt every a2
     int *row_ptr, *col_ptr, *col_k, *csc_row, *csc_pos, *cntp, *n0p, *n1p, *act, *ainv, *order, *order2, *pos, *rownz,
         *phizok, *dcnt, *dlist, *colpw, *nmask;
     int4* chinfo;
@@ -381,13 +383,14 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
 __device__ void gram_rows(const Ctx& c, int i0, int nb, double sigma) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int cap = GEMM_SMEM_DOUBLES / NW;       // row-buffer doubles per warp
-    const int* __restrict__ ainv = c.ainv;
-    const int* __restrict__ csc_row = c.csc_row;
-    const double* __restrict__ lamT = c.lamT;
+    const int tagcap = ((c.smd - GEMM_SMEM_DOUBLES) * 8) / NW;   // conflict-tag bytes per warp (behind the GEMM ring)
+    const double2* __restrict__ cscq = c.cscq;
     for (int r = wid; r < nb; r += NW) {
         const int ia = i0 + r;
         const int n = c.act[ia];
         double* acc = (ia + 1 <= cap) ? (c.sm + (size_t)wid * cap) : (c.growbuf + (size_t)wid * (c.N + 2));
+        unsigned char* tags = reinterpret_cast<unsigned char*>(c.sm + GEMM_SMEM_DOUBLES) + (size_t)wid * tagcap;
+        const bool use_tags = ia + 1 <= tagcap;
         for (int q = lane; q <= ia; q += 32) acc[q] = 0.0;
         __syncwarp();
         const int beg = c.row_ptr[n], end = c.row_ptr[n + 1];
@@ -410,37 +413,48 @@ __device__ void gram_rows(const Ctx& c, int i0, int nb, double sigma) {
                 int ibs[8];
                 double vs[8];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {                  // independent loads first (memory-level parallelism)
+                for (int u = 0; u < 8; ++u) {                  // independent 16-byte loads (memory-level parallelism)
                     const int t = t0 + u;
-                    int rw = -1;
+                    int ib = -1;
                     double lv = 0.0;
-                    if (t < len) { rw = csc_row[cb + t]; lv = lamT[cb + t]; }
-                    ibs[u] = rw;
-                    vs[u] = la * lv;
-                }
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    int ib = ibs[u] >= 0 ? ainv[ibs[u]] : -1;
+                    if (t < len) {
+                        const double2 rec = cscq[cb + t];
+                        ib = (int)__double_as_longlong(rec.x);
+                        lv = rec.y;
+                    }
                     if (ib > ia) ib = -1;
                     ibs[u] = ib;
+                    vs[u] = la * lv;
                 }
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
                     if (t0 + u >= maxlen) break;               // warp-uniform
                     const int ib = ibs[u];
                     const double v = vs[u];
-                    const unsigned amask = __ballot_sync(0xffffffffu, ib >= 0);
-                    if (ib >= 0) {
-                        const unsigned grp = __match_any_sync(amask, ib);
-                        const int leader = __ffs(grp) - 1;
-                        unsigned rest = grp & ~(1u << leader);
-                        double ssum = __shfl_sync(amask, v, leader);
-                        while (__any_sync(amask, rest != 0)) {
-                            const int src = rest ? (__ffs(rest) - 1) : lane;
-                            const double ov = __shfl_sync(amask, v, src);
-                            if (rest) { ssum += ov; rest &= rest - 1; }
+                    // conflict check: every lane tags its target; a lane that reads back another id shares the target
+                    bool lost = false;
+                    if (use_tags) {
+                        if (ib >= 0) tags[ib] = (unsigned char)lane;
+                        __syncwarp();
+                        lost = (ib >= 0) && (tags[ib] != (unsigned char)lane);
+                    }
+                    if (use_tags && !__any_sync(0xffffffffu, lost)) {
+                        if (ib >= 0) acc[ib] += v;             // all targets distinct: plain read-modify-write
+                    } else {
+                        // same target hit by several lanes: combine them in lane order (deterministic)
+                        const unsigned amask = __ballot_sync(0xffffffffu, ib >= 0);
+                        if (ib >= 0) {
+                            const unsigned grp = __match_any_sync(amask, ib);
+                            const int leader = __ffs(grp) - 1;
+                            unsigned rest = grp & ~(1u << leader);
+                            double ssum = __shfl_sync(amask, v, leader);
+                            while (__any_sync(amask, rest != 0)) {
+                                const int src = rest ? (__ffs(rest) - 1) : lane;
+                                const double ov = __shfl_sync(amask, v, src);
+                                if (rest) { ssum += ov; rest &= rest - 1; }
+                            }
+                            if (lane == leader) acc[ib] += ssum;
                         }
-                        if (lane == leader) acc[ib] += ssum;
                     }
                     __syncwarp();
                 }
@@ -528,27 +542,47 @@ __device__ void panel_gemm(const Ctx& c, int ldr, int i0, int nb, const double* 
             if (cmin < i0 && !(g_phase_enable & 2)) {                       // debug bit 2: no math
                 const double* ab = stage0 + (size_t)st * STAGE_GEMM_DOUBLES;
                 const double* xb = ab + GK * NB;
+                // interior chunk of the triangle: every (kk, cc) pair of this warp is valid -> no masking at all
+                const bool interior = (nb == NB) && (cmax < i0) && (kk0 + GK <= i0) &&
+                                      (UPPER ? (kk0 + GK - 1 <= cmin) : (kk0 >= cmax));
+                if (interior) {
+                    double af[GK / 4][4], bf[GK / 4][2];
 #pragma unroll
-                for (int ks = 0; ks < GK / 4; ++ks) {
-                    const int kbase = kk0 + 4 * ks;
-                    const bool skip = UPPER ? (kbase > cmax) : (kbase + 3 < cmin);
-                    if (skip || kbase >= i0) continue;                   // warp-uniform
-                    const int kk = kbase + lr;
-                    double af[4];
+                    for (int ks = 0; ks < GK / 4; ++ks) {
 #pragma unroll
-                    for (int mt = 0; mt < 4; ++mt) {
-                        const double av = ab[(4 * ks + lr) * NB + ((8 * mt + lq) ^ sw)];
-                        af[mt] = (8 * mt + lq < nb && kk < i0) ? av : 0.0;
+                        for (int mt = 0; mt < 4; ++mt) af[ks][mt] = ab[(4 * ks + lr) * NB + ((8 * mt + lq) ^ sw)];
+#pragma unroll
+                        for (int nt = 0; nt < 2; ++nt) bf[ks][nt] = xb[(4 * ks + lr) * GCT + ((wc + 8 * nt + lq) ^ sw)];
                     }
 #pragma unroll
-                    for (int nt = 0; nt < 2; ++nt) {
-                        const int cl = wc + 8 * nt + lq;
-                        const int cc = ct0 + cl;
-                        const bool in = (kk < i0) && (cc < i0) && (UPPER ? (kk <= cc) : (kk >= cc));
-                        const double xv = xb[(4 * ks + lr) * GCT + (cl ^ sw)];
-                        const double bv = in ? xv : 0.0;
+                    for (int ks = 0; ks < GK / 4; ++ks)
 #pragma unroll
-                        for (int mt = 0; mt < 4; ++mt) dmma8x8x4(acc[mt][nt][0], acc[mt][nt][1], af[mt], bv);
+                        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                            for (int mt = 0; mt < 4; ++mt) dmma8x8x4(acc[mt][nt][0], acc[mt][nt][1], af[ks][mt], bf[ks][nt]);
+                } else {
+#pragma unroll
+                    for (int ks = 0; ks < GK / 4; ++ks) {
+                        const int kbase = kk0 + 4 * ks;
+                        const bool skip = UPPER ? (kbase > cmax) : (kbase + 3 < cmin);
+                        if (skip || kbase >= i0) continue;                   // warp-uniform
+                        const int kk = kbase + lr;
+                        double af[4];
+#pragma unroll
+                        for (int mt = 0; mt < 4; ++mt) {
+                            const double av = ab[(4 * ks + lr) * NB + ((8 * mt + lq) ^ sw)];
+                            af[mt] = (8 * mt + lq < nb && kk < i0) ? av : 0.0;
+                        }
+#pragma unroll
+                        for (int nt = 0; nt < 2; ++nt) {
+                            const int cl = wc + 8 * nt + lq;
+                            const int cc = ct0 + cl;
+                            const bool in = (kk < i0) && (cc < i0) && (UPPER ? (kk <= cc) : (kk >= cc));
+                            const double xv = xb[(4 * ks + lr) * GCT + (cl ^ sw)];
+                            const double bv = in ? xv : 0.0;
+#pragma unroll
+                            for (int mt = 0; mt < 4; ++mt) dmma8x8x4(acc[mt][nt][0], acc[mt][nt][1], af[mt], bv);
+                        }
                     }
                 }
             }
@@ -583,6 +617,9 @@ __device__ __noinline__ void phase_a2(const Ctx& c, double sigma, int* na_s, Gem
     // inactive rows decouple: mu = mu0, beta = beta0^2 (variance)
     for (int n = threadIdx.x; n < N; n += NT)
         if (c.rownz[n] == 0) { c.mu[n] = c.mu0[n]; c.beta[n] = c.beta0[n] * c.beta0[n]; }
+    // per CSC entry: (active index of its row, lam) in one 16-byte record for the Gram expansion
+    for (int i = threadIdx.x; i < c.nnz; i += NT)
+        c.cscq[i] = make_double2(__longlong_as_double((long long)c.ainv[c.csc_row[i]]), c.lamT[i]);
     // per active row: D = sum lam(1-lam), b = sigma * sum lam*y + mu0/beta0^2
     for (int ia = wid; ia < na; ia += NW) {
         const int n = c.act[ia];
@@ -984,11 +1021,6 @@ __device__ __noinline__ void rng_iteration(int N, int rounds, uint32_t& k0, uint
 }
 
 // ------------------------------------------------------------------------------------------------ a7
-struct NewtonStats {
-    int P;
-    double pv[PMAX + 1], cnt[PMAX + 1], S[PMAX + 1], n0[PMAX + 1], n1[PMAX + 1];
-};
-
 __device__ __forceinline__ double group_loglik(double f, double cnt, double S, double n0, double n1) {
     if (cnt == 0.0) return 0.0;
     if (f != f) return 0.0;                                   // nan_to_num(nan) = 0
@@ -997,96 +1029,133 @@ __device__ __forceinline__ double group_loglik(double f, double cnt, double S, d
     return S * log(f) + (cnt - S) * log(1.0 - f);
 }
 
-// negloglik_with_barrier (caviar.py:312-316) from per-power sufficient statistics
-__device__ double nll_reduced(const NewtonStats& s, double p0, double p1, const double* prior, const double* prec,
-                              double t) {
+constexpr int GPL = (PMAX + 1 + 3) / 4;       // power groups per lane of a quad (group 0 = untargeted trials)
+
+struct QuadStats {                             // the groups g = m, m+4, ... owned by member m of the quad
+    double pv[GPL], cnt[GPL], S[GPL], n0[GPL], n1[GPL];
+    int ng;
+};
+
+__device__ __forceinline__ double quad_sum(double v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    return v;
+}
+
+// negloglik_with_barrier (caviar.py:312-316) from per-power sufficient statistics; the power groups are spread over
+// the 4 lanes of a quad (one sigmoid + two logs per lane for P <= 3)
+__device__ __forceinline__ double nll_quad(const QuadStats& s, double p0, double p1, const double* prior,
+                                           const double* prec, double t) {
     double ll = 0.0;
-    for (int g = 0; g <= s.P; ++g) {
-        const double f = sigmoid_d(p0 * s.pv[g] - p1);
-        ll += group_loglik(f, s.cnt[g], s.S[g], s.n0[g], s.n1[g]);
-    }
+#pragma unroll
+    for (int i = 0; i < GPL; ++i)
+        if (i < s.ng) {
+            const double f = sigmoid_d(p0 * s.pv[i] - p1);
+            ll += group_loglik(f, s.cnt[i], s.S[i], s.n0[i], s.n1[i]);
+        }
+    ll = quad_sum(ll);
     const double d0 = p0 - prior[0], d1 = p1 - prior[1];
     const double quad = 0.5 * (d0 * (prec[0] * d0 + prec[1] * d1) + d1 * (prec[2] * d0 + prec[3] * d1));
     return -ll - (log(p0) + log(p1)) / t + quad;
 }
 
-// _laplace_approx (caviar.py:253-308): 10 damped Newton steps from the PRIOR mean; covariance = H^-1 before the last step.
-// The sigmoids of the gradient pass are reused for the objective at the current point, and the accepted trial value
-// of one step is the base value of the next (identical inputs give identical fp results, so this is exact).
-__device__ void laplace_newton(const NewtonStats& s, const double* prior, const double* cov0, double* phi_out,
-                               double* cov_out) {
+// update_phi for the rows list[0..nlist): _laplace_approx (caviar.py:253-308), 10 damped Newton steps from the PRIOR
+// mean, covariance = H^-1 before the last step.  Eight rows per warp (one per quad); every loop is warp-convergent
+// (predicated) so the quad shuffles stay legal while rows need different numbers of backtracking steps.
+// The sigmoids of the gradient pass are reused for the objective at the current point (same inputs, same fp result).
+__device__ __noinline__ void newton_rows(const Ctx& c, const double* powers, const int* list, int nlist) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int quad = lane >> 2, mem = lane & 3;
     const double t = 10.0, alpha = 0.25, bbeta = 0.5;
-    const double det0 = cov0[0] * cov0[3] - cov0[1] * cov0[2];
-    const double prec[4] = {cov0[3] / det0, -cov0[1] / det0, -cov0[2] / det0, cov0[0] / det0};
-    double p0 = prior[0], p1 = prior[1];
-    double hi[4] = {0, 0, 0, 0};
-    for (int step = 0; step < 10; ++step) {
-        double j1 = 0, j2 = 0, h11 = 0, h12 = 0, h22 = 0, ll = 0;
-        for (int g = 0; g <= s.P; ++g) {
-            const double f = sigmoid_d(p0 * s.pv[g] - p1);
-            const double r = s.S[g] - s.cnt[g] * f;
-            const double w = s.cnt[g] * f * (1.0 - f);
-            j1 -= s.pv[g] * r;
-            j2 += r;
-            h11 += s.pv[g] * s.pv[g] * w;
-            h12 -= s.pv[g] * w;
-            h22 += w;
-            ll += group_loglik(f, s.cnt[g], s.S[g], s.n0[g], s.n1[g]);
+    for (int base = wid * 8; base < nlist; base += NW * 8) {
+        const int idx = base + quad;
+        const bool live = idx < nlist;
+        const int n = live ? list[idx] : list[0];
+        QuadStats s;
+        s.ng = 0;
+        double ctot = 0.0;
+        for (int p = 0; p < c.P; ++p) ctot += (double)c.cntp[n * PMAX + p];
+#pragma unroll
+        for (int i = 0; i < GPL; ++i) {
+            const int g = mem + 4 * i;
+            s.pv[i] = 0.0; s.cnt[i] = 0.0; s.S[i] = 0.0; s.n0[i] = 0.0; s.n1[i] = 0.0;
+            if (g <= c.P) {
+                s.ng = i + 1;
+                if (g == 0) { s.cnt[i] = (double)c.K - ctot; s.n0[i] = s.cnt[i]; }
+                else {
+                    const int p = g - 1;
+                    s.pv[i] = powers[p];
+                    s.cnt[i] = (double)c.cntp[n * PMAX + p];
+                    s.S[i] = c.sp[n * PMAX + p];
+                    s.n0[i] = (double)c.n0p[n * PMAX + p];
+                    s.n1[i] = (double)c.n1p[n * PMAX + p];
+                }
+            }
         }
-        const double d0 = p0 - prior[0], d1 = p1 - prior[1];
-        const double quad = 0.5 * (d0 * (prec[0] * d0 + prec[1] * d1) + d1 * (prec[2] * d0 + prec[3] * d1));
-        const double base = -ll - (log(p0) + log(p1)) / t + quad;
-        const double J0 = j1 + (prec[0] * d0 + prec[1] * d1) - 1.0 / (t * p0);
-        const double J1 = j2 + (prec[2] * d0 + prec[3] * d1) - 1.0 / (t * p1);
-        const double H00 = h11 + prec[0] + 1.0 / (t * p0 * p0);
-        const double H01 = h12 + prec[1];
-        const double H10 = h12 + prec[2];
-        const double H11 = h22 + prec[3] + 1.0 / (t * p1 * p1);
-        const double det = H00 * H11 - H01 * H10;
-        hi[0] = H11 / det; hi[1] = -H01 / det; hi[2] = -H10 / det; hi[3] = H00 / det;
-        const double v0 = -(hi[0] * J0 + hi[1] * J1), v1 = -(hi[2] * J0 + hi[3] * J1);
-        double stp = 1.0;
-        const double Jv = J0 * v0 + J1 * v1;
-        double lhs = nll_reduced(s, p0 + stp * v0, p1 + stp * v1, prior, prec, t);
-        double rhs = base + alpha * stp * Jv;
-        int bt = 0;
-        while (bt < 40 && ((lhs != lhs) || lhs > rhs)) {
-            ++bt;
-            stp *= bbeta;
-            lhs = nll_reduced(s, p0 + stp * v0, p1 + stp * v1, prior, prec, t);
-            rhs = base + alpha * stp * Jv;
+        const double prior[2] = {c.phi0[2 * n], c.phi0[2 * n + 1]};
+        const double* cov0 = c.phicov0 + 4 * n;
+        const double det0 = cov0[0] * cov0[3] - cov0[1] * cov0[2];
+        const double prec[4] = {cov0[3] / det0, -cov0[1] / det0, -cov0[2] / det0, cov0[0] / det0};
+        double p0 = prior[0], p1 = prior[1];
+        double hi[4] = {0, 0, 0, 0};
+        for (int step = 0; step < 10; ++step) {
+            double j1 = 0, j2 = 0, h11 = 0, h12 = 0, h22 = 0, ll = 0;
+#pragma unroll
+            for (int i = 0; i < GPL; ++i)
+                if (i < s.ng) {
+                    const double f = sigmoid_d(p0 * s.pv[i] - p1);
+                    const double r = s.S[i] - s.cnt[i] * f;
+                    const double w = s.cnt[i] * f * (1.0 - f);
+                    j1 -= s.pv[i] * r;
+                    j2 += r;
+                    h11 += s.pv[i] * s.pv[i] * w;
+                    h12 -= s.pv[i] * w;
+                    h22 += w;
+                    ll += group_loglik(f, s.cnt[i], s.S[i], s.n0[i], s.n1[i]);
+                }
+            j1 = quad_sum(j1); j2 = quad_sum(j2); h11 = quad_sum(h11); h12 = quad_sum(h12); h22 = quad_sum(h22);
+            ll = quad_sum(ll);
+            const double d0 = p0 - prior[0], d1 = p1 - prior[1];
+            const double quadf = 0.5 * (d0 * (prec[0] * d0 + prec[1] * d1) + d1 * (prec[2] * d0 + prec[3] * d1));
+            const double basev = -ll - (log(p0) + log(p1)) / t + quadf;
+            const double J0 = j1 + (prec[0] * d0 + prec[1] * d1) - 1.0 / (t * p0);
+            const double J1 = j2 + (prec[2] * d0 + prec[3] * d1) - 1.0 / (t * p1);
+            const double H00 = h11 + prec[0] + 1.0 / (t * p0 * p0);
+            const double H01 = h12 + prec[1];
+            const double H10 = h12 + prec[2];
+            const double H11 = h22 + prec[3] + 1.0 / (t * p1 * p1);
+            const double det = H00 * H11 - H01 * H10;
+            hi[0] = H11 / det; hi[1] = -H01 / det; hi[2] = -H10 / det; hi[3] = H00 / det;
+            const double v0 = -(hi[0] * J0 + hi[1] * J1), v1 = -(hi[2] * J0 + hi[3] * J1);
+            double stp = 1.0;
+            const double Jv = J0 * v0 + J1 * v1;
+            double lhs = nll_quad(s, p0 + stp * v0, p1 + stp * v1, prior, prec, t);
+            double rhs = basev + alpha * stp * Jv;
+            int bt = 0;
+            bool go = (bt < 40) && ((lhs != lhs) || lhs > rhs);
+            while (__any_sync(0xffffffffu, go)) {
+                const double stp_try = go ? stp * bbeta : stp;
+                const double lhs_try = nll_quad(s, p0 + stp_try * v0, p1 + stp_try * v1, prior, prec, t);
+                if (go) {
+                    ++bt;
+                    stp = stp_try;
+                    lhs = lhs_try;
+                    rhs = basev + alpha * stp * Jv;
+                }
+                go = go && (bt < 40) && ((lhs != lhs) || lhs > rhs);
+            }
+            p0 += stp * v0;
+            p1 += stp * v1;
         }
-        p0 += stp * v0;
-        p1 += stp * v1;
-    }
-    phi_out[0] = p0; phi_out[1] = p1;
-    cov_out[0] = hi[0]; cov_out[1] = hi[1]; cov_out[2] = hi[2]; cov_out[3] = hi[3];
-}
-
-__device__ __noinline__ void newton_row(const Ctx& c, const double* powers, int n) {
-    const bool zero_row = c.rownz[n] == 0;
-    if (zero_row && c.phizok[n]) {
-        c.phi[2 * n] = c.phiz[2 * n]; c.phi[2 * n + 1] = c.phiz[2 * n + 1];
-        for (int q = 0; q < 4; ++q) c.phicov[4 * n + q] = c.phicovz[4 * n + q];
-        return;
-    }
-    NewtonStats s;
-    s.P = c.P;
-    double ctot = 0.0;
-    for (int p = 0; p < c.P; ++p) {
-        s.pv[p + 1] = powers[p];
-        s.cnt[p + 1] = (double)c.cntp[n * PMAX + p];
-        s.S[p + 1] = c.sp[n * PMAX + p];
-        s.n0[p + 1] = (double)c.n0p[n * PMAX + p];
-        s.n1[p + 1] = (double)c.n1p[n * PMAX + p];
-        ctot += s.cnt[p + 1];
-    }
-    s.pv[0] = 0.0; s.cnt[0] = (double)c.K - ctot; s.S[0] = 0.0; s.n0[0] = s.cnt[0]; s.n1[0] = 0.0;
-    laplace_newton(s, c.phi0 + 2 * n, c.phicov0 + 4 * n, c.phi + 2 * n, c.phicov + 4 * n);
-    if (zero_row) {
-        c.phiz[2 * n] = c.phi[2 * n]; c.phiz[2 * n + 1] = c.phi[2 * n + 1];
-        for (int q = 0; q < 4; ++q) c.phicovz[4 * n + q] = c.phicov[4 * n + q];
-        c.phizok[n] = 1;
+        if (live && mem == 0) {
+            c.phi[2 * n] = p0; c.phi[2 * n + 1] = p1;
+            for (int q = 0; q < 4; ++q) c.phicov[4 * n + q] = hi[q];
+            if (c.rownz[n] == 0) {                       // all-zero rows always give the same answer: cache it
+                c.phiz[2 * n] = p0; c.phiz[2 * n + 1] = p1;
+                for (int q = 0; q < 4; ++q) c.phicovz[4 * n + q] = hi[q];
+                c.phizok[n] = 1;
+            }
+        }
     }
 }
 
@@ -1119,6 +1188,7 @@ __global__ void __launch_bounds__(NT, 1) caviar_fit_kernel(const FitParams p) {
 #undef CM_D
 #undef CM_I
     c.chinfo = reinterpret_cast<int4*>(base + L.chinfo);
+    c.cscq = reinterpret_cast<double2*>(base + L.cscq);
     c.sortkeys = reinterpret_cast<uint32_t*>(base + L.sortkeys);
     c.keys = reinterpret_cast<uint32_t*>(base + L.keys);
     c.pw = reinterpret_cast<unsigned char*>(base + L.pw);
@@ -1347,7 +1417,15 @@ __global__ void __launch_bounds__(NT, 1) caviar_fit_kernel(const FitParams p) {
         __syncthreads();
         phase_mark(c, 11);
         // ================= a7: update_phi (caviar.py:246-310) =================
-        for (int n = threadIdx.x; n < N; n += NT) newton_row(c, sc_powers, n);
+        {
+            const int nl = block_compact(N, [&](int n) { return !(c.rownz[n] == 0 && c.phizok[n]); }, c.dlist, nullptr, red);
+            for (int n = threadIdx.x; n < N; n += NT)
+                if (c.rownz[n] == 0 && c.phizok[n]) {
+                    c.phi[2 * n] = c.phiz[2 * n]; c.phi[2 * n + 1] = c.phiz[2 * n + 1];
+                    for (int q = 0; q < 4; ++q) c.phicov[4 * n + q] = c.phicovz[4 * n + q];
+                }
+            if (nl > 0) newton_rows(c, sc_powers, c.dlist, nl);
+        }
         __syncthreads();
         phase_mark(c, 12);
         // ================= a8: estimate_spont_act_soft_thresh (caviar.py:146-163, 86-88) =================
@@ -1540,8 +1618,10 @@ __global__ void __launch_bounds__(NT, 1) caviar_fit_kernel(const FitParams p) {
             if (lane == 0) c.rownz[n] = nz;
         }
         __syncthreads();
-        for (int n = threadIdx.x; n < N; n += NT)
-            if (c.pos[n]) newton_row(c, sc_powers, n);
+        {
+            const int nl = block_compact(N, [&](int n) { return c.pos[n] != 0; }, c.dlist, nullptr, red);
+            if (nl > 0) newton_rows(c, sc_powers, c.dlist, nl);
+        }
         __syncthreads();
     }
 
