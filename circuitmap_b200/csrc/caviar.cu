@@ -618,6 +618,7 @@ __device__ __noinline__ void phase_a2(const Ctx& c, double sigma, int* na_s, Gem
     for (int n = threadIdx.x; n < N; n += NT)
         if (c.rownz[n] == 0) { c.mu[n] = c.mu0[n]; c.beta[n] = c.beta0[n] * c.beta0[n]; }
     // per CSC entry: (active index of its row, lam) in one 16-byte record for the Gram expansion
+#pragma unroll 8
     for (int i = threadIdx.x; i < c.nnz; i += NT)
         c.cscq[i] = make_double2(__longlong_as_double((long long)c.ainv[c.csc_row[i]]), c.lamT[i]);
     // per active row: D = sum lam(1-lam), b = sigma * sum lam*y + mu0/beta0^2
@@ -683,28 +684,35 @@ __device__ __noinline__ void phase_a2(const Ctx& c, double sigma, int* na_s, Gem
             }
         }
         __syncthreads();
-        if (wid == 0) {
-            // Cholesky of the nb x nb block (lane = row), then its inverse (lane = column)
-            for (int j = 0; j < nb; ++j) {
-                const double djj = sqrt(Sd[j][j]);
-                __syncwarp();
-                if (lane == j) Sd[j][j] = djj;
-                if (lane > j && lane < nb) Sd[lane][j] /= djj;
-                __syncwarp();
-                if (lane > j && lane < nb)
-                    for (int q = j + 1; q <= lane; ++q) Sd[lane][q] -= Sd[lane][j] * Sd[q][j];
-                __syncwarp();
+        // Cholesky of the nb x nb diagonal block with the whole CTA (thread per trailing element), then its inverse by
+        // forward substitution, 16 lanes per column.
+        for (int j = 0; j < nb; ++j) {
+            __syncthreads();
+            const double djj = sqrt(Sd[j][j]);
+            __syncthreads();
+            if (threadIdx.x == 0) Sd[j][j] = djj;
+            if (threadIdx.x > j && threadIdx.x < nb) Sd[threadIdx.x][j] /= djj;
+            __syncthreads();
+            for (int e = threadIdx.x; e < NB * NB; e += NT) {
+                const int r = e >> 5, q = e & 31;
+                if (q > j && q <= r && r < nb) Sd[r][q] -= Sd[r][j] * Sd[q][j];
             }
-            for (int r = 0; r < NB; ++r) Xd[r][lane] = 0.0;       // column `lane`
-            __syncwarp();
-            if (lane < nb) {
-                const int cc = lane;
-                Xd[cc][cc] = 1.0 / Sd[cc][cc];
-                for (int r = cc + 1; r < nb; ++r) {
-                    double s = 0.0;
-                    for (int t = cc; t < r; ++t) s += Sd[r][t] * Xd[t][cc];
-                    Xd[r][cc] = -s / Sd[r][r];
+        }
+        __syncthreads();
+        for (int e = threadIdx.x; e < NB * XD_LD; e += NT) (&Xd[0][0])[e] = 0.0;
+        __syncthreads();
+        if (threadIdx.x < nb) Xd[threadIdx.x][threadIdx.x] = 1.0 / Sd[threadIdx.x][threadIdx.x];
+        {
+            const int cc = threadIdx.x >> 4, l16 = threadIdx.x & 15;       // column, lane within its 16-lane group
+            for (int r = 1; r < nb; ++r) {
+                __syncthreads();
+                double sacc = 0.0;
+                if (cc < r) {
+                    for (int t = cc + l16; t < r; t += 16) sacc += Sd[r][t] * Xd[t][cc];
                 }
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
+                if (cc < r && l16 == 0) Xd[r][cc] = -sacc / Sd[r][r];
             }
         }
         __syncthreads();
@@ -1390,6 +1398,7 @@ __global__ void __launch_bounds__(NT, 1) caviar_fit_kernel(const FitParams p) {
             }
         }
         __syncthreads();
+#pragma unroll 8
         for (int i = threadIdx.x; i < c.nnz; i += NT) c.lamT[i] = c.lam[c.csc_pos[i]];   // CSC-ordered copy of the new lam
         __syncthreads();
         phase_mark(c, 10);
