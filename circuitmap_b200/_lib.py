@@ -45,6 +45,7 @@ class CaviarArgs(C.Structure):
 
 # every symbol include/circuitmap_b200.h declares
 EXPORTS = ["cm_version", "cm_last_error", "cm_device_info", "cm_nwd_create", "cm_nwd_destroy", "cm_nwd_forward",
+           "cm_nwd_set_precision",
            "cm_caviar_workspace_bytes", "cm_caviar_fit", "cm_last_launch_count", "cm_last_main_kernel_ms",
            "cm_caviar_debug_phase_cycles"]
 
@@ -69,6 +70,7 @@ def load():
     lib.cm_nwd_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_void_p)]
     lib.cm_nwd_destroy.argtypes = [C.c_void_p]
     lib.cm_nwd_destroy.restype = None
+    lib.cm_nwd_set_precision.argtypes = [C.c_void_p, C.c_int]
     lib.cm_nwd_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                    C.c_void_p, C.c_void_p, C.c_void_p]
     lib.cm_caviar_workspace_bytes.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int]

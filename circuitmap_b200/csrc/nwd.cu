@@ -5,7 +5,7 @@
 // This translation unit holds the fp32 CUDA-core path (bit-for-bit fp32 arithmetic, BN folded):
 // one persistent CTA per SM walks over traces; every layer reads/writes shared memory only, HBM is
 // touched once for the trace in and once for the demixed trace out (7.2 KB/trace fp32).
-#include "common.cuh"
+#include "nwd_common.cuh"
 #include <vector>
 #include <cmath>
 #include <cstring>
@@ -280,11 +280,6 @@ nwd_forward_fp32_kernel(const float* __restrict__ W, const TIn* __restrict__ tra
 }  // namespace nwd
 }  // namespace cm
 
-struct cm_nwd {
-    float* w_dev = nullptr;
-    int device = 0;
-    int sm_count = 0;
-};
 
 using namespace cm;
 using namespace cm::nwd;
@@ -332,6 +327,10 @@ extern "C" int cm_nwd_create(const float* const* tensors, int n_tensors, cm_nwd_
     CM_CUDA_CHECK(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->device));
     CM_CUDA_CHECK(cudaMalloc(&h->w_dev, W.size() * sizeof(float)));
     CM_CUDA_CHECK(cudaMemcpy(h->w_dev, W.data(), W.size() * sizeof(float), cudaMemcpyHostToDevice));
+    std::vector<float> Wtc;
+    cm::nwdtc::pack_tc_weights(tensors, Wtc);
+    CM_CUDA_CHECK(cudaMalloc(&h->wtc_dev, Wtc.size() * sizeof(float)));
+    CM_CUDA_CHECK(cudaMemcpy(h->wtc_dev, Wtc.data(), Wtc.size() * sizeof(float), cudaMemcpyHostToDevice));
     *out = h;
     return CM_OK;
 }
@@ -339,6 +338,7 @@ extern "C" int cm_nwd_create(const float* const* tensors, int n_tensors, cm_nwd_
 extern "C" void cm_nwd_destroy(cm_nwd_t* h) {
     if (!h) return;
     cudaFree(h->w_dev);
+    cudaFree(h->wtc_dev);
     delete h;
 }
 
@@ -363,10 +363,17 @@ extern "C" int cm_nwd_forward(cm_nwd_t* h, const void* traces_dev, int in_dtype,
     if (K == 0) return CM_OK;
     if (!h || !traces_dev || !out_dev) { set_error("cm_nwd_forward: null argument"); return CM_EINVAL; }
     cudaStream_t st = (cudaStream_t)stream;
+    if (h->precision == 1) return cm::nwdtc::launch(h, traces_dev, in_dtype, out_dev, out_dtype, K, monotone_start, y_dev, ss_dev, st);
     if (in_dtype == CM_F32 && out_dtype == CM_F32) return launch_fp32<float, float>(h, traces_dev, out_dev, K, monotone_start, y_dev, ss_dev, st);
     if (in_dtype == CM_F64 && out_dtype == CM_F64) return launch_fp32<double, double>(h, traces_dev, out_dev, K, monotone_start, y_dev, ss_dev, st);
     if (in_dtype == CM_F32 && out_dtype == CM_F64) return launch_fp32<float, double>(h, traces_dev, out_dev, K, monotone_start, y_dev, ss_dev, st);
     if (in_dtype == CM_F64 && out_dtype == CM_F32) return launch_fp32<double, float>(h, traces_dev, out_dev, K, monotone_start, y_dev, ss_dev, st);
     set_error("cm_nwd_forward: bad dtype %d/%d", in_dtype, out_dtype);
     return CM_EINVAL;
+}
+
+extern "C" int cm_nwd_set_precision(cm_nwd_t* h, int precision) {
+    if (!h || (precision != 0 && precision != 1)) { set_error("cm_nwd_set_precision: precision must be 0 (fp32) or 1 (tf32)"); return CM_EINVAL; }
+    h->precision = precision;
+    return CM_OK;
 }

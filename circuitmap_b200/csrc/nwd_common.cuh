@@ -1,0 +1,21 @@
+// Shared definitions of the NWD handle between the fp32 (nwd.cu) and tensor-core (nwd_tc.cu) paths.
+#pragma once
+#include "common.cuh"
+#include <vector>
+
+struct cm_nwd {
+    float* w_dev = nullptr;      // fp32 packed weights (nwd.cu layout), BN folded
+    float* wtc_dev = nullptr;    // tf32-rounded weights of the 7 tensor-core layers in UMMA canonical K-major blocks
+    int device = 0;
+    int sm_count = 0;
+    int precision = 0;           // 0 = fp32 CUDA cores, 1 = tf32 tcgen05
+};
+
+namespace cm {
+namespace nwdtc {
+// packs the tensor-core layers (d2,d3,d4,u1,u2,u3,u4) from the 54 state_dict tensors; returns floats
+void pack_tc_weights(const float* const* tensors, std::vector<float>& out);
+int launch(cm_nwd* h, const void* in, int in_dtype, void* out, int out_dtype, int K, int monotone_start, double* y,
+           double* ss, cudaStream_t st);
+}  // namespace nwdtc
+}  // namespace cm

@@ -57,7 +57,10 @@ def random_weights(seed=0):
 
 
 class NeuralDemixer:
-    def __init__(self, path=None, eval_mode=True, device=None):
+    def __init__(self, path=None, eval_mode=True, device=None, precision="fp32"):
+        """precision (extension of the reference signature): 'fp32' = fp32 CUDA-core convolutions (default, the
+        reference's arithmetic); 'tf32' = tcgen05 tensor-core path (TF32 operands, fp32 accumulate; max-abs error
+        <= 2e-2 on unit-normalised traces)."""
         torch = _lib.require_cuda()
         self.device = torch.device("cuda" if device is None else device)
         if self.device.type != "cuda":
@@ -75,6 +78,14 @@ class NeuralDemixer:
         with torch.cuda.device(self.device):
             _lib.check(self._lib.cm_nwd_create(ptrs, _lib.CM_NWD_NUM_TENSORS, C.byref(h)), "cm_nwd_create")
         self._h = h
+        self.set_precision(precision)
+
+    def set_precision(self, precision):
+        mode = {"fp32": 0, "tf32": 1}.get(precision)
+        if mode is None:
+            raise ValueError("precision must be 'fp32' or 'tf32'")
+        _lib.check(self._lib.cm_nwd_set_precision(self._h, mode), "cm_nwd_set_precision")
+        self.precision = precision
 
     def __del__(self):
         h = getattr(self, "_h", None)

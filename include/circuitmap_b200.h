@@ -52,6 +52,11 @@ typedef struct cm_nwd cm_nwd_t;
 #define CM_NWD_T 900
 CM_API int  cm_nwd_create(const float* const* tensors, int n_tensors, cm_nwd_t** out);
 CM_API void cm_nwd_destroy(cm_nwd_t* h);
+/* arithmetic of the convolution layers: 0 = fp32 on CUDA cores (default; same arithmetic as the reference's fp32
+ * network), 1 = TF32 operands / fp32 accumulation on the 5th-gen tensor cores (tcgen05, TMEM accumulators) for the
+ * seven 16..48-channel layers (first and last convolution stay fp32).  Error bound of mode 1 on unit-normalised
+ * traces: max-abs <= 2e-2, relative L2 <= 3e-3 (asserted in tests/test_nwd_gpu.py). */
+CM_API int  cm_nwd_set_precision(cm_nwd_t* h, int precision);
 
 /* traces_dev: K x T row-major (in_dtype), out_dev: K x T row-major (out_dtype).
  * Per trace: x = trace / max_t(trace); net(x) in fp32; out = net * max; running minimum from

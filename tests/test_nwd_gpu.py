@@ -71,3 +71,27 @@ def test_ragged_and_edge_batches(demixer):
     assert empty.shape == (0, 900)
     with pytest.raises(RuntimeError):
         demixer(np.ones((2, 800)), verbose=False)       # T != 900 is rejected loudly
+
+
+def test_tensor_core_path_within_stated_bound():
+    """precision='tf32': tcgen05 implicit-GEMM convolutions.  Bound stated in include/circuitmap_b200.h:
+    max-abs <= 2e-2 and relative L2 <= 3e-3 on unit-normalised traces, against the fp64 oracle."""
+    from circuitmap_b200 import NeuralDemixer
+    from oracle import nwd as onwd
+    from oracle.make_golden import synth_traces
+    sd = dict(np.load(os.path.join(GOLDEN, "nwd_ie_ChroME2f_weights.npz")))
+    folded = onwd.fold_bn(sd)
+    traces = synth_traces(400, seed=21)
+    tmax = traces.max(1)[:, None]
+    ref = onwd.demix_np(traces.copy(), folded, monotone_start=900) / tmax
+    dem = NeuralDemixer(path=os.path.join(GOLDEN, "nwd_ie_ChroME2f_weights.npz"), precision="tf32")
+    out = dem(traces.copy(), monotone_filter_start=900, verbose=False) / tmax
+    err = np.abs(out - ref)
+    rel_l2 = np.sqrt((err ** 2).sum(1)) / (np.sqrt((ref ** 2).sum(1)) + 1e-3)
+    print("tf32 path: max-abs %.3e, median rel-L2 %.3e, max rel-L2 %.3e" % (err.max(), np.median(rel_l2), rel_l2.max()))
+    assert err.max() < 2e-2
+    assert np.median(rel_l2) < 3e-3
+    # same call in fp32 mode on the same handle is tighter by two orders of magnitude
+    dem.set_precision("fp32")
+    out32 = dem(traces.copy(), monotone_filter_start=900, verbose=False) / tmax
+    assert np.abs(out32 - ref).max() < TOL_UNIT
