@@ -30,14 +30,22 @@ constexpr int D3_PL = 8, D3_TP = 417, D3_PAD = 15;     // dec3 = [up3 (planes 0-
 constexpr int D2_PL = 8, D2_TP = 224, D2_PAD = 31;     // dec2 = [up2 | enc2], zero pad 31 for u3
 constexpr int D1_PL = 12, D1_TP = 95, D1_PAD = 15;     // dec1 = [up1 (0-3) | enc3 (4-11)], zero pad 15 for u2
 constexpr int E4_PL = 8, E4_TP = 47, E4_PAD = 15;      // enc4, zero pad 15 for u1
-constexpr int D4_PAD = 255, D4_STRIDE = 1410;          // dec4 in scalar layout [4][1410] for the fp32 final conv
+// dec4 (4 channels x 900, zero padded by 255 on both sides: u = t + 255) feeds the final convolution (k=256, dil=2).
+// Its even / odd subsequences xs_p[v] = xp[2 v + p] are stored split in 8 phases, XS[p][v % 8][v / 8][4 ch], so that
+// the final convolution becomes two implicit GEMMs with 8 consecutive outputs of one parity per accumulator row.
+constexpr int D4_PAD = 255;
+constexpr int XS_TP = 92;                              // positions per phase plane (705 / 8 = 89 used)
+constexpr int XS_FLOATS = 2 * 8 * XS_TP * 4;           // 5888 floats
+constexpr int G_ROWS = 272;                            // Toeplitz tap table G[r][c] = W[c][r - 7], zero outside
+constexpr int G_FLOATS = G_ROWS * 4;
 
 constexpr int OFF_D3 = 0;
 constexpr int OFF_D2 = OFF_D3 + D3_PL * D3_TP * 4;
 constexpr int OFF_D1 = OFF_D2 + D2_PL * D2_TP * 4;
 constexpr int OFF_E4 = OFF_D1 + D1_PL * D1_TP * 4;
 constexpr int OFF_D4 = OFF_E4 + E4_PL * E4_TP * 4;
-constexpr int OFF_S = OFF_D4 + 4 * D4_STRIDE;
+constexpr int OFF_G = OFF_D4 + XS_FLOATS;
+constexpr int OFF_S = OFF_G + G_FLOATS;
 constexpr int S_FLOATS = 3216;
 constexpr int OFF_W = OFF_S + S_FLOATS;                // weight ring (one layer at a time)
 constexpr int W_FLOATS = 16384;                        // 64 KB: the largest layers (d4, u3)
@@ -60,6 +68,8 @@ constexpr int TC_TOTAL = TC_BIAS_OFF + NL * 32;
 
 // fp32 packed weights of nwd.cu used for the first and last convolution
 constexpr int FW0 = 0, FB0 = 512, FW8 = 74388, FB8 = 75412;
+constexpr int FIN_KSTEPS = 132;
+constexpr int ACC_HALF = 64;                          // TMEM column offset of the second issuer's accumulators                        // window positions v = 0, 2, ..., 262
 
 // ---------------------------------------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -111,6 +121,17 @@ __host__ __device__ constexpr uint32_t idesc_tf32(int n) {        // D = F32, A 
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
+__device__ long long g_nwd_cycles[16];
+__device__ int g_nwd_prof = 0;
+#define NWD_MARK(id)                                                                     \
+    do {                                                                                 \
+        if (g_nwd_prof && blockIdx.x == 0 && threadIdx.x == 0) {                         \
+            const long long t_ = clock64();                                              \
+            g_nwd_cycles[id] += t_ - tmark;                                              \
+            tmark = t_;                                                                  \
+        }                                                                                \
+    } while (0)
+
 // ---------------------------------------------------------------------------------------------- layer pieces
 struct Pipe {
     uint64_t* bar_w;
@@ -120,23 +141,32 @@ struct Pipe {
 };
 
 // Issue all MMAs of one layer (one thread): A planes at `a_base` (floats, plane stride TP positions), weights in wbuf.
+// Descriptors are built once per tile and advanced by constant deltas (the address field counts 16-byte units), so the
+// issuing thread spends a handful of integer instructions per MMA.
+// Two threads (warps 0 and 1) issue concurrently: each takes half of the taps and accumulates into its own TMEM
+// columns (the epilogue adds the halves) -- one issuer alone is bound by its ~56-cycle issue latency, two reach the
+// shared-memory operand bandwidth limit (~39 cycles per 128x16x8 MMA, measured in tests/micro/tc_rate2.cu).
 template <int L, int TP, int DIL, int NTILES>
-__device__ __forceinline__ void issue_layer(const float* a_base, const float* wbuf, uint32_t tmem) {
+__device__ __forceinline__ void issue_layer(const float* a_base, const float* wbuf, uint32_t tmem, int half) {
     constexpr int CI = tc_ci(L), N = tc_n(L), TAPS = tc_taps(L);
     constexpr int QP = CI / 8;                         // channel-group pairs per tap
     constexpr uint32_t idesc = idesc_tf32(N);
-    const uint32_t a0 = smem_u32(a_base), w0 = smem_u32(wbuf);
+    const uint64_t a_desc0 = umma_desc(smem_u32(a_base), TP * 16, 128);
+    const uint64_t b_desc0 = umma_desc(smem_u32(wbuf), (N / 8) * 128, 128);
 #pragma unroll 1
     for (int mt = 0; mt < NTILES; ++mt) {
-#pragma unroll 1
-        for (int j = 0; j < TAPS; ++j) {
+        const int j0 = half * (TAPS / 2);
+        uint64_t ad = a_desc0 + (uint64_t)(128 * mt + j0 * DIL);   // +128 positions per tile, DIL per tap (16 B each)
+        uint64_t bd = b_desc0 + (uint64_t)(j0 * QP * N * 2);
+        const uint32_t td = tmem + half * ACC_HALF + mt * N;
+#pragma unroll 4
+        for (int j = 0; j < TAPS / 2; ++j) {
 #pragma unroll
             for (int q = 0; q < QP; ++q) {
-                const uint32_t a_addr = a0 + (uint32_t)(((2 * q) * TP + 128 * mt + j * DIL) * 16);
-                const uint32_t b_addr = w0 + (uint32_t)((j * QP + q) * N * 32);
-                umma_tf32(tmem + mt * N, umma_desc(a_addr, TP * 16, 128), umma_desc(b_addr, (N / 8) * 128, 128), idesc,
-                          (j | q) ? 1u : 0u);
+                umma_tf32(td, ad + (uint64_t)(2 * q * TP), bd + (uint64_t)(q * N * 2), idesc, (j | q) ? 1u : 0u);
             }
+            ad += DIL;                                           // next tap: shift by DIL positions
+            bd += QP * N * 2;                                    // next tap's weight blocks (N*32 bytes each)
         }
     }
 }
@@ -189,17 +219,18 @@ __device__ __forceinline__ void epilogue_planes(uint32_t tmem, int ntiles, const
         const int t = 128 * mt + 32 * q + lane;
 #pragma unroll
         for (int h = 0; h < N / 16; ++h) {
-            uint32_t v[16];
+            uint32_t v[16], v2[16];
             tmem_ld16(tmem + mt * N + h * 16 + ((uint32_t)(32 * q) << 16), v);
+            tmem_ld16(tmem + ACC_HALF + mt * N + h * 16 + ((uint32_t)(32 * q) << 16), v2);
             tmem_ld_wait();
             if (t < Lout) {
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
                     float4 r;
-                    r.x = fmaxf(__uint_as_float(v[4 * g + 0]) + bias[h * 16 + 4 * g + 0], 0.f);
-                    r.y = fmaxf(__uint_as_float(v[4 * g + 1]) + bias[h * 16 + 4 * g + 1], 0.f);
-                    r.z = fmaxf(__uint_as_float(v[4 * g + 2]) + bias[h * 16 + 4 * g + 2], 0.f);
-                    r.w = fmaxf(__uint_as_float(v[4 * g + 3]) + bias[h * 16 + 4 * g + 3], 0.f);
+                    r.x = fmaxf(__uint_as_float(v[4 * g + 0]) + __uint_as_float(v2[4 * g + 0]) + bias[h * 16 + 4 * g + 0], 0.f);
+                    r.y = fmaxf(__uint_as_float(v[4 * g + 1]) + __uint_as_float(v2[4 * g + 1]) + bias[h * 16 + 4 * g + 1], 0.f);
+                    r.z = fmaxf(__uint_as_float(v[4 * g + 2]) + __uint_as_float(v2[4 * g + 2]) + bias[h * 16 + 4 * g + 2], 0.f);
+                    r.w = fmaxf(__uint_as_float(v[4 * g + 3]) + __uint_as_float(v2[4 * g + 3]) + bias[h * 16 + 4 * g + 3], 0.f);
                     reinterpret_cast<float4*>(dst)[(size_t)(plane0 + h * 4 + g) * dst_tp + dst_pad + t] = tf32r4(r);
                 }
             }
@@ -233,10 +264,10 @@ __device__ __forceinline__ void run_layer(Pipe& pp, const float* a_base, const f
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0 || threadIdx.x == 32) {
         mbar_wait(pp.bar_w, pp.wcount & 1);
         tc_fence_after();
-        issue_layer<L, TP, DIL, NTILES>(a_base, wbuf, pp.tmem);
+        issue_layer<L, TP, DIL, NTILES>(a_base, wbuf, pp.tmem, threadIdx.x >> 5);
         umma_commit(pp.bar_mma);
     }
     pp.wcount++;
@@ -273,14 +304,19 @@ nwd_forward_tc_kernel(const float* __restrict__ W, const float* __restrict__ Wtc
     const int wid = threadIdx.x >> 5;
 
     for (int i = threadIdx.x; i < OFF_S; i += THREADS) smem[i] = 0.f;       // zero pads are never written afterwards
+    __syncthreads();
+    for (int i = threadIdx.x; i < 256 * 4; i += THREADS) {                  // G[r][c] = W_final[c][r - 7] (tf32)
+        const int j = i >> 2, c = i & 3;
+        smem[OFF_G + (j + 7) * 4 + c] = tf32r(W[FW8 + c * 256 + j]);
+    }
     for (int i = threadIdx.x; i < NL * 32; i += THREADS) bias_s[i / 32][i % 32] = Wtc[TC_BIAS_OFF + i];
     if (threadIdx.x == 0) {
         mbar_init(&bars[0], 1);
-        mbar_init(&bars[1], 1);
+        mbar_init(&bars[1], 2);                 // two MMA issuers commit per layer
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     if (wid == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_s)), "r"(64u));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_s)), "r"(128u));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
     }
     tc_fence_before();
@@ -290,6 +326,7 @@ nwd_forward_tc_kernel(const float* __restrict__ W, const float* __restrict__ Wtc
     pp.bar_w = &bars[0]; pp.bar_mma = &bars[1]; pp.wcount = 0; pp.mcount = 0; pp.tmem = tmem_base_s;
     if (threadIdx.x == 0 && blockIdx.x < K) load_weights(tc_woff(0), tc_wfloats(0), Wtc, wbuf, pp.bar_w);
 
+    long long tmark = clock64();
     for (int k = blockIdx.x; k < K; k += gridDim.x) {
         const bool more = k + (int)gridDim.x < K;
         const TIn* tr = traces + (size_t)k * T;
@@ -321,45 +358,53 @@ nwd_forward_tc_kernel(const float* __restrict__ W, const float* __restrict__ Wtc
             reinterpret_cast<float4*>(d3)[(size_t)(4 + pl) * D3_TP + D3_PAD + t] = tf32r4(acc);
         }
         __syncthreads();
+        NWD_MARK(0);
         // ---- encoder on tensor cores ----
         pool_planes(d3 + 4 * D3_TP * 4, D3_TP, D3_PAD, S, 4, L_P2);                       // pool2 -> S [4][193]
         run_layer<0, L_P2, 1, 2>(pp, S, wbuf, Wtc, 1);                                     // d2: 16->16, k32
         epilogue_planes<16>(pp.tmem, 2, bias_s[0], d2, D2_TP, D2_PAD, 4, L_E2);            // enc2 -> dec2 planes 4..7
         tc_fence_before();
         __syncthreads();
+        NWD_MARK(1);
         pool_planes(d2 + 4 * D2_TP * 4, D2_TP, D2_PAD, S, 4, L_P3);                       // pool3 -> S [4][80]
         run_layer<1, L_P3, 1, 1>(pp, S, wbuf, Wtc, 2);                                     // d3: 16->32, k16
         epilogue_planes<32>(pp.tmem, 1, bias_s[1], d1, D1_TP, D1_PAD, 4, L_E3);            // enc3 -> dec1 planes 4..11
         tc_fence_before();
         __syncthreads();
+        NWD_MARK(2);
         pool_planes(d1 + 4 * D1_TP * 4, D1_TP, D1_PAD, S, 8, L_P4);                       // pool4 -> S [8][32]
         run_layer<2, L_P4, 1, 1>(pp, S, wbuf, Wtc, 3);                                     // d4: 32->32, k16
         epilogue_planes<32>(pp.tmem, 1, bias_s[2], e4, E4_TP, E4_PAD, 0, L_E4);            // enc4 -> e4 planes 0..7
         tc_fence_before();
         __syncthreads();
+        NWD_MARK(3);
         // ---- decoder: deconv (as padded valid conv) -> relu -> interp -> concat (up first) ----
         run_layer<3, E4_TP, 1, 1>(pp, e4, wbuf, Wtc, 4);                                   // u1: 32->16, k16
         epilogue_planes<16>(pp.tmem, 1, bias_s[3], S, L_U1, 0, 0, L_U1);
         tc_fence_before();
         __syncthreads();
+        NWD_MARK(4);
         interp_planes(S, L_U1, d1, D1_TP, D1_PAD, L_E3);
         run_layer<4, D1_TP, 1, 1>(pp, d1, wbuf, Wtc, 5);                                   // u2: 48->16, k16
         epilogue_planes<16>(pp.tmem, 1, bias_s[4], S, L_U2, 0, 0, L_U2);
         tc_fence_before();
         __syncthreads();
+        NWD_MARK(5);
         interp_planes(S, L_U2, d2, D2_TP, D2_PAD, L_E2);
         run_layer<5, D2_TP, 1, 2>(pp, d2, wbuf, Wtc, 6);                                   // u3: 32->16, k32
         epilogue_planes<16>(pp.tmem, 2, bias_s[5], S, L_U3, 0, 0, L_U3);
         tc_fence_before();
         __syncthreads();
+        NWD_MARK(6);
         interp_planes(S, L_U3, d3, D3_TP, D3_PAD, L_E1);
         run_layer<6, D3_TP, 1, 4>(pp, d3, wbuf, Wtc, more ? 0 : -1);                       // u4: 32->4, k32, stride 2
         {
             // epilogue of u4: columns (parity p, co) = 8 p + co, rows = input index i; out position 2 i + p; scalar layout
             const int lane = threadIdx.x & 31, q = wid & 3;
             for (int mt = wid >> 2; mt < 4; mt += THREADS / 128) {
-                uint32_t v[16];
+                uint32_t v[16], v2[16];
                 tmem_ld16(pp.tmem + mt * 16 + ((uint32_t)(32 * q) << 16), v);
+                tmem_ld16(pp.tmem + ACC_HALF + mt * 16 + ((uint32_t)(32 * q) << 16), v2);
                 tmem_ld_wait();
                 const int i = 128 * mt + 32 * q + lane;
                 if (i < L_U4H) {
@@ -367,45 +412,81 @@ nwd_forward_tc_kernel(const float* __restrict__ W, const float* __restrict__ Wtc
                     for (int p = 0; p < 2; ++p)
 #pragma unroll
                         for (int co = 0; co < 4; ++co)
-                            S[co * L_U4 + 2 * i + p] = fmaxf(__uint_as_float(v[8 * p + co]) + bias_s[6][co], 0.f);
+                            S[co * L_U4 + 2 * i + p] =
+                                fmaxf(__uint_as_float(v[8 * p + co]) + __uint_as_float(v2[8 * p + co]) + bias_s[6][co], 0.f);
                 }
             }
         }
         tc_fence_before();
         __syncthreads();
-        {   // interp 804 -> 900 into the padded scalar buffer of the final convolution
+        NWD_MARK(7);
+        {   // interp 804 -> 900 (nwd.py:237-238) straight into the parity / phase-split planes of the final convolution
             const float scale = (float)L_U4 / (float)T;
-            for (int idx = threadIdx.x; idx < 4 * T; idx += THREADS) {
-                const int c = idx / T, t = idx - c * T;
+            for (int t = threadIdx.x; t < T; t += THREADS) {
                 float src = scale * ((float)t + 0.5f) - 0.5f;
                 src = src < 0.f ? 0.f : src;
                 int i0 = (int)src;
                 i0 = i0 < L_U4 - 1 ? i0 : L_U4 - 1;
                 const int i1 = i0 + (i0 < L_U4 - 1 ? 1 : 0);
                 const float l1 = fminf(fmaxf(src - (float)i0, 0.f), 1.f), l0 = 1.f - l1;
-                d4[c * D4_STRIDE + D4_PAD + t] = l0 * S[c * L_U4 + i0] + l1 * S[c * L_U4 + i1];
+                float4 r;
+                r.x = l0 * S[0 * L_U4 + i0] + l1 * S[0 * L_U4 + i1];
+                r.y = l0 * S[1 * L_U4 + i0] + l1 * S[1 * L_U4 + i1];
+                r.z = l0 * S[2 * L_U4 + i0] + l1 * S[2 * L_U4 + i1];
+                r.w = l0 * S[3 * L_U4 + i0] + l1 * S[3 * L_U4 + i1];
+                const int u = t + D4_PAD, par = u & 1, v = u >> 1;
+                reinterpret_cast<float4*>(d4)[(size_t)(par * 8 + (v & 7)) * XS_TP + (v >> 3)] = tf32r4(r);
             }
         }
+        NWD_MARK(8);
+        // ---- final conv 4->1, k=256, dil=2, pad=255 (nwd.py:251-252, 285) as two Toeplitz GEMMs (one per output
+        // parity): D[i][n] = sum_v sum_c xs_p[8 i + v][c] * G[v + n][c], output index tau = 8 i + 7 - n, t = 2 tau + p.
+        proxy_fence();
+        tc_fence_before();
         __syncthreads();
-        // ---- final conv 4->1, k=256, dil=2, pad=255 in fp32 (nwd.py:251-252, 285) + rescale ----
-        {
-            const float* wf = W + FW8;
-            const float bf = __ldg(W + FB8);
-            for (int t = threadIdx.x; t < T; t += THREADS) {
-                float a0 = bf, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-                const float* ip = d4 + t;
-#pragma unroll 8
-                for (int j = 0; j < 256; ++j) {
-                    a0 = fmaf(ip[0 * D4_STRIDE + 2 * j], __ldg(wf + 0 * 256 + j), a0);
-                    a1 = fmaf(ip[1 * D4_STRIDE + 2 * j], __ldg(wf + 1 * 256 + j), a1);
-                    a2 = fmaf(ip[2 * D4_STRIDE + 2 * j], __ldg(wf + 2 * 256 + j), a2);
-                    a3 = fmaf(ip[3 * D4_STRIDE + 2 * j], __ldg(wf + 3 * 256 + j), a3);
+        tc_fence_after();
+        if (threadIdx.x == 0 || threadIdx.x == 32) {               // one issuer per output parity
+            constexpr uint32_t idesc = idesc_tf32(16);
+            const uint32_t g0 = smem_u32(smem + OFF_G);
+            const int par = threadIdx.x >> 5;
+            const uint64_t ad0 = umma_desc(smem_u32(d4 + (size_t)par * 8 * XS_TP * 4), XS_TP * 16, 128);
+            uint64_t bd = umma_desc(g0, 16, 0);
+            const uint32_t td = pp.tmem + par * 16;
+#pragma unroll 1
+            for (int s4 = 0; s4 < FIN_KSTEPS / 4; ++s4) {          // v = 8 s4 + {0, 2, 4, 6}: phases 0,2,4,6 at position s4
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    umma_tf32(td, ad0 + (uint64_t)(2 * e * XS_TP + s4), bd, idesc, (s4 | e) ? 1u : 0u);
+                    bd += 2;                                     // G advances by two rows (32 bytes)
                 }
-                const float o = fmaxf((a0 + a1) + (a2 + a3), 0.f);
-                orow[t] = (double)((TOut)o * (TOut)tmax);
+            }
+            umma_commit(pp.bar_mma);
+        }
+        mbar_wait(pp.bar_mma, pp.mcount & 1);
+        pp.mcount++;
+        tc_fence_after();
+        {
+            const int lane = threadIdx.x & 31, q = wid & 3;
+            const float bf = __ldg(W + FB8);
+            if (wid < 8) {                                     // warps 0..3: parity 0, warps 4..7: parity 1
+                const int par = wid >> 2;
+                uint32_t v[16];
+                tmem_ld16(pp.tmem + par * 16 + ((uint32_t)(32 * q) << 16), v);
+                tmem_ld_wait();
+                const int i = 32 * q + lane;
+#pragma unroll
+                for (int n = 0; n < 8; ++n) {
+                    const int t = 2 * (8 * i + 7 - n) + par;
+                    if (t < T) {
+                        const float o = fmaxf(__uint_as_float(v[n]) + bf, 0.f);
+                        orow[t] = (double)((TOut)o * (TOut)tmax);
+                    }
+                }
             }
         }
+        tc_fence_before();
         __syncthreads();
+        NWD_MARK(9);
         if (monotone_start >= 1 && monotone_start < T && threadIdx.x < 32) {
             double carry = orow[monotone_start - 1];
             for (int base = monotone_start; base < T; base += 32) {
@@ -439,10 +520,11 @@ nwd_forward_tc_kernel(const float* __restrict__ W, const float* __restrict__ Wtc
             }
         }
         __syncthreads();
+        NWD_MARK(10);
     }
     tc_fence_before();
     __syncthreads();
-    if (wid == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(pp.tmem), "r"(64u));
+    if (wid == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(pp.tmem), "r"(128u));
 }
 
 // ---------------------------------------------------------------------------------------------- host side
@@ -495,6 +577,23 @@ void pack_tc_weights(const float* const* t, std::vector<float>& out) {
                         }
     }
 }
+
+}  // namespace nwdtc
+}  // namespace cm
+extern "C" int cm_nwd_debug_cycles(long long* out, int n, int enable) {
+    using namespace cm::nwdtc;
+    if (out && n > 0) {
+        long long h[16];
+        CM_CUDA_CHECK(cudaMemcpyFromSymbol(h, g_nwd_cycles, sizeof(h)));
+        for (int i = 0; i < n && i < 16; ++i) out[i] = h[i];
+    }
+    long long z[16] = {0};
+    CM_CUDA_CHECK(cudaMemcpyToSymbol(g_nwd_cycles, z, sizeof(z)));
+    CM_CUDA_CHECK(cudaMemcpyToSymbol(g_nwd_prof, &enable, sizeof(int)));
+    return CM_OK;
+}
+namespace cm {
+namespace nwdtc {
 
 template <typename TIn, typename TOut>
 static int launch_t(cm_nwd* h, const void* in, void* out, int K, int ms, double* y, double* ss, cudaStream_t st) {

@@ -141,6 +141,9 @@ CM_API int    cm_caviar_fit(const cm_caviar_args* a, void* stream);
  * copies up to n counters to `out` (may be NULL), then clears them and sets the enable flag (synchronises). */
 CM_API int cm_caviar_debug_phase_cycles(long long* out, int n, int enable);
 
+/* diagnostics: per-stage SM cycle counters of CTA 0 of the tensor-core demixer kernel (csrc/nwd_tc.cu NWD_MARK ids) */
+CM_API int cm_nwd_debug_cycles(long long* out, int n, int enable);
+
 /* number of kernel launches issued by the last cm_* call on this thread (for bench accounting) */
 CM_API int cm_last_launch_count(void);
 /* device time (ms, CUDA events on the caller's stream) of the dominant kernel of the last cm_nwd_forward /

@@ -1,0 +1,65 @@
+// Microbenchmark (not product code): tcgen05.mma issue rate with 1..4 issuing warps (M=128, N=16, kind::tf32).
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46);
+}
+__device__ __forceinline__ void mma_tf32(uint32_t d, uint64_t da, uint64_t db, uint32_t idesc) {
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, 1, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(d), "l"(da), "l"(db), "r"(idesc) : "memory");
+}
+template <int N>
+__global__ void __launch_bounds__(128) k(long long* cyc, int nissuers) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_base;
+    const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < 160 * 1024 / 4; i += 128) reinterpret_cast<float*>(smem)[i] = 1.0f;
+    if (tid == 0) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar)), "r"(nissuers)); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (wid == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base)), "r"(512u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tb = tmem_base;
+    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    constexpr int REPS = 2048;
+    long long t0 = clock64();
+    if (lane == 0 && wid < nissuers) {
+        uint64_t da = make_desc(smem_u32(smem) + wid * 16384, 8192, 128);
+        const uint64_t db = make_desc(smem_u32(smem + 96 * 1024), (N / 8) * 128, 128);
+        const uint32_t td = tb + wid * 128;
+#pragma unroll 16
+        for (int r = 0; r < REPS; ++r) {
+            mma_tf32(td + (r & 3) * N, da, db, idesc);
+            da += 1;
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+    }
+    uint32_t ok = 0;
+    while (!ok) asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(ok) : "r"(smem_u32(&bar)), "r"(0u) : "memory");
+    long long t1 = clock64();
+    if (tid == 0) cyc[0] = t1 - t0;
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (wid == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tb), "r"(512u));
+}
+template <int N> void run(long long* cyc) {
+    const int smem = 200 * 1024;
+    cudaFuncSetAttribute(k<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    for (int ni = 1; ni <= 4; ++ni) {
+        k<N><<<1, 128, smem>>>(cyc, ni);
+        cudaError_t e = cudaDeviceSynchronize();
+        long long h; cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
+        printf("N=%3d issuers=%d: %.1f cycles per MMA overall (%.1f per issuer-MMA) %s\n", N, ni, (double)h / (2048.0 * ni), (double)h / 2048.0, cudaGetErrorString(e));
+    }
+}
+int main() {
+    long long* cyc; cudaMalloc(&cyc, 8);
+    run<16>(cyc); run<32>(cyc); run<64>(cyc);
+    return 0;
+}
