@@ -1,0 +1,1434 @@
+// The persistent CAVIaR fit kernel and its device functions, compiled twice by caviar.cu:
+//   CM_NT = 512 : one CTA (16 warps) per SM  -- lowest latency of a single fit
+//   CM_NT = 256 : two CTAs (8 warps each) per SM -- the latency-bound phases of one fit (sequential sweep, block
+//                 Cholesky, Newton) overlap with the other fit's work; used when the batch has >= 2 fits per SM
+// Everything that depends on the CTA size lives here, inside namespace CM_FITNS.
+namespace CM_FITNS {
+
+constexpr int NT = CM_NT;          // threads of a fit CTA
+constexpr int NW = NT / 32;
+constexpr int GCT = 16 * NW;       // panel GEMM column tile: 16 columns per warp
+constexpr int GCT_LOG2 = (GCT == 256) ? 8 : 7;
+constexpr int STAGE_GEMM_DOUBLES = GK * NB + GK * GCT;            // A chunk [GK][32] + X chunk [GK][GCT]
+constexpr int GEMM_SMEM_DOUBLES = NST * STAGE_GEMM_DOUBLES;       // 144 KB (NT=512) / 80 KB (NT=256)
+constexpr int SDXD_DOUBLES = NB * (NB + 1) + NB * XD_LD;          // diagonal block + its inverse, behind the ring
+constexpr int FIT_SMEM_BYTES = (NT == 512) ? 200 * 1024 : (GEMM_SMEM_DOUBLES + SDXD_DOUBLES + 96) * 8;
+constexpr int RC = (NT == 512) ? 512 : 256;    // staged row capacity (entries) of the chain warp's prefetch buffers
+
+// X = L^-1 (lower) with X^T mirrored in the upper half is stored in GCT-column tiles, each tile row-major with 256
+// doubles per row, so that a GK x 256 chunk is ONE contiguous block (one bulk copy).  Odd rows have bit 3 of the
+// in-tile column flipped: with this swizzle the DMMA B-fragment loads from the dense shared-memory copy hit every
+// 8-byte bank exactly twice (the minimum for 32 lanes).
+__device__ __forceinline__ size_t xidx(int kk, int cc, int ldr) {
+    return ((size_t)(cc >> GCT_LOG2) * ldr + kk) * GCT + ((cc & (GCT - 1)) ^ ((kk & 1) << 3));
+}
+struct Ctx {
+    long long* tlast;   // shared: last phase timestamp (block 0 / thread 0 only)
+    int N, K, P, nnz, it;
+    double *X, *PA, *PB, *lam, *cst, *y, *ss, *pred, *resid, *z, *mu, *beta, *bvec, *dvec, *wvec, *slam, *slam2, *sp,
+        *phibar, *phi, *phicov, *phiz, *phicovz, *lamhist, *lamT, *growbuf;
+    double2* cscq;    // per CSC entry: (active index of the row as int bits, lam) -- rebuilt every a2
+    int *row_ptr, *col_ptr, *col_k, *csc_row, *csc_pos, *cntp, *n0p, *n1p, *act, *ainv, *order, *order2, *pos, *rownz,
+        *phizok, *dcnt, *dlist, *colpw, *nmask;
+    int4* chinfo;
+    uint32_t *sortkeys, *keys;
+    unsigned char *pw, *mask, *blocked;
+    const double *mu0, *beta0, *phi0, *phicov0;
+    double* red;      // shared: NW doubles scratch
+    double* sm;       // shared: dynamic region
+    int smd;          // its size in doubles
+};
+
+// phase accounting for cm_caviar_debug_phase_cycles (block 0, thread 0; enabled on request only)
+__device__ __forceinline__ void phase_mark(const Ctx& c, int id) {
+    if ((g_phase_enable & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        const long long t = clock64();
+        g_phase_cycles[id] += t - *c.tlast;
+        *c.tlast = t;
+    }
+}
+
+__device__ __forceinline__ double block_sum(double v, double* red) {
+    v = warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double r = 0.0;
+#pragma unroll
+    for (int i = 0; i < NW; ++i) r += red[i];
+    return r;
+}
+__device__ __forceinline__ int block_sum_int(int v, double* red) {
+    v = warp_sum(v);
+    int* ri = reinterpret_cast<int*>(red);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) ri[threadIdx.x >> 5] = v;
+    __syncthreads();
+    int r = 0;
+#pragma unroll
+    for (int i = 0; i < NW; ++i) r += ri[i];
+    return r;
+}
+
+// ordered compaction of {i < n : flag(i)} into out[]; returns the count (block-wide, deterministic)
+template <typename F>
+__device__ int block_compact(int n, F flag, int* out, int* inv, double* red) {
+    int* wcnt = reinterpret_cast<int*>(red);     // NW ints
+    __shared__ int base_s;
+    if (threadIdx.x == 0) base_s = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int i0 = 0; i0 < n; i0 += NT) {
+        const int i = i0 + threadIdx.x;
+        const bool f = i < n && flag(i);
+        const unsigned bal = __ballot_sync(0xffffffffu, f);
+        if (lane == 0) wcnt[wid] = __popc(bal);
+        __syncthreads();
+        int off = base_s;
+        for (int w = 0; w < wid; ++w) off += wcnt[w];
+        if (f) {
+            const int idx = off + __popc(bal & ((1u << lane) - 1u));
+            out[idx] = i;
+            if (inv) inv[i] = idx;
+        } else if (i < n && inv) {
+            inv[i] = -1;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int t = 0;
+            for (int w = 0; w < NW; ++w) t += wcnt[w];
+            base_s += t;
+        }
+        __syncthreads();
+    }
+    return base_s;
+}
+
+// fresh prediction pred[k] = sum_n mu[n] lam[n,k] over the (neuron-sorted) column lists
+__device__ __forceinline__ void compute_pred(const Ctx& c, double* dst) {
+    for (int k = threadIdx.x; k < c.K; k += NT) {
+        double s = 0.0;
+        for (int i = c.col_ptr[k]; i < c.col_ptr[k + 1]; ++i) s += c.mu[c.csc_row[i]] * c.lamT[i];
+        dst[k] = s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ a2
+// block_update_mu (caviar.py:166-172) on the active set A = {n : lam[n,:] != 0}:
+// M = sigma (diag(sum lam(1-lam)) + lam_A lam_A^T) + diag(1/beta0^2);  C = M^-1;  mu = C b;  beta = diag C.
+// C = X^T X with X = L^-1 built by a bordered (block-row) recursion that keeps X (lower) and X^T (upper) in one
+// na x na array, so both panel GEMMs read it with unit stride across threads.
+// ---- async copy helpers (LDGSTS) ----
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+    const unsigned sdst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sdst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+    const unsigned sdst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sdst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N_>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N_) : "memory"); }
+
+// ---- mbarrier / bulk-copy helpers (UBLKCP + SYNCS in SASS) ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {}
+}
+// global -> shared bulk copy (bytes % 16 == 0, both addresses 16-byte aligned), completion on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// Gram rows of one 32-row block of M into PA (lower part incl. the diagonal block).
+// One warp per row; 32 entries of the row are expanded at once (each lane walks the column list of its own
+// trial, 8 list entries prefetched per round), lanes that hit the same target column in the same step are
+// combined in lane order -> deterministic.
+__device__ void gram_rows(const Ctx& c, int i0, int nb, double sigma) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int cap = GEMM_SMEM_DOUBLES / NW;       // row-buffer doubles per warp
+    const int tagcap = ((c.smd - GEMM_SMEM_DOUBLES) * 8) / NW;   // conflict-tag bytes per warp (behind the GEMM ring)
+    const double2* __restrict__ cscq = c.cscq;
+    for (int r = wid; r < nb; r += NW) {
+        const int ia = i0 + r;
+        const int n = c.act[ia];
+        double* acc = (ia + 1 <= cap) ? (c.sm + (size_t)wid * cap) : (c.growbuf + (size_t)wid * (c.N + 2));
+        unsigned char* tags = reinterpret_cast<unsigned char*>(c.sm + GEMM_SMEM_DOUBLES) + (size_t)wid * tagcap;
+        const bool use_tags = ia + 1 <= tagcap;
+        for (int q = lane; q <= ia; q += 32) acc[q] = 0.0;
+        __syncwarp();
+        const int beg = c.row_ptr[n], end = c.row_ptr[n + 1];
+        for (int jb = beg; jb < end; jb += 32) {
+            const int j = jb + lane;
+            double la = 0.0;
+            int cb = 0, len = 0;
+            if (j < end) {
+                la = c.lam[j];
+                if (la != 0.0) {
+                    const int k = c.col_k[j];
+                    cb = c.col_ptr[k];
+                    len = c.col_ptr[k + 1] - cb;
+                }
+            }
+            int maxlen = len;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, o));
+            for (int t0 = 0; t0 < maxlen; t0 += 8) {
+                int ibs[8];
+                double vs[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {                  // independent 16-byte loads (memory-level parallelism)
+                    const int t = t0 + u;
+                    int ib = -1;
+                    double lv = 0.0;
+                    if (t < len) {
+                        const double2 rec = cscq[cb + t];
+                        ib = (int)__double_as_longlong(rec.x);
+                        lv = rec.y;
+                    }
+                    if (ib > ia) ib = -1;
+                    ibs[u] = ib;
+                    vs[u] = la * lv;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    if (t0 + u >= maxlen) break;               // warp-uniform
+                    const int ib = ibs[u];
+                    const double v = vs[u];
+                    // conflict check: every lane tags its target; a lane that reads back another id shares the target
+                    bool lost = false;
+                    if (use_tags) {
+                        if (ib >= 0) tags[ib] = (unsigned char)lane;
+                        __syncwarp();
+                        lost = (ib >= 0) && (tags[ib] != (unsigned char)lane);
+                    }
+                    if (use_tags && !__any_sync(0xffffffffu, lost)) {
+                        if (ib >= 0) acc[ib] += v;             // all targets distinct: plain read-modify-write
+                    } else {
+                        // same target hit by several lanes: combine them in lane order (deterministic)
+                        const unsigned amask = __ballot_sync(0xffffffffu, ib >= 0);
+                        if (ib >= 0) {
+                            const unsigned grp = __match_any_sync(amask, ib);
+                            const int leader = __ffs(grp) - 1;
+                            unsigned rest = grp & ~(1u << leader);
+                            double ssum = __shfl_sync(amask, v, leader);
+                            while (__any_sync(amask, rest != 0)) {
+                                const int src = rest ? (__ffs(rest) - 1) : lane;
+                                const double ov = __shfl_sync(amask, v, src);
+                                if (rest) { ssum += ov; rest &= rest - 1; }
+                            }
+                            if (lane == leader) acc[ib] += ssum;
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+        const double b0 = c.beta0[n];
+        const double dd = c.dvec[ia];
+        for (int q = lane; q <= ia; q += 32) {
+            double v = acc[q];
+            if (q == ia) v = sigma * (dd + v) + 1.0 / (b0 * b0);
+            else v = sigma * v;
+            c.PA[pidx(r, q)] = v;
+        }
+        __syncwarp();
+    }
+}
+
+// D(8x8) += A(8x4, row) * B(4x8, col): the fp64 tensor-core path (SASS DMMA.8x8x4); operands in registers.
+__device__ __forceinline__ void dmma8x8x4(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+// Pipeline state of the panel GEMMs: NST-stage ring of (A chunk, X chunk) filled by bulk copies, one "full" and one
+// "empty" mbarrier per stage.  `seq` counts chunks since kernel start (stage = seq % NST, parity = seq / NST & 1).
+struct GemmPipe {
+    uint64_t* full;      // [NST]
+    uint64_t* empty;     // [NST]
+    unsigned seq;
+};
+
+// OUT[r][cc] = sum_kk IN[r][kk] * X[kk][cc] ; UPPER: kk <= cc (the X^T half), else kk >= cc (the X half).
+// 32 x GK chunks of IN and GK x 256 chunks of X are streamed through shared memory by cp.async.bulk (issued by warp
+// 0, completion on mbarriers, 4 stages in flight); each warp owns the 32 x 16 slice of the 32 x 256 output tile as
+// 4 x 2 DMMA tiles.  Row strides = 4 (mod 16) doubles keep the fragment loads bank-conflict free.
+template <bool UPPER>
+__device__ void panel_gemm(const Ctx& c, int ldr, int i0, int nb, const double* IN, double* OUT, GemmPipe& gp) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int lq = lane >> 2, lr = lane & 3;
+    const int sw = (lr & 1) << 3;                 // swizzle term of this lane's k rows (k = 4*ks + lr)
+    const int wc = wid * 16;
+    double* stage0 = c.sm;
+    const double* Xg = c.X;
+    // the staging ring was last written through the generic proxy (row buffers, pred): order those writes before
+    // the async-proxy bulk copies that reuse the same shared memory
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    __syncthreads();
+    for (int ct0 = 0; ct0 < i0; ct0 += GCT) {
+        const int tile_end = min(i0, ct0 + GCT);
+        const int kfirst = UPPER ? 0 : ct0;
+        const int klast = UPPER ? tile_end : i0;
+        const int nc = (klast - kfirst + GK - 1) / GK;
+        const unsigned seq0 = gp.seq;
+        const double* Xtile = Xg + (size_t)(ct0 >> GCT_LOG2) * ldr * GCT;
+        auto fill = [&](int ci) {                             // warp 0 only: two bulk copies per chunk
+            const unsigned g = seq0 + ci;
+            const int st = g % NST;
+            if (g >= NST) mbar_wait(&gp.empty[st], ((g / NST) - 1) & 1);
+            if (lane == 0) {
+                double* As = stage0 + (size_t)st * STAGE_GEMM_DOUBLES;
+                double* Xs = As + GK * NB;
+                const int kk0 = kfirst + ci * GK;
+                if (g_phase_enable & 4) mbar_arrive(&gp.full[st]);          // debug: no copies
+                else {
+                    mbar_expect_tx(&gp.full[st], (uint32_t)(GK * NB * 8 + GK * GCT * 8));
+                    bulk_g2s(As, IN + (size_t)kk0 * NB, GK * NB * 8, &gp.full[st]);
+                    bulk_g2s(Xs, Xtile + (size_t)kk0 * GCT, GK * GCT * 8, &gp.full[st]);
+                }
+            }
+            __syncwarp();
+        };
+        if (wid == 0)
+            for (int ci = 0; ci < min(nc, NST); ++ci) fill(ci);
+        double acc[4][2][2];
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) { acc[mt][nt][0] = 0.0; acc[mt][nt][1] = 0.0; }
+        const int cmin = ct0 + wc, cmax = cmin + 15;
+        for (int ci = 0; ci < nc; ++ci) {
+            const unsigned g = seq0 + ci;
+            const int st = g % NST;
+            mbar_wait(&gp.full[st], (g / NST) & 1);
+            const int kk0 = kfirst + ci * GK;
+            if (cmin < i0 && !(g_phase_enable & 2)) {                       // debug bit 2: no math
+                const double* ab = stage0 + (size_t)st * STAGE_GEMM_DOUBLES;
+                const double* xb = ab + GK * NB;
+                // interior chunk of the triangle: every (kk, cc) pair of this warp is valid -> no masking at all
+                const bool interior = (nb == NB) && (cmax < i0) && (kk0 + GK <= i0) &&
+                                      (UPPER ? (kk0 + GK - 1 <= cmin) : (kk0 >= cmax));
+                if (interior) {
+                    double af[GK / 4][4], bf[GK / 4][2];
+#pragma unroll
+                    for (int ks = 0; ks < GK / 4; ++ks) {
+#pragma unroll
+                        for (int mt = 0; mt < 4; ++mt) af[ks][mt] = ab[(4 * ks + lr) * NB + ((8 * mt + lq) ^ sw)];
+#pragma unroll
+                        for (int nt = 0; nt < 2; ++nt) bf[ks][nt] = xb[(4 * ks + lr) * GCT + ((wc + 8 * nt + lq) ^ sw)];
+                    }
+#pragma unroll
+                    for (int ks = 0; ks < GK / 4; ++ks)
+#pragma unroll
+                        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                            for (int mt = 0; mt < 4; ++mt) dmma8x8x4(acc[mt][nt][0], acc[mt][nt][1], af[ks][mt], bf[ks][nt]);
+                } else {
+#pragma unroll
+                    for (int ks = 0; ks < GK / 4; ++ks) {
+                        const int kbase = kk0 + 4 * ks;
+                        const bool skip = UPPER ? (kbase > cmax) : (kbase + 3 < cmin);
+                        if (skip || kbase >= i0) continue;                   // warp-uniform
+                        const int kk = kbase + lr;
+                        double af[4];
+#pragma unroll
+                        for (int mt = 0; mt < 4; ++mt) {
+                            const double av = ab[(4 * ks + lr) * NB + ((8 * mt + lq) ^ sw)];
+                            af[mt] = (8 * mt + lq < nb && kk < i0) ? av : 0.0;
+                        }
+#pragma unroll
+                        for (int nt = 0; nt < 2; ++nt) {
+                            const int cl = wc + 8 * nt + lq;
+                            const int cc = ct0 + cl;
+                            const bool in = (kk < i0) && (cc < i0) && (UPPER ? (kk <= cc) : (kk >= cc));
+                            const double xv = xb[(4 * ks + lr) * GCT + (cl ^ sw)];
+                            const double bv = in ? xv : 0.0;
+#pragma unroll
+                            for (int mt = 0; mt < 4; ++mt) dmma8x8x4(acc[mt][nt][0], acc[mt][nt][1], af[mt], bv);
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&gp.empty[st]);
+            if (wid == 0 && ci + NST < nc) fill(ci + NST);
+        }
+        gp.seq = seq0 + nc;
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) {
+            const int r = 8 * mt + lq;
+            if (r < nb) {
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt) {
+                    const int cc = cmin + 8 * nt + 2 * lr;
+                    if (cc < i0) OUT[pidx(r, cc)] = acc[mt][nt][0];
+                    if (cc + 1 < i0) OUT[pidx(r, cc + 1)] = acc[mt][nt][1];
+                }
+            }
+        }
+    }
+    __syncthreads();
+}
+
+__device__ __noinline__ void phase_a2(const Ctx& c, double sigma, int* na_s, GemmPipe& gp) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int lq = lane >> 2, lr = lane & 3;
+    const int N = c.N;
+    const int na = block_compact(N, [&](int i) { return c.rownz[i] > 0; }, c.act, c.ainv, c.red);
+    const int ldr = N + ROWPAD;                   // rows per 256-column tile of X
+    if (threadIdx.x == 0) *na_s = na;
+    // inactive rows decouple: mu = mu0, beta = beta0^2 (variance)
+    for (int n = threadIdx.x; n < N; n += NT)
+        if (c.rownz[n] == 0) { c.mu[n] = c.mu0[n]; c.beta[n] = c.beta0[n] * c.beta0[n]; }
+    // per CSC entry: (active index of its row, lam) in one 16-byte record for the Gram expansion
+#pragma unroll 8
+    for (int i = threadIdx.x; i < c.nnz; i += NT)
+        c.cscq[i] = make_double2(__longlong_as_double((long long)c.ainv[c.csc_row[i]]), c.lamT[i]);
+    // per active row: D = sum lam(1-lam), b = sigma * sum lam*y + mu0/beta0^2
+    for (int ia = wid; ia < na; ia += NW) {
+        const int n = c.act[ia];
+        double d = 0.0, by = 0.0;
+        for (int j = c.row_ptr[n] + lane; j < c.row_ptr[n + 1]; j += 32) {
+            const double l = c.lam[j];
+            d += l * (1.0 - l);
+            by += l * c.y[c.col_k[j]];
+        }
+        d = warp_sum(d); by = warp_sum(by);
+        if (lane == 0) {
+            const double b0 = c.beta0[n];
+            c.dvec[ia] = d;
+            c.bvec[ia] = sigma * by + c.mu0[n] / (b0 * b0);
+        }
+    }
+    __syncthreads();
+    phase_mark(c, 0);
+    if (na == 0) return;
+
+    // diagonal block -> its Cholesky factor, and the inverse of that factor (strict upper part zeroed); both live
+    // behind the GEMM ring (the Gram conflict tags reuse the same bytes at a different time)
+    double (*Sd)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(c.sm + GEMM_SMEM_DOUBLES);
+    double (*Xd)[XD_LD] = reinterpret_cast<double (*)[XD_LD]>(c.sm + GEMM_SMEM_DOUBLES + NB * (NB + 1));
+    double* X = c.X;
+    double* PA = c.PA;
+    double* PB = c.PB;
+    for (int i0 = 0; i0 < na; i0 += NB) {
+        const int nb = min(NB, na - i0);
+        gram_rows(c, i0, nb, sigma);              // PA[r][0..i0+r] = M[i0+r][.]
+        __syncthreads();
+        phase_mark(c, 1);
+        if (i0 > 0) panel_gemm<true>(c, ldr, i0, nb, PA, PB, gp);      // PB = Lrow = A[I,0:i0] X11^T
+        phase_mark(c, 2);
+        // S = A[I,I] - Lrow Lrow^T : warp w owns the 8x8 tile (w/4, w%4) and runs the whole k range with DMMA,
+        // four independent accumulator pairs hide the dependent-issue latency.
+        {
+            for (int tile = wid; tile < 16; tile += NW) {
+                const int mt = tile >> 2, nt = tile & 3;
+                if (nt > mt) continue;
+                double d[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
+                if (i0 > 0) {
+                    const int ra = 8 * mt + lq, rb = 8 * nt + lq;
+                    const bool va = ra < nb, vb = rb < nb;
+                    for (int k0 = 0; k0 < i0; k0 += 16) {
+                        double av[4], bv[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int k = k0 + 4 * u + lr;
+                            av[u] = (va && k < i0) ? PB[pidx(ra, k)] : 0.0;
+                            bv[u] = (vb && k < i0) ? PB[pidx(rb, k)] : 0.0;
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) dmma8x8x4(d[u][0], d[u][1], av[u], bv[u]);
+                    }
+                }
+                const double s0 = (d[0][0] + d[1][0]) + (d[2][0] + d[3][0]);
+                const double s1 = (d[0][1] + d[1][1]) + (d[2][1] + d[3][1]);
+                const int r = 8 * mt + lq, cc = 8 * nt + 2 * lr;
+                if (r < nb) {
+                    Sd[r][cc] = PA[pidx(r, i0 + cc)] - s0;
+                    Sd[r][cc + 1] = PA[pidx(r, i0 + cc + 1)] - s1;
+                }
+            }
+        }
+        __syncthreads();
+        // Cholesky of the nb x nb diagonal block with the whole CTA (thread per trailing element), then its inverse by
+        // forward substitution, 16 lanes per column.
+        for (int j = 0; j < nb; ++j) {
+            __syncthreads();
+            const double djj = sqrt(Sd[j][j]);
+            __syncthreads();
+            if (threadIdx.x == 0) Sd[j][j] = djj;
+            if (threadIdx.x > j && threadIdx.x < nb) Sd[threadIdx.x][j] /= djj;
+            __syncthreads();
+            for (int e = threadIdx.x; e < NB * NB; e += NT) {
+                const int r = e >> 5, q = e & 31;
+                if (q > j && q <= r && r < nb) Sd[r][q] -= Sd[r][j] * Sd[q][j];
+            }
+        }
+        __syncthreads();
+        for (int e = threadIdx.x; e < NB * XD_LD; e += NT) (&Xd[0][0])[e] = 0.0;
+        __syncthreads();
+        if (threadIdx.x < nb) Xd[threadIdx.x][threadIdx.x] = 1.0 / Sd[threadIdx.x][threadIdx.x];
+        {
+            const int l16 = threadIdx.x & 15;                              // lane within a 16-lane column group
+            for (int r = 1; r < nb; ++r) {
+                __syncthreads();
+                for (int cc = threadIdx.x >> 4; cc < NB; cc += NT / 16) {  // column (whole 16-lane groups iterate together)
+                    double sacc = 0.0;
+                    if (cc < r) {
+                        for (int t = cc + l16; t < r; t += 16) sacc += Sd[r][t] * Xd[t][cc];
+                    }
+#pragma unroll
+                    for (int o = 8; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
+                    if (cc < r && l16 == 0) Xd[r][cc] = -sacc / Sd[r][r];
+                }
+            }
+        }
+        __syncthreads();
+        phase_mark(c, 3);
+        if (i0 > 0) {
+            panel_gemm<false>(c, ldr, i0, nb, PB, PA, gp);              // PA = W = Lrow X11
+            phase_mark(c, 4);
+            // X[I, 0:i0] = -Xd W (32x32 lower-triangular times 32 x i0, DMMA), mirrored into the upper half
+            const int nsl = (i0 + 15) / 16;
+            for (int sl = wid; sl < nsl; sl += NW) {
+                const int cb0 = sl * 16;
+                double acc[4][2][2];
+#pragma unroll
+                for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+                    for (int nt = 0; nt < 2; ++nt) { acc[mt][nt][0] = 0.0; acc[mt][nt][1] = 0.0; }
+                double bvv[8][2];
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks)
+#pragma unroll
+                    for (int nt = 0; nt < 2; ++nt) {
+                        const int r2 = 4 * ks + lr, cc = cb0 + 8 * nt + lq;
+                        bvv[ks][nt] = (r2 < nb && cc < i0) ? PA[pidx(r2, cc)] : 0.0;
+                    }
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) {
+                    double af[4];
+#pragma unroll
+                    for (int mt = 0; mt < 4; ++mt) af[mt] = Xd[8 * mt + lq][4 * ks + lr];
+#pragma unroll
+                    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                        for (int mt = 0; mt < 4; ++mt) dmma8x8x4(acc[mt][nt][0], acc[mt][nt][1], af[mt], bvv[ks][nt]);
+                }
+#pragma unroll
+                for (int mt = 0; mt < 4; ++mt) {
+                    const int r = 8 * mt + lq;
+                    if (r >= nb) continue;
+#pragma unroll
+                    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int cc = cb0 + 8 * nt + 2 * lr + e;
+                            if (cc < i0) {
+                                const double v = -acc[mt][nt][e];
+                                X[xidx(i0 + r, cc, ldr)] = v;
+                                X[xidx(cc, i0 + r, ldr)] = v;
+                            }
+                        }
+                }
+            }
+        }
+        for (int e = threadIdx.x; e < nb * nb; e += NT) {
+            const int r = e / nb, r2 = e - r * nb;
+            if (r2 <= r) {
+                X[xidx(i0 + r, i0 + r2, ldr)] = Xd[r][r2];
+                X[xidx(i0 + r2, i0 + r, ldr)] = Xd[r][r2];
+            }
+        }
+        __syncthreads();
+        phase_mark(c, 5);
+    }
+    // w = X b ; mu = X^T w ; beta = column sums of squares of X
+    for (int i = wid; i < na; i += NW) {
+        double s = 0.0;
+        for (int q = lane; q <= i; q += 32) s += X[xidx(i, q, ldr)] * c.bvec[q];
+        s = warp_sum(s);
+        if (lane == 0) c.wvec[i] = s;
+    }
+    __syncthreads();
+    for (int cc = threadIdx.x; cc < na; cc += NT) {
+        double m = 0.0, v = 0.0;
+        for (int i = cc; i < na; ++i) {
+            const double x = X[xidx(i, cc, ldr)];
+            m += x * c.wvec[i];
+            v += x * x;
+        }
+        const int n = c.act[cc];
+        c.mu[n] = m;
+        c.beta[n] = v;
+    }
+    __syncthreads();
+    phase_mark(c, 6);
+}
+
+// ------------------------------------------------------------------------------------------------ a3
+// One neuron of update_lam's sweep (caviar.py:200-227, reduced form App. A.8), executed by one warp.
+// cp/cs/lo: the row's packed (trial | power<<27) entries, sigmoid-argument constants (in) / new posteriors (out),
+// and old posteriors -- either staged in shared memory (chain) or the global arrays themselves.
+// chain=true: the neuron reads and updates the running prediction (mu[n] != 0).
+#define NEG_INF (-CUDART_INF)
+
+// what a sweep step needs, held in registers (the big Ctx lives in local memory; keep it off the critical path)
+struct RowCtx {
+    double *lam, *sp, *slam, *slam2;
+    int *n0p, *n1p, *rownz;
+    int P;
+};
+__device__ __forceinline__ RowCtx make_rowctx(const Ctx& c) {
+    RowCtx r;
+    r.lam = c.lam; r.sp = c.sp; r.slam = c.slam; r.slam2 = c.slam2;
+    r.n0p = c.n0p; r.n1p = c.n1p; r.rownz = c.rownz; r.P = c.P;
+    return r;
+}
+
+template <int PT>
+__device__ __forceinline__ void sweep_row(const RowCtx c, int n, int beg, int len, bool chain, double mu_n,
+                                          const int* cntp, const int* nmask, const int* __restrict__ cp, double* cs,
+                                          const double* lo, double sigma, double thr, double minspk, bool gate,
+                                          double* pred) {
+    const int lane = threadIdx.x & 31;
+    const bool prof = chain && g_phase_enable && blockIdx.x == 0 && lane == 0;
+    long long tp0 = 0;
+    if (prof) tp0 = clock64();
+    const double coef = sigma * mu_n;
+    double tot, accp[PT];
+#pragma unroll
+    for (int p = 0; p < PT; ++p) accp[p] = 0.0;
+    bool rare = false;
+    int q = lane;
+    for (; q + 32 < len; q += 64) {                      // two independent entries per trip (ILP across the exp/div chains)
+        const int pk0 = cp[q], pk1 = cp[q + 32];
+        const double cj0 = cs[q], cj1 = cs[q + 32];
+        const double x0 = chain ? (cj0 - coef * pred[pk0 & 0x7ffffff]) : cj0;
+        const double x1 = chain ? (cj1 - coef * pred[pk1 & 0x7ffffff]) : cj1;
+        const double e0 = sigmoid_d(x0), e1 = sigmoid_d(x1);
+        cs[q] = e0; cs[q + 32] = e1;
+        const int pw0 = pk0 >> 27, pw1 = pk1 >> 27;
+#pragma unroll
+        for (int p = 0; p < PT; ++p) { accp[p] += (pw0 == p) ? e0 : 0.0; accp[p] += (pw1 == p) ? e1 : 0.0; }
+        rare |= (e0 == 1.0) || (e0 == 0.0) || (e1 == 1.0) || (e1 == 0.0);
+    }
+    if (q < len) {
+        const int pk = cp[q];
+        const double cj = cs[q];
+        const double x = chain ? (cj - coef * pred[pk & 0x7ffffff]) : cj;
+        const double est = sigmoid_d(x);
+        cs[q] = est;
+        const int pw = pk >> 27;
+#pragma unroll
+        for (int p = 0; p < PT; ++p) accp[p] += (pw == p) ? est : 0.0;
+        rare |= (est == 1.0) || (est == 0.0);
+    }
+    if (prof) { const long long t = clock64(); g_phase_cycles[20] += t - tp0; tp0 = t; }
+    // per-power sums (warp-uniform guard skips unused slots); the row total is their sum
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {                   // P butterflies interleaved level by level
+        double tmpv[PT];
+#pragma unroll
+        for (int p = 0; p < PT; ++p)
+            if (p < c.P) tmpv[p] = __shfl_xor_sync(0xffffffffu, accp[p], o);
+#pragma unroll
+        for (int p = 0; p < PT; ++p)
+            if (p < c.P) accp[p] += tmpv[p];
+    }
+    tot = 0.0;
+#pragma unroll
+    for (int p = 0; p < PT; ++p)
+        if (p < c.P) tot += accp[p];
+    if (prof) { const long long t = clock64(); g_phase_cycles[21] += t - tp0; tp0 = t; }
+    int c0[PT], c1[PT];
+#pragma unroll
+    for (int p = 0; p < PT; ++p) { c0[p] = (p < c.P) ? nmask[p] : 0; c1[p] = 0; }
+    if (__any_sync(0xffffffffu, rare)) {                 // exact zero / one counts (needed by update_phi's nan_to_num)
+        int z0[PT];
+#pragma unroll
+        for (int p = 0; p < PT; ++p) z0[p] = 0;
+        for (int q = lane; q < len; q += 32) {
+            const int pw = cp[q] >> 27;
+            const double est = cs[q];
+#pragma unroll
+            for (int p = 0; p < PT; ++p) { z0[p] += (pw == p && est == 0.0); c1[p] += (pw == p && est == 1.0); }
+        }
+#pragma unroll
+        for (int p = 0; p < PT; ++p) { c0[p] += warp_sum(z0[p]); c1[p] = warp_sum(c1[p]); }
+    }
+    bool ok = true;
+    if (gate) {
+        // spike rate of power p is computed by lane p (one division latency instead of P), then broadcast
+        double mine = 0.0;
+        {
+            const int pl = lane < c.P ? lane : 0;
+            const int cnt = cntp[pl];
+            double num = accp[0];
+#pragma unroll
+            for (int p = 1; p < PT; ++p) num = (pl == p) ? accp[p] : num;
+            mine = num / ((double)cnt + 1e-4 * (cnt == 0 ? 1.0 : 0.0));
+        }
+        double sr[PT];
+#pragma unroll
+        for (int p = 0; p < PT; ++p) sr[p] = __shfl_sync(0xffffffffu, mine, p);
+        ok = (pava_last_reg<PT>(sr, c.P) >= thr) && (tot >= minspk);
+    }
+    if (prof) { const long long t = clock64(); g_phase_cycles[22] += t - tp0; tp0 = t; }
+    // second pass: commit the row, update the running prediction
+    const double muok = ok ? mu_n : 0.0;
+    double sl2 = 0.0;
+    double* lam_row = c.lam + beg;
+    for (int q = lane; q < len; q += 32) {
+        const double nw = ok ? cs[q] : 0.0;
+        const double old = lo[q];
+        lam_row[q] = nw;
+        if (chain) {
+            const int k = cp[q] & 0x7ffffff;
+            pred[k] = (pred[k] + muok * nw) - mu_n * old;
+        }
+        sl2 += nw * nw;
+    }
+    sl2 = warp_sum(sl2);
+    if (lane == 0) {
+        int zeros = 0;
+#pragma unroll
+        for (int p = 0; p < PT; ++p)
+            if (p < c.P) {
+                zeros += c0[p];
+                c.sp[n * PMAX + p] = ok ? accp[p] : 0.0;
+                c.n0p[n * PMAX + p] = ok ? c0[p] : cntp[p];
+                c.n1p[n * PMAX + p] = ok ? c1[p] : 0;
+            }
+        c.slam[n] = ok ? tot : 0.0;
+        c.slam2[n] = sl2;
+        int masked = 0;
+#pragma unroll
+        for (int p = 0; p < PT; ++p) if (p < c.P) masked += nmask[p];
+        c.rownz[n] = ok ? (len - (zeros - masked)) : 0;
+    }
+    __syncwarp();
+    if (prof) { const long long t = clock64(); g_phase_cycles[23] += t - tp0; g_phase_cycles[19] += 1; g_phase_cycles[24] += len; }
+}
+
+constexpr int NSTAGE = 3;
+constexpr int HD = 18;           // header doubles per stage: mu, then 2*PT ints (cntp, nmask)
+constexpr int STAGE_DOUBLES = NSTAGE * (RC + RC + RC / 2 + HD);   // cs, lo, cp (ints), header
+
+// The sequential part of the sweep: neurons with mu != 0, in update order, by ONE warp.  Rows are prefetched two
+// neurons ahead into shared memory with cp.async so that the chain only waits on shared-memory latency.
+template <int PT>
+__device__ __noinline__ void sweep_chain(const Ctx& c, int nchain, double sigma, double thr, double minspk, bool gate, double* pred,
+                            double* stage_base) {
+    const int lane = threadIdx.x & 31;
+    const RowCtx rc = make_rowctx(c);
+    const int* g_colpw = c.colpw; const double* g_cst = c.cst; const double* g_lam = c.lam; const double* g_mu = c.mu;
+    const int* g_cntp = c.cntp; const int* g_nmask = c.nmask; const int4* g_chinfo = c.chinfo;
+    double* scs = stage_base;                                   // [NSTAGE][RC]
+    double* slo = scs + NSTAGE * RC;                            // [NSTAGE][RC]
+    int* scp = reinterpret_cast<int*>(slo + NSTAGE * RC);       // [NSTAGE][RC]
+    double* shd = reinterpret_cast<double*>(scp + NSTAGE * RC); // [NSTAGE][HD]: mu, then ints cntp[PT], nmask[PT]
+    auto stage = [&](int4 inf, int buf) {
+        const int n = inf.x, beg = inf.y, len = inf.z;
+        if (len <= RC) {
+            for (int q = lane; q < len; q += 32) {
+                cp_async4(scp + buf * RC + q, g_colpw + beg + q);
+                cp_async8(scs + buf * RC + q, g_cst + beg + q);
+                cp_async8(slo + buf * RC + q, g_lam + beg + q);
+            }
+        }
+        if (lane == 0) cp_async8(shd + buf * HD, g_mu + n);
+        int* hi = reinterpret_cast<int*>(shd + buf * HD + 1);
+        for (int q = lane; q < 2 * PT; q += 32)
+            cp_async4(hi + q, (q < PT) ? (g_cntp + n * PMAX + q) : (g_nmask + n * PMAX + (q - PT)));
+        cp_async_commit();
+    };
+    int4 infA = make_int4(0, 0, 0, 0), infB = infA;
+    if (nchain > 0) stage(g_chinfo[0], 0);
+    if (nchain > 1) stage(g_chinfo[1], 1);
+    if (nchain > 2) infA = g_chinfo[2];
+    if (nchain > 3) infB = g_chinfo[3];
+    int4 cur = nchain > 0 ? g_chinfo[0] : infA, nxt = nchain > 1 ? g_chinfo[1] : infA;
+    for (int i = 0; i < nchain; ++i) {
+        if (i + 2 < nchain) { stage(infA, (i + 2) % NSTAGE); cp_async_wait<2>(); }
+        else if (i + 1 < nchain) cp_async_wait<1>();
+        else cp_async_wait<0>();
+        __syncwarp();
+        const int4 after = infA;
+        infA = infB;
+        if (i + 4 < nchain) infB = g_chinfo[i + 4];
+        const int buf = i % NSTAGE;
+        const int n = cur.x, beg = cur.y, len = cur.z;
+        const double mu_n = shd[buf * HD];
+        const int* hi = reinterpret_cast<const int*>(shd + buf * HD + 1);
+        if (len <= RC)
+            sweep_row<PT>(rc, n, beg, len, true, mu_n, hi, hi + PT, scp + buf * RC, scs + buf * RC, slo + buf * RC, sigma,
+                          thr, minspk, gate, pred);
+        else
+            sweep_row<PT>(rc, n, beg, len, true, mu_n, hi, hi + PT, g_colpw + beg, const_cast<double*>(g_cst) + beg,
+                          g_lam + beg, sigma, thr, minspk, gate, pred);
+        cur = nxt;
+        nxt = after;
+    }
+}
+
+// PRNG work for one iteration, done by ONE warp: shuffle sub-keys, the N per-neuron sample keys
+// (key, key_next = split(key), caviar.py:209) and the key the next iteration starts from (caviar.py:251,304).
+__device__ __noinline__ void rng_iteration(int N, int rounds, uint32_t& k0, uint32_t& k1, uint32_t* keys_out, uint32_t* subkeys) {
+    const int lane = threadIdx.x & 31;
+    uint32_t p0 = k0, p1 = k1;
+    for (int r = 0; r < rounds; ++r) {                 // permutation(key): key, subkey = split(key) per round
+        uint32_t a, b, s0, s1;
+        warp_split(p0, p1, a, b, s0, s1);
+        p0 = a; p1 = b;
+        if (lane == 0) { subkeys[2 * r] = s0; subkeys[2 * r + 1] = s1; }
+    }
+    uint32_t c0 = k0, c1 = k1;
+    for (int m = 0; m < N; ++m) {
+        uint32_t s0, s1, n0, n1;
+        warp_split(c0, c1, s0, s1, n0, n1);
+        if (lane == 0) { keys_out[2 * m] = s0; keys_out[2 * m + 1] = s1; }
+        c0 = n0; c1 = n1;
+    }
+    uint32_t a, b, n0, n1;
+    warp_split(c0, c1, a, b, n0, n1);                  // update_phi returns split(key)[1]
+    k0 = n0; k1 = n1;
+}
+
+// ------------------------------------------------------------------------------------------------ a7
+__device__ __forceinline__ double group_loglik(double f, double cnt, double S, double n0, double n1) {
+    if (cnt == 0.0) return 0.0;
+    if (f != f) return 0.0;                                   // nan_to_num(nan) = 0
+    if (f == 1.0) return -DBL_MAX * (cnt - n1);               // lam<1 elements are -inf -> -DBL_MAX each
+    if (f == 0.0) return -DBL_MAX * (cnt - n0);
+    return S * log(f) + (cnt - S) * log(1.0 - f);
+}
+
+constexpr int GPL = (PMAX + 1 + 3) / 4;       // power groups per lane of a quad (group 0 = untargeted trials)
+
+struct QuadStats {                             // the groups g = m, m+4, ... owned by member m of the quad
+    double pv[GPL], cnt[GPL], S[GPL], n0[GPL], n1[GPL];
+    int ng;
+};
+
+__device__ __forceinline__ double quad_sum(double v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    return v;
+}
+
+// negloglik_with_barrier (caviar.py:312-316) from per-power sufficient statistics; the power groups are spread over
+// the 4 lanes of a quad (one sigmoid + two logs per lane for P <= 3)
+__device__ __forceinline__ double nll_quad(const QuadStats& s, double p0, double p1, const double* prior,
+                                           const double* prec, double t) {
+    double ll = 0.0;
+#pragma unroll
+    for (int i = 0; i < GPL; ++i)
+        if (i < s.ng) {
+            const double f = sigmoid_d(p0 * s.pv[i] - p1);
+            ll += group_loglik(f, s.cnt[i], s.S[i], s.n0[i], s.n1[i]);
+        }
+    ll = quad_sum(ll);
+    const double d0 = p0 - prior[0], d1 = p1 - prior[1];
+    const double quad = 0.5 * (d0 * (prec[0] * d0 + prec[1] * d1) + d1 * (prec[2] * d0 + prec[3] * d1));
+    return -ll - (log(p0) + log(p1)) / t + quad;
+}
+
+// update_phi for the rows list[0..nlist): _laplace_approx (caviar.py:253-308), 10 damped Newton steps from the PRIOR
+// mean, covariance = H^-1 before the last step.  Eight rows per warp (one per quad); every loop is warp-convergent
+// (predicated) so the quad shuffles stay legal while rows need different numbers of backtracking steps.
+// The sigmoids of the gradient pass are reused for the objective at the current point (same inputs, same fp result).
+__device__ __noinline__ void newton_rows(const Ctx& c, const double* powers, const int* list, int nlist) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int quad = lane >> 2, mem = lane & 3;
+    const double t = 10.0, alpha = 0.25, bbeta = 0.5;
+    for (int base = wid * 8; base < nlist; base += NW * 8) {
+        const int idx = base + quad;
+        const bool live = idx < nlist;
+        const int n = live ? list[idx] : list[0];
+        QuadStats s;
+        s.ng = 0;
+        double ctot = 0.0;
+        for (int p = 0; p < c.P; ++p) ctot += (double)c.cntp[n * PMAX + p];
+#pragma unroll
+        for (int i = 0; i < GPL; ++i) {
+            const int g = mem + 4 * i;
+            s.pv[i] = 0.0; s.cnt[i] = 0.0; s.S[i] = 0.0; s.n0[i] = 0.0; s.n1[i] = 0.0;
+            if (g <= c.P) {
+                s.ng = i + 1;
+                if (g == 0) { s.cnt[i] = (double)c.K - ctot; s.n0[i] = s.cnt[i]; }
+                else {
+                    const int p = g - 1;
+                    s.pv[i] = powers[p];
+                    s.cnt[i] = (double)c.cntp[n * PMAX + p];
+                    s.S[i] = c.sp[n * PMAX + p];
+                    s.n0[i] = (double)c.n0p[n * PMAX + p];
+                    s.n1[i] = (double)c.n1p[n * PMAX + p];
+                }
+            }
+        }
+        const double prior[2] = {c.phi0[2 * n], c.phi0[2 * n + 1]};
+        const double* cov0 = c.phicov0 + 4 * n;
+        const double det0 = cov0[0] * cov0[3] - cov0[1] * cov0[2];
+        const double prec[4] = {cov0[3] / det0, -cov0[1] / det0, -cov0[2] / det0, cov0[0] / det0};
+        double p0 = prior[0], p1 = prior[1];
+        double hi[4] = {0, 0, 0, 0};
+        for (int step = 0; step < 10; ++step) {
+            double j1 = 0, j2 = 0, h11 = 0, h12 = 0, h22 = 0, ll = 0;
+#pragma unroll
+            for (int i = 0; i < GPL; ++i)
+                if (i < s.ng) {
+                    const double f = sigmoid_d(p0 * s.pv[i] - p1);
+                    const double r = s.S[i] - s.cnt[i] * f;
+                    const double w = s.cnt[i] * f * (1.0 - f);
+                    j1 -= s.pv[i] * r;
+                    j2 += r;
+                    h11 += s.pv[i] * s.pv[i] * w;
+                    h12 -= s.pv[i] * w;
+                    h22 += w;
+                    ll += group_loglik(f, s.cnt[i], s.S[i], s.n0[i], s.n1[i]);
+                }
+            j1 = quad_sum(j1); j2 = quad_sum(j2); h11 = quad_sum(h11); h12 = quad_sum(h12); h22 = quad_sum(h22);
+            ll = quad_sum(ll);
+            const double d0 = p0 - prior[0], d1 = p1 - prior[1];
+            const double quadf = 0.5 * (d0 * (prec[0] * d0 + prec[1] * d1) + d1 * (prec[2] * d0 + prec[3] * d1));
+            const double basev = -ll - (log(p0) + log(p1)) / t + quadf;
+            const double J0 = j1 + (prec[0] * d0 + prec[1] * d1) - 1.0 / (t * p0);
+            const double J1 = j2 + (prec[2] * d0 + prec[3] * d1) - 1.0 / (t * p1);
+            const double H00 = h11 + prec[0] + 1.0 / (t * p0 * p0);
+            const double H01 = h12 + prec[1];
+            const double H10 = h12 + prec[2];
+            const double H11 = h22 + prec[3] + 1.0 / (t * p1 * p1);
+            const double det = H00 * H11 - H01 * H10;
+            hi[0] = H11 / det; hi[1] = -H01 / det; hi[2] = -H10 / det; hi[3] = H00 / det;
+            const double v0 = -(hi[0] * J0 + hi[1] * J1), v1 = -(hi[2] * J0 + hi[3] * J1);
+            double stp = 1.0;
+            const double Jv = J0 * v0 + J1 * v1;
+            double lhs = nll_quad(s, p0 + stp * v0, p1 + stp * v1, prior, prec, t);
+            double rhs = basev + alpha * stp * Jv;
+            int bt = 0;
+            bool go = (bt < 40) && ((lhs != lhs) || lhs > rhs);
+            while (__any_sync(0xffffffffu, go)) {
+                const double stp_try = go ? stp * bbeta : stp;
+                const double lhs_try = nll_quad(s, p0 + stp_try * v0, p1 + stp_try * v1, prior, prec, t);
+                if (go) {
+                    ++bt;
+                    stp = stp_try;
+                    lhs = lhs_try;
+                    rhs = basev + alpha * stp * Jv;
+                }
+                go = go && (bt < 40) && ((lhs != lhs) || lhs > rhs);
+            }
+            p0 += stp * v0;
+            p1 += stp * v1;
+        }
+        if (live && mem == 0) {
+            c.phi[2 * n] = p0; c.phi[2 * n + 1] = p1;
+            for (int q = 0; q < 4; ++q) c.phicov[4 * n + q] = hi[q];
+            if (c.rownz[n] == 0) {                       // all-zero rows always give the same answer: cache it
+                c.phiz[2 * n] = p0; c.phiz[2 * n + 1] = p1;
+                for (int q = 0; q < 4; ++q) c.phicovz[4 * n + q] = hi[q];
+                c.phizok[n] = 1;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ the fit
+template <int PT>
+__global__ void __launch_bounds__(NT, (NT == 512) ? 1 : 2) caviar_fit_kernel(const FitParams p) {
+    extern __shared__ __align__(16) double dyn_smem[];
+    __shared__ double red[NW + 2];
+    __shared__ double sc_shape, sc_rate, sc_spont;
+    __shared__ int sc_na, sc_flag, sc_focus;
+    __shared__ uint32_t sc_key[2];
+    __shared__ uint32_t sc_subkeys[2 * MAX_SHUFFLE_ROUNDS];
+    __shared__ double sc_powers[PMAX];
+    __shared__ long long sc_tlast;
+    __shared__ __align__(8) uint64_t sc_bar[2 * NST];
+
+    const int b = blockIdx.x;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    char* base = p.ws + (size_t)b * p.L.stride;
+    const Layout& L = p.L;
+    Ctx c;
+    c.N = p.N; c.K = p.K; c.P = p.P; c.it = 0;
+#define CM_D(name) c.name = reinterpret_cast<double*>(base + L.name)
+#define CM_I(name) c.name = reinterpret_cast<int*>(base + L.name)
+    CM_D(X); CM_D(PA); CM_D(PB); CM_D(lam); CM_D(cst); CM_D(y); CM_D(ss); CM_D(pred); CM_D(resid); CM_D(z); CM_D(mu);
+    CM_D(beta); CM_D(bvec); CM_D(dvec); CM_D(wvec); CM_D(slam); CM_D(slam2); CM_D(sp); CM_D(phibar); CM_D(phi);
+    CM_D(phicov); CM_D(phiz); CM_D(phicovz); CM_D(lamhist); CM_D(lamT); CM_D(growbuf);
+    CM_I(row_ptr); CM_I(col_ptr); CM_I(col_k); CM_I(csc_row); CM_I(csc_pos); CM_I(cntp); CM_I(n0p); CM_I(n1p);
+    CM_I(act); CM_I(ainv); CM_I(order); CM_I(order2); CM_I(pos); CM_I(rownz); CM_I(phizok); CM_I(dcnt); CM_I(dlist); CM_I(colpw); CM_I(nmask);
+#undef CM_D
+#undef CM_I
+    c.chinfo = reinterpret_cast<int4*>(base + L.chinfo);
+    c.cscq = reinterpret_cast<double2*>(base + L.cscq);
+    c.sortkeys = reinterpret_cast<uint32_t*>(base + L.sortkeys);
+    c.keys = reinterpret_cast<uint32_t*>(base + L.keys);
+    c.pw = reinterpret_cast<unsigned char*>(base + L.pw);
+    c.mask = reinterpret_cast<unsigned char*>(base + L.mask);
+    c.blocked = reinterpret_cast<unsigned char*>(base + L.blocked);
+    c.mu0 = p.mu0 + (size_t)b * p.N;
+    c.beta0 = p.beta0 + (size_t)b * p.N;
+    c.phi0 = p.phi0 + (size_t)b * p.N * 2;
+    c.phicov0 = p.phicov0 + (size_t)b * p.N * 4;
+    c.red = red;
+    c.tlast = &sc_tlast;
+    if (threadIdx.x == 0) sc_tlast = clock64();
+    c.sm = dyn_smem;
+    c.smd = p.smem_doubles;
+    const int N = c.N, K = c.K, P = c.P;
+    const cm_caviar_options& o = p.opt;
+    if (p.status[b] != 0) return;                     // prologue reported an error for this fit
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NST; ++i) { mbar_init(&sc_bar[i], 1); mbar_init(&sc_bar[NST + i], NW); }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    GemmPipe gp;
+    gp.full = sc_bar; gp.empty = sc_bar + NST; gp.seq = 0;
+    c.nnz = c.row_ptr[N];
+    const int iters = o.iters;
+    const int S = o.num_mc_samples;
+    // number of shuffle rounds of jax.random.permutation: ceil(3 ln N / ln(2^32-1))
+    int rounds = (int)ceil(3.0 * log((double)max(1, N)) / log(4294967295.0));
+    rounds = min(rounds, MAX_SHUFFLE_ROUNDS);
+    // a3 shared-memory plan: [pred (K doubles, when it fits)] [row staging of the chain warp]
+    const int kpad = (K + 1) & ~1;
+    const bool pred_smem = kpad + STAGE_DOUBLES <= c.smd;
+    double* pred = pred_smem ? c.sm : c.pred;
+    double* stage_base = pred_smem ? c.sm + kpad : c.sm;
+
+    // ---------------- init (caviar.py:28-51) ----------------
+    if (threadIdx.x < PMAX) sc_powers[threadIdx.x] = threadIdx.x < P ? p.powers[threadIdx.x] : 0.0;
+    if (threadIdx.x == 0) {
+        sc_shape = p.shape0_arr ? p.shape0_arr[b] : p.shape0;
+        sc_rate = p.rate0_arr ? p.rate0_arr[b] : p.rate0;
+        sc_spont = 0.0;
+        const unsigned long long seed = p.seeds[b];
+        sc_key[0] = (uint32_t)(seed >> 32);
+        sc_key[1] = (uint32_t)(seed & 0xffffffffull);
+    }
+    for (int k = threadIdx.x; k < K; k += NT) {
+        c.mask[k] = c.ss[k] > o.y_xcorr_thresh ? 1 : 0;
+        c.z[k] = 0.0;
+    }
+    for (int n = threadIdx.x; n < N; n += NT) {
+        c.phi[2 * n] = c.phi0[2 * n]; c.phi[2 * n + 1] = c.phi0[2 * n + 1];
+        for (int q = 0; q < 4; ++q) c.phicov[4 * n + q] = c.phicov0[4 * n + q];
+        c.phizok[n] = 0;
+        c.mu[n] = c.mu0[n]; c.beta[n] = c.beta0[n];
+    }
+    __syncthreads();
+    for (int n = threadIdx.x; n < N; n += NT) {       // lam0 = 0.95 [I>0] lam_mask: every indexed entry is unmasked
+        const int len = c.row_ptr[n + 1] - c.row_ptr[n];
+        c.slam[n] = 0.95 * len; c.slam2[n] = 0.95 * 0.95 * len; c.rownz[n] = len;
+    }
+    for (int j = threadIdx.x; j < c.nnz; j += NT) c.lam[j] = 0.95;
+    __syncthreads();
+    for (int i = threadIdx.x; i < c.nnz; i += NT) c.lamT[i] = c.lam[c.csc_pos[i]];
+    double sumy = 0.0, ysq = 0.0;
+    for (int k = threadIdx.x; k < K; k += NT) { const double v = c.y[k]; sumy += v; ysq += v * v; }
+    sumy = block_sum(sumy, red);
+    ysq = block_sum(ysq, red) + 1e-5;
+    // PRNG stream for iteration 0
+    uint32_t rk0 = sc_key[0], rk1 = sc_key[1];
+    if (wid == NW - 1) rng_iteration(N, rounds, rk0, rk1, c.keys, sc_subkeys);
+    __syncthreads();
+    phase_mark(c, 15);
+
+    for (int it = 0; it < iters; ++it) {
+        c.it = it;
+        const double sigma = sc_shape / sc_rate;
+        // ================= a2: block_update_mu =================
+        phase_a2(c, sigma, &sc_na, gp);
+        // ================= a3: update_lam =================
+        uint32_t* keys_cur = c.keys + (size_t)(it & 1) * 2 * N;
+        uint32_t* keys_nxt = c.keys + (size_t)((it + 1) & 1) * 2 * N;
+        // update order: permutation(key, N) by `rounds` stable sorts on fresh 32-bit keys (caviar.py:196)
+        for (int n = threadIdx.x; n < N; n += NT) c.order[n] = n;
+        __syncthreads();
+        for (int r = 0; r < rounds; ++r) {
+            const uint32_t s0 = sc_subkeys[2 * r], s1 = sc_subkeys[2 * r + 1];
+            const int h = (N + 1) / 2;
+            for (int q = threadIdx.x; q < h; q += NT) {
+                uint32_t x0 = (uint32_t)q, x1 = (h + q < N) ? (uint32_t)(h + q) : 0u;
+                threefry2x32(s0, s1, x0, x1);
+                c.sortkeys[q] = x0;
+                if (h + q < N) c.sortkeys[h + q] = x1;
+            }
+            __syncthreads();
+            for (int i = threadIdx.x; i < N; i += NT) {
+                const uint32_t ki = c.sortkeys[i];
+                int rank = 0;
+                for (int j = 0; j < N; ++j) {
+                    const uint32_t kj = c.sortkeys[j];
+                    rank += (kj < ki) || (kj == ki && j < i);
+                }
+                c.order2[rank] = c.order[i];
+            }
+            __syncthreads();
+            for (int n = threadIdx.x; n < N; n += NT) c.order[n] = c.order2[n];
+            __syncthreads();
+        }
+        for (int m = threadIdx.x; m < N; m += NT) c.pos[c.order[m]] = m;
+        __syncthreads();
+        phase_mark(c, 7);
+        // Rows that are all-zero with mu == 0 and cannot reach minimum_spike_count are rejected again whatever the
+        // samples are: est_k <= sigmoid((m0 + 8.3 s0) Imax - sigma beta^2 / 2) because the truncated-normal samples
+        // obey phi_0 <= m0 + ndtri(1 - 2^-53) s0 and phi_1 >= 0.  Their row stays zero -> no work at all (exact).
+        {
+            const bool gate_on = it > o.delay_spont_est;
+            const double imax = sc_powers[P - 1];
+            for (int n = threadIdx.x; n < N; n += NT) {
+                int skip = 0;
+                if (gate_on && c.rownz[n] == 0 && c.mu[n] == 0.0) {
+                    const double m0 = c.phi[2 * n], s0 = c.phicov[4 * n], be = c.beta[n];
+                    const double len = (double)(c.row_ptr[n + 1] - c.row_ptr[n]);
+                    if (s0 > 0.0 && m0 == m0) {
+                        const double xmax = (m0 + 8.3 * s0) * imax - 0.5 * sigma * be * be;
+                        const double ub = len * sigmoid_d(xmax) * (1.0 + 1e-9);
+                        skip = (ub < o.minimum_spike_count) ? 1 : 0;
+                    }
+                    if (len == 0.0) skip = 1;
+                }
+                c.dcnt[n] = skip;
+            }
+        }
+        __syncthreads();
+        // Monte-Carlo means of the truncated-normal sigmoid coefficients (caviar.py:209-215, App. A.2)
+        for (int n = wid; n < N; n += NW) {
+            if (c.dcnt[n]) continue;
+            const int m = c.pos[n];
+            const uint32_t k0 = keys_cur[2 * m], k1 = keys_cur[2 * m + 1];
+            const int cc = lane & 1;                                   // flat index e = 2 s + component
+            const double mean = c.phi[2 * n + cc];
+            const double sd = c.phicov[4 * n + 3 * cc];                // diag(phi_cov): a variance used as sd
+            const double cdf0 = normcdf(-mean / sd);
+            double acc = 0.0;
+            for (int e = lane; e < 2 * S; e += 32) {
+                uint32_t x0 = (uint32_t)e, x1 = (uint32_t)(2 * S + e);
+                threefry2x32(k0, k1, x0, x1);
+                const double u = bits_to_unit_double(x0, x1);
+                acc += normcdfinv(cdf0 + u * (1.0 - cdf0)) * sd + mean;
+            }
+#pragma unroll
+            for (int off = 16; off > 1; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+            if (lane < 2) c.phibar[2 * n + lane] = acc / (double)S;
+        }
+        __syncthreads();
+        phase_mark(c, 8);
+        compute_pred(c, pred);
+        __syncthreads();
+        // per-entry constant part of the sigmoid argument
+        for (int n = wid; n < N; n += NW) {
+            if (c.dcnt[n]) continue;
+            const double mu_n = c.mu[n], be = c.beta[n];
+            const double pb0 = c.phibar[2 * n], pb1 = c.phibar[2 * n + 1];
+            const double cterm = 0.5 * sigma * (mu_n * mu_n + be * be);
+            for (int j = c.row_ptr[n] + lane; j < c.row_ptr[n + 1]; j += 32) {
+                const int k = c.col_k[j];
+                const double pwv = sc_powers[c.pw[j]];
+                c.cst[j] = (pb0 * pwv - pb1 - cterm) + sigma * mu_n * c.y[k] + sigma * mu_n * mu_n * c.lam[j];
+            }
+        }
+        __syncthreads();
+        phase_mark(c, 9);
+        // chain = neurons with mu != 0 in update order; (n, row begin, row length) table for the prefetching warp
+        const int nchain = block_compact(N, [&](int m) { return c.mu[c.order[m]] != 0.0; }, c.dlist, nullptr, red);
+        for (int i = threadIdx.x; i < nchain; i += NT) {
+            const int n = c.order[c.dlist[i]];
+            c.chinfo[i] = make_int4(n, c.row_ptr[n], c.row_ptr[n + 1] - c.row_ptr[n], 0);
+        }
+        __syncthreads();
+        {
+            const double thr = o.msrmp + sc_spont;
+            const bool gate = it > o.delay_spont_est;
+            const long long role_t0 = clock64();
+            if (wid == 0) {
+                sweep_chain<PT>(c, nchain, sigma, thr, o.minimum_spike_count, gate, pred, stage_base);
+                if (g_phase_enable && blockIdx.x == 0 && lane == 0) g_phase_cycles[16] += clock64() - role_t0;
+            } else if (wid == NW - 1) {
+                if (it + 1 < iters) rng_iteration(N, rounds, rk0, rk1, keys_nxt, sc_subkeys);
+                if (g_phase_enable && blockIdx.x == 0 && lane == 0) g_phase_cycles[17] += clock64() - role_t0;
+            } else {
+                // mu == 0: the row neither reads nor changes the prediction -> order-free, run concurrently
+                for (int m = wid - 1; m < N; m += NW - 2) {
+                    const int n = c.order[m];
+                    if (c.mu[n] == 0.0 && !c.dcnt[n]) {
+                        const int beg = c.row_ptr[n], len = c.row_ptr[n + 1] - beg;
+                        sweep_row<PT>(make_rowctx(c), n, beg, len, false, 0.0, c.cntp + n * PMAX, c.nmask + n * PMAX,
+                                      c.colpw + beg, c.cst + beg, c.lam + beg, sigma, thr, o.minimum_spike_count, gate, pred);
+                    }
+                }
+                if (g_phase_enable && blockIdx.x == 0 && wid == 1 && lane == 0) g_phase_cycles[18] += clock64() - role_t0;
+            }
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int i = threadIdx.x; i < c.nnz; i += NT) c.lamT[i] = c.lam[c.csc_pos[i]];   // CSC-ordered copy of the new lam
+        __syncthreads();
+        phase_mark(c, 10);
+        // ================= a6: update_sigma (caviar.py:238-244), with a2's mu =================
+        compute_pred(c, pred);
+        __syncthreads();
+        {
+            double s1 = 0.0, s2 = 0.0, s3 = 0.0;
+            for (int k = threadIdx.x; k < K; k += NT) {
+                const double r = c.y[k] - pred[k];
+                c.resid[k] = r;
+                s1 += r * r;
+            }
+            for (int n = threadIdx.x; n < N; n += NT) {
+                const double m = c.mu[n], be = c.beta[n];
+                s2 += m * m * c.slam2[n];
+                s3 += (m * m + be * be) * c.slam[n];
+            }
+            s1 = block_sum(s1, red); s2 = block_sum(s2, red); s3 = block_sum(s3, red);
+            if (threadIdx.x == 0) {
+                sc_shape = (p.shape0_arr ? p.shape0_arr[b] : p.shape0) + (double)K / 2.0;
+                sc_rate = (p.rate0_arr ? p.rate0_arr[b] : p.rate0) + 0.5 * (s1 - s2 + s3);
+            }
+        }
+        __syncthreads();
+        phase_mark(c, 11);
+        // ================= a7: update_phi (caviar.py:246-310) =================
+        {
+            const int nl = block_compact(N, [&](int n) { return !(c.rownz[n] == 0 && c.phizok[n]); }, c.dlist, nullptr, red);
+            for (int n = threadIdx.x; n < N; n += NT)
+                if (c.rownz[n] == 0 && c.phizok[n]) {
+                    c.phi[2 * n] = c.phiz[2 * n]; c.phi[2 * n + 1] = c.phiz[2 * n + 1];
+                    for (int q = 0; q < 4; ++q) c.phicov[4 * n + q] = c.phicovz[4 * n + q];
+                }
+            if (nl > 0) newton_rows(c, sc_powers, c.dlist, nl);
+        }
+        __syncthreads();
+        phase_mark(c, 12);
+        // ================= a8: estimate_spont_act_soft_thresh (caviar.py:146-163, 86-88) =================
+        for (int k = threadIdx.x; k < K; k += NT) {
+            unsigned char bl = 0;
+            for (int i = c.col_ptr[k]; i < c.col_ptr[k + 1]; ++i) bl |= (c.lamT[i] >= o.spont_orthogonality);
+            c.blocked[k] = bl;
+        }
+        __syncthreads();
+        {
+            double err = sumy, pen = o.penalty;
+            int j = it;
+            while (j < o.max_backtrack_iters && err > o.tol) {
+                double e = 0.0;
+                for (int k = threadIdx.x; k < K; k += NT) {
+                    const double r = c.resid[k];
+                    double zz = (r < pen) ? 0.0 : r - pen;
+                    zz = zz < 0.0 ? 0.0 : zz;
+                    if (c.blocked[k]) zz = 0.0;
+                    zz *= (double)c.mask[k];
+                    c.z[k] = zz;
+                    const double d = r - zz;
+                    e += d * d;
+                }
+                err = block_sum(e, red) / ysq;
+                ++j;
+                pen *= o.scale_factor;
+            }
+            int nzz = 0;
+            for (int k = threadIdx.x; k < K; k += NT) nzz += (c.z[k] != 0.0);
+            nzz = block_sum_int(nzz, red);
+            if (threadIdx.x == 0) sc_spont = (double)nzz / (double)K;
+        }
+        __syncthreads();
+        phase_mark(c, 13);
+        // ================= histories (caviar.py:90-92) =================
+        if (o.save_histories) {
+            const size_t hb = (size_t)b * iters + it;
+            if (p.mu_hist) for (int n = threadIdx.x; n < N; n += NT) p.mu_hist[hb * N + n] = c.mu[n];
+            if (p.beta_hist) for (int n = threadIdx.x; n < N; n += NT) p.beta_hist[hb * N + n] = c.beta[n];
+            if (p.phi_hist) for (int n = threadIdx.x; n < 2 * N; n += NT) p.phi_hist[hb * 2 * N + n] = c.phi[n];
+            if (p.phicov_hist) for (int n = threadIdx.x; n < 4 * N; n += NT) p.phicov_hist[hb * 4 * N + n] = c.phicov[n];
+            if (p.z_hist) for (int k = threadIdx.x; k < K; k += NT) p.z_hist[hb * K + k] = c.z[k];
+            if (threadIdx.x == 0) {
+                if (p.shape_hist) p.shape_hist[hb] = sc_shape;
+                if (p.rate_hist) p.rate_hist[hb] = sc_rate;
+            }
+            if (p.lamhist) for (int j = threadIdx.x; j < c.nnz; j += NT) c.lamhist[(size_t)it * c.nnz + j] = c.lam[j];
+            __syncthreads();
+        }
+    }
+
+    // ================= a9: reconnect_spont_cells (caviar.py:102-144) + final update_phi (caviar.py:98) =================
+    if (o.fn_scan) {
+        // disconnected cells in ascending order; per-cell count of spontaneous events on its stimulated trials
+        const int nd = block_compact(N, [&](int i) { return c.mu[i] == 0.0; }, c.dlist, nullptr, red);
+        int* alive = c.order2;               // 1 while the cell is still a candidate
+        for (int i = threadIdx.x; i < nd; i += NT) alive[i] = 1;
+        for (int n = threadIdx.x; n < N; n += NT) c.pos[n] = 0;      // "row changed" flags for the final update_phi
+        __syncthreads();
+        int remaining = nd;
+        bool recount = true;
+        while (remaining > 0) {
+            int nzz = 0;
+            for (int k = threadIdx.x; k < K; k += NT) nzz += (c.z[k] != 0.0);
+            nzz = block_sum_int(nzz, red);
+            if (!((double)nzz > o.minimum_spike_count)) break;
+            if (recount) {
+                for (int i = wid; i < nd; i += NW) {
+                    if (!alive[i]) continue;
+                    const int n = c.dlist[i];
+                    int cnt = 0;
+                    for (int j = c.row_ptr[n] + lane; j < c.row_ptr[n + 1]; j += 32) cnt += (c.z[c.col_k[j]] != 0.0);
+                    cnt = warp_sum(cnt);
+                    if (lane == 0) c.dcnt[i] = cnt;
+                }
+                recount = false;
+                __syncthreads();
+            }
+            // focus = first maximum of the counts among remaining cells (np.argmax, caviar.py:117)
+            long long best = -1;
+            for (int i = threadIdx.x; i < nd; i += NT)
+                if (alive[i]) {
+                    const long long key = ((long long)c.dcnt[i] << 32) | (unsigned)(0x7fffffff - i);
+                    best = key > best ? key : best;
+                }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const long long oth = __shfl_xor_sync(0xffffffffu, best, off);
+                best = oth > best ? oth : best;
+            }
+            long long* redl = reinterpret_cast<long long*>(red);
+            __syncthreads();
+            if (lane == 0) redl[wid] = best;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                long long bb = -1;
+                for (int w = 0; w < NW; ++w) bb = redl[w] > bb ? redl[w] : bb;
+                sc_focus = 0x7fffffff - (int)(bb & 0xffffffffll);
+                sc_flag = 0;
+            }
+            __syncthreads();
+            const int fi = sc_focus;
+            const int focus = c.dlist[fi];
+            const int maxcnt = c.dcnt[fi];
+            if ((double)maxcnt < o.minimum_spike_count) break;        // no remaining cell can pass (exact shortcut)
+            if (wid == 0) {
+                int cz[PT];
+#pragma unroll
+                for (int q = 0; q < PT; ++q) cz[q] = 0;
+                for (int j = c.row_ptr[focus] + lane; j < c.row_ptr[focus + 1]; j += 32) {
+                    const bool nzv = c.z[c.col_k[j]] != 0.0;
+                    const int pw = c.pw[j];
+#pragma unroll
+                    for (int q = 0; q < PT; ++q) cz[q] += (pw == q && nzv);
+                }
+                double sr[PMAX];
+                int spike_count = 0;
+                for (int pp = 0; pp < P; ++pp) {
+                    int v = 0;
+#pragma unroll
+                    for (int q = 0; q < PT; ++q) if (q == pp) v = cz[q];
+                    v = warp_sum(v);
+                    const int cnt = c.cntp[focus * PMAX + pp];
+                    sr[pp] = cnt > 0 ? (double)v / (double)cnt : 0.0;
+                    spike_count += v;
+                }
+                const double pv = pava_last(sr, P);
+                if (pv >= o.msrmp && (double)spike_count >= o.minimum_spike_count) {
+                    // mu = mean(z[locs]), beta = sem(z[locs]) (ddof=1), lam[focus, locs] = 1, z[locs] = 0
+                    double s = 0.0;
+                    for (int j = c.row_ptr[focus] + lane; j < c.row_ptr[focus + 1]; j += 32) s += c.z[c.col_k[j]];
+                    s = warp_sum(s);
+                    const double mean = s / (double)spike_count;
+                    double q2 = 0.0;
+                    for (int j = c.row_ptr[focus] + lane; j < c.row_ptr[focus + 1]; j += 32) {
+                        const double zv = c.z[c.col_k[j]];
+                        if (zv != 0.0) q2 += (zv - mean) * (zv - mean);
+                    }
+                    q2 = warp_sum(q2);
+                    __syncwarp();
+                    for (int j = c.row_ptr[focus] + lane; j < c.row_ptr[focus + 1]; j += 32) {
+                        const int k = c.col_k[j];
+                        if (c.z[k] != 0.0) {
+                            c.lam[j] = 1.0;
+                            c.z[k] = 0.0;
+                        }
+                    }
+                    if (lane == 0) {
+                        c.mu[focus] = mean;
+                        c.beta[focus] = spike_count > 1 ? sqrt(q2 / (double)(spike_count - 1)) / sqrt((double)spike_count)
+                                                        : __longlong_as_double(0x7ff8000000000000ll);
+                        c.pos[focus] = 1;
+                        sc_flag = 1;
+                    }
+                }
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) alive[fi] = 0;
+            if (sc_flag) recount = true;
+            --remaining;
+            __syncthreads();
+        }
+        __syncthreads();
+        // rows touched by reconnection: exact statistics from the row, then the Laplace/Newton update
+        for (int n = wid; n < N; n += NW) {
+            if (!c.pos[n]) continue;
+            double accp[PT]; int c0[PT], c1[PT];
+#pragma unroll
+            for (int q = 0; q < PT; ++q) { accp[q] = 0.0; c0[q] = 0; c1[q] = 0; }
+            int nz = 0;
+            for (int j = c.row_ptr[n] + lane; j < c.row_ptr[n + 1]; j += 32) {
+                const double l = c.lam[j];
+                const int pw = c.pw[j];
+                nz += (l != 0.0);
+#pragma unroll
+                for (int q = 0; q < PT; ++q) {
+                    const bool m = pw == q;
+                    accp[q] += m ? l : 0.0; c0[q] += (m && l == 0.0); c1[q] += (m && l == 1.0);
+                }
+            }
+            nz = warp_sum(nz);
+            for (int pp = 0; pp < P; ++pp) {
+                double s = 0.0; int a0 = 0, a1 = 0;
+#pragma unroll
+                for (int q = 0; q < PT; ++q) if (q == pp) { s = accp[q]; a0 = c0[q]; a1 = c1[q]; }
+                s = warp_sum(s); a0 = warp_sum(a0); a1 = warp_sum(a1);
+                if (lane == 0) { c.sp[n * PMAX + pp] = s; c.n0p[n * PMAX + pp] = a0 + c.nmask[n * PMAX + pp]; c.n1p[n * PMAX + pp] = a1; }
+            }
+            if (lane == 0) c.rownz[n] = nz;
+        }
+        __syncthreads();
+        {
+            const int nl = block_compact(N, [&](int n) { return c.pos[n] != 0; }, c.dlist, nullptr, red);
+            if (nl > 0) newton_rows(c, sc_powers, c.dlist, nl);
+        }
+        __syncthreads();
+    }
+
+    phase_mark(c, 14);
+    // ---------------- outputs ----------------
+    for (int n = threadIdx.x; n < N; n += NT) {
+        p.mu_out[(size_t)b * N + n] = c.mu[n];
+        p.beta_out[(size_t)b * N + n] = c.beta[n];
+    }
+    for (int n = threadIdx.x; n < 2 * N; n += NT) p.phi_out[(size_t)b * 2 * N + n] = c.phi[n];
+    for (int n = threadIdx.x; n < 4 * N; n += NT) p.phicov_out[(size_t)b * 4 * N + n] = c.phicov[n];
+    for (int k = threadIdx.x; k < K; k += NT) p.z_out[(size_t)b * K + k] = c.z[k];
+    if (threadIdx.x == 0) { p.shape_out[b] = sc_shape; p.rate_out[b] = sc_rate; }
+}
+
+}  // namespace CM_FITNS

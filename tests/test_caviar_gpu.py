@@ -196,3 +196,33 @@ def test_full_size_single_fit_properties():
     assert torch.all((lam >= 0) & (lam <= 1)) and torch.isfinite(out["phi"]).all()
     truth = set(np.nonzero(sim["weights"])[0]); got = set(np.nonzero(mu.cpu().numpy())[0])
     assert len(got - truth) <= 2 and len(truth & got) >= 0.75 * len(truth)     # recovers the planted connectivity
+
+
+def test_two_ctas_per_sm_variant_matches_single_fits():
+    """Batches with >= 2 fits per SM run the 8-warp CTA variant of the persistent kernel (two CTAs per SM).
+    Its results must agree with the 16-warp variant used for small batches (different reduction widths -> not bitwise)."""
+    import torch
+    from oracle import simulate as osim
+    from circuitmap_b200 import optimise
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    B = 2 * sms
+    sims = [osim.simulate_fast(N=40, K=320, H=5, seed=s) for s in range(4)]
+    powers = np.unique(sims[0]["stim_matrix"])[1:]
+    f64 = dict(dtype=torch.float64, device="cuda")
+    stim4 = torch.from_numpy(np.stack([s["stim_matrix"] for s in sims])).cuda()
+    psc4 = torch.from_numpy(np.stack([s["psc"] for s in sims])).cuda()
+    idx = torch.arange(B, device="cuda") % 4
+
+    def priors(b):
+        cov = torch.zeros(b, 40, 2, 2, **f64); cov[..., 0, 0] = 0.1; cov[..., 1, 1] = 1.0
+        phi = torch.stack([0.1 * torch.ones(b, 40, **f64), 5 * torch.ones(b, 40, **f64)], -1).contiguous()
+        return torch.zeros(b, 40, **f64), 10 * torch.ones(b, 40, **f64), 1.0, 0.1, phi, cov
+
+    big = optimise.caviar_batched(stim4[idx].contiguous(), powers, *priors(B), psc=psc4[idx].contiguous(),
+                                  seeds=[7] * B, iters=14, msrmp=0.4)
+    optimise.check_status(big)
+    small = optimise.caviar_batched(stim4, powers, *priors(4), psc=psc4, seeds=[7] * 4, iters=14, msrmp=0.4)
+    for b in (0, 1, 2, 3, 4, B - 1):
+        for nm in NAMES:
+            assert torch.equal(big["mu"][b] != 0, small["mu"][b % 4] != 0)
+            assert torch.allclose(big[nm][b], small[nm][b % 4], rtol=1e-6, atol=1e-9), (b, nm)
