@@ -153,11 +153,17 @@ def measured_peaks():
     return 6650.0, 1590.0, 1400.0, "fallback"
 
 
-def read_traffic(name):
+def read_traffic(name, units=None):
+    """DRAM bytes per launch from the committed ncu --set full capture (profiles/traffic.json), scaled linearly to
+    the number of fits / traces of this launch when the capture used a different batch size."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(p):
-        return json.load(open(p)).get(name)
-    return None
+    if not os.path.exists(p):
+        return None
+    e = json.load(open(p)).get(name)
+    if not e:
+        return None
+    per = e.get("fits_per_launch") or e.get("traces_per_launch")
+    return e["bytes_per_launch"] * (units / per if (units and per) else 1.0)
 
 
 # ----------------------------------------------------------------------------------------- CPU legs (oracle)
@@ -222,7 +228,7 @@ def workload_config(args, B):
                         "caviar %d iters%s" % (args.N, args.K, args.H, args.iters,
                                                "" if B is None else ", %d independent maps per GPU per step" % B),
             "fits_per_gpu_per_step": B, "distinct_maps": args.maps,
-            "l2_hygiene": "inputs larger than L2 (each fit reads its own 152 MB of psc+stim; >20 GB per step)",
+            "l2_hygiene": "inputs larger than L2 (each fit reads its own 152 MB of psc+stim; 45 GB per step at B=296)",
             "parallelism": "independent fits sharded over GPUs, no data-path collective"}
 
 
@@ -237,7 +243,7 @@ def main():
     ap.add_argument("--K", type=int, default=10000)
     ap.add_argument("--H", type=int, default=10)
     ap.add_argument("--iters", type=int, default=50)
-    ap.add_argument("--fits-per-gpu", type=int, default=0, help="B; default = number of SMs")
+    ap.add_argument("--fits-per-gpu", type=int, default=0, help="B; default = 2 x number of SMs (two fit CTAs per SM)")
     ap.add_argument("--maps", type=int, default=2, help="distinct synthetic maps tiled to B")
     ap.add_argument("--nwd-traces", type=int, default=20000)
     ap.add_argument("--ref-iters", type=int, default=8, help="CPU oracle iterations per step (scaled to a full fit)")
@@ -265,7 +271,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
     sms = torch.cuda.get_device_properties(dev).multi_processor_count
-    B = args.fits_per_gpu or sms
+    B = args.fits_per_gpu or 2 * sms
     N, K, H, iters = args.N, args.K, args.H, args.iters
     hbm_peak, bf16_burst, bf16_sust, peak_kind = measured_peaks()
 
@@ -331,7 +337,7 @@ def main():
     algo = algorithmic_bytes_per_fit(N, K, iters) * B
     achieved = algo / (kms / 1e3) / 1e9
     roofline = {"bound": "hbm", "kernel": "caviar_fit_kernel", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved / hbm_peak, "traffic": read_traffic("caviar_fit_kernel"),
+                "frac": achieved / hbm_peak, "traffic": read_traffic("caviar_fit_kernel", B),
                 "peak_kind": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback",
                 "kernel_ms_per_launch": kms, "algorithmic_bytes_per_launch": algo, "algorithmic_model": ALGO_NOTE,
                 "note": "kernel works on a CSR/CSC index of the design (supp(lam) within supp(stim)); achieved is the "
@@ -438,7 +444,7 @@ def main():
                           "l2_hygiene": "in+out = %.0f MB > L2" % (2 * Kt * 3600 / 1e6)},
                "ms_per_step": ms_tc,
                "roofline": {"bound": "tensor", "kernel": "nwd_forward_tc_kernel", "achieved": ach, "peak": bf16_burst,
-                            "unit": "TFLOP/s", "frac": ach / bf16_burst, "traffic": read_traffic("nwd_forward_tc_kernel"),
+                            "unit": "TFLOP/s", "frac": ach / bf16_burst, "traffic": read_traffic("nwd_forward_tc_kernel", Kt),
                             "kernel_ms_per_launch": kms_tc,
                             "peak_kind": peak_kind + " bf16 burst (MEASURED_PEAKS.json); operands are TF32 (tcgen05 "
                                                      "kind::tf32, nominal dense peak = half of bf16); 16.87 MFLOP/trace, "
