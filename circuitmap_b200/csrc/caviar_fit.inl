@@ -691,6 +691,7 @@ __device__ __forceinline__ void sweep_row(const RowCtx c, int n, int beg, int le
 #pragma unroll
         for (int p = 0; p < PT; ++p) sr[p] = __shfl_sync(0xffffffffu, mine, p);
         ok = (pava_last_reg<PT>(sr, c.P) >= thr) && (tot >= minspk);
+        if (g_phase_enable & 32) ok = true;          // debug
     }
     if (prof) { const long long t = clock64(); g_phase_cycles[22] += t - tp0; tp0 = t; }
     // second pass: commit the row, update the running prediction
@@ -700,7 +701,7 @@ __device__ __forceinline__ void sweep_row(const RowCtx c, int n, int beg, int le
     for (int q = lane; q < len; q += 32) {
         const double nw = ok ? cs[q] : 0.0;
         const double old = lo[q];
-        lam_row[q] = nw;
+        if (!(g_phase_enable & 16)) lam_row[q] = nw;
         if (chain) {
             const int k = cp[q] & 0x7ffffff;
             pred[k] = (pred[k] + muok * nw) - mu_n * old;
@@ -708,7 +709,7 @@ __device__ __forceinline__ void sweep_row(const RowCtx c, int n, int beg, int le
         sl2 += nw * nw;
     }
     sl2 = warp_sum(sl2);
-    if (lane == 0) {
+    if (lane == 0 && !(g_phase_enable & 8)) {
         int zeros = 0;
 #pragma unroll
         for (int p = 0; p < PT; ++p)
