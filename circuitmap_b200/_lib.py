@@ -47,7 +47,7 @@ class CaviarArgs(C.Structure):
 EXPORTS = ["cm_version", "cm_last_error", "cm_device_info", "cm_nwd_create", "cm_nwd_destroy", "cm_nwd_forward",
            "cm_nwd_set_precision",
            "cm_caviar_workspace_bytes", "cm_caviar_fit", "cm_last_launch_count", "cm_last_main_kernel_ms",
-           "cm_caviar_debug_phase_cycles", "cm_nwd_debug_cycles"]
+           "cm_caviar_debug_phase_cycles", "cm_nwd_debug_cycles", "cm_nwd_mt_debug_cycles", "cm_nwd_mt_debug_dump", "cm_nwd_mt_pack"]
 
 _lib = None
 

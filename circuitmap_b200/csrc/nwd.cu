@@ -331,6 +331,10 @@ extern "C" int cm_nwd_create(const float* const* tensors, int n_tensors, cm_nwd_
     cm::nwdtc::pack_tc_weights(tensors, Wtc);
     CM_CUDA_CHECK(cudaMalloc(&h->wtc_dev, Wtc.size() * sizeof(float)));
     CM_CUDA_CHECK(cudaMemcpy(h->wtc_dev, Wtc.data(), Wtc.size() * sizeof(float), cudaMemcpyHostToDevice));
+    std::vector<unsigned char> Wmt;
+    cm::nwdmt::pack_weights(tensors, Wmt);
+    CM_CUDA_CHECK(cudaMalloc(&h->wmt_dev, Wmt.size()));
+    CM_CUDA_CHECK(cudaMemcpy(h->wmt_dev, Wmt.data(), Wmt.size(), cudaMemcpyHostToDevice));
     *out = h;
     return CM_OK;
 }
@@ -339,6 +343,7 @@ extern "C" void cm_nwd_destroy(cm_nwd_t* h) {
     if (!h) return;
     cudaFree(h->w_dev);
     cudaFree(h->wtc_dev);
+    cudaFree(h->wmt_dev);
     delete h;
 }
 
@@ -363,6 +368,7 @@ extern "C" int cm_nwd_forward(cm_nwd_t* h, const void* traces_dev, int in_dtype,
     if (K == 0) return CM_OK;
     if (!h || !traces_dev || !out_dev) { set_error("cm_nwd_forward: null argument"); return CM_EINVAL; }
     cudaStream_t st = (cudaStream_t)stream;
+    if (h->precision == 2) return cm::nwdmt::launch(h, traces_dev, in_dtype, out_dev, out_dtype, K, monotone_start, y_dev, ss_dev, st);
     if (h->precision == 1) return cm::nwdtc::launch(h, traces_dev, in_dtype, out_dev, out_dtype, K, monotone_start, y_dev, ss_dev, st);
     if (in_dtype == CM_F32 && out_dtype == CM_F32) return launch_fp32<float, float>(h, traces_dev, out_dev, K, monotone_start, y_dev, ss_dev, st);
     if (in_dtype == CM_F64 && out_dtype == CM_F64) return launch_fp32<double, double>(h, traces_dev, out_dev, K, monotone_start, y_dev, ss_dev, st);
@@ -373,7 +379,23 @@ extern "C" int cm_nwd_forward(cm_nwd_t* h, const void* traces_dev, int in_dtype,
 }
 
 extern "C" int cm_nwd_set_precision(cm_nwd_t* h, int precision) {
-    if (!h || (precision != 0 && precision != 1)) { set_error("cm_nwd_set_precision: precision must be 0 (fp32) or 1 (tf32)"); return CM_EINVAL; }
+    if (!h || precision < 0 || precision > 2) { set_error("cm_nwd_set_precision: precision must be 0 (fp32), 1 (tf32) or 2 (fp16)"); return CM_EINVAL; }
     h->precision = precision;
+    return CM_OK;
+}
+
+extern "C" int cm_nwd_mt_debug_cycles(long long* out, int n, int enable) { return cm::nwdmt::debug_cycles(out, n, enable); }
+extern "C" int cm_nwd_mt_debug_dump(void* dev_buf, int stage) { return cm::nwdmt::debug_dump(dev_buf, stage); }
+
+/* test hook: the packed fp16 tap tables + biases of the multi-trace kernel (host memory, BLOB bytes) */
+extern "C" int cm_nwd_mt_pack(const float* const* tensors, int n_tensors, unsigned char* out, size_t cap, size_t* need) {
+    if (!tensors || n_tensors != CM_NWD_NUM_TENSORS) { set_error("cm_nwd_mt_pack: expected %d tensors", CM_NWD_NUM_TENSORS); return CM_EINVAL; }
+    std::vector<unsigned char> W;
+    cm::nwdmt::pack_weights(tensors, W);
+    if (need) *need = W.size();
+    if (out) {
+        if (cap < W.size()) { set_error("cm_nwd_mt_pack: buffer too small"); return CM_EINVAL; }
+        std::memcpy(out, W.data(), W.size());
+    }
     return CM_OK;
 }

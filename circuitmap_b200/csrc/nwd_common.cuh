@@ -8,7 +8,8 @@ struct cm_nwd {
     float* wtc_dev = nullptr;    // tf32-rounded weights of the 7 tensor-core layers in UMMA canonical K-major blocks
     int device = 0;
     int sm_count = 0;
-    int precision = 0;           // 0 = fp32 CUDA cores, 1 = tf32 tcgen05
+    unsigned char* wmt_dev = nullptr;   // fp16 tap tables + biases of the multi-trace tensor-core kernel (nwd_mt.cu)
+    int precision = 0;           // 0 = fp32 CUDA cores, 1 = tf32 tcgen05 (one trace per CTA), 2 = fp16 tcgen05 (multi-trace)
 };
 
 namespace cm {
@@ -18,4 +19,11 @@ void pack_tc_weights(const float* const* tensors, std::vector<float>& out);
 int launch(cm_nwd* h, const void* in, int in_dtype, void* out, int out_dtype, int K, int monotone_start, double* y,
            double* ss, cudaStream_t st);
 }  // namespace nwdtc
+namespace nwdmt {
+void pack_weights(const float* const* tensors, std::vector<unsigned char>& out);
+int launch(cm_nwd* h, const void* in, int in_dtype, void* out, int out_dtype, int K, int monotone_start, double* y,
+           double* ss, cudaStream_t st);
+int debug_cycles(long long* out, int n, int enable);
+int debug_dump(void* dev_buf, int stage);
+}  // namespace nwdmt
 }  // namespace cm

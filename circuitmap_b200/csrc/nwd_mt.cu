@@ -1,0 +1,806 @@
+// NWD demixer forward, multi-trace tensor-core kernel (sm_100a): all nine convolutions of the U-Net
+// (circuitmap/neural_waveform_demixing.py:204-287) as tcgen05.mma kind::f16 implicit GEMMs with fp32 accumulators in
+// TMEM.  See nwd_mt.cuh for the GEMM formulation.  What is different from csrc/nwd_tc.cu (one trace per CTA, TF32,
+// N = C_out = 16): G = 4 traces share each 128-row M tile, N is widened to PH x C_out = 32..128 by computing PH output
+// positions per row against a sliding tap table, and operands are fp16 (11-bit significand = TF32's precision, half
+// the shared-memory bytes, twice the MMA rate) -- ~100 MMAs per trace instead of ~1900.
+//
+// Shared memory (210 KB) holds the three concat buffers of the decoder for G traces in phase-split layout:
+//   A = dec3 [up3 | enc1], B = dec2 [up2 | enc2], C = dec1 [up1 | enc3];  the halves that are only written late in the
+//   pass (A_lo, B_lo) double as weight buffer / encoder scratch before that, C is reused for the raw decoder outputs.
+// One pass = input (normalise, pool) -> 9 x [prepare A operand on CUDA cores -> MMAs by one thread -> epilogue from
+// TMEM: bias, ReLU, fp16, next layer's layout] -> rescale, monotone filter, store.
+#include "nwd_common.cuh"
+#include "nwd_mt.cuh"
+#include <cuda_fp16.h>
+#include <cmath>
+#include <cstring>
+
+namespace cm {
+namespace nwdmt {
+
+// ------------------------------------------------------------------------------------------------ shared-memory map
+constexpr int DEC3_RL = G * 27 + 2, DEC3_PL = 16 * DEC3_RL * 16;       // u4's A: PH 16
+constexpr int DEC2_RL = G * 28 + 4, DEC2_PL = 8 * DEC2_RL * 16;        // u3's A: PH 8
+constexpr int DEC1_RL = G * 24 + 4, DEC1_PL = 4 * DEC1_RL * 16;        // u2's A: PH 4
+constexpr int A_LO = 0, A_HI = A_LO + 2 * DEC3_PL, A_END = A_LO + 4 * DEC3_PL;
+constexpr int B_LO = A_END, B_HI = B_LO + 2 * DEC2_PL, B_END = B_LO + 4 * DEC2_PL;
+constexpr int C_LO = B_END, C_END = C_LO + 6 * DEC1_PL;
+constexpr int SMEM_BYTES = C_END + 1024 + 128;                          // tail: junk rows of the last tile read past C
+
+struct AB { int off, PH, RL, Q, PAD; };        // byte offset, phases, units per phase row, units per sequence, left pad
+constexpr int X_OFF = B_LO;                                             // fp32 normalised input, G x 900
+constexpr AB AB_P1 = {B_LO + G * T * 4, 1, G * 2 * 29 + 6, 29, 0};      // d1's A: raw parity sequences, 1 plane
+constexpr AB AB_P2 = {B_LO, 8, G * 25 + 4, 25, 0};                      // 2 planes
+constexpr AB AB_P3 = {B_LO, 4, G * 20 + 4, 20, 0};                      // 2 planes
+constexpr AB AB_P4 = {B_LO, 1, G * 32 + 16, 32, 0};                     // 4 planes
+constexpr AB AB_E4 = {B_LO + 4 * (G * 32 + 16) * 16, 2, G * 24 + 8, 24, 15};   // 4 planes
+constexpr AB AB_D1 = {C_LO, 4, DEC1_RL, 24, 15};                        // 6 planes
+constexpr AB AB_D2 = {B_LO, 8, DEC2_RL, 28, 31};                        // 4 planes
+constexpr AB AB_D3 = {A_LO, 16, DEC3_RL, 27, 15};                       // 4 planes
+constexpr AB AB_FIN = {A_LO, 32, G * 2 * 12 + 4, 12, 0};                // 1 plane, 2 sequences per trace
+constexpr int RAW1_OFF = AB_E4.off + 4 * 2 * AB_E4.RL * 16;            // [g][32][16 ch] fp16
+constexpr int RAW_OFF = C_LO;                                           // raw2 [g][80][16], raw3 [g][193][16], raw4 [g][402][2 x 4]
+constexpr int OROW_OFF = C_LO, OROW_STRIDE = 928;                       // fp32, index t + 4 (t >> 7)
+constexpr int W0_OFF = A_LO;                                            // weights of d1 .. u3, one layer at a time
+constexpr int W7_OFF = B_LO;                                            // u4
+constexpr int W8_OFF = C_LO + G * L_U4H * 16;                           // fin, behind raw4
+static_assert(X_OFF + G * T * 4 + AB_P1.RL * 16 <= B_HI, "input scratch");
+static_assert(2 * 8 * AB_P2.RL * 16 <= B_HI - B_LO && RAW1_OFF + G * 32 * 32 <= B_HI, "encoder scratch");
+static_assert(lc_wbytes(6) <= A_HI - A_LO && lc_wbytes(5) <= A_HI - A_LO && 32 * AB_FIN.RL * 16 <= A_HI - A_LO, "A_lo");
+static_assert(lc_wbytes(7) <= B_HI - B_LO && W8_OFF + lc_wbytes(8) <= C_END && G * OROW_STRIDE * 4 <= C_END - C_LO, "late buffers");
+static_assert(G * L_U3 * 32 <= W8_OFF - C_LO, "raw3 must not reach the final-layer weights");
+static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46);       // version 1, no swizzle
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+                 ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0;
+    while (!ok)
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 ::"r"(smem_dst), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void proxy_fence() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+
+// D = F32, A = B = F16, both K-major, M = 128
+__host__ __device__ constexpr uint32_t idesc_f16(int n) {
+    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+// two floats -> packed fp16 pair (lo in the low half), round to nearest even, finite saturation
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ float2 unpack_h2(uint32_t u) {
+    return __half22float2(*reinterpret_cast<const __half2*>(&u));
+}
+
+__device__ long long g_mt_cycles[32];
+__device__ int g_mt_prof = 0;
+__device__ unsigned char* g_mt_dump = nullptr;     // debug: CTA 0 copies its shared memory here when it reaches mark g_mt_dump_stage
+__device__ int g_mt_dump_stage = -1;
+#define MT_MARK(id)                                                                      \
+    do {                                                                                 \
+        if (g_mt_prof && blockIdx.x == 0 && threadIdx.x == 0) {                          \
+            const long long t_ = clock64();                                              \
+            g_mt_cycles[id] += t_ - tmark;                                               \
+            tmark = t_;                                                                  \
+        }                                                                                \
+        if (g_mt_dump_stage == (id) && blockIdx.x == 0 && pass == 0) {                   \
+            __syncthreads();                                                             \
+            for (int i_ = threadIdx.x; i_ < SMEM_BYTES / 16; i_ += THREADS)              \
+                reinterpret_cast<uint4*>(g_mt_dump)[i_] = sm4[i_];                       \
+            __syncthreads();                                                             \
+        }                                                                                \
+    } while (0)
+
+// unit (16-byte) index inside an activation buffer: channel plane cp, sequence seq, padded position pp
+__device__ __forceinline__ int ab_unit(const AB b, int cp, int seq, int pp) {
+    return (cp * b.PH + pp % b.PH) * b.RL + seq * b.Q + pp / b.PH;
+}
+
+// ------------------------------------------------------------------------------------------------ MMA issue
+// All MMAs of layer L by one thread.  `abase` / `wbase` are shared-memory byte addresses of the A buffer (plane 0)
+// and of the tap table.  Descriptor start addresses advance in 16-byte units.
+template <int L, int RL>
+__device__ __forceinline__ void issue_layer(uint32_t abase, uint32_t wbase, uint32_t tmem) {
+    constexpr int PH = lcfg(L).PH, CIN = lcfg(L).CIN, COUT = lcfg(L).COUT, U = lcfg(L).UPAD, V = lc_v(L), N = lc_n(L);
+    constexpr int TILES = lc_tiles(L);
+    constexpr uint32_t idesc = idesc_f16(N);
+    if constexpr (CIN >= 16) {
+        constexpr int CQ = CIN / 16;                                       // K steps (pairs of 8-channel planes) per window position
+        const uint64_t a0 = umma_desc(abase, PH * RL * 16, 128);
+        const uint64_t b0 = umma_desc(wbase, U * COUT * 16, 128);
+#pragma unroll 1
+        for (int mt = 0; mt < TILES; ++mt) {
+            uint32_t acc = 0;
+#pragma unroll 1
+            for (int a = 0; a * PH < V; ++a) {
+#pragma unroll
+                for (int j = 0; j < PH; ++j) {
+                    const int v = a * PH + j;
+                    if (v < V) {
+#pragma unroll
+                        for (int cq = 0; cq < CQ; ++cq) {
+                            umma_f16(tmem + mt * N, a0 + (uint64_t)((2 * cq * PH + j) * RL + 128 * mt + a),
+                                     b0 + (uint64_t)((2 * cq * U + v) * COUT), idesc, acc);
+                            acc = 1;
+                        }
+                    }
+                }
+            }
+        }
+    } else if constexpr (PH == 1) {                                        // d1: K step = two consecutive units
+        const uint64_t a0 = umma_desc(abase, 16, 128);
+        const uint64_t b0 = umma_desc(wbase, COUT * 16, 128);
+#pragma unroll 1
+        for (int mt = 0; mt < TILES; ++mt)
+#pragma unroll
+            for (int v = 0; v < V; v += 2)
+                umma_f16(tmem + mt * N, a0 + (uint64_t)(128 * mt + v), b0 + (uint64_t)(v * COUT), idesc, v ? 1u : 0u);
+    } else {                                                               // fin: K step = phases j, j + 1
+        static_assert(TILES == 1, "single tile");
+        const uint64_t a0 = umma_desc(abase, RL * 16, 128);
+        const uint64_t b0 = umma_desc(wbase, COUT * 16, 128);
+#pragma unroll 1
+        for (int a = 0; a * PH < V; ++a)
+#pragma unroll 4
+            for (int j = 0; j < PH; j += 2) {
+                const int v = a * PH + j;
+                if (v < V) umma_f16(tmem, a0 + (uint64_t)(j * RL + a), b0 + (uint64_t)(v * COUT), idesc, v ? 1u : 0u);
+            }
+    }
+}
+
+struct Pipe {
+    uint64_t* bar_w;
+    uint64_t* bar_mma;
+    uint32_t wcount, mcount;        // phases consumed so far (uniform across threads)
+    uint32_t tmem;
+    uint32_t smem0;                 // shared-memory address of the dynamic buffer
+    const unsigned char* blob;
+};
+
+__device__ __forceinline__ void load_weights(const Pipe& pp, int l_off, int l_bytes, int dst_off, bool first) {
+    if (first) mbar_expect_tx(pp.bar_w, (uint32_t)l_bytes);
+    bulk_g2s(pp.smem0 + dst_off, pp.blob + l_off, (uint32_t)l_bytes, pp.bar_w);
+}
+
+// make the A operand visible to the async proxy, issue, wait for completion (all threads)
+template <int L, int RL>
+__device__ __forceinline__ void run_layer(Pipe& pp, int a_off, int w_off, bool wait_w) {
+    proxy_fence();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (threadIdx.x == 0) {
+        if (wait_w) mbar_wait(pp.bar_w, pp.wcount & 1);
+        tc_fence_after();
+        issue_layer<L, RL>(pp.smem0 + a_off, pp.smem0 + w_off, pp.tmem);
+        umma_commit(pp.bar_mma);
+    }
+    if (wait_w) pp.wcount++;
+    mbar_wait(pp.bar_mma, pp.mcount & 1);
+    pp.mcount++;
+    tc_fence_after();
+}
+
+// ------------------------------------------------------------------------------------------------ CUDA-core passes
+__device__ __forceinline__ uint4 avg3_units(uint4 a, uint4 b, uint4 c) {
+    uint4 r;
+    const uint32_t* pa = &a.x; const uint32_t* pb = &b.x; const uint32_t* pc = &c.x; uint32_t* pr = &r.x;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 fa = unpack_h2(pa[i]), fb = unpack_h2(pb[i]), fc = unpack_h2(pc[i]);
+        pr[i] = pack_h2((fa.x + fb.x + fc.x) / 3.0f, (fa.y + fb.y + fc.y) / 3.0f);
+    }
+    return r;
+}
+__device__ __forceinline__ uint4 lerp_units(uint4 a, uint4 b, float l0, float l1) {
+    uint4 r;
+    const uint32_t* pa = &a.x; const uint32_t* pb = &b.x; uint32_t* pr = &r.x;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 fa = unpack_h2(pa[i]), fb = unpack_h2(pb[i]);
+        pr[i] = pack_h2(l0 * fa.x + l1 * fb.x, l0 * fa.y + l1 * fb.y);
+    }
+    return r;
+}
+
+// AvgPool1d(3, 2) (nwd.py:210) of the encoder half (planes PL0..) of a concat buffer into the next layer's A buffer.
+// Covers every unit of the destination (zero outside the valid range, so that whatever a valid GEMM row reads is finite).
+template <int NPL>
+__device__ __forceinline__ void pool_pass(unsigned char* smem, const AB src, int src_pl0, const AB dst, int Lout) {
+    const uint4* s = reinterpret_cast<const uint4*>(smem + src.off);
+    uint4* d = reinterpret_cast<uint4*>(smem + dst.off);
+    const int total = NPL * dst.PH * dst.RL;
+    for (int idx = threadIdx.x; idx < total; idx += THREADS) {
+        const int r = idx % dst.RL, cj = idx / dst.RL, j = cj % dst.PH, cp = cj / dst.PH;
+        const int g = r / dst.Q, t = (r % dst.Q) * dst.PH + j;
+        uint4 o = make_uint4(0, 0, 0, 0);
+        if (g < G && t < Lout) {
+            const int p0 = 2 * t + src.PAD;
+            o = avg3_units(s[ab_unit(src, src_pl0 + cp, g, p0)], s[ab_unit(src, src_pl0 + cp, g, p0 + 1)],
+                           s[ab_unit(src, src_pl0 + cp, g, p0 + 2)]);
+        }
+        d[idx] = o;
+    }
+}
+
+// F.interpolate(linear, align_corners=False) (nwd.py:237-238) of a raw decoder output [g][Lin][16 ch] into planes 0..1
+// of a concat buffer; covers every unit of the two planes (zero in the pads).
+__device__ __forceinline__ void interp_pass(unsigned char* smem, int raw_off, int Lin, const AB dst, int Lout) {
+    const uint4* s = reinterpret_cast<const uint4*>(smem + raw_off);
+    uint4* d = reinterpret_cast<uint4*>(smem + dst.off);
+    const float scale = (float)Lin / (float)Lout;
+    const int total = 2 * dst.PH * dst.RL;
+    for (int idx = threadIdx.x; idx < total; idx += THREADS) {
+        const int r = idx % dst.RL, cj = idx / dst.RL, j = cj % dst.PH, cp = cj / dst.PH;
+        const int g = r / dst.Q, t = (r % dst.Q) * dst.PH + j - dst.PAD;
+        uint4 o = make_uint4(0, 0, 0, 0);
+        if (g < G && t >= 0 && t < Lout) {
+            float src = scale * ((float)t + 0.5f) - 0.5f;
+            src = src < 0.f ? 0.f : src;
+            int i0 = (int)src;
+            i0 = i0 < Lin - 1 ? i0 : Lin - 1;
+            const int i1 = i0 + (i0 < Lin - 1 ? 1 : 0);
+            const float l1 = fminf(fmaxf(src - (float)i0, 0.f), 1.f), l0 = 1.f - l1;
+            o = lerp_units(s[(g * Lin + i0) * 2 + cp], s[(g * Lin + i1) * 2 + cp], l0, l1);
+        }
+        d[idx] = o;
+    }
+}
+
+// 16 accumulator columns -> bias, ReLU, fp16: two 16-byte units (channels 0..7, 8..15 of the chunk)
+__device__ __forceinline__ void finish16(const uint32_t* v, const float* bias, uint4& u0, uint4& u1) {
+    float f[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) f[i] = fmaxf(__uint_as_float(v[i]) + bias[i], 0.f);
+    u0 = make_uint4(pack_h2(f[0], f[1]), pack_h2(f[2], f[3]), pack_h2(f[4], f[5]), pack_h2(f[6], f[7]));
+    u1 = make_uint4(pack_h2(f[8], f[9]), pack_h2(f[10], f[11]), pack_h2(f[12], f[13]), pack_h2(f[14], f[15]));
+}
+
+template <typename TIn, typename TOut>
+__global__ void __launch_bounds__(THREADS, 1)
+nwd_forward_mt_kernel(const unsigned char* __restrict__ blob, const TIn* __restrict__ traces, TOut* __restrict__ outp, int K,
+                      int monotone_start, double* __restrict__ y_out, double* __restrict__ ss_out) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) uint64_t bars[2];
+    __shared__ uint32_t tmem_base_s;
+    __shared__ float bias_s[NLAYER][32];
+    __shared__ double red_max[THREADS / 32], red_amax[THREADS / 32], red_s1[THREADS / 32], red_s2[THREADS / 32];
+    __shared__ int red_bad[THREADS / 32];
+    __shared__ double tmax_s[G];
+    __shared__ int bad_s[G];
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int lq = wid & 3, cgp = wid >> 2;                 // TMEM lane quadrant of this warp, column group
+    const int row = 32 * lq + lane;                         // accumulator row (TMEM lane) this thread reads
+    uint4* sm4 = reinterpret_cast<uint4*>(smem);
+
+    for (int i = threadIdx.x; i < SMEM_BYTES / 16; i += THREADS) sm4[i] = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < NLAYER * 32; i += THREADS)
+        bias_s[i / 32][i % 32] = reinterpret_cast<const float*>(blob + BIAS_OFF)[i];
+    if (threadIdx.x == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    if (wid == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_s)), "r"(256u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+    }
+    proxy_fence();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    Pipe pp;
+    pp.bar_w = &bars[0]; pp.bar_mma = &bars[1]; pp.wcount = 0; pp.mcount = 0; pp.tmem = tmem_base_s;
+    pp.smem0 = smem_u32(smem); pp.blob = blob;
+    const int npass = (K + G - 1) / G;
+    if (threadIdx.x == 0 && (int)blockIdx.x < npass) load_weights(pp, lc_woff(0), lc_wbytes(0), W0_OFF, true);
+
+    long long tmark = clock64();
+    for (int pass = blockIdx.x; pass < npass; pass += gridDim.x) {
+        const int k0 = pass * G;
+        const bool more = pass + (int)gridDim.x < npass;
+        // ---- input: per-trace max (nwd.py:43), normalise, AvgPool -> parity sequences of the pooled trace (d1's A) ----
+        {
+            const int g = wid >> 2, k = k0 + g;
+            const bool act = k < K;
+            const TIn* tr = traces + (size_t)(act ? k : 0) * T;
+            TIn v[8];
+            double mx = -INFINITY, amx = 0.0;
+            int bad = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int t = lq * 32 + lane + 128 * i;
+                v[i] = (act && t < T) ? tr[t] : (TIn)0;
+                if (t < T) {
+                    mx = fmax(mx, (double)v[i]);
+                    const double a = fabs((double)v[i]);
+                    bad |= !(a <= 1e300);
+                    amx = fmax(amx, a);
+                }
+            }
+            mx = warp_max(mx);
+            amx = warp_max(amx);
+            bad = __any_sync(0xffffffffu, bad);
+            if (lane == 0) { red_max[wid] = mx; red_amax[wid] = amx; red_bad[wid] = bad; }
+            __syncthreads();
+            double tmax = fmax(fmax(red_max[4 * g], red_max[4 * g + 1]), fmax(red_max[4 * g + 2], red_max[4 * g + 3]));
+            const double am = fmax(fmax(red_amax[4 * g], red_amax[4 * g + 1]), fmax(red_amax[4 * g + 2], red_amax[4 * g + 3]));
+            int isbad = red_bad[4 * g] | red_bad[4 * g + 1] | red_bad[4 * g + 2] | red_bad[4 * g + 3];
+            isbad |= !(tmax != 0.0) || !(am <= 60000.0 * fabs(tmax));     // fp16 operand range: |x / tmax| must stay finite
+            if (!act) { tmax = 1.0; isbad = 0; }
+            if (lq == 0 && lane == 0) { tmax_s[g] = tmax; bad_s[g] = isbad; }
+            float* X = reinterpret_cast<float*>(smem + X_OFF) + g * T;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int t = lq * 32 + lane + 128 * i;
+                if (t < T) X[t] = isbad ? 0.f : (float)(v[i] / (TIn)tmax);
+            }
+        }
+        __syncthreads();
+        {
+            const float* X = reinterpret_cast<const float*>(smem + X_OFF);
+            for (int u = threadIdx.x; u < AB_P1.RL; u += THREADS) {
+                const int seq = u / 29, sg = u % 29;                 // seq = 2 g + parity
+                uint32_t h[4] = {0, 0, 0, 0};
+                if (seq < 2 * G) {
+                    const float* xg = X + (seq >> 1) * T;
+                    const int p = seq & 1;
+                    float f[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int pu = 2 * (8 * sg + i) + p;         // pooled index
+                        f[i] = pu < L_P1 ? (xg[2 * pu] + xg[2 * pu + 1] + xg[2 * pu + 2]) / 3.0f : 0.f;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) h[i] = pack_h2(f[2 * i], f[2 * i + 1]);
+                }
+                reinterpret_cast<uint4*>(smem + AB_P1.off)[u] = make_uint4(h[0], h[1], h[2], h[3]);
+            }
+            // dec1 is scratch for the raw decoder outputs of the previous pass: restore its zero pads
+            uint4* c4 = reinterpret_cast<uint4*>(smem + C_LO);
+            for (int i = threadIdx.x; i < (C_END - C_LO) / 16; i += THREADS) c4[i] = make_uint4(0, 0, 0, 0);
+        }
+        MT_MARK(0);
+        // ---- d1: 1 -> 16, k 32, dilation 2 (nwd.py:259): rows = groups of 8 outputs of one parity sequence ----
+        run_layer<0, AB_P1.RL>(pp, AB_P1.off, W0_OFF, true);
+        if (threadIdx.x == 0) load_weights(pp, lc_woff(1), lc_wbytes(1), W0_OFF, true);
+        MT_MARK(1);
+        {
+            uint4* d3 = reinterpret_cast<uint4*>(smem + AB_D3.off);
+#pragma unroll 1
+            for (int mt = 0; mt < 2; ++mt) {
+                const int rho = 128 * mt + row, seq = rho / 29, sg = rho % 29, p = seq & 1;
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const int m = cgp + 4 * c;                       // sub-position = column chunk
+                    uint32_t v[16];
+                    tmem_ld16(pp.tmem + mt * 128 + m * 16 + ((uint32_t)(32 * lq) << 16), v);
+                    tmem_ld_wait();
+                    const int t = 2 * (8 * sg + m) + p;
+                    if (seq < 2 * G && t < L_E1) {
+                        uint4 u0, u1;
+                        finish16(v, bias_s[0], u0, u1);
+                        d3[ab_unit(AB_D3, 2, seq >> 1, t + AB_D3.PAD)] = u0;
+                        d3[ab_unit(AB_D3, 3, seq >> 1, t + AB_D3.PAD)] = u1;
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+        __syncthreads();
+        MT_MARK(2);
+        // ---- d2: 16 -> 16, k 32 ----
+        pool_pass<2>(smem, AB_D3, 2, AB_P2, L_P2);
+        MT_MARK(3);
+        run_layer<1, AB_P2.RL>(pp, AB_P2.off, W0_OFF, true);
+        if (threadIdx.x == 0) load_weights(pp, lc_woff(2), lc_wbytes(2), W0_OFF, true);
+        MT_MARK(4);
+        {
+            uint4* d2 = reinterpret_cast<uint4*>(smem + AB_D2.off);
+            const int g = row / 25, q = row % 25;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const int n = cgp + 4 * c;
+                uint32_t v[16];
+                tmem_ld16(pp.tmem + n * 16 + ((uint32_t)(32 * lq) << 16), v);
+                tmem_ld_wait();
+                const int t = 8 * q + 7 - n;
+                if (g < G && t < L_E2) {
+                    uint4 u0, u1;
+                    finish16(v, bias_s[1], u0, u1);
+                    d2[ab_unit(AB_D2, 2, g, t + AB_D2.PAD)] = u0;
+                    d2[ab_unit(AB_D2, 3, g, t + AB_D2.PAD)] = u1;
+                }
+            }
+        }
+        tc_fence_before();
+        __syncthreads();
+        MT_MARK(5);
+        // ---- d3: 16 -> 32, k 16 ----
+        pool_pass<2>(smem, AB_D2, 2, AB_P3, L_P3);
+        run_layer<2, AB_P3.RL>(pp, AB_P3.off, W0_OFF, true);
+        if (threadIdx.x == 0) load_weights(pp, lc_woff(3), lc_wbytes(3), W0_OFF, true);
+        {
+            uint4* d1 = reinterpret_cast<uint4*>(smem + AB_D1.off);
+            const int g = row / 20, q = row % 20;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const int kc = cgp + 4 * c, n = kc >> 1, hf = kc & 1;   // chunk = (phase n, channel half)
+                uint32_t v[16];
+                tmem_ld16(pp.tmem + kc * 16 + ((uint32_t)(32 * lq) << 16), v);
+                tmem_ld_wait();
+                const int t = 4 * q + 3 - n;
+                if (g < G && t < L_E3) {
+                    uint4 u0, u1;
+                    finish16(v, bias_s[2] + 16 * hf, u0, u1);
+                    d1[ab_unit(AB_D1, 2 + 2 * hf, g, t + AB_D1.PAD)] = u0;
+                    d1[ab_unit(AB_D1, 3 + 2 * hf, g, t + AB_D1.PAD)] = u1;
+                }
+            }
+        }
+        tc_fence_before();
+        __syncthreads();
+        MT_MARK(6);
+        // ---- d4: 32 -> 32, k 16 ----
+        pool_pass<4>(smem, AB_D1, 2, AB_P4, L_P4);
+        for (int i = threadIdx.x; i < 4 * 2 * AB_E4.RL; i += THREADS)     // zero pads of u1's input (region held P2 / P3 before)
+            reinterpret_cast<uint4*>(smem + AB_E4.off)[i] = make_uint4(0, 0, 0, 0);
+        run_layer<3, AB_P4.RL>(pp, AB_P4.off, W0_OFF, true);
+        if (threadIdx.x == 0) load_weights(pp, lc_woff(4), lc_wbytes(4), W0_OFF, true);
+        if (cgp < 2) {
+            uint4* e4 = reinterpret_cast<uint4*>(smem + AB_E4.off);
+            const int g = row / 32, t = row % 32;
+            uint32_t v[16];
+            tmem_ld16(pp.tmem + cgp * 16 + ((uint32_t)(32 * lq) << 16), v);
+            tmem_ld_wait();
+            if (t < L_E4) {
+                uint4 u0, u1;
+                finish16(v, bias_s[3] + 16 * cgp, u0, u1);
+                e4[ab_unit(AB_E4, 2 * cgp, g, t + AB_E4.PAD)] = u0;
+                e4[ab_unit(AB_E4, 2 * cgp + 1, g, t + AB_E4.PAD)] = u1;
+            }
+        }
+        tc_fence_before();
+        __syncthreads();
+        MT_MARK(7);
+        // ---- u1: ConvTranspose 32 -> 16, k 16 (valid convolution over the zero-padded input, flipped taps) ----
+        run_layer<4, AB_E4.RL>(pp, AB_E4.off, W0_OFF, true);
+        if (threadIdx.x == 0) load_weights(pp, lc_woff(5), lc_wbytes(5), W0_OFF, true);
+        if (cgp < 2) {
+            uint4* raw = reinterpret_cast<uint4*>(smem + RAW1_OFF);
+            const int g = row / 24, q = row % 24, n = cgp;
+            uint32_t v[16];
+            tmem_ld16(pp.tmem + n * 16 + ((uint32_t)(32 * lq) << 16), v);
+            tmem_ld_wait();
+            const int t = 2 * q + 1 - n;
+            if (g < G && t < L_U1) {
+                uint4 u0, u1;
+                finish16(v, bias_s[4], u0, u1);
+                raw[(g * L_U1 + t) * 2] = u0;
+                raw[(g * L_U1 + t) * 2 + 1] = u1;
+            }
+        }
+        tc_fence_before();
+        __syncthreads();
+        interp_pass(smem, RAW1_OFF, L_U1, AB_D1, L_E3);
+        MT_MARK(8);
+        // ---- u2: 48 -> 16, k 16 ----
+        run_layer<5, AB_D1.RL>(pp, AB_D1.off, W0_OFF, true);
+        if (threadIdx.x == 0) load_weights(pp, lc_woff(6), lc_wbytes(6), W0_OFF, true);
+        {
+            uint4* raw = reinterpret_cast<uint4*>(smem + RAW_OFF);
+            const int g = row / 24, q = row % 24, n = cgp;
+            uint32_t v[16];
+            tmem_ld16(pp.tmem + n * 16 + ((uint32_t)(32 * lq) << 16), v);
+            tmem_ld_wait();
+            const int t = 4 * q + 3 - n;
+            if (g < G && t < L_U2) {
+                uint4 u0, u1;
+                finish16(v, bias_s[5], u0, u1);
+                raw[(g * L_U2 + t) * 2] = u0;
+                raw[(g * L_U2 + t) * 2 + 1] = u1;
+            }
+        }
+        tc_fence_before();
+        __syncthreads();
+        interp_pass(smem, RAW_OFF, L_U2, AB_D2, L_E2);
+        MT_MARK(9);
+        // ---- u3: 32 -> 16, k 32 ----
+        run_layer<6, AB_D2.RL>(pp, AB_D2.off, W0_OFF, true);
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(pp.bar_w, (uint32_t)(lc_wbytes(7) + lc_wbytes(8)));
+            load_weights(pp, lc_woff(7), lc_wbytes(7), W7_OFF, false);
+            load_weights(pp, lc_woff(8), lc_wbytes(8), W8_OFF, false);
+        }
+        MT_MARK(10);
+        {
+            uint4* raw = reinterpret_cast<uint4*>(smem + RAW_OFF);
+            const int g = row / 28, q = row % 28;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const int n = cgp + 4 * c;
+                uint32_t v[16];
+                tmem_ld16(pp.tmem + n * 16 + ((uint32_t)(32 * lq) << 16), v);
+                tmem_ld_wait();
+                const int t = 8 * q + 7 - n;
+                if (g < G && t < L_U3) {
+                    uint4 u0, u1;
+                    finish16(v, bias_s[6], u0, u1);
+                    raw[(g * L_U3 + t) * 2] = u0;
+                    raw[(g * L_U3 + t) * 2 + 1] = u1;
+                }
+            }
+        }
+        tc_fence_before();
+        __syncthreads();
+        MT_MARK(11);
+        interp_pass(smem, RAW_OFF, L_U3, AB_D3, L_E1);
+        MT_MARK(12);
+        // ---- u4: ConvTranspose 32 -> 4, k 32, stride 2: output channels (parity, co) over input positions ----
+        run_layer<7, AB_D3.RL>(pp, AB_D3.off, W7_OFF, true);
+        MT_MARK(13);
+        {
+            uint4* raw = reinterpret_cast<uint4*>(smem + RAW_OFF);
+            const int g = row / 27, q = row % 27;
+            float bb[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) bb[i] = bias_s[7][i & 3];
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const int kc = cgp + 4 * c;                          // phases n = 2 kc, 2 kc + 1
+                uint32_t v[16];
+                tmem_ld16(pp.tmem + kc * 16 + ((uint32_t)(32 * lq) << 16), v);
+                tmem_ld_wait();
+                uint4 u0, u1;
+                finish16(v, bb, u0, u1);
+                const int i0 = 16 * q + 15 - 2 * kc, i1 = i0 - 1;   // input positions of the two phases
+                if (g < G && i0 < L_U4H) raw[g * L_U4H + i0] = u0;
+                if (g < G && i1 >= 0 && i1 < L_U4H) raw[g * L_U4H + i1] = u1;
+            }
+        }
+        tc_fence_before();
+        __syncthreads();
+        MT_MARK(14);
+        {   // interp 804 -> 900 (nwd.py:237-238), zero pad 255, parity / pair / phase split: the final layer's A buffer.
+            // unit (seq = 2 g + p, s): samples xs_p[2 s + e][c] = h[4 s + 2 e + p - 255][c], e = 0, 1
+            const uint2* raw = reinterpret_cast<const uint2*>(smem + RAW_OFF);     // [g][804 positions][4 ch]
+            uint4* fb = reinterpret_cast<uint4*>(smem + AB_FIN.off);
+            const float scale = (float)L_U4 / (float)T;
+            const int total = 32 * AB_FIN.RL;
+            for (int idx = threadIdx.x; idx < total; idx += THREADS) {
+                const int r = idx % AB_FIN.RL, j = idx / AB_FIN.RL;
+                const int seq = r / 12, s = (r % 12) * 32 + j;
+                uint32_t h[4] = {0, 0, 0, 0};
+                if (seq < 2 * G) {
+                    const int g = seq >> 1, p = seq & 1;
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int t = 4 * s + 2 * e + p - 255;
+                        if (t >= 0 && t < T) {
+                            float src = scale * ((float)t + 0.5f) - 0.5f;
+                            src = src < 0.f ? 0.f : src;
+                            int i0 = (int)src;
+                            i0 = i0 < L_U4 - 1 ? i0 : L_U4 - 1;
+                            const int i1 = i0 + (i0 < L_U4 - 1 ? 1 : 0);
+                            const float l1 = fminf(fmaxf(src - (float)i0, 0.f), 1.f), l0 = 1.f - l1;
+                            const uint2 a = raw[g * L_U4 + i0], b = raw[g * L_U4 + i1];
+                            const float2 a0 = unpack_h2(a.x), a1 = unpack_h2(a.y), b0 = unpack_h2(b.x), b1 = unpack_h2(b.y);
+                            h[2 * e] = pack_h2(l0 * a0.x + l1 * b0.x, l0 * a0.y + l1 * b0.y);
+                            h[2 * e + 1] = pack_h2(l0 * a1.x + l1 * b1.x, l0 * a1.y + l1 * b1.y);
+                        }
+                    }
+                }
+                fb[idx] = make_uint4(h[0], h[1], h[2], h[3]);
+            }
+        }
+        MT_MARK(15);
+        // ---- final conv 4 -> 1, k 256, dilation 2, padding 255 (nwd.py:251-252, 285) ----
+        run_layer<8, AB_FIN.RL>(pp, AB_FIN.off, W8_OFF, false);
+        if (threadIdx.x == 0 && more) load_weights(pp, lc_woff(0), lc_wbytes(0), W0_OFF, true);
+        MT_MARK(16);
+        {
+            float* orow = reinterpret_cast<float*>(smem + OROW_OFF);
+            const int seq = row / 12, q = row % 12, g = seq >> 1, p = seq & 1;
+            const float bf = bias_s[8][0];
+            uint32_t v[16];
+            tmem_ld16(pp.tmem + cgp * 16 + ((uint32_t)(32 * lq) << 16), v);
+            tmem_ld_wait();
+            if (seq < 2 * G) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int n = 8 * cgp + (i >> 1), co = i & 1;
+                    const int t = 4 * (32 * q + 31 - n) + 2 * co + p;
+                    if (t < T) orow[g * OROW_STRIDE + t + 4 * (t >> 7)] = fmaxf(__uint_as_float(v[i]) + bf, 0.f);
+                }
+            }
+        }
+        tc_fence_before();
+        __syncthreads();
+        MT_MARK(17);
+        // ---- rescale by tmax (nwd.py:46), monotone decay filter (nwd.py:337-343), store, CAVIaR prologue sums ----
+        {
+            const int g = wid >> 2, k = k0 + g;
+            const float* orow = reinterpret_cast<const float*>(smem + OROW_OFF) + g * OROW_STRIDE;
+            const TOut tm = (TOut)tmax_s[g];
+            const bool isbad = bad_s[g] != 0;
+            const bool filt = monotone_start >= 1 && monotone_start < T;
+            int t0, t1;
+            if (filt) {
+                const int third = (monotone_start + 2) / 3;
+                t0 = lq < 3 ? min(lq * third, monotone_start) : monotone_start;
+                t1 = lq < 3 ? min((lq + 1) * third, monotone_start) : T;
+            } else {
+                t0 = lq * 225; t1 = t0 + 225;
+            }
+            double s1 = 0.0, s2 = 0.0;
+            if (k < K) {
+                TOut* op = outp + (size_t)k * T;
+                double carry = 0.0;
+                if (filt && lq == 3) {
+                    const int tp = monotone_start - 1;
+                    carry = (double)((TOut)orow[tp + 4 * (tp >> 7)] * tm);
+                }
+                for (int base = t0; base < t1; base += 32) {
+                    const int t = base + lane;
+                    double val = t < t1 ? (double)((TOut)orow[t + 4 * (t >> 7)] * tm) : INFINITY;
+                    if (filt && lq == 3) {
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const double u = __shfl_up_sync(0xffffffffu, val, o);
+                            if (lane >= o) val = fmin(val, u);
+                        }
+                        val = fmin(val, carry);
+                        carry = __shfl_sync(0xffffffffu, val, 31);
+                    }
+                    if (isbad) val = NAN;
+                    if (t < t1) {
+                        op[t] = (TOut)val;
+                        s1 += (t == 0 || t == T - 1) ? 0.5 * val : val;       // unit-spacing trapezoid, caviar.py:28
+                        s2 += val * val;                                      // autocorrelation at lag 0, caviar.py:30
+                    }
+                }
+            }
+            if (y_out != nullptr || ss_out != nullptr) {
+                s1 = warp_sum(s1);
+                s2 = warp_sum(s2);
+                if (lane == 0) { red_s1[wid] = s1; red_s2[wid] = s2; }
+                __syncthreads();
+                if (lq == 0 && lane == 0 && k < K) {
+                    if (y_out) y_out[k] = (red_s1[wid] + red_s1[wid + 1]) + (red_s1[wid + 2] + red_s1[wid + 3]);
+                    if (ss_out) ss_out[k] = (red_s2[wid] + red_s2[wid + 1]) + (red_s2[wid + 2] + red_s2[wid + 3]);
+                }
+            }
+        }
+        __syncthreads();
+        MT_MARK(18);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (wid == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(pp.tmem), "r"(256u));
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+static uint16_t f2h(double x) { return __half_as_ushort(__float2half_rn((float)x)); }
+
+// Tap tables WS[cp][u][co][8 ci] (fp16) of the nine layers + folded biases, BatchNorm (eval) folded in fp64.
+void pack_weights(const float* const* t, std::vector<unsigned char>& out) {
+    out.assign(BLOB_BYTES, 0);
+    float* bias = reinterpret_cast<float*>(out.data() + BIAS_OFF);
+    // real layer shapes (nwd.py:259-269): kind 0 Conv1d (co, ci, k); 1 ConvTranspose1d stride 1 (ci, co, k); 2 stride 2; 3 final
+    struct RL_ { int kind, ci, co, k; };
+    const RL_ real[NLAYER] = {{0, 1, 16, 32}, {0, 16, 16, 32}, {0, 16, 32, 16}, {0, 32, 32, 16}, {1, 32, 16, 16},
+                              {1, 48, 16, 16}, {1, 32, 16, 32}, {2, 32, 4, 32}, {3, 4, 1, 256}};
+    for (int l = 0; l < NLAYER; ++l) {
+        const float *w = t[6 * l], *b = t[6 * l + 1], *g = t[6 * l + 2], *be = t[6 * l + 3], *rm = t[6 * l + 4], *rv = t[6 * l + 5];
+        const RL_& s = real[l];
+        const LayerCfg c = lcfg(l);
+        std::vector<double> sc(s.co);
+        for (int co = 0; co < s.co; ++co) {
+            sc[co] = (double)g[co] / std::sqrt((double)rv[co] + 1e-5);
+            bias[l * 32 + co] = (float)(((double)b[co] - (double)rm[co]) * sc[co] + (double)be[co]);
+        }
+        // wtap(j, ci, co): weight of GEMM input channel ci at window tap j for GEMM output channel co
+        auto wtap = [&](int j, int ci, int co) -> double {
+            if (j < 0 || j >= c.TAPS) return 0.0;
+            if (l == 0) {                                   // co' = 16 m + co, ci = sample i of the group: w[8 j + i - m]
+                const int m = co >> 4, cr = co & 15, idx = 8 * j + ci - m;
+                return (idx >= 0 && idx < 32) ? (double)w[cr * 32 + idx] * sc[cr] : 0.0;
+            }
+            if (s.kind == 0) return (double)w[(co * s.ci + ci) * s.k + j] * sc[co];
+            if (s.kind == 1) return (double)w[(ci * s.co + co) * s.k + (s.k - 1 - j)] * sc[co];
+            if (s.kind == 2) {                              // co' = 4 par + co: tap par + 2 (15 - j)
+                const int par = co >> 2, cr = co & 3;
+                return (double)w[(ci * s.co + cr) * s.k + (par + 2 * (15 - j))] * sc[cr];
+            }
+            // final: ci = 4 e + c (e = sample of the pair), co = inner parity of the output index: w[c][2 j + e - co]
+            const int e = ci >> 2, cr = ci & 3, idx = 2 * j + e - co;
+            return (idx >= 0 && idx < 256) ? (double)w[cr * 256 + idx] * sc[0] : 0.0;
+        };
+        uint16_t* dst = reinterpret_cast<uint16_t*>(out.data() + lc_woff(l));
+        for (int cp = 0; cp < c.CIN / 8; ++cp)
+            for (int u = 0; u < c.UPAD; ++u)
+                for (int co = 0; co < c.COUT; ++co)
+                    for (int i = 0; i < 8; ++i)
+                        dst[((size_t)(cp * c.UPAD + u) * c.COUT + co) * 8 + i] = f2h(wtap(u - (c.PH - 1), 8 * cp + i, co));
+    }
+}
+
+template <typename TIn, typename TOut>
+static int launch_t(cm_nwd* h, const void* in, void* out, int K, int ms, double* y, double* ss, cudaStream_t st) {
+    auto kern = nwd_forward_mt_kernel<TIn, TOut>;
+    CM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    const int npass = (K + G - 1) / G;
+    const int grid = npass < h->sm_count ? npass : h->sm_count;
+    main_kernel_begin(st);
+    kern<<<grid, THREADS, SMEM_BYTES, st>>>(h->wmt_dev, (const TIn*)in, (TOut*)out, K, ms, y, ss);
+    main_kernel_end(st);
+    count_launch();
+    CM_CUDA_CHECK(cudaGetLastError());
+    return CM_OK;
+}
+
+int launch(cm_nwd* h, const void* in, int in_dtype, void* out, int out_dtype, int K, int ms, double* y, double* ss,
+           cudaStream_t st) {
+    if (in_dtype == CM_F32 && out_dtype == CM_F32) return launch_t<float, float>(h, in, out, K, ms, y, ss, st);
+    if (in_dtype == CM_F64 && out_dtype == CM_F64) return launch_t<double, double>(h, in, out, K, ms, y, ss, st);
+    if (in_dtype == CM_F32 && out_dtype == CM_F64) return launch_t<float, double>(h, in, out, K, ms, y, ss, st);
+    if (in_dtype == CM_F64 && out_dtype == CM_F32) return launch_t<double, float>(h, in, out, K, ms, y, ss, st);
+    set_error("cm_nwd_forward: bad dtype %d/%d", in_dtype, out_dtype);
+    return CM_EINVAL;
+}
+
+int debug_dump(void* dev_buf, int stage) {
+    CM_CUDA_CHECK(cudaMemcpyToSymbol(g_mt_dump, &dev_buf, sizeof(void*)));
+    CM_CUDA_CHECK(cudaMemcpyToSymbol(g_mt_dump_stage, &stage, sizeof(int)));
+    return CM_OK;
+}
+
+int debug_cycles(long long* out, int n, int enable) {
+    if (out && n > 0) {
+        long long hbuf[32];
+        CM_CUDA_CHECK(cudaMemcpyFromSymbol(hbuf, g_mt_cycles, sizeof(hbuf)));
+        for (int i = 0; i < n && i < 32; ++i) out[i] = hbuf[i];
+    }
+    long long z[32] = {0};
+    CM_CUDA_CHECK(cudaMemcpyToSymbol(g_mt_cycles, z, sizeof(z)));
+    CM_CUDA_CHECK(cudaMemcpyToSymbol(g_mt_prof, &enable, sizeof(int)));
+    return CM_OK;
+}
+
+}  // namespace nwdmt
+}  // namespace cm

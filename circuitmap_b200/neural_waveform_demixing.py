@@ -59,8 +59,10 @@ def random_weights(seed=0):
 class NeuralDemixer:
     def __init__(self, path=None, eval_mode=True, device=None, precision="fp32"):
         """precision (extension of the reference signature): 'fp32' = fp32 CUDA-core convolutions (default, the
-        reference's arithmetic); 'tf32' = tcgen05 tensor-core path (TF32 operands, fp32 accumulate; max-abs error
-        <= 2e-2 on unit-normalised traces)."""
+        reference's arithmetic); 'tf32' = tcgen05 tensor-core path, one trace per CTA (TF32 operands, fp32
+        accumulate); 'fp16' = the fast tcgen05 path: all nine convolutions as widened implicit GEMMs with several
+        traces per M tile (fp16 operands = TF32's 11-bit significand, fp32 accumulate).  Both tensor-core modes:
+        max-abs error <= 2e-2 on unit-normalised traces."""
         torch = _lib.require_cuda()
         self.device = torch.device("cuda" if device is None else device)
         if self.device.type != "cuda":
@@ -81,9 +83,9 @@ class NeuralDemixer:
         self.set_precision(precision)
 
     def set_precision(self, precision):
-        mode = {"fp32": 0, "tf32": 1}.get(precision)
+        mode = {"fp32": 0, "tf32": 1, "fp16": 2}.get(precision)
         if mode is None:
-            raise ValueError("precision must be 'fp32' or 'tf32'")
+            raise ValueError("precision must be 'fp32', 'tf32' or 'fp16'")
         _lib.check(self._lib.cm_nwd_set_precision(self._h, mode), "cm_nwd_set_precision")
         self.precision = precision
 

@@ -53,9 +53,12 @@ typedef struct cm_nwd cm_nwd_t;
 CM_API int  cm_nwd_create(const float* const* tensors, int n_tensors, cm_nwd_t** out);
 CM_API void cm_nwd_destroy(cm_nwd_t* h);
 /* arithmetic of the convolution layers: 0 = fp32 on CUDA cores (default; same arithmetic as the reference's fp32
- * network), 1 = TF32 operands / fp32 accumulation on the 5th-gen tensor cores (tcgen05, TMEM accumulators) for the
- * seven 16..48-channel layers (first and last convolution stay fp32).  Error bound of mode 1 on unit-normalised
- * traces: max-abs <= 2e-2, relative L2 <= 3e-3 (asserted in tests/test_nwd_gpu.py). */
+ * network); 1 = TF32 operands / fp32 accumulation on the 5th-gen tensor cores (tcgen05, TMEM accumulators), one trace
+ * per CTA (csrc/nwd_tc.cu); 2 = fp16 operands (11-bit significand, as TF32) / fp32 accumulation, all nine
+ * convolutions on tcgen05 with several traces per M tile (csrc/nwd_mt.cu) -- the fast path.  Error bound of modes 1
+ * and 2 on unit-normalised traces: max-abs <= 2e-2, relative L2 <= 3e-3 (asserted in tests/test_nwd_gpu.py).
+ * Mode 2 keeps activations in fp16: a trace whose normalised samples |x / max(x)| exceed 6e4, whose max is 0 or that
+ * holds a non-finite sample yields an all-NaN row instead of a silently saturated one. */
 CM_API int  cm_nwd_set_precision(cm_nwd_t* h, int precision);
 
 /* traces_dev: K x T row-major (in_dtype), out_dev: K x T row-major (out_dtype).
@@ -143,6 +146,14 @@ CM_API int cm_caviar_debug_phase_cycles(long long* out, int n, int enable);
 
 /* diagnostics: per-stage SM cycle counters of CTA 0 of the tensor-core demixer kernel (csrc/nwd_tc.cu NWD_MARK ids) */
 CM_API int cm_nwd_debug_cycles(long long* out, int n, int enable);
+/* same for the multi-trace kernel (csrc/nwd_mt.cu MT_MARK ids) */
+CM_API int cm_nwd_mt_debug_cycles(long long* out, int n, int enable);
+/* diagnostics: CTA 0 of the next multi-trace forward copies its shared memory (>= 216 KB) to dev_buf when it reaches
+ * MT_MARK `stage` of its first pass (stage < 0 disables) */
+CM_API int cm_nwd_mt_debug_dump(void* dev_buf, int stage);
+/* test hook (host only, no device work): the packed fp16 tap tables + fp32 biases the multi-trace kernel streams
+ * (layout: csrc/nwd_mt.cuh).  out may be NULL to query the size. */
+CM_API int cm_nwd_mt_pack(const float* const* tensors, int n_tensors, unsigned char* out, size_t cap, size_t* need);
 
 /* number of kernel launches issued by the last cm_* call on this thread (for bench accounting) */
 CM_API int cm_last_launch_count(void);
