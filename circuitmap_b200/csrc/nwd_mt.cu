@@ -20,9 +20,11 @@ namespace cm {
 namespace nwdmt {
 
 // ------------------------------------------------------------------------------------------------ shared-memory map
-constexpr int DEC3_RL = G * 27 + 2, DEC3_PL = 16 * DEC3_RL * 16;       // u4's A: PH 16
-constexpr int DEC2_RL = G * 28 + 4, DEC2_PL = 8 * DEC2_RL * 16;        // u3's A: PH 8
-constexpr int DEC1_RL = G * 24 + 4, DEC1_PL = 4 * DEC1_RL * 16;        // u2's A: PH 4
+// Row lengths (units per phase row) are chosen odd mod 8 (PH >= 8) resp. 2 mod 8 (PH 4) so that lanes writing
+// consecutive positions -- which land in consecutive phase rows -- hit distinct 16-byte bank groups.
+constexpr int DEC3_RL = G * 27 + 3, DEC3_PL = 16 * DEC3_RL * 16;       // u4's A: PH 16
+constexpr int DEC2_RL = G * 28 + 5, DEC2_PL = 8 * DEC2_RL * 16;        // u3's A: PH 8
+constexpr int DEC1_RL = G * 24 + 10, DEC1_PL = 4 * DEC1_RL * 16;       // u2's A: PH 4
 constexpr int A_LO = 0, A_HI = A_LO + 2 * DEC3_PL, A_END = A_LO + 4 * DEC3_PL;
 constexpr int B_LO = A_END, B_HI = B_LO + 2 * DEC2_PL, B_END = B_LO + 4 * DEC2_PL;
 constexpr int C_LO = B_END, C_END = C_LO + 6 * DEC1_PL;
@@ -38,18 +40,21 @@ constexpr AB AB_E4 = {B_LO + 4 * (G * 32 + 16) * 16, 2, G * 24 + 8, 24, 15};   /
 constexpr AB AB_D1 = {C_LO, 4, DEC1_RL, 24, 15};                        // 6 planes
 constexpr AB AB_D2 = {B_LO, 8, DEC2_RL, 28, 31};                        // 4 planes
 constexpr AB AB_D3 = {A_LO, 16, DEC3_RL, 27, 15};                       // 4 planes
-constexpr AB AB_FIN = {A_LO, 32, G * 2 * 12 + 4, 12, 0};                // 1 plane, 2 sequences per trace
-constexpr int RAW1_OFF = AB_E4.off + 4 * 2 * AB_E4.RL * 16;            // [g][32][16 ch] fp16
-constexpr int RAW_OFF = C_LO;                                           // raw2 [g][80][16], raw3 [g][193][16], raw4 [g][402][2 x 4]
+constexpr AB AB_FIN = {A_LO, 32, G * 2 * 12 + 5, 12, 0};                // 1 plane, 2 sequences per trace
+// raw decoder outputs (before interpolation), phase-split like the GEMM rows that produce them: unit (cp, t % PH, g Q + t / PH)
+constexpr AB AB_R1 = {AB_E4.off + 4 * 2 * AB_E4.RL * 16, 2, G * 24 + 1, 24, 0};      // 2 planes (16 ch)
+constexpr AB AB_R2 = {C_LO, 4, G * 24 + 1, 24, 0};
+constexpr AB AB_R3 = {C_LO, 8, G * 28 + 1, 28, 0};
+constexpr AB AB_R4 = {C_LO, 16, G * 27 + 1, 27, 0};                                   // 1 plane: unit = 2 positions x 4 ch
 constexpr int OROW_OFF = C_LO, OROW_STRIDE = 928;                       // fp32, index t + 4 (t >> 7)
 constexpr int W0_OFF = A_LO;                                            // weights of d1 .. u3, one layer at a time
 constexpr int W7_OFF = B_LO;                                            // u4
-constexpr int W8_OFF = C_LO + G * L_U4H * 16;                           // fin, behind raw4
+constexpr int W8_OFF = C_END - lc_wbytes(8);                            // fin, at the end of C behind raw3 / raw4
 static_assert(X_OFF + G * T * 4 + AB_P1.RL * 16 <= B_HI, "input scratch");
-static_assert(2 * 8 * AB_P2.RL * 16 <= B_HI - B_LO && RAW1_OFF + G * 32 * 32 <= B_HI, "encoder scratch");
+static_assert(2 * 8 * AB_P2.RL * 16 <= B_HI - B_LO && AB_R1.off + 2 * 2 * AB_R1.RL * 16 <= B_HI, "encoder scratch");
 static_assert(lc_wbytes(6) <= A_HI - A_LO && lc_wbytes(5) <= A_HI - A_LO && 32 * AB_FIN.RL * 16 <= A_HI - A_LO, "A_lo");
 static_assert(lc_wbytes(7) <= B_HI - B_LO && W8_OFF + lc_wbytes(8) <= C_END && G * OROW_STRIDE * 4 <= C_END - C_LO, "late buffers");
-static_assert(G * L_U3 * 32 <= W8_OFF - C_LO, "raw3 must not reach the final-layer weights");
+static_assert(C_LO + 2 * 8 * AB_R3.RL * 16 <= W8_OFF && C_LO + 16 * AB_R4.RL * 16 <= W8_OFF, "raw3 / raw4 must not reach the final-layer weights");
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
@@ -58,9 +63,17 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
     return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
            ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46);       // version 1, no swizzle
 }
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
-    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
-                 ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+// descriptors are passed as (lo, hi) words: only the low word (start address, in 16-byte units) changes between MMAs
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                         uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n.reg .pred p;\n.reg .b64 da, db;\nsetp.ne.b32 p, %6, 0;\nmov.b64 da, {%1, %2};\nmov.b64 db, {%3, %4};\n"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n}\n"
+                 ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
@@ -134,14 +147,15 @@ __device__ __forceinline__ int ab_unit(const AB b, int cp, int seq, int pp) {
 // All MMAs of layer L by one thread.  `abase` / `wbase` are shared-memory byte addresses of the A buffer (plane 0)
 // and of the tap table.  Descriptor start addresses advance in 16-byte units.
 template <int L, int RL>
-__device__ __forceinline__ void issue_layer(uint32_t abase, uint32_t wbase, uint32_t tmem) {
+__device__ __forceinline__ void issue_layer(uint32_t abase, uint32_t wbase, uint32_t tmem, bool leader) {
     constexpr int PH = lcfg(L).PH, CIN = lcfg(L).CIN, COUT = lcfg(L).COUT, U = lcfg(L).UPAD, V = lc_v(L), N = lc_n(L);
     constexpr int TILES = lc_tiles(L);
     constexpr uint32_t idesc = idesc_f16(N);
+    constexpr uint32_t HI_SBO = (128u >> 4) | (1u << 14);                  // high word: SBO = 128 B, descriptor version 1
     if constexpr (CIN >= 16) {
         constexpr int CQ = CIN / 16;                                       // K steps (pairs of 8-channel planes) per window position
-        const uint64_t a0 = umma_desc(abase, PH * RL * 16, 128);
-        const uint64_t b0 = umma_desc(wbase, U * COUT * 16, 128);
+        const uint32_t a0 = ((abase >> 4) & 0x3FFF) | ((uint32_t)(PH * RL) << 16);      // LBO = plane stride
+        const uint32_t b0 = ((wbase >> 4) & 0x3FFF) | ((uint32_t)(U * COUT) << 16);
 #pragma unroll 1
         for (int mt = 0; mt < TILES; ++mt) {
             uint32_t acc = 0;
@@ -153,8 +167,9 @@ __device__ __forceinline__ void issue_layer(uint32_t abase, uint32_t wbase, uint
                     if (v < V) {
 #pragma unroll
                         for (int cq = 0; cq < CQ; ++cq) {
-                            umma_f16(tmem + mt * N, a0 + (uint64_t)((2 * cq * PH + j) * RL + 128 * mt + a),
-                                     b0 + (uint64_t)((2 * cq * U + v) * COUT), idesc, acc);
+                            if (leader)
+                                umma_f16(tmem + mt * N, a0 + (uint32_t)((2 * cq * PH + j) * RL + 128 * mt + a), HI_SBO,
+                                         b0 + (uint32_t)((2 * cq * U + v) * COUT), HI_SBO, idesc, acc);
                             acc = 1;
                         }
                     }
@@ -162,23 +177,25 @@ __device__ __forceinline__ void issue_layer(uint32_t abase, uint32_t wbase, uint
             }
         }
     } else if constexpr (PH == 1) {                                        // d1: K step = two consecutive units
-        const uint64_t a0 = umma_desc(abase, 16, 128);
-        const uint64_t b0 = umma_desc(wbase, COUT * 16, 128);
+        const uint32_t a0 = ((abase >> 4) & 0x3FFF) | (1u << 16);
+        const uint32_t b0 = ((wbase >> 4) & 0x3FFF) | ((uint32_t)COUT << 16);
 #pragma unroll 1
         for (int mt = 0; mt < TILES; ++mt)
 #pragma unroll
             for (int v = 0; v < V; v += 2)
-                umma_f16(tmem + mt * N, a0 + (uint64_t)(128 * mt + v), b0 + (uint64_t)(v * COUT), idesc, v ? 1u : 0u);
+                if (leader)
+                    umma_f16(tmem + mt * N, a0 + (uint32_t)(128 * mt + v), HI_SBO, b0 + (uint32_t)(v * COUT), HI_SBO, idesc, v ? 1u : 0u);
     } else {                                                               // fin: K step = phases j, j + 1
         static_assert(TILES == 1, "single tile");
-        const uint64_t a0 = umma_desc(abase, RL * 16, 128);
-        const uint64_t b0 = umma_desc(wbase, COUT * 16, 128);
+        const uint32_t a0 = ((abase >> 4) & 0x3FFF) | ((uint32_t)RL << 16);
+        const uint32_t b0 = ((wbase >> 4) & 0x3FFF) | ((uint32_t)COUT << 16);
 #pragma unroll 1
         for (int a = 0; a * PH < V; ++a)
-#pragma unroll 4
+#pragma unroll
             for (int j = 0; j < PH; j += 2) {
                 const int v = a * PH + j;
-                if (v < V) umma_f16(tmem, a0 + (uint64_t)(j * RL + a), b0 + (uint64_t)(v * COUT), idesc, v ? 1u : 0u);
+                if (v < V && leader)
+                    umma_f16(tmem, a0 + (uint32_t)(j * RL + a), HI_SBO, b0 + (uint32_t)(v * COUT), HI_SBO, idesc, v ? 1u : 0u);
             }
     }
 }
@@ -189,6 +206,7 @@ struct Pipe {
     uint32_t wcount, mcount;        // phases consumed so far (uniform across threads)
     uint32_t tmem;
     uint32_t smem0;                 // shared-memory address of the dynamic buffer
+    bool warp0;                     // warp-uniform: this is the issuing warp
     const unsigned char* blob;
 };
 
@@ -197,33 +215,38 @@ __device__ __forceinline__ void load_weights(const Pipe& pp, int l_off, int l_by
     bulk_g2s(pp.smem0 + dst_off, pp.blob + l_off, (uint32_t)l_bytes, pp.bar_w);
 }
 
-// make the A operand visible to the async proxy, issue, wait for completion (all threads)
+// make the A operand visible to the async proxy; warp 0 issues (one elected lane) and waits for the completion
+// barrier while the other warps park at the hardware barrier (no shared-memory polling next to the MMA operand reads)
 template <int L, int RL>
 __device__ __forceinline__ void run_layer(Pipe& pp, int a_off, int w_off, bool wait_w) {
     proxy_fence();
     tc_fence_before();
     __syncthreads();
-    tc_fence_after();
-    if (threadIdx.x == 0) {
+    if (pp.warp0) {
+        tc_fence_after();
         if (wait_w) mbar_wait(pp.bar_w, pp.wcount & 1);
         tc_fence_after();
-        issue_layer<L, RL>(pp.smem0 + a_off, pp.smem0 + w_off, pp.tmem);
-        umma_commit(pp.bar_mma);
+        const bool leader = elect_one();
+        issue_layer<L, RL>(pp.smem0 + a_off, pp.smem0 + w_off, pp.tmem, leader);
+        if (leader) umma_commit(pp.bar_mma);
+        __syncwarp();
+        mbar_wait(pp.bar_mma, pp.mcount & 1);
     }
     if (wait_w) pp.wcount++;
-    mbar_wait(pp.bar_mma, pp.mcount & 1);
     pp.mcount++;
+    __syncthreads();
     tc_fence_after();
 }
 
 // ------------------------------------------------------------------------------------------------ CUDA-core passes
+constexpr float THIRD = 1.0f / 3.0f;      // the pooled value is rounded to fp16 right after: a multiply is as good as the divide
 __device__ __forceinline__ uint4 avg3_units(uint4 a, uint4 b, uint4 c) {
     uint4 r;
     const uint32_t* pa = &a.x; const uint32_t* pb = &b.x; const uint32_t* pc = &c.x; uint32_t* pr = &r.x;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const float2 fa = unpack_h2(pa[i]), fb = unpack_h2(pb[i]), fc = unpack_h2(pc[i]);
-        pr[i] = pack_h2((fa.x + fb.x + fc.x) / 3.0f, (fa.y + fb.y + fc.y) / 3.0f);
+        pr[i] = pack_h2((fa.x + fb.x + fc.x) * THIRD, (fa.y + fb.y + fc.y) * THIRD);
     }
     return r;
 }
@@ -240,6 +263,7 @@ __device__ __forceinline__ uint4 lerp_units(uint4 a, uint4 b, float l0, float l1
 
 // AvgPool1d(3, 2) (nwd.py:210) of the encoder half (planes PL0..) of a concat buffer into the next layer's A buffer.
 // Covers every unit of the destination (zero outside the valid range, so that whatever a valid GEMM row reads is finite).
+// Lanes walk one destination phase row: source and destination units are consecutive -> conflict-free.
 template <int NPL>
 __device__ __forceinline__ void pool_pass(unsigned char* smem, const AB src, int src_pl0, const AB dst, int Lout) {
     const uint4* s = reinterpret_cast<const uint4*>(smem + src.off);
@@ -258,28 +282,38 @@ __device__ __forceinline__ void pool_pass(unsigned char* smem, const AB src, int
     }
 }
 
-// F.interpolate(linear, align_corners=False) (nwd.py:237-238) of a raw decoder output [g][Lin][16 ch] into planes 0..1
-// of a concat buffer; covers every unit of the two planes (zero in the pads).
-__device__ __forceinline__ void interp_pass(unsigned char* smem, int raw_off, int Lin, const AB dst, int Lout) {
-    const uint4* s = reinterpret_cast<const uint4*>(smem + raw_off);
+// F.interpolate(linear, align_corners=False) (nwd.py:237-238) of a raw decoder output (phase-split buffer `raw`, Lin
+// positions) into planes 0..1 of a concat buffer; covers every unit of the two planes (zero in the pads and the slack).
+// An item is 32 consecutive padded positions of one (trace, plane): lanes read neighbouring source units (distinct phase
+// rows) and write distinct phase rows -> conflict-free with the row lengths chosen above.
+__device__ __forceinline__ void interp_pass(unsigned char* smem, const AB raw, int Lin, const AB dst, int Lout) {
+    const uint4* s = reinterpret_cast<const uint4*>(smem + raw.off);
     uint4* d = reinterpret_cast<uint4*>(smem + dst.off);
     const float scale = (float)Lin / (float)Lout;
-    const int total = 2 * dst.PH * dst.RL;
-    for (int idx = threadIdx.x; idx < total; idx += THREADS) {
-        const int r = idx % dst.RL, cj = idx / dst.RL, j = cj % dst.PH, cp = cj / dst.PH;
-        const int g = r / dst.Q, t = (r % dst.Q) * dst.PH + j - dst.PAD;
-        uint4 o = make_uint4(0, 0, 0, 0);
-        if (g < G && t >= 0 && t < Lout) {
-            float src = scale * ((float)t + 0.5f) - 0.5f;
-            src = src < 0.f ? 0.f : src;
-            int i0 = (int)src;
-            i0 = i0 < Lin - 1 ? i0 : Lin - 1;
-            const int i1 = i0 + (i0 < Lin - 1 ? 1 : 0);
-            const float l1 = fminf(fmaxf(src - (float)i0, 0.f), 1.f), l0 = 1.f - l1;
-            o = lerp_units(s[(g * Lin + i0) * 2 + cp], s[(g * Lin + i1) * 2 + cp], l0, l1);
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int LP = dst.PH * dst.Q, CH = (LP + 31) / 32, items = G * 2 * CH;
+#pragma unroll 2
+    for (int it = wid; it < items; it += THREADS / 32) {
+        const int gc = it / CH, pp = (it - gc * CH) * 32 + lane;          // gc = 2 g + cp
+        const int g = gc >> 1, cp = gc & 1;
+        if (pp < LP) {
+            const int t = pp - dst.PAD;
+            uint4 o = make_uint4(0, 0, 0, 0);
+            if (t >= 0 && t < Lout) {
+                float src = scale * ((float)t + 0.5f) - 0.5f;
+                src = src < 0.f ? 0.f : src;
+                int i0 = (int)src;
+                i0 = i0 < Lin - 1 ? i0 : Lin - 1;
+                const int i1 = i0 + (i0 < Lin - 1 ? 1 : 0);
+                const float l1 = fminf(fmaxf(src - (float)i0, 0.f), 1.f), l0 = 1.f - l1;
+                o = lerp_units(s[ab_unit(raw, cp, g, i0)], s[ab_unit(raw, cp, g, i1)], l0, l1);
+            }
+            d[ab_unit(dst, cp, g, pp)] = o;
         }
-        d[idx] = o;
     }
+    const int slack = dst.RL - G * dst.Q;                                 // units behind the last trace of every phase row
+    for (int idx = threadIdx.x; idx < 2 * dst.PH * slack; idx += THREADS)
+        d[(idx / slack) * dst.RL + G * dst.Q + idx % slack] = make_uint4(0, 0, 0, 0);
 }
 
 // 16 accumulator columns -> bias, ReLU, fp16: two 16-byte units (channels 0..7, 8..15 of the chunk)
@@ -327,8 +361,23 @@ nwd_forward_mt_kernel(const unsigned char* __restrict__ blob, const TIn* __restr
     Pipe pp;
     pp.bar_w = &bars[0]; pp.bar_mma = &bars[1]; pp.wcount = 0; pp.mcount = 0; pp.tmem = tmem_base_s;
     pp.smem0 = smem_u32(smem); pp.blob = blob;
+    pp.warp0 = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0) == 0;
     const int npass = (K + G - 1) / G;
     if (threadIdx.x == 0 && (int)blockIdx.x < npass) load_weights(pp, lc_woff(0), lc_wbytes(0), W0_OFF, true);
+
+    // this thread's 8 samples of the pass's traces (warps 4 g .. 4 g + 3 hold trace g); the next pass's are fetched
+    // while the final layer runs
+    TIn vin[8];
+    auto fetch_input = [&](int pass_) {
+        const int k = pass_ * G + (wid >> 2);
+        const TIn* tr = traces + (size_t)(k < K ? k : 0) * T;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int t = lq * 32 + lane + 128 * i;
+            vin[i] = (k < K && t < T) ? tr[t] : (TIn)0;
+        }
+    };
+    if ((int)blockIdx.x < npass) fetch_input(blockIdx.x);
 
     long long tmark = clock64();
     for (int pass = blockIdx.x; pass < npass; pass += gridDim.x) {
@@ -336,19 +385,16 @@ nwd_forward_mt_kernel(const unsigned char* __restrict__ blob, const TIn* __restr
         const bool more = pass + (int)gridDim.x < npass;
         // ---- input: per-trace max (nwd.py:43), normalise, AvgPool -> parity sequences of the pooled trace (d1's A) ----
         {
-            const int g = wid >> 2, k = k0 + g;
-            const bool act = k < K;
-            const TIn* tr = traces + (size_t)(act ? k : 0) * T;
-            TIn v[8];
+            const int g = wid >> 2;
+            const bool act = k0 + g < K;
             double mx = -INFINITY, amx = 0.0;
             int bad = 0;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int t = lq * 32 + lane + 128 * i;
-                v[i] = (act && t < T) ? tr[t] : (TIn)0;
                 if (t < T) {
-                    mx = fmax(mx, (double)v[i]);
-                    const double a = fabs((double)v[i]);
+                    mx = fmax(mx, (double)vin[i]);
+                    const double a = fabs((double)vin[i]);
                     bad |= !(a <= 1e300);
                     amx = fmax(amx, a);
                 }
@@ -365,32 +411,24 @@ nwd_forward_mt_kernel(const unsigned char* __restrict__ blob, const TIn* __restr
             if (!act) { tmax = 1.0; isbad = 0; }
             if (lq == 0 && lane == 0) { tmax_s[g] = tmax; bad_s[g] = isbad; }
             float* X = reinterpret_cast<float*>(smem + X_OFF) + g * T;
+            const TIn inv = isbad ? (TIn)0 : (TIn)1 / (TIn)tmax;          // operands are rounded to fp16 later: x * (1 / tmax) is as good as x / tmax
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int t = lq * 32 + lane + 128 * i;
-                if (t < T) X[t] = isbad ? 0.f : (float)(v[i] / (TIn)tmax);
+                if (t < T) X[t] = isbad ? 0.f : (float)(vin[i] * inv);       // a bad trace runs as zeros and is returned as NaN
             }
         }
         __syncthreads();
         {
             const float* X = reinterpret_cast<const float*>(smem + X_OFF);
-            for (int u = threadIdx.x; u < AB_P1.RL; u += THREADS) {
-                const int seq = u / 29, sg = u % 29;                 // seq = 2 g + parity
-                uint32_t h[4] = {0, 0, 0, 0};
-                if (seq < 2 * G) {
-                    const float* xg = X + (seq >> 1) * T;
-                    const int p = seq & 1;
-                    float f[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int pu = 2 * (8 * sg + i) + p;         // pooled index
-                        f[i] = pu < L_P1 ? (xg[2 * pu] + xg[2 * pu + 1] + xg[2 * pu + 2]) / 3.0f : 0.f;
-                    }
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) h[i] = pack_h2(f[2 * i], f[2 * i + 1]);
-                }
-                reinterpret_cast<uint4*>(smem + AB_P1.off)[u] = make_uint4(h[0], h[1], h[2], h[3]);
+            __half* p1 = reinterpret_cast<__half*>(smem + AB_P1.off);               // [2 g + parity][29 x 8 samples]
+            for (int idx = threadIdx.x; idx < G * 464; idx += THREADS) {            // 464 = 2 x 232 pooled slots per trace
+                const int g = idx / 464, pu = idx - g * 464;
+                const float* xg = X + g * T + 2 * pu;
+                const float v = pu < L_P1 ? (xg[0] + xg[1] + xg[2]) * THIRD : 0.f;
+                p1[(2 * g + (pu & 1)) * 232 + (pu >> 1)] = __float2half_rn(v);
             }
+            if (threadIdx.x < 6) reinterpret_cast<uint4*>(smem + AB_P1.off)[2 * G * 29 + threadIdx.x] = make_uint4(0, 0, 0, 0);
             // dec1 is scratch for the raw decoder outputs of the previous pass: restore its zero pads
             uint4* c4 = reinterpret_cast<uint4*>(smem + C_LO);
             for (int i = threadIdx.x; i < (C_END - C_LO) / 16; i += THREADS) c4[i] = make_uint4(0, 0, 0, 0);
@@ -502,7 +540,7 @@ nwd_forward_mt_kernel(const unsigned char* __restrict__ blob, const TIn* __restr
         run_layer<4, AB_E4.RL>(pp, AB_E4.off, W0_OFF, true);
         if (threadIdx.x == 0) load_weights(pp, lc_woff(5), lc_wbytes(5), W0_OFF, true);
         if (cgp < 2) {
-            uint4* raw = reinterpret_cast<uint4*>(smem + RAW1_OFF);
+            uint4* raw = reinterpret_cast<uint4*>(smem + AB_R1.off);
             const int g = row / 24, q = row % 24, n = cgp;
             uint32_t v[16];
             tmem_ld16(pp.tmem + n * 16 + ((uint32_t)(32 * lq) << 16), v);
@@ -511,19 +549,19 @@ nwd_forward_mt_kernel(const unsigned char* __restrict__ blob, const TIn* __restr
             if (g < G && t < L_U1) {
                 uint4 u0, u1;
                 finish16(v, bias_s[4], u0, u1);
-                raw[(g * L_U1 + t) * 2] = u0;
-                raw[(g * L_U1 + t) * 2 + 1] = u1;
+                raw[ab_unit(AB_R1, 0, g, t)] = u0;
+                raw[ab_unit(AB_R1, 1, g, t)] = u1;
             }
         }
         tc_fence_before();
         __syncthreads();
-        interp_pass(smem, RAW1_OFF, L_U1, AB_D1, L_E3);
+        interp_pass(smem, AB_R1, L_U1, AB_D1, L_E3);
         MT_MARK(8);
         // ---- u2: 48 -> 16, k 16 ----
         run_layer<5, AB_D1.RL>(pp, AB_D1.off, W0_OFF, true);
         if (threadIdx.x == 0) load_weights(pp, lc_woff(6), lc_wbytes(6), W0_OFF, true);
         {
-            uint4* raw = reinterpret_cast<uint4*>(smem + RAW_OFF);
+            uint4* raw = reinterpret_cast<uint4*>(smem + AB_R2.off);
             const int g = row / 24, q = row % 24, n = cgp;
             uint32_t v[16];
             tmem_ld16(pp.tmem + n * 16 + ((uint32_t)(32 * lq) << 16), v);
@@ -532,13 +570,13 @@ nwd_forward_mt_kernel(const unsigned char* __restrict__ blob, const TIn* __restr
             if (g < G && t < L_U2) {
                 uint4 u0, u1;
                 finish16(v, bias_s[5], u0, u1);
-                raw[(g * L_U2 + t) * 2] = u0;
-                raw[(g * L_U2 + t) * 2 + 1] = u1;
+                raw[ab_unit(AB_R2, 0, g, t)] = u0;
+                raw[ab_unit(AB_R2, 1, g, t)] = u1;
             }
         }
         tc_fence_before();
         __syncthreads();
-        interp_pass(smem, RAW_OFF, L_U2, AB_D2, L_E2);
+        interp_pass(smem, AB_R2, L_U2, AB_D2, L_E2);
         MT_MARK(9);
         // ---- u3: 32 -> 16, k 32 ----
         run_layer<6, AB_D2.RL>(pp, AB_D2.off, W0_OFF, true);
@@ -549,7 +587,7 @@ nwd_forward_mt_kernel(const unsigned char* __restrict__ blob, const TIn* __restr
         }
         MT_MARK(10);
         {
-            uint4* raw = reinterpret_cast<uint4*>(smem + RAW_OFF);
+            uint4* raw = reinterpret_cast<uint4*>(smem + AB_R3.off);
             const int g = row / 28, q = row % 28;
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
@@ -561,21 +599,21 @@ nwd_forward_mt_kernel(const unsigned char* __restrict__ blob, const TIn* __restr
                 if (g < G && t < L_U3) {
                     uint4 u0, u1;
                     finish16(v, bias_s[6], u0, u1);
-                    raw[(g * L_U3 + t) * 2] = u0;
-                    raw[(g * L_U3 + t) * 2 + 1] = u1;
+                    raw[ab_unit(AB_R3, 0, g, t)] = u0;
+                    raw[ab_unit(AB_R3, 1, g, t)] = u1;
                 }
             }
         }
         tc_fence_before();
         __syncthreads();
         MT_MARK(11);
-        interp_pass(smem, RAW_OFF, L_U3, AB_D3, L_E1);
+        interp_pass(smem, AB_R3, L_U3, AB_D3, L_E1);
         MT_MARK(12);
         // ---- u4: ConvTranspose 32 -> 4, k 32, stride 2: output channels (parity, co) over input positions ----
         run_layer<7, AB_D3.RL>(pp, AB_D3.off, W7_OFF, true);
         MT_MARK(13);
         {
-            uint4* raw = reinterpret_cast<uint4*>(smem + RAW_OFF);
+            uint4* raw = reinterpret_cast<uint4*>(smem + AB_R4.off);
             const int g = row / 27, q = row % 27;
             float bb[16];
 #pragma unroll
@@ -589,8 +627,8 @@ nwd_forward_mt_kernel(const unsigned char* __restrict__ blob, const TIn* __restr
                 uint4 u0, u1;
                 finish16(v, bb, u0, u1);
                 const int i0 = 16 * q + 15 - 2 * kc, i1 = i0 - 1;   // input positions of the two phases
-                if (g < G && i0 < L_U4H) raw[g * L_U4H + i0] = u0;
-                if (g < G && i1 >= 0 && i1 < L_U4H) raw[g * L_U4H + i1] = u1;
+                if (g < G && i0 < L_U4H) raw[ab_unit(AB_R4, 0, g, i0)] = u0;
+                if (g < G && i1 >= 0 && i1 < L_U4H) raw[ab_unit(AB_R4, 0, g, i1)] = u1;
             }
         }
         tc_fence_before();
@@ -598,38 +636,41 @@ nwd_forward_mt_kernel(const unsigned char* __restrict__ blob, const TIn* __restr
         MT_MARK(14);
         {   // interp 804 -> 900 (nwd.py:237-238), zero pad 255, parity / pair / phase split: the final layer's A buffer.
             // unit (seq = 2 g + p, s): samples xs_p[2 s + e][c] = h[4 s + 2 e + p - 255][c], e = 0, 1
-            const uint2* raw = reinterpret_cast<const uint2*>(smem + RAW_OFF);     // [g][804 positions][4 ch]
+            const uint2* raw = reinterpret_cast<const uint2*>(smem + AB_R4.off);   // unit (g, i) = positions 2 i, 2 i + 1 x 4 ch
             uint4* fb = reinterpret_cast<uint4*>(smem + AB_FIN.off);
             const float scale = (float)L_U4 / (float)T;
-            const int total = 32 * AB_FIN.RL;
-            for (int idx = threadIdx.x; idx < total; idx += THREADS) {
-                const int r = idx % AB_FIN.RL, j = idx / AB_FIN.RL;
-                const int seq = r / 12, s = (r % 12) * 32 + j;
+            constexpr int LP = 32 * 12, CH = LP / 32;                              // 384 units per sequence
+            auto ld4 = [&](int g, int pos) { return raw[ab_unit(AB_R4, 0, g, pos >> 1) * 2 + (pos & 1)]; };
+#pragma unroll 2
+            for (int it = wid; it < 2 * G * CH; it += THREADS / 32) {
+                const int seq = it / CH, s = (it - seq * CH) * 32 + lane;
+                const int g = seq >> 1, p = seq & 1;
                 uint32_t h[4] = {0, 0, 0, 0};
-                if (seq < 2 * G) {
-                    const int g = seq >> 1, p = seq & 1;
 #pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const int t = 4 * s + 2 * e + p - 255;
-                        if (t >= 0 && t < T) {
-                            float src = scale * ((float)t + 0.5f) - 0.5f;
-                            src = src < 0.f ? 0.f : src;
-                            int i0 = (int)src;
-                            i0 = i0 < L_U4 - 1 ? i0 : L_U4 - 1;
-                            const int i1 = i0 + (i0 < L_U4 - 1 ? 1 : 0);
-                            const float l1 = fminf(fmaxf(src - (float)i0, 0.f), 1.f), l0 = 1.f - l1;
-                            const uint2 a = raw[g * L_U4 + i0], b = raw[g * L_U4 + i1];
-                            const float2 a0 = unpack_h2(a.x), a1 = unpack_h2(a.y), b0 = unpack_h2(b.x), b1 = unpack_h2(b.y);
-                            h[2 * e] = pack_h2(l0 * a0.x + l1 * b0.x, l0 * a0.y + l1 * b0.y);
-                            h[2 * e + 1] = pack_h2(l0 * a1.x + l1 * b1.x, l0 * a1.y + l1 * b1.y);
-                        }
+                for (int e = 0; e < 2; ++e) {
+                    const int t = 4 * s + 2 * e + p - 255;
+                    if (t >= 0 && t < T) {
+                        float src = scale * ((float)t + 0.5f) - 0.5f;
+                        src = src < 0.f ? 0.f : src;
+                        int i0 = (int)src;
+                        i0 = i0 < L_U4 - 1 ? i0 : L_U4 - 1;
+                        const int i1 = i0 + (i0 < L_U4 - 1 ? 1 : 0);
+                        const float l1 = fminf(fmaxf(src - (float)i0, 0.f), 1.f), l0 = 1.f - l1;
+                        const uint2 a = ld4(g, i0), b = ld4(g, i1);
+                        const float2 a0 = unpack_h2(a.x), a1 = unpack_h2(a.y), b0 = unpack_h2(b.x), b1 = unpack_h2(b.y);
+                        h[2 * e] = pack_h2(l0 * a0.x + l1 * b0.x, l0 * a0.y + l1 * b0.y);
+                        h[2 * e + 1] = pack_h2(l0 * a1.x + l1 * b1.x, l0 * a1.y + l1 * b1.y);
                     }
                 }
-                fb[idx] = make_uint4(h[0], h[1], h[2], h[3]);
+                fb[ab_unit(AB_FIN, 0, seq, s)] = make_uint4(h[0], h[1], h[2], h[3]);
             }
+            constexpr int slack = AB_FIN.RL - 2 * G * 12;
+            for (int idx = threadIdx.x; idx < 32 * slack; idx += THREADS)
+                fb[(idx / slack) * AB_FIN.RL + 2 * G * 12 + idx % slack] = make_uint4(0, 0, 0, 0);
         }
         MT_MARK(15);
         // ---- final conv 4 -> 1, k 256, dilation 2, padding 255 (nwd.py:251-252, 285) ----
+        if (more) fetch_input(pass + gridDim.x);
         run_layer<8, AB_FIN.RL>(pp, AB_FIN.off, W8_OFF, false);
         if (threadIdx.x == 0 && more) load_weights(pp, lc_woff(0), lc_wbytes(0), W0_OFF, true);
         MT_MARK(16);
@@ -652,46 +693,54 @@ nwd_forward_mt_kernel(const unsigned char* __restrict__ blob, const TIn* __restr
         tc_fence_before();
         __syncthreads();
         MT_MARK(17);
-        // ---- rescale by tmax (nwd.py:46), monotone decay filter (nwd.py:337-343), store, CAVIaR prologue sums ----
+        // ---- monotone decay filter (nwd.py:337-343), rescale by tmax (nwd.py:46), store, CAVIaR prologue sums ----
+        // The running minimum of o * tmax is taken on the fp32 network outputs o: x -> (TOut)x * tmax is monotone
+        // (increasing for tmax > 0, decreasing otherwise -> running maximum), so the result is identical.
+        const bool filt = monotone_start >= 1 && monotone_start < T;
+        if (filt && lq == 0) {
+            const int g = wid >> 2;
+            float* orow = reinterpret_cast<float*>(smem + OROW_OFF) + g * OROW_STRIDE;
+            const bool neg = tmax_s[g] < 0.0;
+            const int len = T - monotone_start, per = (len + 31) / 32;     // lane owns `per` consecutive samples
+            const int b0 = monotone_start + lane * per, b1 = min(b0 + per, T);
+            float run = neg ? -INFINITY : INFINITY;
+            for (int t = b0; t < b1; ++t) {
+                const float o = orow[t + 4 * (t >> 7)];
+                run = neg ? fmaxf(run, o) : fminf(run, o);
+            }
+            float pre = run;                                               // inclusive scan of the lane totals
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const float u = __shfl_up_sync(0xffffffffu, pre, o);
+                if (lane >= o) pre = neg ? fmaxf(pre, u) : fminf(pre, u);
+            }
+            pre = __shfl_up_sync(0xffffffffu, pre, 1);
+            const float seed = orow[(monotone_start - 1) + 4 * ((monotone_start - 1) >> 7)];
+            run = lane == 0 ? seed : (neg ? fmaxf(pre, seed) : fminf(pre, seed));
+            for (int t = b0; t < b1; ++t) {
+                const int ix = t + 4 * (t >> 7);
+                run = neg ? fmaxf(run, orow[ix]) : fminf(run, orow[ix]);
+                orow[ix] = run;
+            }
+        }
+        __syncthreads();
         {
             const int g = wid >> 2, k = k0 + g;
             const float* orow = reinterpret_cast<const float*>(smem + OROW_OFF) + g * OROW_STRIDE;
             const TOut tm = (TOut)tmax_s[g];
             const bool isbad = bad_s[g] != 0;
-            const bool filt = monotone_start >= 1 && monotone_start < T;
-            int t0, t1;
-            if (filt) {
-                const int third = (monotone_start + 2) / 3;
-                t0 = lq < 3 ? min(lq * third, monotone_start) : monotone_start;
-                t1 = lq < 3 ? min((lq + 1) * third, monotone_start) : T;
-            } else {
-                t0 = lq * 225; t1 = t0 + 225;
-            }
             double s1 = 0.0, s2 = 0.0;
             if (k < K) {
                 TOut* op = outp + (size_t)k * T;
-                double carry = 0.0;
-                if (filt && lq == 3) {
-                    const int tp = monotone_start - 1;
-                    carry = (double)((TOut)orow[tp + 4 * (tp >> 7)] * tm);
-                }
-                for (int base = t0; base < t1; base += 32) {
-                    const int t = base + lane;
-                    double val = t < t1 ? (double)((TOut)orow[t + 4 * (t >> 7)] * tm) : INFINITY;
-                    if (filt && lq == 3) {
 #pragma unroll
-                        for (int o = 1; o < 32; o <<= 1) {
-                            const double u = __shfl_up_sync(0xffffffffu, val, o);
-                            if (lane >= o) val = fmin(val, u);
-                        }
-                        val = fmin(val, carry);
-                        carry = __shfl_sync(0xffffffffu, val, 31);
-                    }
-                    if (isbad) val = NAN;
-                    if (t < t1) {
-                        op[t] = (TOut)val;
-                        s1 += (t == 0 || t == T - 1) ? 0.5 * val : val;       // unit-spacing trapezoid, caviar.py:28
-                        s2 += val * val;                                      // autocorrelation at lag 0, caviar.py:30
+                for (int i = 0; i < 8; ++i) {
+                    const int t = lq * 32 + lane + 128 * i;
+                    if (t < T) {
+                        TOut val = (TOut)orow[t + 4 * (t >> 7)] * tm;
+                        if (isbad) val = (TOut)NAN;
+                        op[t] = val;
+                        s1 += (t == 0 || t == T - 1) ? 0.5 * (double)val : (double)val;       // unit-spacing trapezoid, caviar.py:28
+                        s2 += (double)val * (double)val;                                      // autocorrelation at lag 0, caviar.py:30
                     }
                 }
             }

@@ -19,13 +19,14 @@ for g in range(G):
     k = {}; E.emulate(x[g].astype(np.float32).astype(np.float64), ws, bias, cfg, rnd=h16, keep=k); keeps.append(k)
 
 # shared-memory map (mirror of csrc/nwd_mt.cu)
-DEC3_RL, DEC2_RL, DEC1_RL = G * 27 + 2, G * 28 + 4, G * 24 + 4
+DEC3_RL, DEC2_RL, DEC1_RL = G * 27 + 3, G * 28 + 5, G * 24 + 10
 DEC3_PL, DEC2_PL, DEC1_PL = 16 * DEC3_RL * 16, 8 * DEC2_RL * 16, 4 * DEC1_RL * 16
 A_LO = 0; A_END = 4 * DEC3_PL; B_LO = A_END; B_END = B_LO + 4 * DEC2_PL; C_LO = B_END; C_END = C_LO + 6 * DEC1_PL
 SMEM = C_END + 1024 + 128
 AB = dict(P1=(B_LO + G * 900 * 4, 1, G * 2 * 29 + 6, 29, 0), P2=(B_LO, 8, G * 25 + 4, 25, 0), P3=(B_LO, 4, G * 20 + 4, 20, 0),
           P4=(B_LO, 1, G * 32 + 16, 32, 0), E4=(B_LO + 4 * (G * 32 + 16) * 16, 2, G * 24 + 8, 24, 15), D1=(C_LO, 4, DEC1_RL, 24, 15),
-          D2=(B_LO, 8, DEC2_RL, 28, 31), D3=(A_LO, 16, DEC3_RL, 27, 15), FIN=(A_LO, 32, G * 2 * 12 + 4, 12, 0))
+          D2=(B_LO, 8, DEC2_RL, 28, 31), D3=(A_LO, 16, DEC3_RL, 27, 15), FIN=(A_LO, 32, G * 2 * 12 + 5, 12, 0),
+          R3=(C_LO, 8, G * 28 + 1, 28, 0), R4=(C_LO, 16, G * 27 + 1, 27, 0))
 RAW1 = AB["E4"][0] + 4 * 2 * AB["E4"][2] * 16
 
 def read_ab(sm, name, planes, g, L, pl0=0):
@@ -71,12 +72,10 @@ for stage in (only or [0, 2, 3, 5, 6, 7, 8, 9, 11, 12, 14, 15, 17]):
         if stage == 8: rep("dec1 g%d" % g, read_ab(sm, "D1", 6, g, 65), k["dec1"])
         if stage == 9: rep("dec2 g%d" % g, read_ab(sm, "D2", 4, g, 162), k["dec2"])
         if stage == 11:
-            u = sm[C_LO:].view(np.float16)
-            rep("raw3 g%d" % g, u[g * 193 * 16:(g + 1) * 193 * 16].astype(np.float64).reshape(193, 16), k["raw3"])
+            rep("raw3 g%d" % g, read_ab(sm, "R3", 2, g, 193), k["raw3"])
         if stage == 12: rep("dec3 g%d" % g, read_ab(sm, "D3", 4, g, 387), k["dec3"])
         if stage == 14:
-            u = sm[C_LO:].view(np.float16)
-            rep("raw4 g%d" % g, u[g * 804 * 4:(g + 1) * 804 * 4].astype(np.float64).reshape(804, 4), k["raw4"])
+            rep("raw4 g%d" % g, read_ab(sm, "R4", 1, g, 402).reshape(804, 4), k["raw4"])
         if stage == 15:
             off, PH, RL, Q, PAD = AB["FIN"]
             u = sm[off:].view(np.float16)
