@@ -398,7 +398,7 @@ def main():
     nwd = None
     if not args.no_nwd:
         Kt = args.nwd_traces
-        dem = NeuralDemixer(path=os.path.join(GOLD, "nwd_ie_ChroME2f_weights.npz"), device=dev, precision="tf32")
+        dem = NeuralDemixer(path=os.path.join(GOLD, "nwd_ie_ChroME2f_weights.npz"), device=dev, precision="fp16")
         htr = torch.from_numpy(synth_traces(Kt, seed=rank)).pin_memory()
         x32 = htr.to(dev).float()
         o32 = torch.empty_like(x32)
@@ -422,7 +422,7 @@ def main():
 
         dem.set_precision("fp32")
         ms_fp32, _ = time_nwd()
-        dem.set_precision("tf32")
+        dem.set_precision("fp16")
         ms_tc, kms_tc = time_nwd()
         nms = torch.tensor([ms_tc], dtype=torch.float64, device=dev)
         kms_n = [kms_tc]
@@ -448,18 +448,19 @@ def main():
         edt = torch.tensor([(time.time() - t0) / 3], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(edt, op=dist.ReduceOp.MAX)
-        nwd = {"metric": "nwd_traces_per_s", "value": tps, "unit": "traces/s", "dtype": "tf32 (fp32 accumulate)",
+        nwd = {"metric": "nwd_traces_per_s", "value": tps, "unit": "traces/s", "dtype": "fp16 operands (fp32 accumulate)",
                "fp32_cuda_core_path_traces_per_s": world * Kt / (ms_fp32 / 1e3),
-               "error_bound": "tf32 path: max-abs <= 2e-2, median rel-L2 <= 3e-3 on unit-normalised traces (tests/test_nwd_gpu.py)",
+               "error_bound": "fp16 tensor-core path: max-abs <= 2e-2, relative L2 <= 3e-3 on unit-normalised traces (tests/test_nwd_gpu.py)",
                "config": {"workload": "C2: NeuralDemixer nwd_ie_ChroME2f forward on %d x 900 traces per GPU" % Kt,
                           "l2_hygiene": "in+out = %.0f MB > L2" % (2 * Kt * 3600 / 1e6)},
                "ms_per_step": ms_tc,
-               "roofline": {"bound": "tensor", "kernel": "nwd_forward_tc_kernel", "achieved": ach, "peak": bf16_burst,
-                            "unit": "TFLOP/s", "frac": ach / bf16_burst, "traffic": read_traffic("nwd_forward_tc_kernel", Kt),
+               "roofline": {"bound": "tensor", "kernel": "nwd_forward_mt_kernel", "achieved": ach, "peak": bf16_burst,
+                            "unit": "TFLOP/s", "frac": ach / bf16_burst, "traffic": read_traffic("nwd_forward_mt_kernel", Kt),
                             "kernel_ms_per_launch": kms_tc,
-                            "peak_kind": peak_kind + " bf16 burst (MEASURED_PEAKS.json); operands are TF32 (tcgen05 "
-                                                     "kind::tf32, nominal dense peak = half of bf16); 16.87 MFLOP/trace, "
-                                                     "SURVEY.md App. C"},
+                            "peak_kind": peak_kind + " bf16 burst (MEASURED_PEAKS.json); operands are fp16 (tcgen05 "
+                                                     "kind::f16, same dense peak as bf16); achieved counts the network's "
+                                                     "16.87 MFLOP/trace (SURVEY.md App. C), not the zero taps of the "
+                                                     "widened implicit GEMMs"},
                "e2e": {"value": world * Kt / float(edt.item()), "unit": "traces/s", "h2d_bytes_per_step": Kt * 7200,
                        "d2h_bytes_per_step": Kt * 7200}}
 

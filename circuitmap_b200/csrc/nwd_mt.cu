@@ -218,7 +218,7 @@ __device__ __forceinline__ void load_weights(const Pipe& pp, int l_off, int l_by
 // make the A operand visible to the async proxy; warp 0 issues (one elected lane) and waits for the completion
 // barrier while the other warps park at the hardware barrier (no shared-memory polling next to the MMA operand reads)
 template <int L, int RL>
-__device__ __forceinline__ void run_layer(Pipe& pp, int a_off, int w_off, bool wait_w) {
+__device__ __forceinline__ void issue_async(Pipe& pp, int a_off, int w_off, bool wait_w) {
     proxy_fence();
     tc_fence_before();
     __syncthreads();
@@ -230,12 +230,19 @@ __device__ __forceinline__ void run_layer(Pipe& pp, int a_off, int w_off, bool w
         issue_layer<L, RL>(pp.smem0 + a_off, pp.smem0 + w_off, pp.tmem, leader);
         if (leader) umma_commit(pp.bar_mma);
         __syncwarp();
-        mbar_wait(pp.bar_mma, pp.mcount & 1);
     }
     if (wait_w) pp.wcount++;
+}
+__device__ __forceinline__ void wait_mma(Pipe& pp) {
+    if (pp.warp0) mbar_wait(pp.bar_mma, pp.mcount & 1);
     pp.mcount++;
     __syncthreads();
     tc_fence_after();
+}
+template <int L, int RL>
+__device__ __forceinline__ void run_layer(Pipe& pp, int a_off, int w_off, bool wait_w) {
+    issue_async<L, RL>(pp, a_off, w_off, wait_w);
+    wait_mma(pp);
 }
 
 // ------------------------------------------------------------------------------------------------ CUDA-core passes
@@ -335,8 +342,8 @@ nwd_forward_mt_kernel(const unsigned char* __restrict__ blob, const TIn* __restr
     __shared__ float bias_s[NLAYER][32];
     __shared__ double red_max[THREADS / 32], red_amax[THREADS / 32], red_s1[THREADS / 32], red_s2[THREADS / 32];
     __shared__ int red_bad[THREADS / 32];
-    __shared__ double tmax_s[G];
-    __shared__ int bad_s[G];
+    __shared__ double tmax_s[2][G];      // [pass parity]: the next pass's input stage runs while the final layer is in flight
+    __shared__ int bad_s[2][G];
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int lq = wid & 3, cgp = wid >> 2;                 // TMEM lane quadrant of this warp, column group
     const int row = 32 * lq + lane;                         // accumulator row (TMEM lane) this thread reads
@@ -378,15 +385,11 @@ nwd_forward_mt_kernel(const unsigned char* __restrict__ blob, const TIn* __restr
         }
     };
     if ((int)blockIdx.x < npass) fetch_input(blockIdx.x);
-
-    long long tmark = clock64();
-    for (int pass = blockIdx.x; pass < npass; pass += gridDim.x) {
-        const int k0 = pass * G;
-        const bool more = pass + (int)gridDim.x < npass;
-        // ---- input: per-trace max (nwd.py:43), normalise, AvgPool -> parity sequences of the pooled trace (d1's A) ----
+    // input stage: per-trace max (nwd.py:43), normalise, AvgPool -> parity sequences of the pooled trace (d1's A buffer)
+    auto input_stage = [&](int pass_, int slot_) {
         {
             const int g = wid >> 2;
-            const bool act = k0 + g < K;
+            const bool act = pass_ * G + g < K;
             double mx = -INFINITY, amx = 0.0;
             int bad = 0;
 #pragma unroll
@@ -409,7 +412,7 @@ nwd_forward_mt_kernel(const unsigned char* __restrict__ blob, const TIn* __restr
             int isbad = red_bad[4 * g] | red_bad[4 * g + 1] | red_bad[4 * g + 2] | red_bad[4 * g + 3];
             isbad |= !(tmax != 0.0) || !(am <= 60000.0 * fabs(tmax));     // fp16 operand range: |x / tmax| must stay finite
             if (!act) { tmax = 1.0; isbad = 0; }
-            if (lq == 0 && lane == 0) { tmax_s[g] = tmax; bad_s[g] = isbad; }
+            if (lq == 0 && lane == 0) { tmax_s[slot_][g] = tmax; bad_s[slot_][g] = isbad; }
             float* X = reinterpret_cast<float*>(smem + X_OFF) + g * T;
             const TIn inv = isbad ? (TIn)0 : (TIn)1 / (TIn)tmax;          // operands are rounded to fp16 later: x * (1 / tmax) is as good as x / tmax
 #pragma unroll
@@ -429,6 +432,17 @@ nwd_forward_mt_kernel(const unsigned char* __restrict__ blob, const TIn* __restr
                 p1[(2 * g + (pu & 1)) * 232 + (pu >> 1)] = __float2half_rn(v);
             }
             if (threadIdx.x < 6) reinterpret_cast<uint4*>(smem + AB_P1.off)[2 * G * 29 + threadIdx.x] = make_uint4(0, 0, 0, 0);
+        }
+    };
+    if ((int)blockIdx.x < npass) input_stage(blockIdx.x, 0);
+    int it_count = 0;
+
+    long long tmark = clock64();
+    for (int pass = blockIdx.x; pass < npass; pass += gridDim.x, ++it_count) {
+        const int k0 = pass * G;
+        const bool more = pass + (int)gridDim.x < npass;
+        const int slot = it_count & 1;
+        {
             // dec1 is scratch for the raw decoder outputs of the previous pass: restore its zero pads
             uint4* c4 = reinterpret_cast<uint4*>(smem + C_LO);
             for (int i = threadIdx.x; i < (C_END - C_LO) / 16; i += THREADS) c4[i] = make_uint4(0, 0, 0, 0);
@@ -631,6 +645,7 @@ nwd_forward_mt_kernel(const unsigned char* __restrict__ blob, const TIn* __restr
                 if (g < G && i1 >= 0 && i1 < L_U4H) raw[ab_unit(AB_R4, 0, g, i1)] = u1;
             }
         }
+        if (more) fetch_input(pass + gridDim.x);
         tc_fence_before();
         __syncthreads();
         MT_MARK(14);
@@ -670,8 +685,9 @@ nwd_forward_mt_kernel(const unsigned char* __restrict__ blob, const TIn* __restr
         }
         MT_MARK(15);
         // ---- final conv 4 -> 1, k 256, dilation 2, padding 255 (nwd.py:251-252, 285) ----
-        if (more) fetch_input(pass + gridDim.x);
-        run_layer<8, AB_FIN.RL>(pp, AB_FIN.off, W8_OFF, false);
+        issue_async<8, AB_FIN.RL>(pp, AB_FIN.off, W8_OFF, false);
+        if (more) input_stage(pass + gridDim.x, slot ^ 1);            // B_lo (u4's weights) is free: overlap with the MMAs
+        wait_mma(pp);
         if (threadIdx.x == 0 && more) load_weights(pp, lc_woff(0), lc_wbytes(0), W0_OFF, true);
         MT_MARK(16);
         {
@@ -700,7 +716,7 @@ nwd_forward_mt_kernel(const unsigned char* __restrict__ blob, const TIn* __restr
         if (filt && lq == 0) {
             const int g = wid >> 2;
             float* orow = reinterpret_cast<float*>(smem + OROW_OFF) + g * OROW_STRIDE;
-            const bool neg = tmax_s[g] < 0.0;
+            const bool neg = tmax_s[slot][g] < 0.0;
             const int len = T - monotone_start, per = (len + 31) / 32;     // lane owns `per` consecutive samples
             const int b0 = monotone_start + lane * per, b1 = min(b0 + per, T);
             float run = neg ? -INFINITY : INFINITY;
@@ -727,8 +743,8 @@ nwd_forward_mt_kernel(const unsigned char* __restrict__ blob, const TIn* __restr
         {
             const int g = wid >> 2, k = k0 + g;
             const float* orow = reinterpret_cast<const float*>(smem + OROW_OFF) + g * OROW_STRIDE;
-            const TOut tm = (TOut)tmax_s[g];
-            const bool isbad = bad_s[g] != 0;
+            const TOut tm = (TOut)tmax_s[slot][g];
+            const bool isbad = bad_s[slot][g] != 0;
             double s1 = 0.0, s2 = 0.0;
             if (k < K) {
                 TOut* op = outp + (size_t)k * T;

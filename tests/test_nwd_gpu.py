@@ -96,3 +96,87 @@ def test_tensor_core_path_within_stated_bound():
     dem.set_precision("fp32")
     out32 = dem(traces.copy(), monotone_filter_start=900, verbose=False) / tmax
     assert np.abs(out32 - ref).max() < TOL_UNIT
+
+
+# ---- multi-trace fp16 tensor-core path (csrc/nwd_mt.cu) ---------------------------------------------------------------
+@pytest.fixture(scope="module")
+def demixer16():
+    from circuitmap_b200 import NeuralDemixer
+    return NeuralDemixer(path=os.path.join(GOLDEN, "nwd_ie_ChroME2f_weights.npz"), precision="fp16")
+
+
+def test_fp16_multitrace_path_within_stated_bound(demixer16):
+    """precision='fp16': every convolution as a widened tcgen05 implicit GEMM, 4 traces per M tile.  Bound stated in
+    include/circuitmap_b200.h: max-abs <= 2e-2 and relative L2 <= 3e-3 on unit-normalised traces vs the fp64 oracle;
+    also checked against the reference's own golden vectors."""
+    from oracle import nwd as onwd
+    from oracle.make_golden import synth_traces
+    sd = dict(np.load(os.path.join(GOLDEN, "nwd_ie_ChroME2f_weights.npz")))
+    folded = onwd.fold_bn(sd)
+    traces = synth_traces(403, seed=21)                    # not a multiple of 4: the last pass is ragged
+    tmax = traces.max(1)[:, None]
+    ref = onwd.demix_np(traces.copy(), folded, monotone_start=900) / tmax
+    out = demixer16(traces.copy(), monotone_filter_start=900, verbose=False) / tmax
+    err = np.abs(out - ref)
+    rel_l2 = np.sqrt((err ** 2).sum(1)) / (np.sqrt((ref ** 2).sum(1)) + 1e-3)
+    print("fp16 path: max-abs %.3e, median rel-L2 %.3e, pooled rel-L2 %.3e" % (
+        err.max(), np.median(rel_l2), np.sqrt((err ** 2).sum()) / np.sqrt((ref ** 2).sum())))
+    assert err.max() < 2e-2
+    assert np.median(rel_l2) < 3e-3
+    assert np.sqrt((err ** 2).sum()) / np.sqrt((ref ** 2).sum()) < 3e-3
+    g = np.load(os.path.join(GOLDEN, "nwd_golden.npz"))
+    gt = g["traces"]
+    gout = demixer16(gt.copy(), verbose=False)
+    assert np.max(np.abs(gout - g["out"]) / gt.max(1)[:, None]) < 2e-2
+    assert np.all(np.diff(gout[:, 499:], axis=1) <= 0)      # monotone decay beyond sample 500
+
+
+def test_fp16_path_rows_are_independent_of_their_tile_mates(demixer16):
+    """Several traces share one 128-row MMA tile; a trace's result must not depend on which traces sit next to it,
+    on its slot in the pass, or on the batch size (bit exact)."""
+    from oracle.make_golden import synth_traces
+    traces = synth_traces(37, seed=3)
+    full = demixer16(traces.copy(), verbose=False)
+    for idx in ([0], [5, 6], [36, 1, 17], list(range(36, -1, -1)), [9] * 5):
+        sub = demixer16(traces[idx].copy(), verbose=False)
+        assert np.array_equal(sub, full[idx])
+    again = demixer16(traces.copy(), verbose=False)
+    assert np.array_equal(again, full)                      # run-to-run determinism
+    assert demixer16(np.zeros((0, 900)), verbose=False).shape == (0, 900)
+
+
+def test_fp16_path_io_dtypes_stats_and_large_batch(demixer16):
+    import torch
+    from oracle.make_golden import synth_traces
+    traces = synth_traces(70, seed=5)
+    x64 = torch.from_numpy(traces).cuda()
+    o64, y, ss = demixer16.forward_device(x64, stats=True)
+    o32 = demixer16.forward_device(x64.float())
+    tmax = torch.from_numpy(traces.max(1)[:, None]).cuda()
+    assert torch.max(torch.abs(o32.double() - o64) / tmax).item() < 1e-3
+    ref_y = o64.sum(1) - 0.5 * (o64[:, 0] + o64[:, -1])
+    assert torch.allclose(y, ref_y, rtol=1e-12, atol=1e-12)
+    assert torch.allclose(ss, (o64 * o64).sum(1), rtol=1e-12, atol=1e-14)
+    # full C2 size (20000 traces, > 33 passes per SM): every block of 70 traces repeats the small batch bit for bit
+    big = x64.float().repeat(286, 1)[:20000].contiguous()
+    ob = demixer16.forward_device(big)
+    assert torch.equal(ob[:70], o32) and torch.equal(ob[19950:20000], ob[19950 - 70 * 100:20000 - 70 * 100])
+    assert torch.isfinite(ob).all()
+
+
+def test_fp16_path_flags_traces_outside_the_fp16_range(demixer16):
+    """fp16 operands: a trace that cannot be normalised into the fp16 range (max 0, non-finite samples, |x / max| > 6e4)
+    comes back as an all-NaN row -- loudly, never saturated -- and does not disturb the other traces of its tile."""
+    from oracle.make_golden import synth_traces
+    traces = synth_traces(8, seed=9)
+    good = demixer16(traces.copy(), verbose=False)
+    bad = traces.copy()
+    bad[1] = 0.0                      # max == 0 (the reference divides by zero here, too)
+    bad[2, 100] = np.nan
+    bad[5] = -np.abs(bad[5]) * 1e6    # max is tiny and negative, min is huge
+    bad[5, 0] = -1e-3
+    out = demixer16(bad, verbose=False)
+    for i in (1, 2, 5):
+        assert np.isnan(out[i]).all()
+    for i in (0, 3, 4, 6, 7):
+        assert np.array_equal(out[i], good[i])
