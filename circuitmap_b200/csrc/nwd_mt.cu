@@ -104,6 +104,17 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
 __device__ __forceinline__ void proxy_fence() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+// Named barriers.  The CTA has 16 worker warps (CUDA-core passes, epilogues) and one MMA-issuing warp:
+//   id 1        workers only (512 threads)
+//   id 2 / 3    "A operand of the next job is ready": workers arrive, the issuer syncs (alternating ids, so that two
+//               signals may be outstanding: the next pass's first layer is signalled while the final layer is in flight)
+constexpr int NTHREADS = THREADS + 32;
+__device__ __forceinline__ void nb_sync(int id, int n) { asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void nb_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;\n" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void wsync() { nb_sync(1, THREADS); }
+// TMEM accumulator columns per layer: a decoder layer's skip-connection half is issued while the previous layer's
+// accumulator is still being read, so consecutive decoder layers use different columns
+__host__ __device__ constexpr int tcol(int l) { return l == 5 ? 256 : l == 6 ? 384 : l == 8 ? 256 : 0; }
 
 // D = F32, A = B = F16, both K-major, M = 128
 __host__ __device__ constexpr uint32_t idesc_f16(int n) {
@@ -131,10 +142,10 @@ __device__ int g_mt_dump_stage = -1;
             tmark = t_;                                                                  \
         }                                                                                \
         if (g_mt_dump_stage == (id) && blockIdx.x == 0 && pass == 0) {                   \
-            __syncthreads();                                                             \
+            wsync();                                                                     \
             for (int i_ = threadIdx.x; i_ < SMEM_BYTES / 16; i_ += THREADS)              \
                 reinterpret_cast<uint4*>(g_mt_dump)[i_] = sm4[i_];                       \
-            __syncthreads();                                                             \
+            wsync();                                                                     \
         }                                                                                \
     } while (0)
 
@@ -146,19 +157,19 @@ __device__ __forceinline__ int ab_unit(const AB b, int cp, int seq, int pp) {
 // ------------------------------------------------------------------------------------------------ MMA issue
 // All MMAs of layer L by one thread.  `abase` / `wbase` are shared-memory byte addresses of the A buffer (plane 0)
 // and of the tap table.  Descriptor start addresses advance in 16-byte units.
-template <int L, int RL>
-__device__ __forceinline__ void issue_layer(uint32_t abase, uint32_t wbase, uint32_t tmem, bool leader) {
+template <int L, int RL, int CQ0 = 0, int CQ1 = lcfg(L).CIN / 16>
+__device__ __forceinline__ void issue_layer(uint32_t abase, uint32_t wbase, uint32_t tmem, bool leader, uint32_t acc0 = 0) {
     constexpr int PH = lcfg(L).PH, CIN = lcfg(L).CIN, COUT = lcfg(L).COUT, U = lcfg(L).UPAD, V = lc_v(L), N = lc_n(L);
     constexpr int TILES = lc_tiles(L);
     constexpr uint32_t idesc = idesc_f16(N);
     constexpr uint32_t HI_SBO = (128u >> 4) | (1u << 14);                  // high word: SBO = 128 B, descriptor version 1
     if constexpr (CIN >= 16) {
-        constexpr int CQ = CIN / 16;                                       // K steps (pairs of 8-channel planes) per window position
+        // K steps per window position = pairs of 8-channel planes CQ0 .. CQ1 - 1 (the whole layer by default)
         const uint32_t a0 = ((abase >> 4) & 0x3FFF) | ((uint32_t)(PH * RL) << 16);      // LBO = plane stride
         const uint32_t b0 = ((wbase >> 4) & 0x3FFF) | ((uint32_t)(U * COUT) << 16);
 #pragma unroll 1
         for (int mt = 0; mt < TILES; ++mt) {
-            uint32_t acc = 0;
+            uint32_t acc = acc0;
 #pragma unroll 1
             for (int a = 0; a * PH < V; ++a) {
 #pragma unroll
@@ -166,7 +177,7 @@ __device__ __forceinline__ void issue_layer(uint32_t abase, uint32_t wbase, uint
                     const int v = a * PH + j;
                     if (v < V) {
 #pragma unroll
-                        for (int cq = 0; cq < CQ; ++cq) {
+                        for (int cq = CQ0; cq < CQ1; ++cq) {
                             if (leader)
                                 umma_f16(tmem + mt * N, a0 + (uint32_t)((2 * cq * PH + j) * RL + 128 * mt + a), HI_SBO,
                                          b0 + (uint32_t)((2 * cq * U + v) * COUT), HI_SBO, idesc, acc);
@@ -203,46 +214,46 @@ __device__ __forceinline__ void issue_layer(uint32_t abase, uint32_t wbase, uint
 struct Pipe {
     uint64_t* bar_w;
     uint64_t* bar_mma;
-    uint32_t wcount, mcount;        // phases consumed so far (uniform across threads)
+    uint32_t wcount, mcount, acount;   // weight phases, MMA phases, A-ready signals consumed so far (uniform per role)
     uint32_t tmem;
-    uint32_t smem0;                 // shared-memory address of the dynamic buffer
-    bool warp0;                     // warp-uniform: this is the issuing warp
+    uint32_t smem0;                    // shared-memory address of the dynamic buffer
     const unsigned char* blob;
 };
 
-__device__ __forceinline__ void load_weights(const Pipe& pp, int l_off, int l_bytes, int dst_off, bool first) {
-    if (first) mbar_expect_tx(pp.bar_w, (uint32_t)l_bytes);
-    bulk_g2s(pp.smem0 + dst_off, pp.blob + l_off, (uint32_t)l_bytes, pp.bar_w);
-}
-
-// make the A operand visible to the async proxy; warp 0 issues (one elected lane) and waits for the completion
-// barrier while the other warps park at the hardware barrier (no shared-memory polling next to the MMA operand reads)
-template <int L, int RL>
-__device__ __forceinline__ void issue_async(Pipe& pp, int a_off, int w_off, bool wait_w) {
+// ---- worker side ----
+// "the A operand of the next job is in shared memory": make it visible to the async proxy and tell the issuer
+__device__ __forceinline__ void signal_a(Pipe& pp) {
     proxy_fence();
     tc_fence_before();
-    __syncthreads();
-    if (pp.warp0) {
-        tc_fence_after();
-        if (wait_w) mbar_wait(pp.bar_w, pp.wcount & 1);
-        tc_fence_after();
-        const bool leader = elect_one();
-        issue_layer<L, RL>(pp.smem0 + a_off, pp.smem0 + w_off, pp.tmem, leader);
-        if (leader) umma_commit(pp.bar_mma);
-        __syncwarp();
-    }
-    if (wait_w) pp.wcount++;
+    nb_arrive(2 + (pp.acount & 1), NTHREADS);
+    pp.acount++;
 }
+// wait for the next MMA batch to complete: one warp polls the mbarrier, the others park at the hardware barrier
 __device__ __forceinline__ void wait_mma(Pipe& pp) {
-    if (pp.warp0) mbar_wait(pp.bar_mma, pp.mcount & 1);
+    if (threadIdx.x < 32) mbar_wait(pp.bar_mma, pp.mcount & 1);
     pp.mcount++;
-    __syncthreads();
+    wsync();
     tc_fence_after();
 }
-template <int L, int RL>
-__device__ __forceinline__ void run_layer(Pipe& pp, int a_off, int w_off, bool wait_w) {
-    issue_async<L, RL>(pp, a_off, w_off, wait_w);
-    wait_mma(pp);
+
+// ---- issuer side (one warp, one elected lane issues) ----
+__device__ __forceinline__ void iss_wait_a(Pipe& pp) {
+    nb_sync(2 + (pp.acount & 1), NTHREADS);
+    pp.acount++;
+    tc_fence_after();
+}
+__device__ __forceinline__ void iss_wait_w(Pipe& pp) { mbar_wait(pp.bar_w, pp.wcount & 1); pp.wcount++; }
+__device__ __forceinline__ void iss_commit_wait(Pipe& pp, bool leader) {
+    if (leader) umma_commit(pp.bar_mma);
+    __syncwarp();
+    mbar_wait(pp.bar_mma, pp.mcount & 1);
+    pp.mcount++;
+}
+__device__ __forceinline__ void iss_load(const Pipe& pp, bool leader, int l, int dst_off) {
+    if (leader) {
+        mbar_expect_tx(pp.bar_w, (uint32_t)lc_wbytes(l));
+        bulk_g2s(pp.smem0 + dst_off, pp.blob + lc_woff(l), (uint32_t)lc_wbytes(l), pp.bar_w);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ CUDA-core passes
@@ -333,7 +344,7 @@ __device__ __forceinline__ void finish16(const uint32_t* v, const float* bias, u
 }
 
 template <typename TIn, typename TOut>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(NTHREADS, 1)
 nwd_forward_mt_kernel(const unsigned char* __restrict__ blob, const TIn* __restrict__ traces, TOut* __restrict__ outp, int K,
                       int monotone_start, double* __restrict__ y_out, double* __restrict__ ss_out) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -349,8 +360,8 @@ nwd_forward_mt_kernel(const unsigned char* __restrict__ blob, const TIn* __restr
     const int row = 32 * lq + lane;                         // accumulator row (TMEM lane) this thread reads
     uint4* sm4 = reinterpret_cast<uint4*>(smem);
 
-    for (int i = threadIdx.x; i < SMEM_BYTES / 16; i += THREADS) sm4[i] = make_uint4(0, 0, 0, 0);
-    for (int i = threadIdx.x; i < NLAYER * 32; i += THREADS)
+    for (int i = threadIdx.x; i < SMEM_BYTES / 16; i += NTHREADS) sm4[i] = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < NLAYER * 32; i += NTHREADS)
         bias_s[i / 32][i % 32] = reinterpret_cast<const float*>(blob + BIAS_OFF)[i];
     if (threadIdx.x == 0) {
         mbar_init(&bars[0], 1);
@@ -358,7 +369,7 @@ nwd_forward_mt_kernel(const unsigned char* __restrict__ blob, const TIn* __restr
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     if (wid == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_s)), "r"(256u));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_s)), "r"(512u));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
     }
     proxy_fence();
@@ -366,11 +377,66 @@ nwd_forward_mt_kernel(const unsigned char* __restrict__ blob, const TIn* __restr
     __syncthreads();
     tc_fence_after();
     Pipe pp;
-    pp.bar_w = &bars[0]; pp.bar_mma = &bars[1]; pp.wcount = 0; pp.mcount = 0; pp.tmem = tmem_base_s;
+    pp.bar_w = &bars[0]; pp.bar_mma = &bars[1]; pp.wcount = 0; pp.mcount = 0; pp.acount = 0; pp.tmem = tmem_base_s;
     pp.smem0 = smem_u32(smem); pp.blob = blob;
-    pp.warp0 = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0) == 0;
     const int npass = (K + G - 1) / G;
-    if (threadIdx.x == 0 && (int)blockIdx.x < npass) load_weights(pp, lc_woff(0), lc_wbytes(0), W0_OFF, true);
+    if (__shfl_sync(0xffffffffu, wid, 0) == THREADS / 32) {
+        // ================================ MMA-issuing warp ================================
+        // Jobs in order; weights are streamed one layer ahead into whichever region is dead at that time (see the map
+        // above).  The skip-connection halves of the decoder layers (enc3 / enc2 / enc1: channel planes 2..) do not
+        // depend on the previous decoder layer: they are issued as soon as the layer's weights have landed, while
+        // the workers are still busy with the previous layer's epilogue and interpolation.
+        const bool leader = elect_one();
+        const uint32_t sm0 = pp.smem0, tm = pp.tmem;
+        if ((int)blockIdx.x < npass) iss_load(pp, leader, 0, W0_OFF);
+        for (int pass = blockIdx.x; pass < npass; pass += gridDim.x) {
+            const bool more = pass + (int)gridDim.x < npass;
+            iss_wait_a(pp); iss_wait_w(pp); tc_fence_after();
+            issue_layer<0, AB_P1.RL>(sm0 + AB_P1.off, sm0 + W0_OFF, tm + tcol(0), leader);
+            iss_commit_wait(pp, leader); iss_load(pp, leader, 1, W0_OFF);
+            iss_wait_a(pp); iss_wait_w(pp); tc_fence_after();
+            issue_layer<1, AB_P2.RL>(sm0 + AB_P2.off, sm0 + W0_OFF, tm + tcol(1), leader);
+            iss_commit_wait(pp, leader); iss_load(pp, leader, 2, W0_OFF);
+            iss_wait_a(pp); iss_wait_w(pp); tc_fence_after();
+            issue_layer<2, AB_P3.RL>(sm0 + AB_P3.off, sm0 + W0_OFF, tm + tcol(2), leader);
+            iss_commit_wait(pp, leader); iss_load(pp, leader, 3, W0_OFF);
+            iss_wait_a(pp); iss_wait_w(pp); tc_fence_after();
+            issue_layer<3, AB_P4.RL>(sm0 + AB_P4.off, sm0 + W0_OFF, tm + tcol(3), leader);
+            iss_commit_wait(pp, leader); iss_load(pp, leader, 4, W0_OFF);
+            iss_wait_a(pp); iss_wait_w(pp); tc_fence_after();
+            issue_layer<4, AB_E4.RL>(sm0 + AB_E4.off, sm0 + W0_OFF, tm + tcol(4), leader);
+            iss_commit_wait(pp, leader); iss_load(pp, leader, 5, W0_OFF);
+            // u2: enc3 part (planes 2..5) first, up1 part when interp1 is done
+            iss_wait_w(pp); tc_fence_after();
+            issue_layer<5, AB_D1.RL, 1, 3>(sm0 + AB_D1.off, sm0 + W0_OFF, tm + tcol(5), leader);
+            iss_wait_a(pp);
+            issue_layer<5, AB_D1.RL, 0, 1>(sm0 + AB_D1.off, sm0 + W0_OFF, tm + tcol(5), leader, 1);
+            iss_commit_wait(pp, leader); iss_load(pp, leader, 6, W0_OFF);
+            // u3: enc2 half, then up2 half
+            iss_wait_w(pp); tc_fence_after();
+            issue_layer<6, AB_D2.RL, 1, 2>(sm0 + AB_D2.off, sm0 + W0_OFF, tm + tcol(6), leader);
+            iss_wait_a(pp);
+            issue_layer<6, AB_D2.RL, 0, 1>(sm0 + AB_D2.off, sm0 + W0_OFF, tm + tcol(6), leader, 1);
+            iss_commit_wait(pp, leader);
+            if (leader) {
+                mbar_expect_tx(pp.bar_w, (uint32_t)(lc_wbytes(7) + lc_wbytes(8)));
+                bulk_g2s(sm0 + W7_OFF, pp.blob + lc_woff(7), (uint32_t)lc_wbytes(7), pp.bar_w);
+                bulk_g2s(sm0 + W8_OFF, pp.blob + lc_woff(8), (uint32_t)lc_wbytes(8), pp.bar_w);
+            }
+            // u4: enc1 half, then up3 half
+            iss_wait_w(pp); tc_fence_after();
+            issue_layer<7, AB_D3.RL, 1, 2>(sm0 + AB_D3.off, sm0 + W7_OFF, tm + tcol(7), leader);
+            iss_wait_a(pp);
+            issue_layer<7, AB_D3.RL, 0, 1>(sm0 + AB_D3.off, sm0 + W7_OFF, tm + tcol(7), leader, 1);
+            iss_commit_wait(pp, leader);
+            // final convolution
+            iss_wait_a(pp);
+            issue_layer<8, AB_FIN.RL>(sm0 + AB_FIN.off, sm0 + W8_OFF, tm + tcol(8), leader);
+            iss_commit_wait(pp, leader);
+            if (more) iss_load(pp, leader, 0, W0_OFF);
+        }
+    } else {
+    // ================================ worker warps ================================
 
     // this thread's 8 samples of the pass's traces (warps 4 g .. 4 g + 3 hold trace g); the next pass's are fetched
     // while the final layer runs
@@ -406,7 +472,7 @@ nwd_forward_mt_kernel(const unsigned char* __restrict__ blob, const TIn* __restr
             amx = warp_max(amx);
             bad = __any_sync(0xffffffffu, bad);
             if (lane == 0) { red_max[wid] = mx; red_amax[wid] = amx; red_bad[wid] = bad; }
-            __syncthreads();
+            wsync();
             double tmax = fmax(fmax(red_max[4 * g], red_max[4 * g + 1]), fmax(red_max[4 * g + 2], red_max[4 * g + 3]));
             const double am = fmax(fmax(red_amax[4 * g], red_amax[4 * g + 1]), fmax(red_amax[4 * g + 2], red_amax[4 * g + 3]));
             int isbad = red_bad[4 * g] | red_bad[4 * g + 1] | red_bad[4 * g + 2] | red_bad[4 * g + 3];
@@ -421,7 +487,7 @@ nwd_forward_mt_kernel(const unsigned char* __restrict__ blob, const TIn* __restr
                 if (t < T) X[t] = isbad ? 0.f : (float)(vin[i] * inv);       // a bad trace runs as zeros and is returned as NaN
             }
         }
-        __syncthreads();
+        wsync();
         {
             const float* X = reinterpret_cast<const float*>(smem + X_OFF);
             __half* p1 = reinterpret_cast<__half*>(smem + AB_P1.off);               // [2 g + parity][29 x 8 samples]
@@ -434,7 +500,7 @@ nwd_forward_mt_kernel(const unsigned char* __restrict__ blob, const TIn* __restr
             if (threadIdx.x < 6) reinterpret_cast<uint4*>(smem + AB_P1.off)[2 * G * 29 + threadIdx.x] = make_uint4(0, 0, 0, 0);
         }
     };
-    if ((int)blockIdx.x < npass) input_stage(blockIdx.x, 0);
+    if ((int)blockIdx.x < npass) { input_stage(blockIdx.x, 0); signal_a(pp); }
     int it_count = 0;
 
     long long tmark = clock64();
@@ -449,8 +515,7 @@ nwd_forward_mt_kernel(const unsigned char* __restrict__ blob, const TIn* __restr
         }
         MT_MARK(0);
         // ---- d1: 1 -> 16, k 32, dilation 2 (nwd.py:259): rows = groups of 8 outputs of one parity sequence ----
-        run_layer<0, AB_P1.RL>(pp, AB_P1.off, W0_OFF, true);
-        if (threadIdx.x == 0) load_weights(pp, lc_woff(1), lc_wbytes(1), W0_OFF, true);
+        wait_mma(pp);                                                  // signalled by the input stage
         MT_MARK(1);
         {
             uint4* d3 = reinterpret_cast<uint4*>(smem + AB_D3.off);
@@ -461,7 +526,7 @@ nwd_forward_mt_kernel(const unsigned char* __restrict__ blob, const TIn* __restr
                 for (int c = 0; c < 2; ++c) {
                     const int m = cgp + 4 * c;                       // sub-position = column chunk
                     uint32_t v[16];
-                    tmem_ld16(pp.tmem + mt * 128 + m * 16 + ((uint32_t)(32 * lq) << 16), v);
+                    tmem_ld16(pp.tmem + tcol(0) + mt * 128 + m * 16 + ((uint32_t)(32 * lq) << 16), v);
                     tmem_ld_wait();
                     const int t = 2 * (8 * sg + m) + p;
                     if (seq < 2 * G && t < L_E1) {
@@ -474,13 +539,13 @@ nwd_forward_mt_kernel(const unsigned char* __restrict__ blob, const TIn* __restr
             }
         }
         tc_fence_before();
-        __syncthreads();
+        wsync();
         MT_MARK(2);
         // ---- d2: 16 -> 16, k 32 ----
         pool_pass<2>(smem, AB_D3, 2, AB_P2, L_P2);
         MT_MARK(3);
-        run_layer<1, AB_P2.RL>(pp, AB_P2.off, W0_OFF, true);
-        if (threadIdx.x == 0) load_weights(pp, lc_woff(2), lc_wbytes(2), W0_OFF, true);
+        signal_a(pp);
+        wait_mma(pp);
         MT_MARK(4);
         {
             uint4* d2 = reinterpret_cast<uint4*>(smem + AB_D2.off);
@@ -489,7 +554,7 @@ nwd_forward_mt_kernel(const unsigned char* __restrict__ blob, const TIn* __restr
             for (int c = 0; c < 2; ++c) {
                 const int n = cgp + 4 * c;
                 uint32_t v[16];
-                tmem_ld16(pp.tmem + n * 16 + ((uint32_t)(32 * lq) << 16), v);
+                tmem_ld16(pp.tmem + tcol(1) + n * 16 + ((uint32_t)(32 * lq) << 16), v);
                 tmem_ld_wait();
                 const int t = 8 * q + 7 - n;
                 if (g < G && t < L_E2) {
@@ -501,12 +566,12 @@ nwd_forward_mt_kernel(const unsigned char* __restrict__ blob, const TIn* __restr
             }
         }
         tc_fence_before();
-        __syncthreads();
+        wsync();
         MT_MARK(5);
         // ---- d3: 16 -> 32, k 16 ----
         pool_pass<2>(smem, AB_D2, 2, AB_P3, L_P3);
-        run_layer<2, AB_P3.RL>(pp, AB_P3.off, W0_OFF, true);
-        if (threadIdx.x == 0) load_weights(pp, lc_woff(3), lc_wbytes(3), W0_OFF, true);
+        signal_a(pp);
+        wait_mma(pp);
         {
             uint4* d1 = reinterpret_cast<uint4*>(smem + AB_D1.off);
             const int g = row / 20, q = row % 20;
@@ -514,7 +579,7 @@ nwd_forward_mt_kernel(const unsigned char* __restrict__ blob, const TIn* __restr
             for (int c = 0; c < 2; ++c) {
                 const int kc = cgp + 4 * c, n = kc >> 1, hf = kc & 1;   // chunk = (phase n, channel half)
                 uint32_t v[16];
-                tmem_ld16(pp.tmem + kc * 16 + ((uint32_t)(32 * lq) << 16), v);
+                tmem_ld16(pp.tmem + tcol(2) + kc * 16 + ((uint32_t)(32 * lq) << 16), v);
                 tmem_ld_wait();
                 const int t = 4 * q + 3 - n;
                 if (g < G && t < L_E3) {
@@ -526,19 +591,19 @@ nwd_forward_mt_kernel(const unsigned char* __restrict__ blob, const TIn* __restr
             }
         }
         tc_fence_before();
-        __syncthreads();
+        wsync();
         MT_MARK(6);
         // ---- d4: 32 -> 32, k 16 ----
         pool_pass<4>(smem, AB_D1, 2, AB_P4, L_P4);
         for (int i = threadIdx.x; i < 4 * 2 * AB_E4.RL; i += THREADS)     // zero pads of u1's input (region held P2 / P3 before)
             reinterpret_cast<uint4*>(smem + AB_E4.off)[i] = make_uint4(0, 0, 0, 0);
-        run_layer<3, AB_P4.RL>(pp, AB_P4.off, W0_OFF, true);
-        if (threadIdx.x == 0) load_weights(pp, lc_woff(4), lc_wbytes(4), W0_OFF, true);
+        signal_a(pp);
+        wait_mma(pp);
         if (cgp < 2) {
             uint4* e4 = reinterpret_cast<uint4*>(smem + AB_E4.off);
             const int g = row / 32, t = row % 32;
             uint32_t v[16];
-            tmem_ld16(pp.tmem + cgp * 16 + ((uint32_t)(32 * lq) << 16), v);
+            tmem_ld16(pp.tmem + tcol(3) + cgp * 16 + ((uint32_t)(32 * lq) << 16), v);
             tmem_ld_wait();
             if (t < L_E4) {
                 uint4 u0, u1;
@@ -548,16 +613,16 @@ nwd_forward_mt_kernel(const unsigned char* __restrict__ blob, const TIn* __restr
             }
         }
         tc_fence_before();
-        __syncthreads();
+        wsync();
         MT_MARK(7);
         // ---- u1: ConvTranspose 32 -> 16, k 16 (valid convolution over the zero-padded input, flipped taps) ----
-        run_layer<4, AB_E4.RL>(pp, AB_E4.off, W0_OFF, true);
-        if (threadIdx.x == 0) load_weights(pp, lc_woff(5), lc_wbytes(5), W0_OFF, true);
+        signal_a(pp);
+        wait_mma(pp);
         if (cgp < 2) {
             uint4* raw = reinterpret_cast<uint4*>(smem + AB_R1.off);
             const int g = row / 24, q = row % 24, n = cgp;
             uint32_t v[16];
-            tmem_ld16(pp.tmem + n * 16 + ((uint32_t)(32 * lq) << 16), v);
+            tmem_ld16(pp.tmem + tcol(4) + n * 16 + ((uint32_t)(32 * lq) << 16), v);
             tmem_ld_wait();
             const int t = 2 * q + 1 - n;
             if (g < G && t < L_U1) {
@@ -568,17 +633,17 @@ nwd_forward_mt_kernel(const unsigned char* __restrict__ blob, const TIn* __restr
             }
         }
         tc_fence_before();
-        __syncthreads();
+        wsync();
         interp_pass(smem, AB_R1, L_U1, AB_D1, L_E3);
         MT_MARK(8);
         // ---- u2: 48 -> 16, k 16 ----
-        run_layer<5, AB_D1.RL>(pp, AB_D1.off, W0_OFF, true);
-        if (threadIdx.x == 0) load_weights(pp, lc_woff(6), lc_wbytes(6), W0_OFF, true);
+        signal_a(pp);
+        wait_mma(pp);
         {
             uint4* raw = reinterpret_cast<uint4*>(smem + AB_R2.off);
             const int g = row / 24, q = row % 24, n = cgp;
             uint32_t v[16];
-            tmem_ld16(pp.tmem + n * 16 + ((uint32_t)(32 * lq) << 16), v);
+            tmem_ld16(pp.tmem + tcol(5) + n * 16 + ((uint32_t)(32 * lq) << 16), v);
             tmem_ld_wait();
             const int t = 4 * q + 3 - n;
             if (g < G && t < L_U2) {
@@ -589,16 +654,12 @@ nwd_forward_mt_kernel(const unsigned char* __restrict__ blob, const TIn* __restr
             }
         }
         tc_fence_before();
-        __syncthreads();
+        wsync();
         interp_pass(smem, AB_R2, L_U2, AB_D2, L_E2);
         MT_MARK(9);
         // ---- u3: 32 -> 16, k 32 ----
-        run_layer<6, AB_D2.RL>(pp, AB_D2.off, W0_OFF, true);
-        if (threadIdx.x == 0) {
-            mbar_expect_tx(pp.bar_w, (uint32_t)(lc_wbytes(7) + lc_wbytes(8)));
-            load_weights(pp, lc_woff(7), lc_wbytes(7), W7_OFF, false);
-            load_weights(pp, lc_woff(8), lc_wbytes(8), W8_OFF, false);
-        }
+        signal_a(pp);
+        wait_mma(pp);
         MT_MARK(10);
         {
             uint4* raw = reinterpret_cast<uint4*>(smem + AB_R3.off);
@@ -607,7 +668,7 @@ nwd_forward_mt_kernel(const unsigned char* __restrict__ blob, const TIn* __restr
             for (int c = 0; c < 2; ++c) {
                 const int n = cgp + 4 * c;
                 uint32_t v[16];
-                tmem_ld16(pp.tmem + n * 16 + ((uint32_t)(32 * lq) << 16), v);
+                tmem_ld16(pp.tmem + tcol(6) + n * 16 + ((uint32_t)(32 * lq) << 16), v);
                 tmem_ld_wait();
                 const int t = 8 * q + 7 - n;
                 if (g < G && t < L_U3) {
@@ -619,12 +680,13 @@ nwd_forward_mt_kernel(const unsigned char* __restrict__ blob, const TIn* __restr
             }
         }
         tc_fence_before();
-        __syncthreads();
+        wsync();
         MT_MARK(11);
         interp_pass(smem, AB_R3, L_U3, AB_D3, L_E1);
         MT_MARK(12);
         // ---- u4: ConvTranspose 32 -> 4, k 32, stride 2: output channels (parity, co) over input positions ----
-        run_layer<7, AB_D3.RL>(pp, AB_D3.off, W7_OFF, true);
+        signal_a(pp);
+        wait_mma(pp);
         MT_MARK(13);
         {
             uint4* raw = reinterpret_cast<uint4*>(smem + AB_R4.off);
@@ -636,7 +698,7 @@ nwd_forward_mt_kernel(const unsigned char* __restrict__ blob, const TIn* __restr
             for (int c = 0; c < 2; ++c) {
                 const int kc = cgp + 4 * c;                          // phases n = 2 kc, 2 kc + 1
                 uint32_t v[16];
-                tmem_ld16(pp.tmem + kc * 16 + ((uint32_t)(32 * lq) << 16), v);
+                tmem_ld16(pp.tmem + tcol(7) + kc * 16 + ((uint32_t)(32 * lq) << 16), v);
                 tmem_ld_wait();
                 uint4 u0, u1;
                 finish16(v, bb, u0, u1);
@@ -647,7 +709,7 @@ nwd_forward_mt_kernel(const unsigned char* __restrict__ blob, const TIn* __restr
         }
         if (more) fetch_input(pass + gridDim.x);
         tc_fence_before();
-        __syncthreads();
+        wsync();
         MT_MARK(14);
         {   // interp 804 -> 900 (nwd.py:237-238), zero pad 255, parity / pair / phase split: the final layer's A buffer.
             // unit (seq = 2 g + p, s): samples xs_p[2 s + e][c] = h[4 s + 2 e + p - 255][c], e = 0, 1
@@ -685,17 +747,16 @@ nwd_forward_mt_kernel(const unsigned char* __restrict__ blob, const TIn* __restr
         }
         MT_MARK(15);
         // ---- final conv 4 -> 1, k 256, dilation 2, padding 255 (nwd.py:251-252, 285) ----
-        issue_async<8, AB_FIN.RL>(pp, AB_FIN.off, W8_OFF, false);
-        if (more) input_stage(pass + gridDim.x, slot ^ 1);            // B_lo (u4's weights) is free: overlap with the MMAs
+        signal_a(pp);
+        if (more) { input_stage(pass + gridDim.x, slot ^ 1); signal_a(pp); }   // B_lo (u4's weights) is free: runs under the MMAs
         wait_mma(pp);
-        if (threadIdx.x == 0 && more) load_weights(pp, lc_woff(0), lc_wbytes(0), W0_OFF, true);
         MT_MARK(16);
         {
             float* orow = reinterpret_cast<float*>(smem + OROW_OFF);
             const int seq = row / 12, q = row % 12, g = seq >> 1, p = seq & 1;
             const float bf = bias_s[8][0];
             uint32_t v[16];
-            tmem_ld16(pp.tmem + cgp * 16 + ((uint32_t)(32 * lq) << 16), v);
+            tmem_ld16(pp.tmem + tcol(8) + cgp * 16 + ((uint32_t)(32 * lq) << 16), v);
             tmem_ld_wait();
             if (seq < 2 * G) {
 #pragma unroll
@@ -707,7 +768,7 @@ nwd_forward_mt_kernel(const unsigned char* __restrict__ blob, const TIn* __restr
             }
         }
         tc_fence_before();
-        __syncthreads();
+        wsync();
         MT_MARK(17);
         // ---- monotone decay filter (nwd.py:337-343), rescale by tmax (nwd.py:46), store, CAVIaR prologue sums ----
         // The running minimum of o * tmax is taken on the fp32 network outputs o: x -> (TOut)x * tmax is monotone
@@ -739,7 +800,7 @@ nwd_forward_mt_kernel(const unsigned char* __restrict__ blob, const TIn* __restr
                 orow[ix] = run;
             }
         }
-        __syncthreads();
+        wsync();
         {
             const int g = wid >> 2, k = k0 + g;
             const float* orow = reinterpret_cast<const float*>(smem + OROW_OFF) + g * OROW_STRIDE;
@@ -764,19 +825,20 @@ nwd_forward_mt_kernel(const unsigned char* __restrict__ blob, const TIn* __restr
                 s1 = warp_sum(s1);
                 s2 = warp_sum(s2);
                 if (lane == 0) { red_s1[wid] = s1; red_s2[wid] = s2; }
-                __syncthreads();
+                wsync();
                 if (lq == 0 && lane == 0 && k < K) {
                     if (y_out) y_out[k] = (red_s1[wid] + red_s1[wid + 1]) + (red_s1[wid + 2] + red_s1[wid + 3]);
                     if (ss_out) ss_out[k] = (red_s2[wid] + red_s2[wid + 1]) + (red_s2[wid + 2] + red_s2[wid + 3]);
                 }
             }
         }
-        __syncthreads();
+        wsync();
         MT_MARK(18);
     }
+    }   // worker warps
     tc_fence_before();
     __syncthreads();
-    if (wid == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(pp.tmem), "r"(256u));
+    if (wid == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(pp.tmem), "r"(512u));
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -832,7 +894,7 @@ static int launch_t(cm_nwd* h, const void* in, void* out, int K, int ms, double*
     const int npass = (K + G - 1) / G;
     const int grid = npass < h->sm_count ? npass : h->sm_count;
     main_kernel_begin(st);
-    kern<<<grid, THREADS, SMEM_BYTES, st>>>(h->wmt_dev, (const TIn*)in, (TOut*)out, K, ms, y, ss);
+    kern<<<grid, NTHREADS, SMEM_BYTES, st>>>(h->wmt_dev, (const TIn*)in, (TOut*)out, K, ms, y, ss);
     main_kernel_end(st);
     count_launch();
     CM_CUDA_CHECK(cudaGetLastError());
