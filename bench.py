@@ -228,7 +228,7 @@ def workload_config(args, B):
                         "caviar %d iters%s" % (args.N, args.K, args.H, args.iters,
                                                "" if B is None else ", %d independent maps per GPU per step" % B),
             "fits_per_gpu_per_step": B, "distinct_maps": args.maps,
-            "l2_hygiene": "inputs larger than L2 (each fit reads its own 152 MB of psc+stim; 45 GB per step at B=296)",
+            "l2_hygiene": "inputs larger than L2 (each fit reads its own %.0f MB of psc+stim)" % ((args.N * args.K * 8 + args.K * 7200) / 1e6),
             "parallelism": "independent fits sharded over GPUs, no data-path collective"}
 
 
@@ -365,17 +365,19 @@ def main():
         h2d = B * (N * K * 8 + K * 900 * 8)
         d2h = sum(v.numel() * 8 for v in pin.values()) + B * N * K * 8
 
+        from circuitmap_b200 import streaming
+        pin["lam"] = pin_lam
+        hs = [host_stim[b % args.maps] for b in range(B)]
+        hp = [host_psc[b % args.maps] for b in range(B)]
+        streams = streaming._Streams(dev)
+        wsp = {}
+
         def e2e_step():
-            for b in range(B):
-                stim[b].copy_(host_stim[b % args.maps], non_blocking=True)
-                psc[b].copy_(host_psc[b % args.maps], non_blocking=True)
-            o = step()
-            for k in pin:
-                pin[k].copy_(o[k], non_blocking=True)
-            for b0 in range(0, B, slab):
-                n = min(slab, B - b0)
-                pin_lam[:n].copy_(o["lam"][b0:b0 + n], non_blocking=True)
+            # chunks of one fit per SM: H2D of chunk i+1, the fit kernels of chunk i and D2H of chunk i-1 overlap
+            st_ = streaming.fit_pinned(hs, hp, stim, psc, powers, pri, seeds, pin, chunk=sms, nnz_cap=nnz,
+                                       workspaces=wsp, streams=streams, **opts)
             torch.cuda.synchronize()
+            return st_
 
         e2e_step()
         sync_all()
@@ -389,7 +391,10 @@ def main():
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         e2e = {"value": world * B / float(dt.item()), "unit": "fits/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * float(dt.item()),
-               "note": "NumPy-compatible fp64 host buffers (pinned) -> cm_caviar_fit -> full state incl. dense lam back"}
+               "note": "circuitmap_b200.streaming.fit_pinned: fp64 host buffers (pinned) -> cm_caviar_fit -> full state incl. "
+                       "dense lam back (lam through a ring of %d pinned slabs), copies and kernels overlapped in chunks "
+                       "of %d fits" % (slab, sms)}
+        wsp.clear()
     del stim, psc, out
     ws[0] = None
     torch.cuda.empty_cache()
@@ -433,10 +438,11 @@ def main():
         x64 = torch.empty((Kt, 900), **f64)
         o64 = torch.empty((Kt, 900), **f64)
 
+        from circuitmap_b200 import streaming as _streaming
+        nstreams = _streaming._Streams(dev)
+
         def nwd_e2e():
-            x64.copy_(htr, non_blocking=True)
-            dem.forward_device(x64, out=o64)
-            hout.copy_(o64, non_blocking=True)
+            _streaming.demix_pinned(dem, htr, hout, x64, o64, chunk=max(1, Kt // 4), streams=nstreams)
             torch.cuda.synchronize()
 
         nwd_e2e()
