@@ -250,6 +250,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-nwd", action="store_true")
+    ap.add_argument("--no-c4", action="store_true", help="skip the C4 (1024 maps of N=500, K=5000) secondary measurement")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -399,6 +400,54 @@ def main():
     ws[0] = None
     torch.cuda.empty_cache()
 
+    # ---- C4 (BASELINE.json configs[3]): sweep of 1024 independent maps N=500, K=5000, sharded 1024 / world per GPU ----
+    c4 = None
+    if not args.no_c4:
+        N4, K4, Btot = 500, 5000, 1024
+        lo4, hi4 = (rank * Btot) // world, ((rank + 1) * Btot) // world
+        B4 = hi4 - lo4
+        m4 = [synth_map(N4, K4, H, seed=7000 + i) for i in range(2)]
+        nnz4 = int(max(np.count_nonzero(m[0]) for m in m4))
+        stim4 = torch.empty((B4, N4, K4), **f64)
+        psc4 = torch.empty((B4, K4, 900), dtype=torch.float32, device=dev)
+        for i in range(2):
+            stim4[i::2] = torch.from_numpy(m4[i][0]).to(dev)
+            psc4[i::2] = torch.from_numpy(m4[i][1]).float().to(dev)
+        cov4 = torch.zeros(B4, N4, 2, 2, **f64)
+        cov4[..., 0, 0] = 0.1
+        cov4[..., 1, 1] = 1.0
+        phi4 = torch.stack([0.1 * torch.ones(B4, N4, **f64), 5 * torch.ones(B4, N4, **f64)], -1).contiguous()
+        pri4 = (torch.zeros(B4, N4, **f64), 10 * torch.ones(B4, N4, **f64), 1.0, 0.1, phi4, cov4)
+        seeds4 = [1 + lo4 + b for b in range(B4)]
+        ws4 = None
+        for _ in range(2):
+            o4 = optimise.caviar_batched(stim4, powers, *pri4, psc=psc4, seeds=seeds4, nnz_cap=nnz4, want_lam=False,
+                                         workspace=ws4, **opts)
+            ws4 = o4["_workspace"]
+        sync_all()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        o4 = optimise.caviar_batched(stim4, powers, *pri4, psc=psc4, seeds=seeds4, nnz_cap=nnz4, want_lam=False,
+                                     workspace=ws4, **opts)
+        k4 = lib.cm_last_main_kernel_ms()
+        c1.record()
+        sync_all()
+        t4 = torch.tensor([c0.elapsed_time(c1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t4, op=dist.ReduceOp.MAX)
+        assert int(o4["status"].sum().item()) == 0
+        algo4 = algorithmic_bytes_per_fit(N4, K4, iters) * B4
+        c4 = {"metric": "caviar_fits_per_s", "value": Btot / (float(t4.item()) / 1e3), "unit": "fits/s", "scaling": "strong",
+              "config": {"workload": "C4 batched sweep: 1024 independent maps N=500, K=5000, H=%d, %d iters, sharded %d per GPU "
+                                     "(2 distinct maps tiled, distinct seeds; psc fp32, posteriors without the dense lam)"
+                                     % (H, iters, B4)},
+              "ms_per_step": float(t4.item()), "connected_in_fit0": int((o4["mu"][0] != 0).sum().item()),
+              "roofline": {"bound": "hbm", "kernel": "caviar_fit_kernel", "achieved": algo4 / (k4 / 1e3) / 1e9,
+                           "peak": hbm_peak, "unit": "GB/s", "frac": algo4 / (k4 / 1e3) / 1e9 / hbm_peak, "traffic": None,
+                           "kernel_ms_per_launch": k4, "algorithmic_model": ALGO_NOTE}}
+        del stim4, psc4, o4, ws4
+        torch.cuda.empty_cache()
+
     # ---- NWD (C2): K traces through cm_nwd_forward ----
     nwd = None
     if not args.no_nwd:
@@ -489,7 +538,7 @@ def main():
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": workload_config(args, B), "iters_per_s": fits_per_s * iters,
                 "connected_in_fit0": connected, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-                "gpu_launches": int(launches_per_step * args.steps), "clocks": clocks, "nwd": nwd}
+                "gpu_launches": int(launches_per_step * args.steps), "clocks": clocks, "nwd": nwd, "c4": c4}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

@@ -226,3 +226,50 @@ def test_two_ctas_per_sm_variant_matches_single_fits():
         for nm in NAMES:
             assert torch.equal(big["mu"][b] != 0, small["mu"][b % 4] != 0)
             assert torch.allclose(big[nm][b], small[nm][b % 4], rtol=1e-6, atol=1e-9), (b, nm)
+
+
+def test_c4_batched_sweep_shape():
+    """BASELINE.json configs[3] shape: a batch of independent maps with N=500, K=5000 (here 2 fits per SM of distinct
+    seeds over 6 distinct maps, so the two-CTAs-per-SM variant runs).  One map is checked against the oracle run for
+    the full 50 iterations; all of them against the size-independent properties and against their own single fit."""
+    import torch
+    from oracle import caviar as oc, simulate as osim
+    from circuitmap_b200 import optimise
+    N, K, nmaps = 500, 5000, 6
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    B = 2 * sms
+    sims = [osim.simulate_fast(N=N, K=K, H=10, seed=40 + s) for s in range(nmaps)]
+    powers = np.unique(sims[0]["stim_matrix"])[1:]
+    f64 = dict(dtype=torch.float64, device="cuda")
+    stim_m = torch.from_numpy(np.stack([s["stim_matrix"] for s in sims])).cuda()
+    psc_m = torch.from_numpy(np.stack([s["psc"] for s in sims])).float().cuda()
+    idx = torch.arange(B, device="cuda") % nmaps
+
+    def priors(b):
+        cov = torch.zeros(b, N, 2, 2, **f64); cov[..., 0, 0] = 0.1; cov[..., 1, 1] = 1.0
+        phi = torch.stack([0.1 * torch.ones(b, N, **f64), 5 * torch.ones(b, N, **f64)], -1).contiguous()
+        return torch.zeros(b, N, **f64), 10 * torch.ones(b, N, **f64), 1.0, 0.1, phi, cov
+
+    seeds = [1 + b for b in range(B)]
+    out = optimise.caviar_batched(stim_m[idx].contiguous(), powers, *priors(B), psc=psc_m[idx].contiguous(), seeds=seeds,
+                                  iters=50, msrmp=0.4, want_lam=False)
+    optimise.check_status(out)
+    assert torch.all(out["shape"] == 1.0 + K / 2) and torch.isfinite(out["phi"]).all() and torch.isfinite(out["mu"]).all()
+    for b in (0, 1, B - 1):
+        truth = set(np.nonzero(sims[b % nmaps]["weights"])[0]); got = set(np.nonzero(out["mu"][b].cpu().numpy())[0])
+        assert len(got - truth) <= 2 and len(truth & got) >= 0.7 * len(truth)
+    # fit 7 alone (16-warp CTA variant) and in the oracle
+    b = 7
+    m = b % nmaps
+    one = optimise.caviar_batched(stim_m[m:m + 1].contiguous(), powers, *priors(1), psc=psc_m[m:m + 1].contiguous(),
+                                  seeds=[seeds[b]], iters=50, msrmp=0.4)
+    assert torch.equal(one["mu"][0] != 0, out["mu"][b] != 0)
+    for nm in ("mu", "beta", "shape", "rate", "phi", "phi_cov", "z"):
+        assert torch.allclose(one[nm][0], out[nm][b], rtol=1e-6, atol=1e-9), nm
+    pr = oc.default_priors(N)
+    ref = oc.caviar(psc_m[m].double().cpu().numpy(), sims[m]["stim_matrix"], pr["mu"], pr["beta"], pr["shape"], pr["rate"],
+                    pr["phi"], pr["phi_cov"], iters=50, seed=seeds[b], msrmp=0.4)
+    assert np.array_equal(one["mu"][0].cpu().numpy() != 0, ref[0] != 0)          # identical connected set
+    for i, nm in enumerate(["mu", "beta", "lam", "shape", "rate", "phi", "phi_cov", "z"]):
+        a_, b_ = one[nm][0].cpu().numpy(), np.asarray(ref[i], float)
+        assert np.allclose(a_, b_, rtol=1e-4, atol=1e-7 * max(np.max(np.abs(b_)), 1e-300), equal_nan=True), nm
