@@ -136,12 +136,12 @@ __device__ unsigned char* g_mt_dump = nullptr;     // debug: CTA 0 copies its sh
 __device__ int g_mt_dump_stage = -1;
 #define MT_MARK(id)                                                                      \
     do {                                                                                 \
-        if (g_mt_prof && blockIdx.x == 0 && threadIdx.x == 0) {                          \
+        if (prof_on && threadIdx.x == 0) {                                               \
             const long long t_ = clock64();                                              \
             g_mt_cycles[id] += t_ - tmark;                                               \
             tmark = t_;                                                                  \
         }                                                                                \
-        if (g_mt_dump_stage == (id) && blockIdx.x == 0 && pass == 0) {                   \
+        if (dump_stage == (id) && pass == 0) {                                           \
             wsync();                                                                     \
             for (int i_ = threadIdx.x; i_ < SMEM_BYTES / 16; i_ += THREADS)              \
                 reinterpret_cast<uint4*>(g_mt_dump)[i_] = sm4[i_];                       \
@@ -218,6 +218,7 @@ struct Pipe {
     uint32_t tmem;
     uint32_t smem0;                    // shared-memory address of the dynamic buffer
     const unsigned char* blob;
+    bool prof;                         // diagnostics: cycle counters of CTA 0 enabled
 };
 
 // ---- worker side ----
@@ -238,15 +239,24 @@ __device__ __forceinline__ void wait_mma(Pipe& pp) {
 
 // ---- issuer side (one warp, one elected lane issues) ----
 __device__ __forceinline__ void iss_wait_a(Pipe& pp) {
+    const long long t0 = pp.prof ? clock64() : 0;
     nb_sync(2 + (pp.acount & 1), NTHREADS);
+    if (pp.prof && (threadIdx.x & 31) == 0) g_mt_cycles[28] += clock64() - t0;
     pp.acount++;
     tc_fence_after();
 }
-__device__ __forceinline__ void iss_wait_w(Pipe& pp) { mbar_wait(pp.bar_w, pp.wcount & 1); pp.wcount++; }
+__device__ __forceinline__ void iss_wait_w(Pipe& pp) {
+    const long long t0 = pp.prof ? clock64() : 0;
+    mbar_wait(pp.bar_w, pp.wcount & 1);
+    if (pp.prof && (threadIdx.x & 31) == 0) g_mt_cycles[19 + (pp.wcount & 7)] += clock64() - t0;   // 8 loads per pass
+    pp.wcount++;
+}
 __device__ __forceinline__ void iss_commit_wait(Pipe& pp, bool leader) {
     if (leader) umma_commit(pp.bar_mma);
     __syncwarp();
+    const long long t0 = pp.prof ? clock64() : 0;
     mbar_wait(pp.bar_mma, pp.mcount & 1);
+    if (pp.prof && (threadIdx.x & 31) == 0) g_mt_cycles[29] += clock64() - t0;
     pp.mcount++;
 }
 __device__ __forceinline__ void iss_load(const Pipe& pp, bool leader, int l, int dst_off) {
@@ -379,6 +389,10 @@ nwd_forward_mt_kernel(const unsigned char* __restrict__ blob, const TIn* __restr
     Pipe pp;
     pp.bar_w = &bars[0]; pp.bar_mma = &bars[1]; pp.wcount = 0; pp.mcount = 0; pp.acount = 0; pp.tmem = tmem_base_s;
     pp.smem0 = smem_u32(smem); pp.blob = blob;
+    // diagnostics switches are read once (a global load per mark would sit on the critical path)
+    const bool prof_on = g_mt_prof != 0 && blockIdx.x == 0;
+    const int dump_stage = blockIdx.x == 0 ? g_mt_dump_stage : -1;
+    pp.prof = prof_on;
     const int npass = (K + G - 1) / G;
     if (__shfl_sync(0xffffffffu, wid, 0) == THREADS / 32) {
         // ================================ MMA-issuing warp ================================

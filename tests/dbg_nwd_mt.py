@@ -51,3 +51,5 @@ tot = sum(buf[:19])
 for i, nm in enumerate(names):
     print("  %-18s %8.0f cycles/pass %5.1f%%" % (nm, buf[i] / npass, 100.0 * buf[i] / max(tot, 1)))
 print("  total %.0f cycles/pass = %.0f cycles/trace" % (tot / npass, tot / npass / 4))
+print("  issuer: wait for weights per load (d1 d2 d3 d4 u1 u2 u3 u4+fin):", " ".join("%.0f" % (buf[19 + i] / npass) for i in range(8)))
+print("  issuer: wait for A %.0f, wait for MMA completion %.0f cycles/pass" % (buf[28] / npass, buf[29] / npass))
