@@ -96,6 +96,32 @@ def synth_map(N, K, H, seed, T=900, powers=(45.0, 55.0, 65.0), connection_prob=0
     return stim, psc, w
 
 
+def _gen_map_compact(a):
+    """Pool worker: one synthetic map, returned compactly (sparse design, fp32 traces) to keep the pipe traffic small."""
+    N, K, H, seed = a
+    from threadpoolctl import threadpool_limits
+    with threadpool_limits(1):                 # one BLAS thread per worker: the pool already fills the cores
+        stim, psc, _ = synth_map(N, K, H, seed)
+    nz = np.nonzero(stim)
+    return (nz[0].astype(np.int32), nz[1].astype(np.int32), stim[nz].astype(np.float32), psc.astype(np.float32))
+
+
+def synth_maps_parallel(specs, procs):
+    """Distinct synthetic maps generated on the host cores in parallel (fork pool; call BEFORE CUDA is initialised)."""
+    import multiprocessing as mp
+    procs = max(1, min(procs, len(specs)))
+    if procs == 1:
+        return [_gen_map_compact(a) for a in specs]
+    with mp.get_context("fork").Pool(procs) as pool:
+        return pool.map(_gen_map_compact, specs, chunksize=1)
+
+
+def dense_stim(m, N, K):
+    s = np.zeros((N, K))
+    s[m[0], m[1]] = m[2]
+    return s
+
+
 def synth_traces(K, seed, T=900):
     rng = np.random.default_rng(seed)
     t = np.arange(T)[None, :]
@@ -244,7 +270,7 @@ def main():
     ap.add_argument("--H", type=int, default=10)
     ap.add_argument("--iters", type=int, default=50)
     ap.add_argument("--fits-per-gpu", type=int, default=0, help="B; default = 2 x number of SMs (two fit CTAs per SM)")
-    ap.add_argument("--maps", type=int, default=2, help="distinct synthetic maps tiled to B")
+    ap.add_argument("--maps", type=int, default=32, help="distinct synthetic maps (generated in parallel on the host) tiled to B")
     ap.add_argument("--nwd-traces", type=int, default=20000)
     ap.add_argument("--ref-iters", type=int, default=8, help="CPU oracle iterations per step (scaled to a full fit)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -259,6 +285,11 @@ def main():
     if args.impl == "reference":
         reference_arm(args, rank)
         return
+
+    # synthetic inputs first (fork pool on the host cores, before CUDA exists in this process)
+    procs = max(1, (os.cpu_count() or 1) // max(world, 1))
+    gen3 = synth_maps_parallel([(args.N, args.K, args.H, 1000 * rank + i) for i in range(args.maps)], procs)
+    gen4 = None if args.no_c4 else synth_maps_parallel([(500, 5000, args.H, 7000 + 100 * rank + i) for i in range(16)], procs)
 
     import torch
     import torch.distributed as dist
@@ -288,19 +319,24 @@ def main():
     hbm_peak, bf16_burst, bf16_sust, peak_kind = measured_peaks()
 
     # ---- synthetic inputs: `maps` distinct maps (seeded per rank), tiled to B fits, pinned on the host ----
+    # `maps` distinct maps per rank, tiled to B fits; the first two also live in pinned host memory for the e2e leg
     host_stim, host_psc = [], []
-    for i in range(args.maps):
-        s, p, _ = synth_map(N, K, H, seed=1000 * rank + i)
-        host_stim.append(torch.from_numpy(s).pin_memory())
-        host_psc.append(torch.from_numpy(p).pin_memory())
+    for i in range(min(2, args.maps)):
+        host_stim.append(torch.from_numpy(dense_stim(gen3[i], N, K)).pin_memory())
+        host_psc.append(torch.from_numpy(gen3[i][3].astype(np.float64)).pin_memory())
     powers = np.array([45.0, 55.0, 65.0])
-    nnz = int(max(np.count_nonzero(s.numpy()) for s in host_stim))
+    nnz = int(max(m[0].size for m in gen3))
     f64 = dict(dtype=torch.float64, device=dev)
     stim = torch.empty((B, N, K), **f64)
     psc = torch.empty((B, K, 900), **f64)
-    for b in range(B):
-        stim[b].copy_(host_stim[b % args.maps], non_blocking=True)
-        psc[b].copy_(host_psc[b % args.maps], non_blocking=True)
+    for i in range(args.maps):
+        if i >= B:
+            break
+        stim[i].copy_(torch.from_numpy(dense_stim(gen3[i], N, K)))
+        psc[i].copy_(torch.from_numpy(gen3[i][3]))
+    for b in range(args.maps, B):
+        stim[b].copy_(stim[b % args.maps])
+        psc[b].copy_(psc[b % args.maps])
     cov = torch.zeros(B, N, 2, 2, **f64)
     cov[..., 0, 0] = 0.1
     cov[..., 1, 1] = 1.0
@@ -368,8 +404,8 @@ def main():
 
         from circuitmap_b200 import streaming
         pin["lam"] = pin_lam
-        hs = [host_stim[b % args.maps] for b in range(B)]
-        hp = [host_psc[b % args.maps] for b in range(B)]
+        hs = [host_stim[b % len(host_stim)] for b in range(B)]
+        hp = [host_psc[b % len(host_psc)] for b in range(B)]
         streams = streaming._Streams(dev)
         wsp = {}
 
@@ -392,7 +428,7 @@ def main():
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         e2e = {"value": world * B / float(dt.item()), "unit": "fits/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * float(dt.item()),
-               "note": "circuitmap_b200.streaming.fit_pinned: fp64 host buffers (pinned) -> cm_caviar_fit -> full state incl. "
+               "note": "circuitmap_b200.streaming.fit_pinned: fp64 host buffers (pinned; two distinct maps tiled) -> cm_caviar_fit -> full state incl. "
                        "dense lam back (lam through a ring of %d pinned slabs), copies and kernels overlapped in chunks "
                        "of %d fits" % (slab, sms)}
         wsp.clear()
@@ -406,13 +442,16 @@ def main():
         N4, K4, Btot = 500, 5000, 1024
         lo4, hi4 = (rank * Btot) // world, ((rank + 1) * Btot) // world
         B4 = hi4 - lo4
-        m4 = [synth_map(N4, K4, H, seed=7000 + i) for i in range(2)]
-        nnz4 = int(max(np.count_nonzero(m[0]) for m in m4))
+        nnz4 = int(max(m[0].size for m in gen4))
         stim4 = torch.empty((B4, N4, K4), **f64)
         psc4 = torch.empty((B4, K4, 900), dtype=torch.float32, device=dev)
-        for i in range(2):
-            stim4[i::2] = torch.from_numpy(m4[i][0]).to(dev)
-            psc4[i::2] = torch.from_numpy(m4[i][1]).float().to(dev)
+        nm4 = len(gen4)
+        for i in range(min(nm4, B4)):
+            stim4[i].copy_(torch.from_numpy(dense_stim(gen4[i], N4, K4)))
+            psc4[i].copy_(torch.from_numpy(gen4[i][3]))
+        for b in range(nm4, B4):
+            stim4[b].copy_(stim4[b % nm4])
+            psc4[b].copy_(psc4[b % nm4])
         cov4 = torch.zeros(B4, N4, 2, 2, **f64)
         cov4[..., 0, 0] = 0.1
         cov4[..., 1, 1] = 1.0
@@ -439,7 +478,7 @@ def main():
         algo4 = algorithmic_bytes_per_fit(N4, K4, iters) * B4
         c4 = {"metric": "caviar_fits_per_s", "value": Btot / (float(t4.item()) / 1e3), "unit": "fits/s", "scaling": "strong",
               "config": {"workload": "C4 batched sweep: 1024 independent maps N=500, K=5000, H=%d, %d iters, sharded %d per GPU "
-                                     "(2 distinct maps tiled, distinct seeds; psc fp32, posteriors without the dense lam)"
+                                     "(16 distinct maps tiled, distinct seeds; psc fp32, posteriors without the dense lam)"
                                      % (H, iters, B4)},
               "ms_per_step": float(t4.item()), "connected_in_fit0": int((o4["mu"][0] != 0).sum().item()),
               "roofline": {"bound": "hbm", "kernel": "caviar_fit_kernel", "achieved": algo4 / (k4 / 1e3) / 1e9,
