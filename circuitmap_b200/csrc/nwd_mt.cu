@@ -28,7 +28,12 @@ constexpr int DEC1_RL = G * 24 + 10, DEC1_PL = 4 * DEC1_RL * 16;       // u2's A
 constexpr int A_LO = 0, A_HI = A_LO + 2 * DEC3_PL, A_END = A_LO + 4 * DEC3_PL;
 constexpr int B_LO = A_END, B_HI = B_LO + 2 * DEC2_PL, B_END = B_LO + 4 * DEC2_PL;
 constexpr int C_LO = B_END, C_END = C_LO + 6 * DEC1_PL;
-constexpr int SMEM_BYTES = C_END + 1024 + 128;                          // tail: junk rows of the last tile read past C
+// interpolation tables (built once per CTA): per output position {source unit offsets i0 | i1 << 16, weight l1}
+constexpr int TAB1_OFF = C_END + 1024;                                  // tail before it: junk rows of the last tile read past C
+constexpr int TAB2_OFF = TAB1_OFF + 4 * 24 * 8;                         // interp1: 96 padded positions of dec1
+constexpr int TAB3_OFF = TAB2_OFF + 8 * 28 * 8;                         // interp2: 224 of dec2
+constexpr int TAB4_OFF = TAB3_OFF + 16 * 27 * 8;                        // interp3: 432 of dec3
+constexpr int SMEM_BYTES = TAB4_OFF + T * 8 + 128;                      // interp4: 900 output samples
 
 struct AB { int off, PH, RL, Q, PAD; };        // byte offset, phases, units per phase row, units per sequence, left pad
 constexpr int X_OFF = B_LO;                                             // fp32 normalised input, G x 900
@@ -314,10 +319,29 @@ __device__ __forceinline__ void pool_pass(unsigned char* smem, const AB src, int
 // positions) into planes 0..1 of a concat buffer; covers every unit of the two planes (zero in the pads and the slack).
 // An item is 32 consecutive padded positions of one (trace, plane): lanes read neighbouring source units (distinct phase
 // rows) and write distinct phase rows -> conflict-free with the row lengths chosen above.
-__device__ __forceinline__ void interp_pass(unsigned char* smem, const AB raw, int Lin, const AB dst, int Lout) {
+__device__ __forceinline__ void build_interp_table(unsigned char* smem, int tab_off, const AB raw, int Lin, const AB dst, int Lout) {
+    uint2* tab = reinterpret_cast<uint2*>(smem + tab_off);
+    const float scale = (float)Lin / (float)Lout;
+    for (int pp = threadIdx.x; pp < dst.PH * dst.Q; pp += NTHREADS) {
+        const int t = pp - dst.PAD;
+        uint2 e = make_uint2(0xFFFFFFFFu, 0u);                              // pad position: zero
+        if (t >= 0 && t < Lout) {
+            float src = scale * ((float)t + 0.5f) - 0.5f;
+            src = src < 0.f ? 0.f : src;
+            int i0 = (int)src;
+            i0 = i0 < Lin - 1 ? i0 : Lin - 1;
+            const int i1 = i0 + (i0 < Lin - 1 ? 1 : 0);
+            const float l1 = fminf(fmaxf(src - (float)i0, 0.f), 1.f);
+            e.x = (uint32_t)ab_unit(raw, 0, 0, i0) | ((uint32_t)ab_unit(raw, 0, 0, i1) << 16);
+            e.y = __float_as_uint(l1);
+        }
+        tab[pp] = e;
+    }
+}
+__device__ __forceinline__ void interp_pass(unsigned char* smem, const AB raw, int tab_off, const AB dst) {
     const uint4* s = reinterpret_cast<const uint4*>(smem + raw.off);
     uint4* d = reinterpret_cast<uint4*>(smem + dst.off);
-    const float scale = (float)Lin / (float)Lout;
+    const uint2* tab = reinterpret_cast<const uint2*>(smem + tab_off);
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int LP = dst.PH * dst.Q, CH = (LP + 31) / 32, items = G * 2 * CH;
 #pragma unroll 2
@@ -325,16 +349,12 @@ __device__ __forceinline__ void interp_pass(unsigned char* smem, const AB raw, i
         const int gc = it / CH, pp = (it - gc * CH) * 32 + lane;          // gc = 2 g + cp
         const int g = gc >> 1, cp = gc & 1;
         if (pp < LP) {
-            const int t = pp - dst.PAD;
+            const uint2 e = tab[pp];
             uint4 o = make_uint4(0, 0, 0, 0);
-            if (t >= 0 && t < Lout) {
-                float src = scale * ((float)t + 0.5f) - 0.5f;
-                src = src < 0.f ? 0.f : src;
-                int i0 = (int)src;
-                i0 = i0 < Lin - 1 ? i0 : Lin - 1;
-                const int i1 = i0 + (i0 < Lin - 1 ? 1 : 0);
-                const float l1 = fminf(fmaxf(src - (float)i0, 0.f), 1.f), l0 = 1.f - l1;
-                o = lerp_units(s[ab_unit(raw, cp, g, i0)], s[ab_unit(raw, cp, g, i1)], l0, l1);
+            if (e.x != 0xFFFFFFFFu) {
+                const uint4* sb = s + (cp * raw.PH) * raw.RL + g * raw.Q;
+                const float l1 = __uint_as_float(e.y), l0 = 1.f - l1;
+                o = lerp_units(sb[e.x & 0xFFFFu], sb[e.x >> 16], l0, l1);
             }
             d[ab_unit(dst, cp, g, pp)] = o;
         }
@@ -373,6 +393,21 @@ nwd_forward_mt_kernel(const unsigned char* __restrict__ blob, const TIn* __restr
     for (int i = threadIdx.x; i < SMEM_BYTES / 16; i += NTHREADS) sm4[i] = make_uint4(0, 0, 0, 0);
     for (int i = threadIdx.x; i < NLAYER * 32; i += NTHREADS)
         bias_s[i / 32][i % 32] = reinterpret_cast<const float*>(blob + BIAS_OFF)[i];
+    __syncthreads();                                                        // the zero fill above covers the table area
+    build_interp_table(smem, TAB1_OFF, AB_R1, L_U1, AB_D1, L_E3);
+    build_interp_table(smem, TAB2_OFF, AB_R2, L_U2, AB_D2, L_E2);
+    build_interp_table(smem, TAB3_OFF, AB_R3, L_U3, AB_D3, L_E1);
+    for (int t = threadIdx.x; t < T; t += NTHREADS) {                       // interp4: 804 -> 900, raw4 in (pair, 4 ch) units
+        const float scale = (float)L_U4 / (float)T;
+        float src = scale * ((float)t + 0.5f) - 0.5f;
+        src = src < 0.f ? 0.f : src;
+        int i0 = (int)src;
+        i0 = i0 < L_U4 - 1 ? i0 : L_U4 - 1;
+        const int i1 = i0 + (i0 < L_U4 - 1 ? 1 : 0);
+        const float l1 = fminf(fmaxf(src - (float)i0, 0.f), 1.f);
+        const uint32_t o0 = (uint32_t)(ab_unit(AB_R4, 0, 0, i0 >> 1) * 2 + (i0 & 1)), o1 = (uint32_t)(ab_unit(AB_R4, 0, 0, i1 >> 1) * 2 + (i1 & 1));
+        reinterpret_cast<uint2*>(smem + TAB4_OFF)[t] = make_uint2(o0 | (o1 << 16), __float_as_uint(l1));
+    }
     if (threadIdx.x == 0) {
         mbar_init(&bars[0], 1);
         mbar_init(&bars[1], 1);
@@ -648,7 +683,7 @@ nwd_forward_mt_kernel(const unsigned char* __restrict__ blob, const TIn* __restr
         }
         tc_fence_before();
         wsync();
-        interp_pass(smem, AB_R1, L_U1, AB_D1, L_E3);
+        interp_pass(smem, AB_R1, TAB1_OFF, AB_D1);
         MT_MARK(8);
         // ---- u2: 48 -> 16, k 16 ----
         signal_a(pp);
@@ -669,7 +704,7 @@ nwd_forward_mt_kernel(const unsigned char* __restrict__ blob, const TIn* __restr
         }
         tc_fence_before();
         wsync();
-        interp_pass(smem, AB_R2, L_U2, AB_D2, L_E2);
+        interp_pass(smem, AB_R2, TAB2_OFF, AB_D2);
         MT_MARK(9);
         // ---- u3: 32 -> 16, k 32 ----
         signal_a(pp);
@@ -696,7 +731,7 @@ nwd_forward_mt_kernel(const unsigned char* __restrict__ blob, const TIn* __restr
         tc_fence_before();
         wsync();
         MT_MARK(11);
-        interp_pass(smem, AB_R3, L_U3, AB_D3, L_E1);
+        interp_pass(smem, AB_R3, TAB3_OFF, AB_D3);
         MT_MARK(12);
         // ---- u4: ConvTranspose 32 -> 4, k 32, stride 2: output channels (parity, co) over input positions ----
         signal_a(pp);
@@ -729,25 +764,21 @@ nwd_forward_mt_kernel(const unsigned char* __restrict__ blob, const TIn* __restr
             // unit (seq = 2 g + p, s): samples xs_p[2 s + e][c] = h[4 s + 2 e + p - 255][c], e = 0, 1
             const uint2* raw = reinterpret_cast<const uint2*>(smem + AB_R4.off);   // unit (g, i) = positions 2 i, 2 i + 1 x 4 ch
             uint4* fb = reinterpret_cast<uint4*>(smem + AB_FIN.off);
-            const float scale = (float)L_U4 / (float)T;
+            const uint2* tab = reinterpret_cast<const uint2*>(smem + TAB4_OFF);     // per output sample t: raw4 offsets, weight
             constexpr int LP = 32 * 12, CH = LP / 32;                              // 384 units per sequence
-            auto ld4 = [&](int g, int pos) { return raw[ab_unit(AB_R4, 0, g, pos >> 1) * 2 + (pos & 1)]; };
 #pragma unroll 2
             for (int it = wid; it < 2 * G * CH; it += THREADS / 32) {
                 const int seq = it / CH, s = (it - seq * CH) * 32 + lane;
                 const int g = seq >> 1, p = seq & 1;
+                const uint2* rg = raw + g * (AB_R4.Q * 2);
                 uint32_t h[4] = {0, 0, 0, 0};
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     const int t = 4 * s + 2 * e + p - 255;
                     if (t >= 0 && t < T) {
-                        float src = scale * ((float)t + 0.5f) - 0.5f;
-                        src = src < 0.f ? 0.f : src;
-                        int i0 = (int)src;
-                        i0 = i0 < L_U4 - 1 ? i0 : L_U4 - 1;
-                        const int i1 = i0 + (i0 < L_U4 - 1 ? 1 : 0);
-                        const float l1 = fminf(fmaxf(src - (float)i0, 0.f), 1.f), l0 = 1.f - l1;
-                        const uint2 a = ld4(g, i0), b = ld4(g, i1);
+                        const uint2 te = tab[t];
+                        const float l1 = __uint_as_float(te.y), l0 = 1.f - l1;
+                        const uint2 a = rg[te.x & 0xFFFFu], b = rg[te.x >> 16];
                         const float2 a0 = unpack_h2(a.x), a1 = unpack_h2(a.y), b0 = unpack_h2(b.x), b1 = unpack_h2(b.y);
                         h[2 * e] = pack_h2(l0 * a0.x + l1 * b0.x, l0 * a0.y + l1 * b0.y);
                         h[2 * e + 1] = pack_h2(l0 * a1.x + l1 * b1.x, l0 * a1.y + l1 * b1.y);
