@@ -145,7 +145,7 @@ struct Pipe {
 // issuing thread spends a handful of integer instructions per MMA.
 // Two threads (warps 0 and 1) issue concurrently: each takes half of the taps and accumulates into its own TMEM
 // columns (the epilogue adds the halves) -- one issuer alone is bound by its ~56-cycle issue latency, two reach the
-// shared-memory operand bandwidth limit (~39 cycles per 128x16x8 MMA, measured in tools/micro/tc_rate2.cu).
+// shared-memory operand bandwidth limit (~39 cycles per 128x16x8 MMA, measured in tests/tools/micro/tc_rate2.cu).
 template <int L, int TP, int DIL, int NTILES>
 __device__ __forceinline__ void issue_layer(const float* a_base, const float* wbuf, uint32_t tmem, int half) {
     constexpr int CI = tc_ci(L), N = tc_n(L), TAPS = tc_taps(L);
