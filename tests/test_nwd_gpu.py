@@ -180,3 +180,35 @@ def test_fp16_path_flags_traces_outside_the_fp16_range(demixer16):
         assert np.isnan(out[i]).all()
     for i in (0, 3, 4, 6, 7):
         assert np.array_equal(out[i], good[i])
+
+
+@pytest.mark.parametrize("weights", ["nwd_ee_ChroME1_weights.npz", "random"])
+def test_fp16_path_bound_holds_for_other_networks(weights):
+    """The stated bound of the fp16 tensor-core path is not specific to one checkpoint: second reference checkpoint
+    (excitatory ChroME1 demixer) and a random-init network of the same architecture, against the fp64 oracle."""
+    from circuitmap_b200 import NeuralDemixer
+    from circuitmap_b200.neural_waveform_demixing import random_weights
+    from oracle import nwd as onwd
+    from oracle.make_golden import synth_traces
+    if weights == "random":
+        sd = random_weights(seed=3)
+        dem = NeuralDemixer(path=None, precision="fp16")
+        dem2 = NeuralDemixer(path=None, precision="fp32")
+        assert all(np.array_equal(dem.weights[k], random_weights(seed=0)[k]) for k in dem.weights)   # path=None -> seed 0
+        sd = random_weights(seed=0)
+    else:
+        sd = dict(np.load(os.path.join(GOLDEN, weights)))
+        dem = NeuralDemixer(path=os.path.join(GOLDEN, weights), precision="fp16")
+        dem2 = NeuralDemixer(path=os.path.join(GOLDEN, weights), precision="fp32")
+    folded = onwd.fold_bn(sd)
+    traces = synth_traces(200, seed=33)
+    tmax = traces.max(1)[:, None]
+    ref = onwd.demix_np(traces.copy(), folded, monotone_start=900) / tmax
+    out = dem(traces.copy(), monotone_filter_start=900, verbose=False) / tmax
+    out32 = dem2(traces.copy(), monotone_filter_start=900, verbose=False) / tmax
+    scale = max(1.0, np.abs(ref).max())                      # a random network is not normalised to unit output
+    err = np.abs(out - ref).max() / scale
+    print("%s: fp16 max-abs %.3e (output scale %.2f), fp32 %.3e" % (weights, err, scale, np.abs(out32 - ref).max() / scale))
+    assert err < 2e-2
+    assert np.sqrt(((out - ref) ** 2).sum()) / (np.sqrt((ref ** 2).sum()) + 1e-12) < 3e-3
+    assert np.abs(out32 - ref).max() / scale < TOL_UNIT
