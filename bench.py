@@ -277,6 +277,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-nwd", action="store_true")
     ap.add_argument("--no-c4", action="store_true", help="skip the C4 (1024 maps of N=500, K=5000) secondary measurement")
+    ap.add_argument("--no-c5", action="store_true", help="skip the C5 (one map of N=5000, K=100000) secondary measurement")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -290,6 +291,7 @@ def main():
     procs = max(1, (os.cpu_count() or 1) // max(world, 1))
     gen3 = synth_maps_parallel([(args.N, args.K, args.H, 1000 * rank + i) for i in range(args.maps)], procs)
     gen4 = None if args.no_c4 else synth_maps_parallel([(500, 5000, args.H, 7000 + 100 * rank + i) for i in range(16)], procs)
+    gen5 = None if (args.no_c5 or rank != 0) else _gen_map_compact((5000, 100000, args.H, 9000))
 
     import torch
     import torch.distributed as dist
@@ -487,6 +489,42 @@ def main():
         del stim4, psc4, o4, ws4
         torch.cuda.empty_cache()
 
+    # ---- C5 (BASELINE.json configs[4]): ONE large map N=5000, K=100000 on one GPU (rank 0).  The K-sharded multi-GPU fit
+    # is not built; this is the single-GPU latency of the same map (one persistent CTA), reported for the record. ----
+    c5 = None
+    if gen5 is not None:
+        N5, K5 = 5000, 100000
+        stim5 = torch.from_numpy(dense_stim(gen5, N5, K5)).to(dev)[None]
+        psc5 = torch.from_numpy(gen5[3]).to(dev)[None]
+        cov5 = torch.zeros(1, N5, 2, 2, **f64)
+        cov5[..., 0, 0] = 0.1
+        cov5[..., 1, 1] = 1.0
+        phi5 = torch.stack([0.1 * torch.ones(1, N5, **f64), 5 * torch.ones(1, N5, **f64)], -1).contiguous()
+        pri5 = (torch.zeros(1, N5, **f64), 10 * torch.ones(1, N5, **f64), 1.0, 0.1, phi5, cov5)
+        ws5 = None
+        t5 = []
+        for rep in range(2):
+            torch.cuda.synchronize()
+            q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            q0.record()
+            o5 = optimise.caviar_batched(stim5, powers, *pri5, psc=psc5, seeds=[1], nnz_cap=int(gen5[0].size), want_lam=False,
+                                         workspace=ws5, **opts)
+            ws5 = o5["_workspace"]
+            q1.record()
+            torch.cuda.synchronize()
+            t5.append(q0.elapsed_time(q1))
+        assert int(o5["status"].sum().item()) == 0
+        algo5 = algorithmic_bytes_per_fit(N5, K5, iters)
+        c5 = {"metric": "caviar_fits_per_s", "value": 1e3 / t5[-1], "unit": "fits/s", "ms_per_fit": t5[-1],
+              "iters_per_s": iters * 1e3 / t5[-1],
+              "config": {"workload": "C5 large single map: N=5000, K=100000, H=%d, %d iters, ONE B200 (single persistent CTA; the "
+                                     "K-sharded 8-GPU variant is not built)" % (H, iters)},
+              "connected": int((o5["mu"][0] != 0).sum().item()),
+              "roofline": {"bound": "hbm", "achieved": algo5 / (t5[-1] / 1e3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                           "frac": algo5 / (t5[-1] / 1e3) / 1e9 / hbm_peak, "algorithmic_model": ALGO_NOTE}}
+        del stim5, psc5, o5, ws5
+        torch.cuda.empty_cache()
+
     # ---- NWD (C2): K traces through cm_nwd_forward ----
     nwd = None
     if not args.no_nwd:
@@ -577,7 +615,7 @@ def main():
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": workload_config(args, B), "iters_per_s": fits_per_s * iters,
                 "connected_in_fit0": connected, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-                "gpu_launches": int(launches_per_step * args.steps), "clocks": clocks, "nwd": nwd, "c4": c4}
+                "gpu_launches": int(launches_per_step * args.steps), "clocks": clocks, "nwd": nwd, "c4": c4, "c5": c5}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

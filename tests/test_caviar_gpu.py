@@ -273,3 +273,28 @@ def test_c4_batched_sweep_shape():
     for i, nm in enumerate(["mu", "beta", "lam", "shape", "rate", "phi", "phi_cov", "z"]):
         a_, b_ = one[nm][0].cpu().numpy(), np.asarray(ref[i], float)
         assert np.allclose(a_, b_, rtol=1e-4, atol=1e-7 * max(np.max(np.abs(b_)), 1e-300), equal_nan=True), nm
+
+
+def test_c5_large_single_map_shape():
+    """BASELINE.json configs[4] shape (N=5000, K=100000, H=10, 50 iterations) as ONE fit on one GPU: size-independent
+    properties (the oracle needs hours at this size) and recovery of the planted connectivity."""
+    import torch
+    from oracle import simulate as osim
+    from circuitmap_b200 import optimise
+    N, K = 5000, 100000
+    sim = osim.simulate_fast(N=N, K=K, H=10, seed=0, dtype=np.float32)
+    f64 = dict(dtype=torch.float64, device="cuda")
+    cov = torch.zeros(1, N, 2, 2, **f64); cov[..., 0, 0] = 0.1; cov[..., 1, 1] = 1.0
+    phi = torch.stack([0.1 * torch.ones(1, N, **f64), 5 * torch.ones(1, N, **f64)], -1).contiguous()
+    stim = torch.from_numpy(sim["stim_matrix"]).cuda()[None].contiguous()
+    out = optimise.caviar_batched(stim, np.unique(sim["stim_matrix"])[1:], torch.zeros(1, N, **f64),
+                                  10 * torch.ones(1, N, **f64), 1.0, 0.1, phi, cov,
+                                  psc=torch.from_numpy(sim["psc"]).cuda()[None].contiguous(), seeds=[1], iters=50, msrmp=0.4)
+    optimise.check_status(out)
+    lam, mu = out["lam"][0], out["mu"][0]
+    assert not torch.any(lam[stim[0] == 0] != 0)                   # supp(lam) within supp(stim)
+    assert out["shape"][0].item() == 1.0 + K / 2                   # caviar.py:241
+    assert torch.all(lam.sum(1)[mu != 0] > 0)
+    assert torch.all((lam >= 0) & (lam <= 1)) and torch.isfinite(out["phi"]).all() and torch.isfinite(out["rate"]).all()
+    truth = set(np.nonzero(sim["weights"])[0]); got = set(np.nonzero(mu.cpu().numpy())[0])
+    assert len(got - truth) <= 5 and len(truth & got) >= 0.7 * len(truth)
