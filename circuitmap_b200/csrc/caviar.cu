@@ -43,6 +43,7 @@ struct Layout {
         phizok, sortkeys, keys, dcnt, dlist, colpw, nmask, chinfo;
     // bytes
     size_t pw, mask, blocked;
+    size_t job;      // job board of the panel-GEMM helper CTAs (ints)
 };
 
 static Layout make_layout(int N, int K, int64_t nnz, int iters, bool lamhist, int GCT, int NW) {
@@ -103,6 +104,7 @@ static Layout make_layout(int N, int K, int64_t nnz, int iters, bool lamhist, in
     L.pw = take(z);
     L.mask = take(k);
     L.blocked = take(k);
+    L.job = take(256);
     L.stride = o;
     return L;
 }
@@ -123,6 +125,7 @@ struct FitParams {
     int lamhist;
     int* status;
     int smem_doubles;                 // dynamic shared memory available for pred / row buffers
+    int ct;                           // CTAs per fit: 1 + panel-GEMM helpers (single large fits only)
 };
 
 // ------------------------------------------------------------------------------------------------ PRNG
@@ -581,12 +584,32 @@ extern "C" int cm_caviar_fit(const cm_caviar_args* a, void* stream) {
     p.status = a->status_dev;
     const int smem_bytes = small_cta ? fit256::FIT_SMEM_BYTES : fit512::FIT_SMEM_BYTES;
     p.smem_doubles = smem_bytes / 8;
+    // helper CTAs for the panel GEMMs of single large fits: only when every CTA of the launch is co-resident
+    int ct = 1;
+    if (!small_cta && a->N > 256) {
+        int dev = 0, sms = 0;
+        CM_CUDA_CHECK(cudaGetDevice(&dev));
+        CM_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        int want = 15;
+        if (const char* e = getenv("CM_CAVIAR_HELPERS")) want = atoi(e);
+        want = want < 0 ? 0 : (want > 31 ? 31 : want);
+        if (want > 0 && (long long)a->B * (want + 1) <= sms) ct = want + 1;
+    }
+    p.ct = ct;
+    if (ct > 1)
+        for (int b = 0; b < a->B; ++b) CM_CUDA_CHECK(cudaMemsetAsync(ws + (size_t)b * L.stride + L.job, 0, 256, st));
     main_kernel_begin(st);
 #define CM_LAUNCH_FIT(NS, PT)                                                                                      \
     do {                                                                                                           \
         CM_CUDA_CHECK(cudaFuncSetAttribute(NS::caviar_fit_kernel<PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                            smem_bytes));                                                           \
-        NS::caviar_fit_kernel<PT><<<a->B, NS::NT, smem_bytes, st>>>(p);                                            \
+        if (ct > 1) {       /* helpers spin on the job board: cooperative launch guarantees co-residency */        \
+            void* kargs[] = {(void*)&p};                                                                           \
+            CM_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)NS::caviar_fit_kernel<PT>, dim3(a->B * ct),           \
+                                                      dim3(NS::NT), kargs, (size_t)smem_bytes, st));               \
+        } else {                                                                                                   \
+            NS::caviar_fit_kernel<PT><<<a->B, NS::NT, smem_bytes, st>>>(p);                                        \
+        }                                                                                                          \
     } while (0)
     if (small_cta) {
         if (a->n_powers <= 4) CM_LAUNCH_FIT(fit256, 4); else CM_LAUNCH_FIT(fit256, PMAX);

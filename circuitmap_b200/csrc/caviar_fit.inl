@@ -37,6 +37,8 @@ struct Ctx {
     double* red;      // shared: NW doubles scratch
     double* sm;       // shared: dynamic region
     int smd;          // its size in doubles
+    int ct, role;     // CTAs working on this fit (1 = none but this one), role of this CTA (0 = the fit itself, > 0 = helper)
+    int* job;         // global: job board between the fit CTA and its helpers (see panel_gemm_dist)
 };
 
 // phase accounting for cm_caviar_debug_phase_cycles (block 0, thread 0; enabled on request only)
@@ -272,7 +274,8 @@ struct GemmPipe {
 // 0, completion on mbarriers, 4 stages in flight); each warp owns the 32 x 16 slice of the 32 x 256 output tile as
 // 4 x 2 DMMA tiles.  Row strides = 4 (mod 16) doubles keep the fragment loads bank-conflict free.
 template <bool UPPER>
-__device__ void panel_gemm(const Ctx& c, int ldr, int i0, int nb, const double* IN, double* OUT, GemmPipe& gp) {
+__device__ void panel_gemm(const Ctx& c, int ldr, int i0, int nb, const double* IN, double* OUT, GemmPipe& gp,
+                           int part = 0, int nparts = 1) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int lq = lane >> 2, lr = lane & 3;
     const int sw = (lr & 1) << 3;                 // swizzle term of this lane's k rows (k = 4*ks + lr)
@@ -283,7 +286,7 @@ __device__ void panel_gemm(const Ctx& c, int ldr, int i0, int nb, const double* 
     // the async-proxy bulk copies that reuse the same shared memory
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
     __syncthreads();
-    for (int ct0 = 0; ct0 < i0; ct0 += GCT) {
+    for (int ct0 = part * GCT; ct0 < i0; ct0 += nparts * GCT) {      // column tiles part, part + nparts, ...
         const int tile_end = min(i0, ct0 + GCT);
         const int kfirst = UPPER ? 0 : ct0;
         const int klast = UPPER ? tile_end : i0;
@@ -388,6 +391,80 @@ __device__ void panel_gemm(const Ctx& c, int ldr, int i0, int nb, const double* 
     __syncthreads();
 }
 
+// ---- helper CTAs: the column tiles of a panel GEMM are independent, so for a single large fit the launch adds
+// `ct - 1` helper CTAs (on otherwise idle SMs) that take tiles part, part + ct, ... of every panel GEMM with more than
+// one tile.  All operands (IN panel, X, OUT panel) live in global memory; every output element is still computed by
+// one warp in the same order, so the result is bitwise identical to the single-CTA run.
+// Job board (ints, global, zeroed by the host): [0] sequence number (release/acquire), [1] type (0 quit, 1 upper,
+// 2 lower), [2] i0, [3] nb, [16] number of helper completions, [20] watchdog flag.
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(int* p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void red_release_gpu(int* p, int v) {
+    asm volatile("red.release.gpu.global.add.s32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+constexpr long long WATCHDOG_CYCLES = 1ll << 38;      // minutes: a helper idles while the fit CTA runs the other phases
+
+template <bool UPPER>
+__device__ void panel_gemm_dist(const Ctx& c, int ldr, int i0, int nb, const double* IN, double* OUT, GemmPipe& gp) {
+    __shared__ int s_seq;
+    const bool dist = c.ct > 1 && i0 > GCT;           // at least two column tiles
+    if (dist) {
+        __syncthreads();                              // IN and X are complete (written by this CTA)
+        if (threadIdx.x == 0) {
+            const int s = c.job[0] + 1;
+            c.job[1] = UPPER ? 1 : 2; c.job[2] = i0; c.job[3] = nb;
+            __threadfence();
+            st_release_gpu(&c.job[0], s);
+            s_seq = s;
+        }
+    }
+    panel_gemm<UPPER>(c, ldr, i0, nb, IN, OUT, gp, 0, dist ? c.ct : 1);
+    if (dist) {
+        if (threadIdx.x == 0) {
+            const long long t0 = clock64();
+            const int want = s_seq * (c.ct - 1);
+            while (ld_acquire_gpu(&c.job[16]) < want)
+                if (clock64() - t0 > WATCHDOG_CYCLES) { c.job[20] = 1; break; }
+        }
+        __syncthreads();
+        __threadfence();                              // the helpers' tiles of OUT are visible to every thread from here
+    }
+}
+
+__device__ void helper_loop(const Ctx& c, GemmPipe& gp) {
+    __shared__ int s_job[3];
+    const int ldr = c.N + ROWPAD;
+    int seen = 0;
+    __syncthreads();                                  // mbarriers initialised
+    for (;;) {
+        if (threadIdx.x == 0) {
+            const long long t0 = clock64();
+            int type = -1;
+            while (type < 0) {
+                if (ld_acquire_gpu(&c.job[0]) != seen) type = c.job[1];
+                else if (clock64() - t0 > WATCHDOG_CYCLES) type = 0;
+                else __nanosleep(200);
+            }
+            s_job[0] = type; s_job[1] = c.job[2]; s_job[2] = c.job[3];
+        }
+        __syncthreads();
+        const int type = s_job[0], i0 = s_job[1], nb = s_job[2];
+        __syncthreads();
+        if (type == 0) break;
+        ++seen;
+        asm volatile("fence.proxy.async;\n" ::: "memory");          // operands were written through the generic proxy of another SM
+        if (type == 1) panel_gemm<true>(c, ldr, i0, nb, c.PA, c.PB, gp, c.role, c.ct);
+        else panel_gemm<false>(c, ldr, i0, nb, c.PB, c.PA, gp, c.role, c.ct);
+        if (threadIdx.x == 0) { __threadfence(); red_release_gpu(&c.job[16], 1); }
+    }
+}
+
 __device__ __noinline__ void phase_a2(const Ctx& c, double sigma, int* na_s, GemmPipe& gp) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int lq = lane >> 2, lr = lane & 3;
@@ -434,7 +511,7 @@ __device__ __noinline__ void phase_a2(const Ctx& c, double sigma, int* na_s, Gem
         gram_rows(c, i0, nb, sigma);              // PA[r][0..i0+r] = M[i0+r][.]
         __syncthreads();
         phase_mark(c, 1);
-        if (i0 > 0) panel_gemm<true>(c, ldr, i0, nb, PA, PB, gp);      // PB = Lrow = A[I,0:i0] X11^T
+        if (i0 > 0) panel_gemm_dist<true>(c, ldr, i0, nb, PA, PB, gp); // PB = Lrow = A[I,0:i0] X11^T
         phase_mark(c, 2);
         // S = A[I,I] - Lrow Lrow^T : warp w owns the 8x8 tile (w/4, w%4) and runs the whole k range with DMMA,
         // four independent accumulator pairs hide the dependent-issue latency.
@@ -504,7 +581,7 @@ __device__ __noinline__ void phase_a2(const Ctx& c, double sigma, int* na_s, Gem
         __syncthreads();
         phase_mark(c, 3);
         if (i0 > 0) {
-            panel_gemm<false>(c, ldr, i0, nb, PB, PA, gp);              // PA = W = Lrow X11
+            panel_gemm_dist<false>(c, ldr, i0, nb, PB, PA, gp);         // PA = W = Lrow X11
             phase_mark(c, 4);
             // X[I, 0:i0] = -Xd W (32x32 lower-triangular times 32 x i0, DMMA), mirrored into the upper half
             const int nsl = (i0 + 15) / 16;
@@ -966,7 +1043,7 @@ __global__ void __launch_bounds__(NT, (NT == 512) ? 1 : 2) caviar_fit_kernel(con
     __shared__ long long sc_tlast;
     __shared__ __align__(8) uint64_t sc_bar[2 * NST];
 
-    const int b = blockIdx.x;
+    const int b = blockIdx.x / p.ct;                  // p.ct CTAs per fit: the fit itself and its panel-GEMM helpers
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     char* base = p.ws + (size_t)b * p.L.stride;
     const Layout& L = p.L;
@@ -982,6 +1059,9 @@ __global__ void __launch_bounds__(NT, (NT == 512) ? 1 : 2) caviar_fit_kernel(con
 #undef CM_D
 #undef CM_I
     c.chinfo = reinterpret_cast<int4*>(base + L.chinfo);
+    c.job = reinterpret_cast<int*>(base + L.job);
+    c.ct = p.ct;
+    c.role = blockIdx.x - b * p.ct;
     c.cscq = reinterpret_cast<double2*>(base + L.cscq);
     c.sortkeys = reinterpret_cast<uint32_t*>(base + L.sortkeys);
     c.keys = reinterpret_cast<uint32_t*>(base + L.keys);
@@ -1006,6 +1086,7 @@ __global__ void __launch_bounds__(NT, (NT == 512) ? 1 : 2) caviar_fit_kernel(con
     }
     GemmPipe gp;
     gp.full = sc_bar; gp.empty = sc_bar + NST; gp.seq = 0;
+    if (c.role > 0) { helper_loop(c, gp); return; }
     c.nnz = c.row_ptr[N];
     const int iters = o.iters;
     const int S = o.num_mc_samples;
@@ -1430,6 +1511,12 @@ __global__ void __launch_bounds__(NT, (NT == 512) ? 1 : 2) caviar_fit_kernel(con
     for (int n = threadIdx.x; n < 4 * N; n += NT) p.phicov_out[(size_t)b * 4 * N + n] = c.phicov[n];
     for (int k = threadIdx.x; k < K; k += NT) p.z_out[(size_t)b * K + k] = c.z[k];
     if (threadIdx.x == 0) { p.shape_out[b] = sc_shape; p.rate_out[b] = sc_rate; }
+    if (c.ct > 1 && threadIdx.x == 0) {               // release the helpers
+        if (c.job[20]) p.status[b] = 9;               // a helper did not answer: results are not to be trusted
+        c.job[1] = 0;
+        __threadfence();
+        st_release_gpu(&c.job[0], c.job[0] + 1);
+    }
 }
 
 }  // namespace CM_FITNS

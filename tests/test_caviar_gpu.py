@@ -3,6 +3,8 @@
 Tolerance (BASELINE.json north_star): connected set and accept/reject pattern IDENTICAL; mu/beta/lam/phi/phi_cov/
 shape/rate/z within 1e-4 relative.  The kernel computes in fp64 and lands around 1e-8.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -298,3 +300,39 @@ def test_c5_large_single_map_shape():
     assert torch.all((lam >= 0) & (lam <= 1)) and torch.isfinite(out["phi"]).all() and torch.isfinite(out["rate"]).all()
     truth = set(np.nonzero(sim["weights"])[0]); got = set(np.nonzero(mu.cpu().numpy())[0])
     assert len(got - truth) <= 5 and len(truth & got) >= 0.7 * len(truth)
+
+
+def test_panel_gemm_helper_ctas_are_bitwise_neutral():
+    """A single large fit gets helper CTAs for the column tiles of its panel GEMMs (csrc/caviar_fit.inl,
+    panel_gemm_dist).  Every output element is still computed by one warp in the same order: the fit must be bitwise
+    identical with and without helpers (CM_CAVIAR_HELPERS=0), also for two fits side by side."""
+    import torch
+    from oracle import simulate as osim
+    from circuitmap_b200 import optimise
+    N, K, B = 700, 6000, 2
+    sims = [osim.simulate_fast(N=N, K=K, H=10, seed=70 + s) for s in range(B)]
+    f64 = dict(dtype=torch.float64, device="cuda")
+    cov = torch.zeros(B, N, 2, 2, **f64); cov[..., 0, 0] = 0.1; cov[..., 1, 1] = 1.0
+    phi = torch.stack([0.1 * torch.ones(B, N, **f64), 5 * torch.ones(B, N, **f64)], -1).contiguous()
+    stim = torch.from_numpy(np.stack([s["stim_matrix"] for s in sims])).cuda()
+    psc = torch.from_numpy(np.stack([s["psc"] for s in sims])).cuda()
+    args = (stim, np.unique(sims[0]["stim_matrix"])[1:], torch.zeros(B, N, **f64), 10 * torch.ones(B, N, **f64), 1.0, 0.1,
+            phi, cov)
+    old = os.environ.get("CM_CAVIAR_HELPERS")
+    try:
+        os.environ["CM_CAVIAR_HELPERS"] = "0"
+        ref = optimise.caviar_batched(*args, psc=psc, seeds=[1, 2], iters=12, msrmp=0.4)
+        os.environ["CM_CAVIAR_HELPERS"] = "15"
+        out = optimise.caviar_batched(*args, psc=psc, seeds=[1, 2], iters=12, msrmp=0.4)
+        os.environ["CM_CAVIAR_HELPERS"] = "5"
+        out5 = optimise.caviar_batched(*args, psc=psc, seeds=[1, 2], iters=12, msrmp=0.4)
+    finally:
+        if old is None:
+            os.environ.pop("CM_CAVIAR_HELPERS", None)
+        else:
+            os.environ["CM_CAVIAR_HELPERS"] = old
+    for o in (ref, out, out5):
+        optimise.check_status(o)
+    for nm in NAMES:
+        assert torch.equal(ref[nm], out[nm]), nm
+        assert torch.equal(ref[nm], out5[nm]), nm
