@@ -411,9 +411,11 @@ def main():
         streams = streaming._Streams(dev)
         wsp = {}
 
+        e2e_chunk = max(1, sms // 2)
+
         def e2e_step():
-            # chunks of one fit per SM: H2D of chunk i+1, the fit kernels of chunk i and D2H of chunk i-1 overlap
-            st_ = streaming.fit_pinned(hs, hp, stim, psc, powers, pri, seeds, pin, chunk=sms, nnz_cap=nnz,
+            # chunks of half a fit per SM (the step is PCIe-bound: finer chunks shorten the pipeline fill and drain): H2D of chunk i+1, the fit kernels of chunk i and D2H of chunk i-1 overlap
+            st_ = streaming.fit_pinned(hs, hp, stim, psc, powers, pri, seeds, pin, chunk=e2e_chunk, nnz_cap=nnz,
                                        workspaces=wsp, streams=streams, **opts)
             torch.cuda.synchronize()
             return st_
@@ -432,7 +434,7 @@ def main():
                "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * float(dt.item()),
                "note": "circuitmap_b200.streaming.fit_pinned: fp64 host buffers (pinned; two distinct maps tiled) -> cm_caviar_fit -> full state incl. "
                        "dense lam back (lam through a ring of %d pinned slabs), copies and kernels overlapped in chunks "
-                       "of %d fits" % (slab, sms)}
+                       "of %d fits" % (slab, e2e_chunk)}
         wsp.clear()
     del stim, psc, out
     ws[0] = None
@@ -568,7 +570,7 @@ def main():
         nstreams = _streaming._Streams(dev)
 
         def nwd_e2e():
-            _streaming.demix_pinned(dem, htr, hout, x64, o64, chunk=max(1, Kt // 4), streams=nstreams)
+            _streaming.demix_pinned(dem, htr, hout, x64, o64, chunk=max(1, Kt // 8), streams=nstreams)
             torch.cuda.synchronize()
 
         nwd_e2e()

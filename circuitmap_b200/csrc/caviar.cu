@@ -585,11 +585,14 @@ extern "C" int cm_caviar_fit(const cm_caviar_args* a, void* stream) {
     const int smem_bytes = small_cta ? fit256::FIT_SMEM_BYTES : fit512::FIT_SMEM_BYTES;
     p.smem_doubles = smem_bytes / 8;
     // helper CTAs for the panel GEMMs of single large fits: only when every CTA of the launch is co-resident
-    int ct = 1;
-    if (!small_cta && a->N > 256) {
-        int dev = 0, sms = 0;
+    int ct = 1, sm_count = 0;
+    {
+        int dev = 0;
         CM_CUDA_CHECK(cudaGetDevice(&dev));
-        CM_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        CM_CUDA_CHECK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+    }
+    if (!small_cta && a->N > 256) {
+        const int sms = sm_count;
         int want = 15;
         if (const char* e = getenv("CM_CAVIAR_HELPERS")) want = atoi(e);
         want = want < 0 ? 0 : (want > 31 ? 31 : want);
@@ -603,7 +606,13 @@ extern "C" int cm_caviar_fit(const cm_caviar_args* a, void* stream) {
     do {                                                                                                           \
         CM_CUDA_CHECK(cudaFuncSetAttribute(NS::caviar_fit_kernel<PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                            smem_bytes));                                                           \
-        if (ct > 1) {       /* helpers spin on the job board: cooperative launch guarantees co-residency */        \
+        if (ct > 1) {       /* helpers spin on the job board: they must all be resident together */                \
+            int occ = 0;                                                                                           \
+            CM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, NS::caviar_fit_kernel<PT>, NS::NT,   \
+                                                                        (size_t)smem_bytes));                      \
+            if ((long long)a->B * ct > (long long)occ * sm_count) { ct = 1; p.ct = 1; }                            \
+        }                                                                                                          \
+        if (ct > 1) {       /* cooperative launch guarantees co-residency (or fails loudly) */                     \
             void* kargs[] = {(void*)&p};                                                                           \
             CM_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)NS::caviar_fit_kernel<PT>, dim3(a->B * ct),           \
                                                       dim3(NS::NT), kargs, (size_t)smem_bytes, st));               \
