@@ -410,36 +410,92 @@ __device__ __forceinline__ void red_release_gpu(int* p, int v) {
 }
 constexpr long long WATCHDOG_CYCLES = 1ll << 38;      // minutes: a helper idles while the fit CTA runs the other phases
 
-template <bool UPPER>
-__device__ void panel_gemm_dist(const Ctx& c, int ldr, int i0, int nb, const double* IN, double* OUT, GemmPipe& gp) {
-    __shared__ int s_seq;
-    const bool dist = c.ct > 1 && i0 > GCT;           // at least two column tiles
-    if (dist) {
-        __syncthreads();                              // IN and X are complete (written by this CTA)
-        if (threadIdx.x == 0) {
-            const int s = c.job[0] + 1;
-            c.job[1] = UPPER ? 1 : 2; c.job[2] = i0; c.job[3] = nb;
-            __threadfence();
-            st_release_gpu(&c.job[0], s);
-            s_seq = s;
+__device__ __noinline__ void newton_rows(const Ctx& c, const double* powers, const int* list, int nlist, int part, int nparts);
+// Monte-Carlo means of the truncated-normal sigmoid coefficients of every neuron (caviar.py:209-215, App. A.2); one warp
+// per neuron, neurons are independent
+__device__ void mc_means(const Ctx& c, const uint32_t* keys_cur, int S, int part, int nparts) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int n = part * NW + wid; n < c.N; n += nparts * NW) {
+        if (c.dcnt[n]) continue;
+        const int m = c.pos[n];
+        const uint32_t k0 = keys_cur[2 * m], k1 = keys_cur[2 * m + 1];
+        const int cc = lane & 1;                                   // flat index e = 2 s + component
+        const double mean = c.phi[2 * n + cc];
+        const double sd = c.phicov[4 * n + 3 * cc];                // diag(phi_cov): a variance used as sd
+        const double cdf0 = normcdf(-mean / sd);
+        double acc = 0.0;
+        for (int e = lane; e < 2 * S; e += 32) {
+            uint32_t x0 = (uint32_t)e, x1 = (uint32_t)(2 * S + e);
+            threefry2x32(k0, k1, x0, x1);
+            const double u = bits_to_unit_double(x0, x1);
+            acc += normcdfinv(cdf0 + u * (1.0 - cdf0)) * sd + mean;
         }
-    }
-    panel_gemm<UPPER>(c, ldr, i0, nb, IN, OUT, gp, 0, dist ? c.ct : 1);
-    if (dist) {
-        if (threadIdx.x == 0) {
-            const long long t0 = clock64();
-            const int want = s_seq * (c.ct - 1);
-            while (ld_acquire_gpu(&c.job[16]) < want)
-                if (clock64() - t0 > WATCHDOG_CYCLES) { c.job[20] = 1; break; }
-        }
-        __syncthreads();
-        __threadfence();                              // the helpers' tiles of OUT are visible to every thread from here
+#pragma unroll
+        for (int off = 16; off > 1; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+        if (lane < 2) c.phibar[2 * n + lane] = acc / (double)S;
     }
 }
 
+// w = X b (rows) and mu = X^T w, beta = column sums of squares of X (columns): the tail of block_update_mu
+__device__ void a2_wvec(const Ctx& c, int na, int ldr, int part, int nparts) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int i = part * NW + wid; i < na; i += nparts * NW) {
+        double s = 0.0;
+        for (int q = lane; q <= i; q += 32) s += c.X[xidx(i, q, ldr)] * c.bvec[q];
+        s = warp_sum(s);
+        if (lane == 0) c.wvec[i] = s;
+    }
+}
+__device__ void a2_mubeta(const Ctx& c, int na, int ldr, int part, int nparts) {
+    for (int cc = part * NT + threadIdx.x; cc < na; cc += nparts * NT) {
+        double m = 0.0, v = 0.0;
+        for (int i = cc; i < na; ++i) {
+            const double x = c.X[xidx(i, cc, ldr)];
+            m += x * c.wvec[i];
+            v += x * x;
+        }
+        const int n = c.act[cc];
+        c.mu[n] = m;
+        c.beta[n] = v;
+    }
+}
+
+// post a job for the helpers (all threads of the fit CTA call this; data written before the call is published)
+__device__ void post_job(const Ctx& c, int type, int a, int b, int d) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        c.job[1] = type; c.job[2] = a; c.job[3] = b; c.job[4] = d;
+        __threadfence();
+        st_release_gpu(&c.job[0], c.job[0] + 1);
+    }
+}
+// wait until every helper has finished the job posted last; their global writes are visible afterwards
+__device__ void wait_helpers(const Ctx& c) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const long long t0 = clock64();
+        const int want = c.job[0] * (c.ct - 1);
+        while (ld_acquire_gpu(&c.job[16]) < want)
+            if (clock64() - t0 > WATCHDOG_CYCLES) { c.job[20] = 1; break; }
+    }
+    __syncthreads();
+    __threadfence();
+}
+
+template <bool UPPER>
+__device__ void panel_gemm_dist(const Ctx& c, int ldr, int i0, int nb, const double* IN, double* OUT, GemmPipe& gp) {
+    const bool dist = c.ct > 1 && i0 > GCT;           // at least two column tiles
+    if (dist) post_job(c, UPPER ? 1 : 2, i0, nb, 0);  // IN and X are complete (written by this CTA)
+    panel_gemm<UPPER>(c, ldr, i0, nb, IN, OUT, gp, 0, dist ? c.ct : 1);
+    if (dist) wait_helpers(c);
+}
+
+// Job types: 1 / 2 panel GEMM (upper / lower; a = i0, b = nb), 3 Newton rows of c.dlist (a = rows), 4 Monte-Carlo means
+// (a = key buffer, b = samples), 5 w = X b, 6 mu / beta (a = active rows), 0 quit.
 __device__ void helper_loop(const Ctx& c, GemmPipe& gp) {
-    __shared__ int s_job[3];
+    __shared__ int s_job[4];
     const int ldr = c.N + ROWPAD;
+    const double* powers = reinterpret_cast<const double*>(c.job + 32);
     int seen = 0;
     __syncthreads();                                  // mbarriers initialised
     for (;;) {
@@ -451,16 +507,27 @@ __device__ void helper_loop(const Ctx& c, GemmPipe& gp) {
                 else if (clock64() - t0 > WATCHDOG_CYCLES) type = 0;
                 else __nanosleep(200);
             }
-            s_job[0] = type; s_job[1] = c.job[2]; s_job[2] = c.job[3];
+            s_job[0] = type; s_job[1] = c.job[2]; s_job[2] = c.job[3]; s_job[3] = c.job[4];
         }
         __syncthreads();
-        const int type = s_job[0], i0 = s_job[1], nb = s_job[2];
+        const int type = s_job[0], a = s_job[1], b = s_job[2];
         __syncthreads();
         if (type == 0) break;
         ++seen;
-        asm volatile("fence.proxy.async;\n" ::: "memory");          // operands were written through the generic proxy of another SM
-        if (type == 1) panel_gemm<true>(c, ldr, i0, nb, c.PA, c.PB, gp, c.role, c.ct);
-        else panel_gemm<false>(c, ldr, i0, nb, c.PB, c.PA, gp, c.role, c.ct);
+        if (type == 1 || type == 2) {
+            asm volatile("fence.proxy.async;\n" ::: "memory");      // operands were written through the generic proxy of another SM
+            if (type == 1) panel_gemm<true>(c, ldr, a, b, c.PA, c.PB, gp, c.role, c.ct);
+            else panel_gemm<false>(c, ldr, a, b, c.PB, c.PA, gp, c.role, c.ct);
+        } else if (type == 3) {
+            newton_rows(c, powers, c.dlist, a, c.role, c.ct);
+        } else if (type == 4) {
+            mc_means(c, c.keys + (size_t)a * 2 * c.N, b, c.role, c.ct);
+        } else if (type == 5) {
+            a2_wvec(c, a, ldr, c.role, c.ct);
+        } else if (type == 6) {
+            a2_mubeta(c, a, ldr, c.role, c.ct);
+        }
+        __syncthreads();
         if (threadIdx.x == 0) { __threadfence(); red_release_gpu(&c.job[16], 1); }
     }
 }
@@ -639,25 +706,19 @@ __device__ __noinline__ void phase_a2(const Ctx& c, double sigma, int* na_s, Gem
         phase_mark(c, 5);
     }
     // w = X b ; mu = X^T w ; beta = column sums of squares of X
-    for (int i = wid; i < na; i += NW) {
-        double s = 0.0;
-        for (int q = lane; q <= i; q += 32) s += X[xidx(i, q, ldr)] * c.bvec[q];
-        s = warp_sum(s);
-        if (lane == 0) c.wvec[i] = s;
+    if (c.ct > 1 && na > 256) {
+        post_job(c, 5, na, 0, 0);
+        a2_wvec(c, na, ldr, 0, c.ct);
+        wait_helpers(c);
+        post_job(c, 6, na, 0, 0);
+        a2_mubeta(c, na, ldr, 0, c.ct);
+        wait_helpers(c);
+    } else {
+        a2_wvec(c, na, ldr, 0, 1);
+        __syncthreads();
+        a2_mubeta(c, na, ldr, 0, 1);
+        __syncthreads();
     }
-    __syncthreads();
-    for (int cc = threadIdx.x; cc < na; cc += NT) {
-        double m = 0.0, v = 0.0;
-        for (int i = cc; i < na; ++i) {
-            const double x = X[xidx(i, cc, ldr)];
-            m += x * c.wvec[i];
-            v += x * x;
-        }
-        const int n = c.act[cc];
-        c.mu[n] = m;
-        c.beta[n] = v;
-    }
-    __syncthreads();
     phase_mark(c, 6);
 }
 
@@ -934,11 +995,11 @@ __device__ __forceinline__ double nll_quad(const QuadStats& s, double p0, double
 // mean, covariance = H^-1 before the last step.  Eight rows per warp (one per quad); every loop is warp-convergent
 // (predicated) so the quad shuffles stay legal while rows need different numbers of backtracking steps.
 // The sigmoids of the gradient pass are reused for the objective at the current point (same inputs, same fp result).
-__device__ __noinline__ void newton_rows(const Ctx& c, const double* powers, const int* list, int nlist) {
+__device__ __noinline__ void newton_rows(const Ctx& c, const double* powers, const int* list, int nlist, int part, int nparts) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int quad = lane >> 2, mem = lane & 3;
     const double t = 10.0, alpha = 0.25, bbeta = 0.5;
-    for (int base = wid * 8; base < nlist; base += NW * 8) {
+    for (int base = (part * NW + wid) * 8; base < nlist; base += nparts * NW * 8) {      // rows are independent
         const int idx = base + quad;
         const bool live = idx < nlist;
         const int n = live ? list[idx] : list[0];
@@ -1100,7 +1161,10 @@ __global__ void __launch_bounds__(NT, (NT == 512) ? 1 : 2) caviar_fit_kernel(con
     double* stage_base = pred_smem ? c.sm + kpad : c.sm;
 
     // ---------------- init (caviar.py:28-51) ----------------
-    if (threadIdx.x < PMAX) sc_powers[threadIdx.x] = threadIdx.x < P ? p.powers[threadIdx.x] : 0.0;
+    if (threadIdx.x < PMAX) {
+        sc_powers[threadIdx.x] = threadIdx.x < P ? p.powers[threadIdx.x] : 0.0;
+        if (c.ct > 1) reinterpret_cast<double*>(c.job + 32)[threadIdx.x] = sc_powers[threadIdx.x];   // for the helpers
+    }
     if (threadIdx.x == 0) {
         sc_shape = p.shape0_arr ? p.shape0_arr[b] : p.shape0;
         sc_rate = p.rate0_arr ? p.rate0_arr[b] : p.rate0;
@@ -1197,24 +1261,12 @@ __global__ void __launch_bounds__(NT, (NT == 512) ? 1 : 2) caviar_fit_kernel(con
         }
         __syncthreads();
         // Monte-Carlo means of the truncated-normal sigmoid coefficients (caviar.py:209-215, App. A.2)
-        for (int n = wid; n < N; n += NW) {
-            if (c.dcnt[n]) continue;
-            const int m = c.pos[n];
-            const uint32_t k0 = keys_cur[2 * m], k1 = keys_cur[2 * m + 1];
-            const int cc = lane & 1;                                   // flat index e = 2 s + component
-            const double mean = c.phi[2 * n + cc];
-            const double sd = c.phicov[4 * n + 3 * cc];                // diag(phi_cov): a variance used as sd
-            const double cdf0 = normcdf(-mean / sd);
-            double acc = 0.0;
-            for (int e = lane; e < 2 * S; e += 32) {
-                uint32_t x0 = (uint32_t)e, x1 = (uint32_t)(2 * S + e);
-                threefry2x32(k0, k1, x0, x1);
-                const double u = bits_to_unit_double(x0, x1);
-                acc += normcdfinv(cdf0 + u * (1.0 - cdf0)) * sd + mean;
-            }
-#pragma unroll
-            for (int off = 16; off > 1; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-            if (lane < 2) c.phibar[2 * n + lane] = acc / (double)S;
+        if (c.ct > 1 && N >= 512) {
+            post_job(c, 4, it & 1, S, 0);
+            mc_means(c, keys_cur, S, 0, c.ct);
+            wait_helpers(c);
+        } else {
+            mc_means(c, keys_cur, S, 0, 1);
         }
         __syncthreads();
         phase_mark(c, 8);
@@ -1300,7 +1352,15 @@ __global__ void __launch_bounds__(NT, (NT == 512) ? 1 : 2) caviar_fit_kernel(con
                     c.phi[2 * n] = c.phiz[2 * n]; c.phi[2 * n + 1] = c.phiz[2 * n + 1];
                     for (int q = 0; q < 4; ++q) c.phicov[4 * n + q] = c.phicovz[4 * n + q];
                 }
-            if (nl > 0) newton_rows(c, sc_powers, c.dlist, nl);
+            if (nl > 0) {
+                if (c.ct > 1 && nl >= 256) {
+                    post_job(c, 3, nl, 0, 0);
+                    newton_rows(c, sc_powers, c.dlist, nl, 0, c.ct);
+                    wait_helpers(c);
+                } else {
+                    newton_rows(c, sc_powers, c.dlist, nl, 0, 1);
+                }
+            }
         }
         __syncthreads();
         phase_mark(c, 12);
@@ -1496,7 +1556,15 @@ __global__ void __launch_bounds__(NT, (NT == 512) ? 1 : 2) caviar_fit_kernel(con
         __syncthreads();
         {
             const int nl = block_compact(N, [&](int n) { return c.pos[n] != 0; }, c.dlist, nullptr, red);
-            if (nl > 0) newton_rows(c, sc_powers, c.dlist, nl);
+            if (nl > 0) {
+                if (c.ct > 1 && nl >= 256) {
+                    post_job(c, 3, nl, 0, 0);
+                    newton_rows(c, sc_powers, c.dlist, nl, 0, c.ct);
+                    wait_helpers(c);
+                } else {
+                    newton_rows(c, sc_powers, c.dlist, nl, 0, 1);
+                }
+            }
         }
         __syncthreads();
     }
