@@ -54,7 +54,7 @@ static Layout make_layout(int N, int K, int64_t nnz, int iters, bool lamhist, in
     L.X = take(((n + GCT - 1) / GCT) * (size_t)GCT * (n + ROWPAD) * 8);
     L.PA = take((size_t)NB * (n + ROWPAD) * 8);
     L.PB = take((size_t)NB * (n + ROWPAD) * 8);
-    L.growbuf = take((size_t)NW * (n + 2) * 8);
+    L.growbuf = take((size_t)(NW > NB ? NW : NB) * (n + 2) * 8);     // one row buffer per row of a 32-row block
     L.cscq = take(z * 16);
     L.lam = take(z * 8);
     L.cst = take(z * 8);

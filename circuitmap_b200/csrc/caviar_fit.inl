@@ -163,15 +163,15 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
 // One warp per row; 32 entries of the row are expanded at once (each lane walks the column list of its own
 // trial, 8 list entries prefetched per round), lanes that hit the same target column in the same step are
 // combined in lane order -> deterministic.
-__device__ void gram_rows(const Ctx& c, int i0, int nb, double sigma) {
+__device__ void gram_rows(const Ctx& c, int i0, int nb, double sigma, int part = 0, int nparts = 1) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int cap = GEMM_SMEM_DOUBLES / NW;       // row-buffer doubles per warp
     const int tagcap = ((c.smd - GEMM_SMEM_DOUBLES) * 8) / NW;   // conflict-tag bytes per warp (behind the GEMM ring)
     const double2* __restrict__ cscq = c.cscq;
-    for (int r = wid; r < nb; r += NW) {
+    for (int r = part + nparts * wid; r < nb; r += nparts * NW) {     // row r of the block: CTA r % nparts, warp r / nparts
         const int ia = i0 + r;
         const int n = c.act[ia];
-        double* acc = (ia + 1 <= cap) ? (c.sm + (size_t)wid * cap) : (c.growbuf + (size_t)wid * (c.N + 2));
+        double* acc = (ia + 1 <= cap) ? (c.sm + (size_t)wid * cap) : (c.growbuf + (size_t)r * (c.N + 2));
         unsigned char* tags = reinterpret_cast<unsigned char*>(c.sm + GEMM_SMEM_DOUBLES) + (size_t)wid * tagcap;
         const bool use_tags = ia + 1 <= tagcap;
         for (int q = lane; q <= ia; q += 32) acc[q] = 0.0;
@@ -491,7 +491,8 @@ __device__ void panel_gemm_dist(const Ctx& c, int ldr, int i0, int nb, const dou
 }
 
 // Job types: 1 / 2 panel GEMM (upper / lower; a = i0, b = nb), 3 Newton rows of c.dlist (a = rows), 4 Monte-Carlo means
-// (a = key buffer, b = samples), 5 w = X b, 6 mu / beta (a = active rows), 0 quit.
+// (a = key buffer, b = samples), 5 w = X b, 6 mu / beta (a = active rows), 7 Gram rows of a block (a = i0, b = nb, sigma at
+// int offset 8), 0 quit.
 __device__ void helper_loop(const Ctx& c, GemmPipe& gp) {
     __shared__ int s_job[4];
     const int ldr = c.N + ROWPAD;
@@ -526,6 +527,8 @@ __device__ void helper_loop(const Ctx& c, GemmPipe& gp) {
             a2_wvec(c, a, ldr, c.role, c.ct);
         } else if (type == 6) {
             a2_mubeta(c, a, ldr, c.role, c.ct);
+        } else if (type == 7) {
+            gram_rows(c, a, b, *reinterpret_cast<const double*>(c.job + 8), c.role, c.ct);
         }
         __syncthreads();
         if (threadIdx.x == 0) { __threadfence(); red_release_gpu(&c.job[16], 1); }
@@ -575,8 +578,15 @@ __device__ __noinline__ void phase_a2(const Ctx& c, double sigma, int* na_s, Gem
     double* PB = c.PB;
     for (int i0 = 0; i0 < na; i0 += NB) {
         const int nb = min(NB, na - i0);
-        gram_rows(c, i0, nb, sigma);              // PA[r][0..i0+r] = M[i0+r][.]
-        __syncthreads();
+        if (c.ct > 1 && nb >= 8) {                // rows of the block spread over the helper CTAs
+            if (threadIdx.x == 0) *reinterpret_cast<double*>(c.job + 8) = sigma;
+            post_job(c, 7, i0, nb, 0);
+            gram_rows(c, i0, nb, sigma, 0, c.ct);
+            wait_helpers(c);
+        } else {
+            gram_rows(c, i0, nb, sigma);          // PA[r][0..i0+r] = M[i0+r][.]
+            __syncthreads();
+        }
         phase_mark(c, 1);
         if (i0 > 0) panel_gemm_dist<true>(c, ldr, i0, nb, PA, PB, gp); // PB = Lrow = A[I,0:i0] X11^T
         phase_mark(c, 2);
