@@ -333,6 +333,7 @@ extern "C" int cm_nwd_create(const float* const* tensors, int n_tensors, cm_nwd_
     CM_CUDA_CHECK(cudaMemcpy(h->wtc_dev, Wtc.data(), Wtc.size() * sizeof(float), cudaMemcpyHostToDevice));
     std::vector<unsigned char> Wmt;
     cm::nwdmt::pack_weights(tensors, Wmt);
+    h->mt_ok = cm::nwdmt::weights_fit_fp16();
     CM_CUDA_CHECK(cudaMalloc(&h->wmt_dev, Wmt.size()));
     CM_CUDA_CHECK(cudaMemcpy(h->wmt_dev, Wmt.data(), Wmt.size(), cudaMemcpyHostToDevice));
     *out = h;
@@ -380,6 +381,10 @@ extern "C" int cm_nwd_forward(cm_nwd_t* h, const void* traces_dev, int in_dtype,
 
 extern "C" int cm_nwd_set_precision(cm_nwd_t* h, int precision) {
     if (!h || precision < 0 || precision > 2) { set_error("cm_nwd_set_precision: precision must be 0 (fp32), 1 (tf32) or 2 (fp16)"); return CM_EINVAL; }
+    if (precision == 2 && !h->mt_ok) {
+        set_error("cm_nwd_set_precision: the BatchNorm-folded weights of this network exceed the fp16 range; use mode 0 or 1");
+        return CM_EINVAL;
+    }
     h->precision = precision;
     return CM_OK;
 }

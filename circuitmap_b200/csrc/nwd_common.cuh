@@ -9,6 +9,7 @@ struct cm_nwd {
     int device = 0;
     int sm_count = 0;
     unsigned char* wmt_dev = nullptr;   // fp16 tap tables + biases of the multi-trace tensor-core kernel (nwd_mt.cu)
+    bool mt_ok = true;           // the BN-folded weights fit fp16 (mode 2 is refused otherwise)
     int precision = 0;           // 0 = fp32 CUDA cores, 1 = tf32 tcgen05 (one trace per CTA), 2 = fp16 tcgen05 (multi-trace)
 };
 
@@ -21,6 +22,7 @@ int launch(cm_nwd* h, const void* in, int in_dtype, void* out, int out_dtype, in
 }  // namespace nwdtc
 namespace nwdmt {
 void pack_weights(const float* const* tensors, std::vector<unsigned char>& out);
+bool weights_fit_fp16();          // result of the last pack_weights on this thread's call (folded weights within +-65504)
 int launch(cm_nwd* h, const void* in, int in_dtype, void* out, int out_dtype, int K, int monotone_start, double* y,
            double* ss, cudaStream_t st);
 int debug_cycles(long long* out, int n, int enable);

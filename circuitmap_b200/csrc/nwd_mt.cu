@@ -365,10 +365,18 @@ __device__ __forceinline__ void interp_pass(unsigned char* smem, const AB raw, i
 }
 
 // 16 accumulator columns -> bias, ReLU, fp16: two 16-byte units (channels 0..7, 8..15 of the chunk)
-__device__ __forceinline__ void finish16(const uint32_t* v, const float* bias, uint4& u0, uint4& u1) {
+// An activation that does not fit fp16 (>= 6e4) would be saturated by the conversion: it marks its trace instead, and
+// the whole output row is returned as NaN (same contract as for inputs that cannot be normalised).
+__device__ __forceinline__ void finish16(const uint32_t* v, const float* bias, uint4& u0, uint4& u1, int* bad_flag) {
     float f[16];
+    bool bad = false;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) f[i] = fmaxf(__uint_as_float(v[i]) + bias[i], 0.f);
+    for (int i = 0; i < 16; ++i) {
+        const float x = __uint_as_float(v[i]) + bias[i];
+        bad |= !(x < 6.0e4f);                                               // too large for fp16, or NaN (fmaxf would hide it)
+        f[i] = fmaxf(x, 0.f);
+    }
+    if (bad) *bad_flag = 1;
     u0 = make_uint4(pack_h2(f[0], f[1]), pack_h2(f[2], f[3]), pack_h2(f[4], f[5]), pack_h2(f[6], f[7]));
     u1 = make_uint4(pack_h2(f[8], f[9]), pack_h2(f[10], f[11]), pack_h2(f[12], f[13]), pack_h2(f[14], f[15]));
 }
@@ -580,7 +588,7 @@ nwd_forward_mt_kernel(const unsigned char* __restrict__ blob, const TIn* __restr
                     const int t = 2 * (8 * sg + m) + p;
                     if (seq < 2 * G && t < L_E1) {
                         uint4 u0, u1;
-                        finish16(v, bias_s[0], u0, u1);
+                        finish16(v, bias_s[0], u0, u1, &bad_s[slot][seq >> 1]);
                         d3[ab_unit(AB_D3, 2, seq >> 1, t + AB_D3.PAD)] = u0;
                         d3[ab_unit(AB_D3, 3, seq >> 1, t + AB_D3.PAD)] = u1;
                     }
@@ -608,7 +616,7 @@ nwd_forward_mt_kernel(const unsigned char* __restrict__ blob, const TIn* __restr
                 const int t = 8 * q + 7 - n;
                 if (g < G && t < L_E2) {
                     uint4 u0, u1;
-                    finish16(v, bias_s[1], u0, u1);
+                    finish16(v, bias_s[1], u0, u1, &bad_s[slot][g]);
                     d2[ab_unit(AB_D2, 2, g, t + AB_D2.PAD)] = u0;
                     d2[ab_unit(AB_D2, 3, g, t + AB_D2.PAD)] = u1;
                 }
@@ -633,7 +641,7 @@ nwd_forward_mt_kernel(const unsigned char* __restrict__ blob, const TIn* __restr
                 const int t = 4 * q + 3 - n;
                 if (g < G && t < L_E3) {
                     uint4 u0, u1;
-                    finish16(v, bias_s[2] + 16 * hf, u0, u1);
+                    finish16(v, bias_s[2] + 16 * hf, u0, u1, &bad_s[slot][g]);
                     d1[ab_unit(AB_D1, 2 + 2 * hf, g, t + AB_D1.PAD)] = u0;
                     d1[ab_unit(AB_D1, 3 + 2 * hf, g, t + AB_D1.PAD)] = u1;
                 }
@@ -656,7 +664,7 @@ nwd_forward_mt_kernel(const unsigned char* __restrict__ blob, const TIn* __restr
             tmem_ld_wait();
             if (t < L_E4) {
                 uint4 u0, u1;
-                finish16(v, bias_s[3] + 16 * cgp, u0, u1);
+                finish16(v, bias_s[3] + 16 * cgp, u0, u1, &bad_s[slot][g]);
                 e4[ab_unit(AB_E4, 2 * cgp, g, t + AB_E4.PAD)] = u0;
                 e4[ab_unit(AB_E4, 2 * cgp + 1, g, t + AB_E4.PAD)] = u1;
             }
@@ -676,7 +684,7 @@ nwd_forward_mt_kernel(const unsigned char* __restrict__ blob, const TIn* __restr
             const int t = 2 * q + 1 - n;
             if (g < G && t < L_U1) {
                 uint4 u0, u1;
-                finish16(v, bias_s[4], u0, u1);
+                finish16(v, bias_s[4], u0, u1, &bad_s[slot][g]);
                 raw[ab_unit(AB_R1, 0, g, t)] = u0;
                 raw[ab_unit(AB_R1, 1, g, t)] = u1;
             }
@@ -697,7 +705,7 @@ nwd_forward_mt_kernel(const unsigned char* __restrict__ blob, const TIn* __restr
             const int t = 4 * q + 3 - n;
             if (g < G && t < L_U2) {
                 uint4 u0, u1;
-                finish16(v, bias_s[5], u0, u1);
+                finish16(v, bias_s[5], u0, u1, &bad_s[slot][g]);
                 raw[ab_unit(AB_R2, 0, g, t)] = u0;
                 raw[ab_unit(AB_R2, 1, g, t)] = u1;
             }
@@ -722,7 +730,7 @@ nwd_forward_mt_kernel(const unsigned char* __restrict__ blob, const TIn* __restr
                 const int t = 8 * q + 7 - n;
                 if (g < G && t < L_U3) {
                     uint4 u0, u1;
-                    finish16(v, bias_s[6], u0, u1);
+                    finish16(v, bias_s[6], u0, u1, &bad_s[slot][g]);
                     raw[ab_unit(AB_R3, 0, g, t)] = u0;
                     raw[ab_unit(AB_R3, 1, g, t)] = u1;
                 }
@@ -749,11 +757,14 @@ nwd_forward_mt_kernel(const unsigned char* __restrict__ blob, const TIn* __restr
                 uint32_t v[16];
                 tmem_ld16(pp.tmem + tcol(7) + kc * 16 + ((uint32_t)(32 * lq) << 16), v);
                 tmem_ld_wait();
-                uint4 u0, u1;
-                finish16(v, bb, u0, u1);
                 const int i0 = 16 * q + 15 - 2 * kc, i1 = i0 - 1;   // input positions of the two phases
-                if (g < G && i0 < L_U4H) raw[ab_unit(AB_R4, 0, g, i0)] = u0;
-                if (g < G && i1 >= 0 && i1 < L_U4H) raw[ab_unit(AB_R4, 0, g, i1)] = u1;
+                const bool ok0 = g < G && i0 < L_U4H, ok1 = g < G && i1 >= 0 && i1 < L_U4H;
+                if (ok0 || ok1) {
+                    uint4 u0, u1;
+                    finish16(v, bb, u0, u1, &bad_s[slot][g]);
+                    if (ok0) raw[ab_unit(AB_R4, 0, g, i0)] = u0;
+                    if (ok1) raw[ab_unit(AB_R4, 0, g, i1)] = u1;
+                }
             }
         }
         if (more) fetch_input(pass + gridDim.x);
@@ -887,11 +898,17 @@ nwd_forward_mt_kernel(const unsigned char* __restrict__ blob, const TIn* __restr
 }
 
 // ------------------------------------------------------------------------------------------------ host side
-static uint16_t f2h(double x) { return __half_as_ushort(__float2half_rn((float)x)); }
+static bool g_pack_overflow = false;      // set by pack_weights when a folded weight does not fit fp16
+static uint16_t f2h(double x) {
+    if (!(std::fabs(x) <= 65504.0)) g_pack_overflow = true;
+    return __half_as_ushort(__float2half_rn((float)x));
+}
+bool weights_fit_fp16() { return !g_pack_overflow; }
 
 // Tap tables WS[cp][u][co][8 ci] (fp16) of the nine layers + folded biases, BatchNorm (eval) folded in fp64.
 void pack_weights(const float* const* t, std::vector<unsigned char>& out) {
     out.assign(BLOB_BYTES, 0);
+    g_pack_overflow = false;
     float* bias = reinterpret_cast<float*>(out.data() + BIAS_OFF);
     // real layer shapes (nwd.py:259-269): kind 0 Conv1d (co, ci, k); 1 ConvTranspose1d stride 1 (ci, co, k); 2 stride 2; 3 final
     struct RL_ { int kind, ci, co, k; };

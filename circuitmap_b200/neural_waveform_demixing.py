@@ -57,7 +57,7 @@ def random_weights(seed=0):
 
 
 class NeuralDemixer:
-    def __init__(self, path=None, eval_mode=True, device=None, precision="fp32"):
+    def __init__(self, path=None, eval_mode=True, device=None, precision="fp32", state_dict=None):
         """precision (extension of the reference signature): 'fp32' = fp32 CUDA-core convolutions (default, the
         reference's arithmetic); 'tf32' = tcgen05 tensor-core path, one trace per CTA (TF32 operands, fp32
         accumulate); 'fp16' = the fast tcgen05 path: all nine convolutions as widened implicit GEMMs with several
@@ -72,7 +72,10 @@ class NeuralDemixer:
             self.device = torch.device("cuda", torch.cuda.current_device())
         if not eval_mode:
             raise NotImplementedError("training-mode BatchNorm (eval_mode=False) is outside the inference hot path")
-        self.weights = load_weights(path) if path is not None else random_weights()
+        if state_dict is not None:        # extension: weights given directly ({state_dict key: float array})
+            self.weights = {k: np.ascontiguousarray(state_dict[k], dtype=np.float32) for k in state_dict_keys()}
+        else:
+            self.weights = load_weights(path) if path is not None else random_weights()
         self._lib = _lib.load()
         ptrs = (C.c_void_p * _lib.CM_NWD_NUM_TENSORS)(
             *[self.weights[k].ctypes.data_as(C.c_void_p) for k in state_dict_keys()])

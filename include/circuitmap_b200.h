@@ -57,8 +57,9 @@ CM_API void cm_nwd_destroy(cm_nwd_t* h);
  * per CTA (csrc/nwd_tc.cu); 2 = fp16 operands (11-bit significand, as TF32) / fp32 accumulation, all nine
  * convolutions on tcgen05 with several traces per M tile (csrc/nwd_mt.cu) -- the fast path.  Error bound of modes 1
  * and 2 on unit-normalised traces: max-abs <= 2e-2, relative L2 <= 3e-3 (asserted in tests/test_nwd_gpu.py).
- * Mode 2 keeps activations in fp16: a trace whose normalised samples |x / max(x)| exceed 6e4, whose max is 0 or that
- * holds a non-finite sample yields an all-NaN row instead of a silently saturated one. */
+ * Mode 2 keeps weights and activations in fp16 and never saturates silently: a trace whose normalised samples
+ * |x / max(x)| exceed 6e4, whose max is 0, that holds a non-finite sample or that drives any activation of the network
+ * beyond 6e4 yields an all-NaN row; cm_nwd_set_precision(h, 2) fails if a BatchNorm-folded weight exceeds the fp16 range. */
 CM_API int  cm_nwd_set_precision(cm_nwd_t* h, int precision);
 
 /* traces_dev: K x T row-major (in_dtype), out_dev: K x T row-major (out_dtype).

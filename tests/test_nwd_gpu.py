@@ -180,6 +180,19 @@ def test_fp16_path_flags_traces_outside_the_fp16_range(demixer16):
         assert np.isnan(out[i]).all()
     for i in (0, 3, 4, 6, 7):
         assert np.array_equal(out[i], good[i])
+    # an activation that overflows fp16 inside the network is flagged the same way (never saturated silently)
+    from circuitmap_b200 import NeuralDemixer
+    from circuitmap_b200.neural_waveform_demixing import random_weights
+    sd = random_weights(seed=1)
+    sd["dblock1.bn.weight"] = sd["dblock1.bn.weight"] * 3e5      # weights still fit fp16 (<= 5.3e4), activations do not
+    big = NeuralDemixer(state_dict=sd, precision="fp16")
+    assert np.isnan(big(traces.copy(), verbose=False)).all()
+    big.set_precision("fp32")
+    assert np.isfinite(big(traces.copy(), verbose=False)).all()
+    sd["dblock1.bn.weight"] = sd["dblock1.bn.weight"] * 10       # now the folded weights themselves overflow fp16
+    with pytest.raises(RuntimeError):
+        NeuralDemixer(state_dict=sd, precision="fp16")
+    assert np.isfinite(NeuralDemixer(state_dict=sd, precision="fp32")(traces.copy(), verbose=False)).all()
 
 
 @pytest.mark.parametrize("weights", ["nwd_ee_ChroME1_weights.npz", "random"])
