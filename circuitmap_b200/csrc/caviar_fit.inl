@@ -7,6 +7,7 @@ namespace CM_FITNS {
 
 constexpr int NT = CM_NT;          // threads of a fit CTA
 constexpr int NW = NT / 32;
+constexpr bool HELPERS = (NT == 512);   // helper CTAs exist for the 16-warp variant only: the 8-warp one compiles them away
 constexpr int GCT = 16 * NW;       // panel GEMM column tile: 16 columns per warp
 constexpr int GCT_LOG2 = (GCT == 256) ? 8 : 7;
 constexpr int STAGE_GEMM_DOUBLES = GK * NB + GK * GCT;            // A chunk [GK][32] + X chunk [GK][GCT]
@@ -484,7 +485,7 @@ __device__ void wait_helpers(const Ctx& c) {
 
 template <bool UPPER>
 __device__ void panel_gemm_dist(const Ctx& c, int ldr, int i0, int nb, const double* IN, double* OUT, GemmPipe& gp) {
-    const bool dist = c.ct > 1 && i0 > GCT;           // at least two column tiles
+    const bool dist = HELPERS && c.ct > 1 && i0 > GCT;           // at least two column tiles
     if (dist) post_job(c, UPPER ? 1 : 2, i0, nb, 0);  // IN and X are complete (written by this CTA)
     panel_gemm<UPPER>(c, ldr, i0, nb, IN, OUT, gp, 0, dist ? c.ct : 1);
     if (dist) wait_helpers(c);
@@ -578,7 +579,7 @@ __device__ __noinline__ void phase_a2(const Ctx& c, double sigma, int* na_s, Gem
     double* PB = c.PB;
     for (int i0 = 0; i0 < na; i0 += NB) {
         const int nb = min(NB, na - i0);
-        if (c.ct > 1 && nb >= 8) {                // rows of the block spread over the helper CTAs
+        if (HELPERS && c.ct > 1 && nb >= 8) {                // rows of the block spread over the helper CTAs
             if (threadIdx.x == 0) *reinterpret_cast<double*>(c.job + 8) = sigma;
             post_job(c, 7, i0, nb, 0);
             gram_rows(c, i0, nb, sigma, 0, c.ct);
@@ -716,7 +717,7 @@ __device__ __noinline__ void phase_a2(const Ctx& c, double sigma, int* na_s, Gem
         phase_mark(c, 5);
     }
     // w = X b ; mu = X^T w ; beta = column sums of squares of X
-    if (c.ct > 1 && na > 256) {
+    if (HELPERS && c.ct > 1 && na > 256) {
         post_job(c, 5, na, 0, 0);
         a2_wvec(c, na, ldr, 0, c.ct);
         wait_helpers(c);
@@ -1157,7 +1158,7 @@ __global__ void __launch_bounds__(NT, (NT == 512) ? 1 : 2) caviar_fit_kernel(con
     }
     GemmPipe gp;
     gp.full = sc_bar; gp.empty = sc_bar + NST; gp.seq = 0;
-    if (c.role > 0) { helper_loop(c, gp); return; }
+    if (HELPERS && c.role > 0) { helper_loop(c, gp); return; }
     c.nnz = c.row_ptr[N];
     const int iters = o.iters;
     const int S = o.num_mc_samples;
@@ -1173,7 +1174,7 @@ __global__ void __launch_bounds__(NT, (NT == 512) ? 1 : 2) caviar_fit_kernel(con
     // ---------------- init (caviar.py:28-51) ----------------
     if (threadIdx.x < PMAX) {
         sc_powers[threadIdx.x] = threadIdx.x < P ? p.powers[threadIdx.x] : 0.0;
-        if (c.ct > 1) reinterpret_cast<double*>(c.job + 32)[threadIdx.x] = sc_powers[threadIdx.x];   // for the helpers
+        if (HELPERS && c.ct > 1) reinterpret_cast<double*>(c.job + 32)[threadIdx.x] = sc_powers[threadIdx.x];   // for the helpers
     }
     if (threadIdx.x == 0) {
         sc_shape = p.shape0_arr ? p.shape0_arr[b] : p.shape0;
@@ -1271,7 +1272,7 @@ __global__ void __launch_bounds__(NT, (NT == 512) ? 1 : 2) caviar_fit_kernel(con
         }
         __syncthreads();
         // Monte-Carlo means of the truncated-normal sigmoid coefficients (caviar.py:209-215, App. A.2)
-        if (c.ct > 1 && N >= 512) {
+        if (HELPERS && c.ct > 1 && N >= 512) {
             post_job(c, 4, it & 1, S, 0);
             mc_means(c, keys_cur, S, 0, c.ct);
             wait_helpers(c);
@@ -1363,7 +1364,7 @@ __global__ void __launch_bounds__(NT, (NT == 512) ? 1 : 2) caviar_fit_kernel(con
                     for (int q = 0; q < 4; ++q) c.phicov[4 * n + q] = c.phicovz[4 * n + q];
                 }
             if (nl > 0) {
-                if (c.ct > 1 && nl >= 256) {
+                if (HELPERS && c.ct > 1 && nl >= 256) {
                     post_job(c, 3, nl, 0, 0);
                     newton_rows(c, sc_powers, c.dlist, nl, 0, c.ct);
                     wait_helpers(c);
@@ -1567,7 +1568,7 @@ __global__ void __launch_bounds__(NT, (NT == 512) ? 1 : 2) caviar_fit_kernel(con
         {
             const int nl = block_compact(N, [&](int n) { return c.pos[n] != 0; }, c.dlist, nullptr, red);
             if (nl > 0) {
-                if (c.ct > 1 && nl >= 256) {
+                if (HELPERS && c.ct > 1 && nl >= 256) {
                     post_job(c, 3, nl, 0, 0);
                     newton_rows(c, sc_powers, c.dlist, nl, 0, c.ct);
                     wait_helpers(c);
@@ -1589,7 +1590,7 @@ __global__ void __launch_bounds__(NT, (NT == 512) ? 1 : 2) caviar_fit_kernel(con
     for (int n = threadIdx.x; n < 4 * N; n += NT) p.phicov_out[(size_t)b * 4 * N + n] = c.phicov[n];
     for (int k = threadIdx.x; k < K; k += NT) p.z_out[(size_t)b * K + k] = c.z[k];
     if (threadIdx.x == 0) { p.shape_out[b] = sc_shape; p.rate_out[b] = sc_rate; }
-    if (c.ct > 1 && threadIdx.x == 0) {               // release the helpers
+    if (HELPERS && c.ct > 1 && threadIdx.x == 0) {               // release the helpers
         if (c.job[20]) p.status[b] = 9;               // a helper did not answer: results are not to be trusted
         c.job[1] = 0;
         __threadfence();
