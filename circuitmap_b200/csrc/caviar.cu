@@ -596,7 +596,9 @@ extern "C" int cm_caviar_fit(const cm_caviar_args* a, void* stream) {
         int want = 15;
         if (const char* e = getenv("CM_CAVIAR_HELPERS")) want = atoi(e);
         want = want < 0 ? 0 : (want > 31 ? 31 : want);
-        if (want > 0 && (long long)a->B * (want + 1) <= sms) ct = want + 1;
+        const int room = sms / a->B - 1;                      // helpers per fit that still leave every CTA resident
+        if (want > room) want = room;
+        if (want > 0) ct = want + 1;
     }
     p.ct = ct;
     if (ct > 1)
