@@ -436,6 +436,25 @@ def main():
                        "dense lam back (lam through a ring of %d pinned slabs), copies and kernels overlapped in chunks "
                        "of %d fits" % (slab, e2e_chunk)}
         wsp.clear()
+    # ---- the reference-facing call itself: Model(N).fit(psc, stim) with NumPy arrays in and out, one map (rank 0) ----
+    if e2e is not None and rank == 0:
+        import contextlib
+        import io
+        from circuitmap_b200 import Model
+        s_np = dense_stim(gen3[0], N, K)
+        p_np = gen3[0][3].astype(np.float64)
+        tcall = []
+        for _ in range(3):
+            mdl = Model(N)
+            torch.cuda.synchronize()
+            t0 = time.time()
+            with contextlib.redirect_stdout(io.StringIO()):
+                mdl.fit(p_np, s_np, method="caviar", fit_options=dict(opts, seed=1))
+            tcall.append(time.time() - t0)
+        e2e["drop_in_call"] = {"fits_per_s": 1.0 / min(tcall), "ms_per_fit": 1e3 * min(tcall),
+                               "note": "Model(N).fit(psc, stim, 'caviar') on pageable float64 NumPy arrays, full state back as NumPy "
+                                       "(one map at a time: latency of the drop-in call, not batch throughput)"}
+        del s_np, p_np, mdl
     del stim, psc, out
     ws[0] = None
     torch.cuda.empty_cache()
@@ -597,6 +616,17 @@ def main():
                                                      "widened implicit GEMMs"},
                "e2e": {"value": world * Kt / float(edt.item()), "unit": "traces/s", "h2d_bytes_per_step": Kt * 7200,
                        "d2h_bytes_per_step": Kt * 7200}}
+        if rank == 0:       # the reference-facing call itself: NeuralDemixer(...)(traces) on a pageable float64 NumPy array
+            tr_np = htr.numpy().copy()
+            dem(tr_np[:256], verbose=False)
+            tcall = []
+            for _ in range(3):
+                t0 = time.time()
+                dem(tr_np, verbose=False)
+                tcall.append(time.time() - t0)
+            nwd["e2e"]["drop_in_call"] = {"traces_per_s": Kt / min(tcall), "ms": 1e3 * min(tcall),
+                                          "note": "NeuralDemixer(path, precision='fp16')(traces) with a pageable float64 NumPy "
+                                                  "array in and out"}
 
     # ---- CPU baseline on the host cores (rank 0, N=1 only) ----
     cpu = None

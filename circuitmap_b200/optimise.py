@@ -164,12 +164,19 @@ def caviar(y_psc, I, mu_prior, beta_prior, shape_prior, rate_prior, phi_prior, p
     if not np.issubdtype(y_psc.dtype, np.floating):
         y_psc = y_psc.astype(float)
     N, K = I.shape
-    powers = np.unique(I)[1:]                        # caviar.py:42 (assumes 0 is present and smallest)
-    nnz = int(np.count_nonzero(I))
+    stim_dev = torch.from_numpy(I).to(dev)
+    # powers = np.unique(I)[1:] (caviar.py:42: the sorted distinct values without the smallest one), computed on the
+    # device from the non-zero entries: sorting 1e7 host doubles costs more than the whole fit
+    nz = stim_dev[stim_dev != 0]
+    nnz = int(nz.numel())
+    distinct = torch.unique(nz)
+    if nnz < N * K:
+        distinct = torch.unique(torch.cat([distinct, torch.zeros(1, dtype=distinct.dtype, device=dev)]))
+    powers = distinct[1:].double().cpu().numpy()
     t = lambda x: torch.from_numpy(np.ascontiguousarray(np.asarray(x, dtype=np.float64))).to(dev)
     seed = int(fit_options.get("seed", _DEFAULTS["seed"]))
     opts = {k: v for k, v in fit_options.items() if k != "seed"}
-    out = caviar_batched(torch.from_numpy(I).to(dev)[None], powers, t(mu_prior)[None], t(beta_prior)[None],
+    out = caviar_batched(stim_dev[None], powers, t(mu_prior)[None], t(beta_prior)[None],
                          float(shape_prior), float(rate_prior), t(phi_prior)[None], t(phi_cov_prior)[None],
                          psc=torch.from_numpy(y_psc).to(dev)[None], seeds=[seed], nnz_cap=nnz, seed=seed, **opts)
     check_status(out)
