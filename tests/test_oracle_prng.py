@@ -20,6 +20,16 @@ def test_split_and_uniform_match_published_jax_values():
     assert abs(float(prng.uniform_f32(k, ())) - 0.41845703) < 1e-8
 
 
+def test_random_bits_match_jax_own_test_vectors():
+    """Known answers of JAX's own test-suite (jax/tests/random_test.py::testRngRandomBits, non-partitionable threefry --
+    the scheme of the JAX <= 0.3.15 the reference pins): key = PRNGKey(1701), shape (3,).  The odd size exercises the
+    padding / split-in-halves convention of random_bits; the 64-bit words are what uniform() consumes under x64."""
+    key = prng.prng_key(1701)
+    assert [int(x) for x in prng.random_bits(key, 32, 3)] == [56197195, 4200222568, 961309823]
+    assert [int(x) for x in prng.random_bits(key, 64, 3)] == [3982329540505020460, 16822122385914693683,
+                                                              7882654074788531506]
+
+
 def test_uniform_f64_range_and_shape():
     u = prng.uniform_f64(prng.prng_key(5), (100, 2))
     assert u.shape == (100, 2) and u.dtype == np.float64
