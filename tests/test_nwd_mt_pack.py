@@ -125,9 +125,9 @@ def emulate(x, ws, bias, cfg, rnd=lambda a: a, keep=None):
     return out
 
 
-@pytest.fixture(scope="module")
-def setup():
-    sd = dict(np.load(os.path.join(GOLDEN, "nwd_ie_ChroME2f_weights.npz")))
+@pytest.fixture(scope="module", params=["nwd_ie_ChroME2f_weights.npz", "nwd_ee_ChroME1_weights.npz"])
+def setup(request):
+    sd = dict(np.load(os.path.join(GOLDEN, request.param)))
     cfg = _cfg()
     ws, bias = _tables(_blob(sd), cfg)
     return sd, cfg, ws, bias
