@@ -5,11 +5,15 @@
 // positions per row against a sliding tap table, and operands are fp16 (11-bit significand = TF32's precision, half
 // the shared-memory bytes, twice the MMA rate) -- ~100 MMAs per trace instead of ~1900.
 //
-// Shared memory (210 KB) holds the three concat buffers of the decoder for G traces in phase-split layout:
+// Shared memory (224 KB) holds the three concat buffers of the decoder for G traces in phase-split layout:
 //   A = dec3 [up3 | enc1], B = dec2 [up2 | enc2], C = dec1 [up1 | enc3];  the halves that are only written late in the
-//   pass (A_lo, B_lo) double as weight buffer / encoder scratch before that, C is reused for the raw decoder outputs.
-// One pass = input (normalise, pool) -> 9 x [prepare A operand on CUDA cores -> MMAs by one thread -> epilogue from
-// TMEM: bias, ReLU, fp16, next layer's layout] -> rescale, monotone filter, store.
+//   pass (A_lo, B_lo) double as weight buffer / encoder scratch before that, C is reused for the raw decoder outputs;
+//   13 KB of interpolation tables sit behind them.
+// Roles: 16 worker warps run the element-wise passes and the epilogues, a 17th warp issues the MMAs (one elected lane),
+// streams the weights one layer ahead (cp.async.bulk + mbarrier) and issues the skip-connection halves of the decoder
+// GEMMs in the background; hand-off by named barriers, completion by tcgen05.commit -> mbarrier.
+// One pass = input (normalise, pool) -> 9 x [prepare A operand on CUDA cores -> MMAs -> epilogue from TMEM: bias, ReLU,
+// fp16, next layer's layout] -> monotone filter, rescale, store.
 #include "nwd_common.cuh"
 #include "nwd_mt.cuh"
 #include <cuda_fp16.h>
