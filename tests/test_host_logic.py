@@ -59,3 +59,26 @@ def test_product_never_imports_the_oracle():
     for f in pathlib.Path(circuitmap_b200.__file__).parent.rglob("*.py"):
         src = f.read_text()
         assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_lightning_checkpoints_load_without_lightning():
+    """`NeuralDemixer(path=...ckpt)` reads the reference's Lightning checkpoints with plain torch.load (no
+    pytorch_lightning needed) and yields the tensors of the committed golden fixtures.  Runs where the reference
+    checkout is mounted (this container); skipped elsewhere."""
+    import glob
+
+    import numpy as np
+    import pytest
+
+    from circuitmap_b200.neural_waveform_demixing import load_weights, state_dict_keys
+    from tests.conftest import GOLDEN
+    ckpts = sorted(glob.glob("/root/reference/demixers/*.ckpt"))
+    if not ckpts:
+        pytest.skip("reference checkpoints not mounted")
+    for f in ckpts:
+        w = load_weights(f)
+        assert list(w) == state_dict_keys() and all(v.dtype == np.float32 for v in w.values())
+    for name in ("nwd_ie_ChroME2f", "nwd_ee_ChroME1"):
+        w = load_weights("/root/reference/demixers/%s.ckpt" % name)
+        g = dict(np.load(os.path.join(GOLDEN, name + "_weights.npz")))
+        assert all(np.array_equal(w[k], g[k]) for k in w)
