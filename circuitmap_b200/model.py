@@ -42,20 +42,22 @@ class Model:
         t_end = time.time()
         mu, beta, lam, shape, rate, phi, phi_cov, z, receptive_fields, mu_hist, beta_hist, lam_hist, shape_hist, \
             rate_hist, phi_hist, phi_cov_hist, z_hist = result
-        self.state["mu"] = np.array(mu)
-        self.state["beta"] = np.array(beta)
-        self.state["shape"] = np.array(shape)
-        self.state["rate"] = np.array(rate)
-        self.state["phi"] = np.array(phi)
-        self.state["phi_cov"] = np.array(phi_cov)
-        self.state["lam"] = np.array(lam)
-        self.state["z"] = np.array(z)
+        # optimise.caviar returns fresh NumPy arrays: np.asarray keeps them (the reference's np.array() converts JAX
+        # arrays here, model.py:138-146; copying the 8 N K bytes of lam again would only cost time)
+        self.state["mu"] = np.asarray(mu)
+        self.state["beta"] = np.asarray(beta)
+        self.state["shape"] = np.asarray(shape)
+        self.state["rate"] = np.asarray(rate)
+        self.state["phi"] = np.asarray(phi)
+        self.state["phi_cov"] = np.asarray(phi_cov)
+        self.state["lam"] = np.asarray(lam)
+        self.state["z"] = np.asarray(z)
         self.state["receptive_fields"] = np.array(receptive_fields)
         self.trial_count = lam.shape[1]
         self.time = t_end - t_start
         self.history = {
-            "mu": np.array(mu_hist), "beta": np.array(beta_hist), "lam": np.array(lam_hist),
-            "shape": np.array(shape_hist), "rate": np.array(rate_hist), "phi": np.array(phi_hist),
-            "phi_cov": np.array(phi_cov_hist), "z": np.array(z_hist),
+            "mu": np.asarray(mu_hist), "beta": np.asarray(beta_hist), "lam": np.asarray(lam_hist),
+            "shape": np.asarray(shape_hist), "rate": np.asarray(rate_hist), "phi": np.asarray(phi_hist),
+            "phi_cov": np.asarray(phi_cov_hist), "z": np.asarray(z_hist),
         }
         return
