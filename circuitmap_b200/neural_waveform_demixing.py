@@ -139,14 +139,78 @@ class NeuralDemixer:
             if arr.dtype not in (np.float32, np.float64):
                 arr = arr.astype(np.float64)
             squeeze = arr.ndim == 1
-            x = torch.from_numpy(arr.reshape(-1, arr.shape[-1])).to(self.device)
-            dem = self.forward_device(x, monotone_filter_start, out_dtype=torch.float64).cpu().numpy()
+            arr2 = arr.reshape(-1, arr.shape[-1])
+            if arr2.shape[0] > self._PIPE_CHUNK and arr2.shape[1] == _lib.CM_NWD_T:
+                dem = self._call_pipelined(arr2, monotone_filter_start)
+            else:
+                x = torch.from_numpy(arr2).to(self.device)
+                dem = self.forward_device(x, monotone_filter_start, out_dtype=torch.float64).cpu().numpy()
             if squeeze:
                 dem = dem[0]
         t2 = time.time()
         if verbose:
             print("complete (elapsed time %.2fs, device=%s)." % (t2 - t1, self.device))
         return dem
+
+    # ---- large NumPy batches: chunked through two pinned staging buffers ------------------------------------------
+    _PIPE_CHUNK = 4096
+
+    def _call_pipelined(self, arr, monotone_filter_start):
+        """NumPy (K, 900) -> float64 NumPy, K > _PIPE_CHUNK: the host copies into / out of pinned staging, the
+        host->device copy, the kernel and the device->host copy of consecutive chunks overlap (results identical to the
+        one-shot path: traces are independent)."""
+        import torch
+        K, T = arr.shape
+        C = self._PIPE_CHUNK
+        st = getattr(self, "_pipe", None)
+        if st is None or st["dtype"] != arr.dtype:
+            tdt = torch.float32 if arr.dtype == np.float32 else torch.float64
+            st = dict(dtype=arr.dtype,
+                      pin_in=[torch.empty((C, T), dtype=tdt).pin_memory() for _ in range(2)],
+                      pin_out=[torch.empty((C, T), dtype=torch.float64).pin_memory() for _ in range(2)],
+                      dev_in=[torch.empty((C, T), dtype=tdt, device=self.device) for _ in range(2)],
+                      dev_out=[torch.empty((C, T), dtype=torch.float64, device=self.device) for _ in range(2)],
+                      streams=[torch.cuda.Stream(device=self.device) for _ in range(3)])
+            self._pipe = st
+        s_in, s_k, s_out = st["streams"]
+        cur = torch.cuda.current_stream(self.device)
+        for s_ in (s_in, s_k, s_out):
+            s_.wait_stream(cur)
+        out = np.empty((K, T), dtype=np.float64)
+        src = torch.from_numpy(arr)
+        dst = torch.from_numpy(out)
+        ev_h2d, ev_k, ev_d2h = [None, None], [None, None], [None, None]
+        bounds = [(lo, min(lo + C, K)) for lo in range(0, K, C)]
+        for i, (lo, hi) in enumerate(bounds):
+            b, n = i & 1, hi - lo
+            if ev_h2d[b] is not None:
+                ev_h2d[b].synchronize()                       # staging buffer b is free again
+            st["pin_in"][b][:n].copy_(src[lo:hi])
+            with torch.cuda.stream(s_in):
+                if ev_k[b] is not None:
+                    s_in.wait_event(ev_k[b])                  # the kernel that read dev_in[b] two chunks ago is done
+                st["dev_in"][b][:n].copy_(st["pin_in"][b][:n], non_blocking=True)
+                ev_h2d[b] = s_in.record_event()
+            with torch.cuda.stream(s_k):
+                s_k.wait_event(ev_h2d[b])
+                if ev_d2h[b] is not None:
+                    s_k.wait_event(ev_d2h[b])                 # dev_out[b] has been copied out
+                self.forward_device(st["dev_in"][b][:n], monotone_filter_start, out=st["dev_out"][b][:n])
+                ev_k[b] = s_k.record_event()
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev_k[b])
+                st["pin_out"][b][:n].copy_(st["dev_out"][b][:n], non_blocking=True)
+                ev_d2h[b] = s_out.record_event()
+            if i >= 1:                                        # drain the previous chunk while this one is in flight
+                plo, phi = bounds[i - 1]
+                ev_d2h[1 - b].synchronize()
+                dst[plo:phi].copy_(st["pin_out"][1 - b][:phi - plo])
+        plo, phi = bounds[-1]
+        lb = (len(bounds) - 1) & 1
+        ev_d2h[lb].synchronize()
+        dst[plo:phi].copy_(st["pin_out"][lb][:phi - plo])
+        cur.wait_stream(s_out)
+        return out
 
     def train(self, *a, **k):
         raise NotImplementedError("demixer training (nwd.py:56-94) is outside the B200 inference hot path")

@@ -9,7 +9,7 @@ import ctypes as C
 
 import numpy as np
 
-from . import _lib
+from . import _lib, _staging
 
 _DEFAULTS = dict(iters=50, num_mc_samples=100, seed=0, y_xcorr_thresh=1e-2, minimum_spike_count=3, delay_spont_est=1,
                  msrmp=0.3, scale_factor=0.75, penalty=5e0, save_histories=False, max_backtrack_iters=20, tol=0.05,
@@ -164,7 +164,9 @@ def caviar(y_psc, I, mu_prior, beta_prior, shape_prior, rate_prior, phi_prior, p
     if not np.issubdtype(y_psc.dtype, np.floating):
         y_psc = y_psc.astype(float)
     N, K = I.shape
-    stim_dev = torch.from_numpy(I).to(dev)
+    with torch.cuda.device(dev):
+        stim_dev = _staging.to_device(I, dev)
+        psc_dev = _staging.to_device(y_psc, dev)
     # powers = np.unique(I)[1:] (caviar.py:42: the sorted distinct values without the smallest one), computed on the
     # device from the non-zero entries: sorting 1e7 host doubles costs more than the whole fit
     nz = stim_dev[stim_dev != 0]
@@ -178,9 +180,11 @@ def caviar(y_psc, I, mu_prior, beta_prior, shape_prior, rate_prior, phi_prior, p
     opts = {k: v for k, v in fit_options.items() if k != "seed"}
     out = caviar_batched(stim_dev[None], powers, t(mu_prior)[None], t(beta_prior)[None],
                          float(shape_prior), float(rate_prior), t(phi_prior)[None], t(phi_cov_prior)[None],
-                         psc=torch.from_numpy(y_psc).to(dev)[None], seeds=[seed], nnz_cap=nnz, seed=seed, **opts)
+                         psc=psc_dev[None], seeds=[seed], nnz_cap=nnz, seed=seed, **opts)
     check_status(out)
-    g = lambda k: out[k][0].cpu().numpy()
+    def g(k):
+        with torch.cuda.device(dev):
+            return _staging.to_numpy(out[k][0])
     mu, beta, lam, phi, phi_cov, z = g("mu"), g("beta"), g("lam"), g("phi"), g("phi_cov"), g("z")
     shape, rate = np.float64(out["shape"][0].item()), np.float64(out["rate"][0].item())
     if out.get("mu_hist") is not None:
