@@ -14,7 +14,7 @@ import os
 
 import numpy as np
 
-from . import optimise
+from . import _staging, optimise
 
 
 def downsample_trial_counts(K, dstime, stim_freq=30):
@@ -69,8 +69,9 @@ def downsampling_weights(psc_dem, stim_matrix, dstime, n_repeats, msrmp, stim_fr
     N, K = stim_matrix.shape
     counts = downsample_trial_counts(K, dstime, stim_freq)
     powers = np.unique(stim_matrix)[1:]
-    stim_dev = torch.from_numpy(stim_matrix).to(dev)
-    psc_dev = torch.from_numpy(psc_dem).to(dev)
+    with torch.cuda.device(dev):
+        stim_dev = _staging.to_device(stim_matrix, dev)
+        psc_dev = _staging.to_device(psc_dem, dev)
     opts = {"save_histories": False, "tol": 0.005, "msrmp": msrmp, "fn_scan": True}
     weights = np.zeros((n_repeats, len(counts), N))
     for st, cnt in enumerate(counts):
@@ -115,8 +116,9 @@ def loho_cv_weights(psc_dem, stim_matrix, msrmp, hologram_ids=None, device=None,
     folds = np.arange(len(uniq)) if hologram_ids is None else np.asarray(hologram_ids, dtype=int)
     stim_multi = np.ascontiguousarray(stim_matrix[:, multi])
     powers = np.unique(stim_multi)[1:]
-    stim_dev = torch.from_numpy(stim_multi).to(dev)
-    psc_dev = torch.from_numpy(np.ascontiguousarray(np.asarray(psc_dem)[multi])).to(dev)
+    with torch.cuda.device(dev):
+        stim_dev = _staging.to_device(stim_multi, dev)
+        psc_dev = _staging.to_device(np.ascontiguousarray(np.asarray(psc_dem)[multi]), dev)
     opts = {"save_histories": False, "msrmp": msrmp}
     N = stim_matrix.shape[0]
     mu = np.zeros((len(folds), N))
