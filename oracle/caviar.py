@@ -1,8 +1,10 @@
 """CAVIaR restated in NumPy fp64 (oracle; test infrastructure only).
 
 Follows circuitmap/optimise/caviar.py line by line (citations on each function).  JAX is
-absent here, so this is a restatement, and parity against live JAX is UNPINNED (see
-oracle/__init__.py).  Two forms are provided and proven equal in tests:
+absent here, so this is a restatement; it is PINNED against the reference's own source
+executed through a NumPy-backed JAX stand-in (oracle/jax_shim.py, fixtures
+tests/golden/caviar_ref_*.npz, tests/test_reference_pin.py; see oracle/__init__.py for what
+that does and does not cover).  Two forms are provided and proven equal in tests:
 
   form='literal'  the reference's own structure: O(N^2 K) masked sum per neuron
                   (caviar.py:204-206), S x K Monte-Carlo logit(sigmoid()) term
