@@ -10,7 +10,8 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcircuitmap_b200.so")
 
-CM_F32, CM_F64 = 0, 1
+CM_F32, CM_F64, CM_U8 = 0, 1, 2
+CM_OK, CM_EINVAL, CM_ESHAPE, CM_EUNSUPPORTED, CM_ECUDA, CM_EWORKSPACE = 0, 1, 2, 3, 4, 5
 CM_NWD_NUM_TENSORS = 54
 CM_NWD_T = 900
 CM_CAVIAR_MAX_POWERS = 16
@@ -40,13 +41,15 @@ class CaviarArgs(C.Structure):
                 ("shape_hist_dev", C.c_void_p), ("rate_hist_dev", C.c_void_p), ("phi_hist_dev", C.c_void_p),
                 ("phi_cov_hist_dev", C.c_void_p), ("z_hist_dev", C.c_void_p),
                 ("nnz_cap", C.c_int64), ("workspace_dev", C.c_void_p), ("workspace_bytes", C.c_size_t),
-                ("status_dev", C.c_void_p)]
+                ("status_dev", C.c_void_p),
+                ("lam_csr_val_dev", C.c_void_p), ("lam_csr_col_dev", C.c_void_p), ("lam_csr_ptr_dev", C.c_void_p)]
 
 
 # every symbol include/circuitmap_b200.h declares
 EXPORTS = ["cm_version", "cm_last_error", "cm_device_info", "cm_nwd_create", "cm_nwd_destroy", "cm_nwd_forward",
            "cm_nwd_set_precision",
-           "cm_caviar_workspace_bytes", "cm_caviar_fit", "cm_last_launch_count", "cm_last_main_kernel_ms",
+           "cm_caviar_workspace_bytes", "cm_caviar_fit", "cm_caviar_scan_stim", "cm_caviar_scan_scratch_bytes",
+           "cm_pack_stim_u8", "cm_last_launch_count", "cm_last_main_kernel_ms",
            "cm_caviar_debug_phase_cycles", "cm_nwd_debug_cycles", "cm_nwd_mt_debug_cycles", "cm_nwd_mt_debug_dump", "cm_nwd_mt_pack"]
 
 _lib = None
@@ -76,6 +79,11 @@ def load():
     lib.cm_caviar_workspace_bytes.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int]
     lib.cm_caviar_workspace_bytes.restype = C.c_size_t
     lib.cm_caviar_fit.argtypes = [C.POINTER(CaviarArgs), C.c_void_p]
+    lib.cm_caviar_scan_scratch_bytes.restype = C.c_size_t
+    lib.cm_caviar_scan_stim.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.POINTER(C.c_int64),
+                                        C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_void_p]
+    lib.cm_pack_stim_u8.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.POINTER(C.c_double), C.POINTER(C.c_int),
+                                    C.POINTER(C.c_int64), C.c_void_p, C.c_int]
     _lib = lib
     return lib
 

@@ -126,6 +126,7 @@ struct FitParams {
     int* status;
     int smem_doubles;                 // dynamic shared memory available for pred / row buffers
     int ct;                           // CTAs per fit: 1 + panel-GEMM helpers (single large fits only)
+    int* queue;                       // device counter handing out fit indices (nullptr: CTA b / ct runs fit b)
 };
 
 // ------------------------------------------------------------------------------------------------ PRNG
@@ -274,6 +275,7 @@ __global__ void __launch_bounds__(256) psc_stats_kernel(const T* __restrict__ ps
         double* ss = reinterpret_cast<double*>(ws + (size_t)b * L.stride + L.ss);
         y[k] = s1 - 0.5 * ((double)row[0] + (double)row[Tn - 1]);
         ss[k] = s2;
+        reinterpret_cast<int*>(ws + (size_t)b * L.stride + L.colfill)[k] = 0;      // column counters of csr_count_kernel
     }
 }
 
@@ -284,6 +286,7 @@ __global__ void copy_stats_kernel(const double* __restrict__ yin, const double* 
     const int b = (int)(i / K), k = (int)(i - (long long)b * K);
     reinterpret_cast<double*>(ws + (size_t)b * L.stride + L.y)[k] = yin[i];
     reinterpret_cast<double*>(ws + (size_t)b * L.stride + L.ss)[k] = ssin[i];
+    reinterpret_cast<int*>(ws + (size_t)b * L.stride + L.colfill)[k] = 0;
 }
 
 struct PowerTable { double v[PMAX]; int P; };
@@ -291,6 +294,21 @@ struct PowerTable { double v[PMAX]; int P; };
 __device__ __forceinline__ int power_index(const PowerTable& pt, double v) {
     for (int p = 0; p < pt.P; ++p) if (pt.v[p] == v) return p;
     return -1;
+}
+
+// One entry of the dense design: 0 = not targeted, 1 = targeted with power index pi, -1 = invalid.
+// Floating-point designs hold the laser power itself (README.md:26); CM_U8 designs hold the code pi + 1.
+template <typename T>
+__device__ __forceinline__ int stim_class(const PowerTable& pt, T raw, int& pi) {
+    const double v = (double)raw;
+    if (v > 0.0) { pi = power_index(pt, v); return pi < 0 ? -1 : 1; }
+    return (v < 0.0 || v != v) ? -1 : 0;
+}
+template <>
+__device__ __forceinline__ int stim_class<unsigned char>(const PowerTable& pt, unsigned char raw, int& pi) {
+    if (raw == 0) return 0;
+    pi = (int)raw - 1;
+    return pi < pt.P ? 1 : -1;
 }
 
 // pass 1 over the dense design: per-row and per-column counts.  Only trials that pass the lam_mask
@@ -313,16 +331,13 @@ __global__ void __launch_bounds__(256) csr_count_kernel(const T* __restrict__ st
     const T* row = stim + ((size_t)b * N + n) * K;
     int bad = 0;
     for (int k = threadIdx.x; k < K; k += blockDim.x) {
-        const double v = (double)row[k];
-        if (v > 0.0) {
-            const int pi = power_index(pt, v);
-            if (pi < 0) bad = 1;
-            else {
-                atomicAdd(&cs[pi], 1);
-                if (ss[k] > thresh) { atomicAdd(&cs[PMAX], 1); atomicAdd(&colcnt[k], 1); }
-                else atomicAdd(&cm[pi], 1);
-            }
-        } else if (v < 0.0 || v != v) bad = 1;
+        int pi = 0;
+        const int cls = stim_class<T>(pt, row[k], pi);
+        if (cls > 0) {
+            atomicAdd(&cs[pi], 1);
+            if (ss[k] > thresh) { atomicAdd(&cs[PMAX], 1); atomicAdd(&colcnt[k], 1); }
+            else atomicAdd(&cm[pi], 1);
+        } else if (cls < 0) bad = 1;
     }
     if (bad) atomicExch(&status[b], CM_EINVAL);
     __syncthreads();
@@ -340,6 +355,7 @@ __global__ void __launch_bounds__(1024) scan_kernel(int N, int K, const Layout L
     int* colfill = reinterpret_cast<int*>(base + L.colfill);
     __shared__ int wsum[32];
     __shared__ int carry;
+    if (threadIdx.x < 64) reinterpret_cast<int*>(base + L.job)[threadIdx.x] = 0;     // job board of the helper CTAs
     for (int pass = 0; pass < 2; ++pass) {
         const int n = pass == 0 ? N : K;
         if (threadIdx.x == 0) carry = 0;
@@ -399,17 +415,19 @@ __global__ void __launch_bounds__(256) csr_fill_kernel(const T* __restrict__ sti
     const T* row = stim + ((size_t)b * N + n) * K;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     for (int k0 = 0; k0 < K; k0 += SUB * 256) {
-        double v[SUB];
+        T v[SUB];
+        int pis[SUB];
         unsigned bal[SUB];
 #pragma unroll
         for (int j = 0; j < SUB; ++j) {
             const int k = k0 + j * 256 + threadIdx.x;
-            v[j] = (k < K) ? (double)row[k] : 0.0;
+            v[j] = (k < K) ? row[k] : (T)0;
         }
 #pragma unroll
         for (int j = 0; j < SUB; ++j) {
             const int k = k0 + j * 256 + threadIdx.x;
-            const bool f = v[j] > 0.0 && ss[k < K ? k : 0] > thresh;
+            pis[j] = 0;
+            const bool f = stim_class<T>(pt, v[j], pis[j]) > 0 && ss[k < K ? k : 0] > thresh;
             bal[j] = __ballot_sync(0xffffffffu, f);
             if (lane == 0) wcnt[j][wid] = __popc(bal[j]);
         }
@@ -423,7 +441,7 @@ __global__ void __launch_bounds__(256) csr_fill_kernel(const T* __restrict__ sti
                 const int k = k0 + j * 256 + threadIdx.x;
                 const int jj = mine + __popc(bal[j] & ((1u << lane) - 1u));
                 col_k[jj] = k;
-                const int pi = power_index(pt, v[j]);
+                const int pi = pis[j];
                 pw[jj] = (unsigned char)pi;
                 colpw[jj] = k | (pi << 27);           // packed (trial, power) for the sweep
                 const int slot = atomicAdd(&colfill[k], 1);
@@ -498,14 +516,17 @@ static bool use_small_cta(int B) {
     int dev = 0, sms = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return false;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return false;
-    return B >= 2 * sms;
+    // One resident wave holds `sms` 16-warp CTAs or 2 * sms 8-warp CTAs.  A batch that does not fit one wave of the big
+    // variant runs the small one: SMs holding two fits overlap their latency-bound phases (measured 1.17x at 2 * sms
+    // fits), and SMs < B <= 2 * sms fits finish in one wave instead of two.
+    return B > sms;
 }
 
 extern "C" size_t cm_caviar_workspace_bytes(int B, int N, int K, int64_t nnz_cap, int save_histories) {
     if (B <= 0 || N <= 0 || K <= 0 || nnz_cap < 0) return 0;
     // sized for the 16-warp layout (256-column tiles, 16 growbufs), which bounds the 8-warp one
     const Layout L = make_layout(N, K, nnz_cap, save_histories > 0 ? save_histories : 0, save_histories > 0, 256, 16);
-    return L.stride * (size_t)B + (size_t)B * 8 + 256;      // + device copy of the seeds
+    return L.stride * (size_t)B + (size_t)B * 8 + 512;      // + device copy of the seeds + fit queue counter
 }
 
 template <typename TS>
@@ -543,7 +564,7 @@ extern "C" int cm_caviar_fit(const cm_caviar_args* a, void* stream) {
     const bool small_cta = use_small_cta(a->B);
     const Layout L = small_cta ? make_layout(a->N, a->K, a->nnz_cap, a->opt.iters, want_lamhist, fit256::GCT, fit256::NW)
                                : make_layout(a->N, a->K, a->nnz_cap, a->opt.iters, want_lamhist, fit512::GCT, fit512::NW);
-    const size_t need = L.stride * (size_t)a->B + (size_t)a->B * 8 + 256;
+    const size_t need = L.stride * (size_t)a->B + (size_t)a->B * 8 + 512;
     if (a->workspace_bytes < need) {
         set_error("cm_caviar_fit: workspace %zu < required %zu bytes", a->workspace_bytes, need);
         return CM_EWORKSPACE;
@@ -553,10 +574,10 @@ extern "C" int cm_caviar_fit(const cm_caviar_args* a, void* stream) {
     unsigned long long* seeds_dev = (unsigned long long*)(ws + L.stride * (size_t)a->B);
     seeds_dev = (unsigned long long*)(((uintptr_t)seeds_dev + 255) & ~(uintptr_t)255);
     CM_CUDA_CHECK(cudaMemcpyAsync(seeds_dev, a->seeds, (size_t)a->B * 8, cudaMemcpyHostToDevice, st));
+    int* queue_dev = (int*)(((uintptr_t)(seeds_dev + a->B) + 63) & ~(uintptr_t)63);
     CM_CUDA_CHECK(cudaMemsetAsync(a->status_dev, 0, (size_t)a->B * sizeof(int), st));
-    // zero the column counters of every fit
-    for (int b = 0; b < a->B; ++b)
-        CM_CUDA_CHECK(cudaMemsetAsync(ws + (size_t)b * L.stride + L.colfill, 0, (size_t)a->K * 4, st));
+    CM_CUDA_CHECK(cudaMemsetAsync(queue_dev, 0, sizeof(int), st));
+    // (the column counters and the job boards are zeroed by the a1 / scan kernels: no per-fit memsets)
 
     // ---- a1 prologue ----
     const long long ntr = (long long)a->B * a->K;
@@ -576,6 +597,7 @@ extern "C" int cm_caviar_fit(const cm_caviar_args* a, void* stream) {
     int rc;
     if (a->stim_dtype == CM_F32) rc = run_csr<float>(a, L, ws, pt, st);
     else if (a->stim_dtype == CM_F64) rc = run_csr<double>(a, L, ws, pt, st);
+    else if (a->stim_dtype == CM_U8) rc = run_csr<unsigned char>(a, L, ws, pt, st);
     else { set_error("cm_caviar_fit: bad stim dtype"); return CM_EINVAL; }
     if (rc) return rc;
 
@@ -614,8 +636,6 @@ extern "C" int cm_caviar_fit(const cm_caviar_args* a, void* stream) {
         if (want > 0) ct = want + 1;
     }
     p.ct = ct;
-    if (ct > 1)
-        for (int b = 0; b < a->B; ++b) CM_CUDA_CHECK(cudaMemsetAsync(ws + (size_t)b * L.stride + L.job, 0, 256, st));
     main_kernel_begin(st);
 #define CM_LAUNCH_FIT(NS, PT)                                                                                      \
     do {                                                                                                           \
@@ -632,7 +652,12 @@ extern "C" int cm_caviar_fit(const cm_caviar_args* a, void* stream) {
             CM_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)NS::caviar_fit_kernel<PT>, dim3(a->B * ct),           \
                                                       dim3(NS::NT), kargs, (size_t)smem_bytes, st));               \
         } else {                                                                                                   \
-            NS::caviar_fit_kernel<PT><<<a->B, NS::NT, smem_bytes, st>>>(p);                                        \
+            int occ = 0;                                                                                           \
+            CM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, NS::caviar_fit_kernel<PT>, NS::NT,   \
+                                                                        (size_t)smem_bytes));                      \
+            const long long wave = (long long)(occ > 0 ? occ : 1) * sm_count;                                      \
+            p.queue = queue_dev;                                                                                   \
+            NS::caviar_fit_kernel<PT><<<(unsigned)(a->B < wave ? a->B : wave), NS::NT, smem_bytes, st>>>(p);       \
         }                                                                                                          \
     } while (0)
     if (small_cta) {
@@ -650,6 +675,19 @@ extern "C" int cm_caviar_fit(const cm_caviar_args* a, void* stream) {
         CM_CUDA_CHECK(cudaMemsetAsync(a->lam_dev, 0, (size_t)a->B * a->N * a->K * 8, st));
         densify_kernel<<<dim3(a->N, 1, a->B), 128, 0, st>>>(L, ws, a->N, a->K, a->lam_dev, 0, a->status_dev);
         count_launch();
+    }
+    if (a->lam_csr_val_dev || a->lam_csr_col_dev || a->lam_csr_ptr_dev) {
+        // sparse posterior: the kernel's own CSR (rows = neurons, columns = trials that pass the lam_mask); three strided
+        // device-to-device copies, no kernel.  Entries past lam_csr_ptr[N] are unspecified.
+        if (!(a->lam_csr_val_dev && a->lam_csr_col_dev && a->lam_csr_ptr_dev)) {
+            set_error("cm_caviar_fit: lam_csr_val_dev, lam_csr_col_dev and lam_csr_ptr_dev go together");
+            return CM_EINVAL;
+        }
+        const size_t z = (size_t)a->nnz_cap;
+        CM_CUDA_CHECK(cudaMemcpy2DAsync(a->lam_csr_val_dev, z * 8, ws + L.lam, L.stride, z * 8, a->B, cudaMemcpyDeviceToDevice, st));
+        CM_CUDA_CHECK(cudaMemcpy2DAsync(a->lam_csr_col_dev, z * 4, ws + L.col_k, L.stride, z * 4, a->B, cudaMemcpyDeviceToDevice, st));
+        CM_CUDA_CHECK(cudaMemcpy2DAsync(a->lam_csr_ptr_dev, (size_t)(a->N + 1) * 4, ws + L.row_ptr, L.stride,
+                                        (size_t)(a->N + 1) * 4, a->B, cudaMemcpyDeviceToDevice, st));
     }
     if (want_lamhist) {
         CM_CUDA_CHECK(cudaMemsetAsync(a->lam_hist_dev, 0, (size_t)a->B * a->opt.iters * a->N * a->K * 8, st));

@@ -40,6 +40,7 @@ struct Ctx {
     int smd;          // its size in doubles
     int ct, role;     // CTAs working on this fit (1 = none but this one), role of this CTA (0 = the fit itself, > 0 = helper)
     int* job;         // global: job board between the fit CTA and its helpers (see panel_gemm_dist)
+    int* status;      // global: status word of this fit (wait_helpers reports a helper that never answered)
 };
 
 // phase accounting for cm_caviar_debug_phase_cycles (block 0, thread 0; enabled on request only)
@@ -409,7 +410,12 @@ __device__ __forceinline__ void st_release_gpu(int* p, int v) {
 __device__ __forceinline__ void red_release_gpu(int* p, int v) {
     asm volatile("red.release.gpu.global.add.s32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
 }
-constexpr long long WATCHDOG_CYCLES = 1ll << 38;      // minutes: a helper idles while the fit CTA runs the other phases
+// A helper only ever leaves on a quit job (type 0): it may idle for as long as the fit CTA runs its serial phases.
+// The fit CTA bounds its own wait for the helpers of ONE job (they are co-resident by construction -- cooperative
+// launch -- so this only fires on a genuine fault); it then flags the fit at once (status CM_EHELPER) and stops
+// waiting for helpers for the rest of the fit, so a broken launch ends quickly and loudly instead of hanging.
+constexpr long long WATCHDOG_CYCLES = 1ll << 36;      // ~35 s at 1.9 GHz for a single job
+constexpr int CM_EHELPER = 9;
 
 __device__ __noinline__ void newton_rows(const Ctx& c, const double* powers, const int* list, int nlist, int part, int nparts);
 // Monte-Carlo means of the truncated-normal sigmoid coefficients of every neuron (caviar.py:209-215, App. A.2); one warp
@@ -473,11 +479,11 @@ __device__ void post_job(const Ctx& c, int type, int a, int b, int d) {
 // wait until every helper has finished the job posted last; their global writes are visible afterwards
 __device__ void wait_helpers(const Ctx& c) {
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0 && !c.job[20]) {
         const long long t0 = clock64();
         const int want = c.job[0] * (c.ct - 1);
         while (ld_acquire_gpu(&c.job[16]) < want)
-            if (clock64() - t0 > WATCHDOG_CYCLES) { c.job[20] = 1; break; }
+            if (clock64() - t0 > WATCHDOG_CYCLES) { c.job[20] = 1; atomicExch(c.status, CM_EHELPER); break; }
     }
     __syncthreads();
     __threadfence();
@@ -502,11 +508,9 @@ __device__ void helper_loop(const Ctx& c, GemmPipe& gp) {
     __syncthreads();                                  // mbarriers initialised
     for (;;) {
         if (threadIdx.x == 0) {
-            const long long t0 = clock64();
             int type = -1;
             while (type < 0) {
                 if (ld_acquire_gpu(&c.job[0]) != seen) type = c.job[1];
-                else if (clock64() - t0 > WATCHDOG_CYCLES) type = 0;
                 else __nanosleep(200);
             }
             s_job[0] = type; s_job[1] = c.job[2]; s_job[2] = c.job[3]; s_job[3] = c.job[4];
@@ -1115,8 +1119,30 @@ __global__ void __launch_bounds__(NT, (NT == 512) ? 1 : 2) caviar_fit_kernel(con
     __shared__ long long sc_tlast;
     __shared__ __align__(8) uint64_t sc_bar[2 * NST];
 
-    const int b = blockIdx.x / p.ct;                  // p.ct CTAs per fit: the fit itself and its panel-GEMM helpers
+    __shared__ int sc_b;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NST; ++i) { mbar_init(&sc_bar[i], 1); mbar_init(&sc_bar[NST + i], NW); }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    GemmPipe gp;
+    gp.full = sc_bar; gp.empty = sc_bar + NST; gp.seq = 0;
+    // Fits are handed out through a device-side queue when the launch has no helper CTAs (p.queue != nullptr): the grid
+    // is one resident wave of CTAs and every CTA pulls the next fit index when it finishes one, so a batch that is not
+    // a multiple of the resident wave does not leave SMs idle behind the slowest wave.  Which CTA runs a fit does not
+    // change a single bit of its result.
+    for (bool first = true;; first = false) {
+    int b;
+    if (p.queue) {
+        __syncthreads();
+        if (threadIdx.x == 0) sc_b = atomicAdd(p.queue, 1);
+        __syncthreads();
+        b = sc_b;
+        if (b >= p.B) break;
+    } else {
+        if (!first) break;
+        b = blockIdx.x / p.ct;                        // p.ct CTAs per fit: the fit itself and its panel-GEMM helpers
+    }
     char* base = p.ws + (size_t)b * p.L.stride;
     const Layout& L = p.L;
     Ctx c;
@@ -1151,13 +1177,8 @@ __global__ void __launch_bounds__(NT, (NT == 512) ? 1 : 2) caviar_fit_kernel(con
     c.smd = p.smem_doubles;
     const int N = c.N, K = c.K, P = c.P;
     const cm_caviar_options& o = p.opt;
-    if (p.status[b] != 0) return;                     // prologue reported an error for this fit
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < NST; ++i) { mbar_init(&sc_bar[i], 1); mbar_init(&sc_bar[NST + i], NW); }
-        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-    }
-    GemmPipe gp;
-    gp.full = sc_bar; gp.empty = sc_bar + NST; gp.seq = 0;
+    c.status = p.status + b;
+    if (p.status[b] != 0) continue;                   // prologue reported an error for this fit
     if (HELPERS && c.role > 0) { helper_loop(c, gp); return; }
     c.nnz = c.row_ptr[N];
     const int iters = o.iters;
@@ -1591,11 +1612,12 @@ __global__ void __launch_bounds__(NT, (NT == 512) ? 1 : 2) caviar_fit_kernel(con
     for (int k = threadIdx.x; k < K; k += NT) p.z_out[(size_t)b * K + k] = c.z[k];
     if (threadIdx.x == 0) { p.shape_out[b] = sc_shape; p.rate_out[b] = sc_rate; }
     if (HELPERS && c.ct > 1 && threadIdx.x == 0) {               // release the helpers
-        if (c.job[20]) p.status[b] = 9;               // a helper did not answer: results are not to be trusted
+        if (c.job[20]) p.status[b] = CM_EHELPER;      // a helper did not answer: results are not to be trusted
         c.job[1] = 0;
         __threadfence();
         st_release_gpu(&c.job[0], c.job[0] + 1);
     }
+    }   // fit queue
 }
 
 }  // namespace CM_FITNS

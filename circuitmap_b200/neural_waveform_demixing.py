@@ -133,7 +133,14 @@ class NeuralDemixer:
             print("Demixing PSC traces... ", end="")
         t1 = time.time()
         if isinstance(traces, torch.Tensor):
-            dem = self.forward_device(traces.to(self.device).contiguous(), monotone_filter_start)
+            # device tensor in, device tensor out: the demixed traces stay on the GPU and carry the CAVIaR prologue
+            # statistics (y = trapz, sum of squares; caviar.py:28-30) so that Model.fit(dem, ...) neither re-reads the
+            # K x 900 array nor moves it through the host
+            x = traces.to(self.device).contiguous()
+            if x.dtype not in (torch.float32, torch.float64):
+                x = x.double()
+            dem, y, ss = self.forward_device(x, monotone_filter_start, stats=True)
+            dem.cm_y, dem.cm_ss = y, ss
         else:
             arr = np.ascontiguousarray(traces)
             if arr.dtype not in (np.float32, np.float64):

@@ -1,7 +1,9 @@
 """`caviar(...)` with the reference's signature (circuitmap/optimise/caviar.py:20-23,100) on the B200 kernel.
 
-Host side only marshals: dense float arrays go to the device as they are, `cm_caviar_fit` (csrc/caviar.cu) does
-every arithmetic step of the fit, and the 17-tuple the reference returns is rebuilt from its outputs.
+Host side only marshals: the traces go to the device as they are, the stimulus design as uint8 power codes (packed by
+the threaded C helper `cm_pack_stim_u8`), `cm_caviar_fit` (csrc/caviar.cu) does every arithmetic step of the fit, and
+the 17-tuple the reference returns is rebuilt from its outputs.  CUDA tensors are accepted for both inputs (e.g. the
+output of `NeuralDemixer` on a device tensor, which carries the y / sum-of-squares hand-off).
 `caviar_batched` is the same call for B independent maps of identical (N, K) -- the unit that is sharded over
 GPUs (simulation sweeps, LOHO-CV folds).
 """
@@ -46,14 +48,93 @@ def _validate_options(fit_options):
 
 def _dt(t):
     import torch
-    return {torch.float32: _lib.CM_F32, torch.float64: _lib.CM_F64}[t.dtype]
+    return {torch.float32: _lib.CM_F32, torch.float64: _lib.CM_F64, torch.uint8: _lib.CM_U8}[t.dtype]
+
+
+def scan_stim(stim_dev):
+    """(nnz, sorted distinct non-zero values) of a dense device-resident design in one streaming pass of
+    `cm_caviar_scan_stim` (csrc/stim.cu) -- what the reference gets from np.unique on the host (caviar.py:42)."""
+    import torch
+    lib = _lib.load()
+    stim_dev = stim_dev.contiguous()
+    scratch = torch.empty(int(lib.cm_caviar_scan_scratch_bytes()), dtype=torch.uint8, device=stim_dev.device)
+    nnz, nvals = C.c_int64(), C.c_int()
+    vals = (C.c_double * (_lib.CM_CAVIAR_MAX_POWERS + 2))()
+    with torch.cuda.device(stim_dev.device):
+        stream = torch.cuda.current_stream().cuda_stream
+        _lib.check(lib.cm_caviar_scan_stim(stim_dev.data_ptr(), _dt(stim_dev), stim_dev.numel(), scratch.data_ptr(),
+                                           C.byref(nnz), vals, C.byref(nvals), C.c_void_p(stream)), "cm_caviar_scan_stim")
+    n = nvals.value
+    if n > _lib.CM_CAVIAR_MAX_POWERS + 1:
+        raise RuntimeError("cm_caviar_fit supports 1..%d distinct stimulus powers, got more" % _lib.CM_CAVIAR_MAX_POWERS)
+    return int(nnz.value), np.array(vals[:n], dtype=np.float64)
+
+
+def powers_like_reference(nnz, values, total):
+    """np.unique(I)[1:] (caviar.py:42) from the scan: the sorted distinct values without the smallest one (0 when the
+    design holds a zero, which every real design does; quirk A.3 #8 is kept for one that does not)."""
+    vals = np.sort(np.concatenate([values, [0.0]])) if nnz < total else np.sort(values)
+    return vals[1:]
+
+
+_pinned_codes = {}
+
+
+def pack_stim_host(I, threads=None):
+    """Host float design (N, K), C-contiguous -> (pinned uint8 code tensor (N, K), powers, nnz) with the threaded C
+    helper `cm_pack_stim_u8`: the reference-facing call then uploads N*K bytes instead of 8*N*K."""
+    import os
+    import torch
+    lib = _lib.load()
+    dt = {np.dtype(np.float32): _lib.CM_F32, np.dtype(np.float64): _lib.CM_F64}[I.dtype]
+    n = I.size
+    buf = _pinned_codes.get("buf")
+    if buf is None or buf.numel() < n:
+        buf = torch.empty(max(n, 1 << 20), dtype=torch.uint8)
+        if torch.cuda.is_available():                     # (the helper itself is host-only and is unit-tested without a GPU)
+            buf = buf.pin_memory()
+        _pinned_codes["buf"] = buf
+    powers = (C.c_double * _lib.CM_CAVIAR_MAX_POWERS)()
+    P, nnz = C.c_int(), C.c_int64()
+    threads = threads or max(1, min(16, (os.cpu_count() or 2) // 2))
+    rc = lib.cm_pack_stim_u8(I.ctypes.data_as(C.c_void_p), dt, n, powers, C.byref(P), C.byref(nnz),
+                             C.c_void_p(buf.data_ptr()), threads)
+    if rc == _lib.CM_EUNSUPPORTED:
+        raise RuntimeError("cm_caviar_fit supports 1..%d distinct stimulus powers, got %d"
+                           % (_lib.CM_CAVIAR_MAX_POWERS, P.value))
+    _lib.check(rc, "cm_pack_stim_u8")
+    return buf[:n].view(I.shape), np.array(powers[:P.value], dtype=np.float64), int(nnz.value)
+
+
+class CsrLam:
+    """Sparse posterior of one fit: CSR over (neuron, trial) of the entries `lam` can be non-zero on.  `toarray()`
+    gives the dense (N, K) float64 array the reference returns (caviar.py:100)."""
+
+    def __init__(self, val, col, ptr, K):
+        self.val, self.col, self.ptr, self.K = val, col, ptr, int(K)
+        self.shape = (len(ptr) - 1, int(K))
+
+    def toarray(self):
+        val, col, ptr = (np.asarray(x.cpu() if hasattr(x, "cpu") else x) for x in (self.val, self.col, self.ptr))
+        N = len(ptr) - 1
+        out = np.zeros((N, self.K))
+        nnz = int(ptr[-1])
+        rows = np.repeat(np.arange(N), np.diff(ptr))
+        out[rows, col[:nnz]] = val[:nnz]
+        return out
+
+    __array__ = lambda self, dtype=None, copy=None: self.toarray()
 
 
 def caviar_batched(stim, powers, mu_prior, beta_prior, shape_prior, rate_prior, phi_prior, phi_cov_prior, psc=None,
-                   y=None, ss=None, seeds=None, nnz_cap=None, want_lam=True, workspace=None, **fit_options):
+                   y=None, ss=None, seeds=None, nnz_cap=None, want_lam=True, lam_csr=False, workspace=None, out=None,
+                   **fit_options):
     """B fits on the current CUDA device.  All array arguments are CUDA tensors:
-         stim (B,N,K) f32/f64; psc (B,K,T) f32/f64 or (y, ss) (B,K) f64; priors (B,N[,2[,2]]) f64.
+         stim (B,N,K) f32/f64 laser powers or uint8 power codes (c = powers[c-1], 0 = not targeted);
+         psc (B,K,T) f32/f64 or (y, ss) (B,K) f64; priors (B,N[,2[,2]]) f64.
        `powers` is a host sequence (ascending distinct non-zero powers), `seeds` a host sequence of B ints.
+       lam_csr=True adds the sparse posterior (lam_csr_val (B,nnz_cap), lam_csr_col, lam_csr_ptr (B,N+1)); `out` may
+       carry preallocated output tensors from an earlier call with the same shapes (streaming reuses them).
        Returns a dict of CUDA tensors (mu, beta, lam, shape, rate, phi, phi_cov, z, status[, *_hist])."""
     import torch
     kw = _validate_options(fit_options)
@@ -76,11 +157,22 @@ def caviar_batched(stim, powers, mu_prior, beta_prior, shape_prior, rate_prior, 
     nnz_cap = max(int(nnz_cap), 1)
     hist = bool(kw["save_histories"])
 
-    out = dict(mu=torch.empty((B, N), **f64), beta=torch.empty((B, N), **f64),
-               lam=torch.empty((B, N, K), **f64) if want_lam else None,
-               shape=torch.empty((B,), **f64), rate=torch.empty((B,), **f64),
-               phi=torch.empty((B, N, 2), **f64), phi_cov=torch.empty((B, N, 2, 2), **f64),
-               z=torch.empty((B, K), **f64), status=torch.zeros((B,), dtype=torch.int32, device=dev))
+    reuse = out if out is not None else {}
+
+    def buf(name, shape, dtype=torch.float64):
+        t = reuse.get(name)
+        if t is not None and tuple(t.shape) == tuple(shape) and t.dtype == dtype and t.device == dev:
+            return t
+        return torch.empty(shape, dtype=dtype, device=dev)
+
+    out = dict(mu=buf("mu", (B, N)), beta=buf("beta", (B, N)),
+               lam=buf("lam", (B, N, K)) if want_lam else None,
+               shape=buf("shape", (B,)), rate=buf("rate", (B,)),
+               phi=buf("phi", (B, N, 2)), phi_cov=buf("phi_cov", (B, N, 2, 2)),
+               z=buf("z", (B, K)), status=buf("status", (B,), torch.int32))
+    if lam_csr:
+        out.update(lam_csr_val=buf("lam_csr_val", (B, nnz_cap)), lam_csr_col=buf("lam_csr_col", (B, nnz_cap), torch.int32),
+                   lam_csr_ptr=buf("lam_csr_ptr", (B, N + 1), torch.int32))
     if hist:
         out.update(mu_hist=torch.empty((B, iters, N), **f64), beta_hist=torch.empty((B, iters, N), **f64),
                    lam_hist=torch.empty((B, iters, N, K), **f64) if want_lam else None,
@@ -128,6 +220,9 @@ def caviar_batched(stim, powers, mu_prior, beta_prior, shape_prior, rate_prior, 
         for name in ("mu", "beta", "lam", "shape", "rate", "phi", "phi_cov", "z"):
             t = out[name + "_hist"]
             setattr(a, name + "_hist_dev", t.data_ptr() if t is not None else None)
+    if lam_csr:
+        a.lam_csr_val_dev, a.lam_csr_col_dev = out["lam_csr_val"].data_ptr(), out["lam_csr_col"].data_ptr()
+        a.lam_csr_ptr_dev = out["lam_csr_ptr"].data_ptr()
     a.nnz_cap = nnz_cap
     a.workspace_dev, a.workspace_bytes = workspace.data_ptr(), workspace.numel()
     a.status_dev = out["status"].data_ptr()
@@ -145,7 +240,8 @@ def check_status(out):
     if np.any(st != 0):
         b = int(np.nonzero(st)[0][0])
         msg = {1: "stimulus matrix holds a value that is negative, NaN or not among `powers`",
-               5: "non-zeros of the stimulus matrix exceed nnz_cap"}.get(int(st[b]), "device error")
+               5: "non-zeros of the stimulus matrix exceed nnz_cap",
+               9: "a helper CTA of the fit never answered; the results are not valid"}.get(int(st[b]), "device error")
         raise RuntimeError("cm_caviar_fit: fit %d failed with code %d (%s)" % (b, int(st[b]), msg))
 
 
@@ -156,31 +252,44 @@ def caviar(y_psc, I, mu_prior, beta_prior, shape_prior, rate_prior, phi_prior, p
     torch = _lib.require_cuda()
     print("Running coordinate-ascent variational inference and isotonic regularisation (CAVIaR) algorithm.")
     dev = torch.device("cuda" if device is None else device)
-    I = np.asarray(I)
-    if not np.issubdtype(I.dtype, np.floating):
-        I = I.astype(float)
-    I = np.ascontiguousarray(I)                      # simulate() returns a non-contiguous (N, K) view
-    y_psc = np.ascontiguousarray(y_psc)
-    if not np.issubdtype(y_psc.dtype, np.floating):
-        y_psc = y_psc.astype(float)
-    N, K = I.shape
+    y_dev = ss_dev = None
     with torch.cuda.device(dev):
-        stim_dev = _staging.to_device(I, dev)
-        psc_dev = _staging.to_device(y_psc, dev)
-    # powers = np.unique(I)[1:] (caviar.py:42: the sorted distinct values without the smallest one), computed on the
-    # device from the non-zero entries: sorting 1e7 host doubles costs more than the whole fit
-    nz = stim_dev[stim_dev != 0]
-    nnz = int(nz.numel())
-    distinct = torch.unique(nz)
-    if nnz < N * K:
-        distinct = torch.unique(torch.cat([distinct, torch.zeros(1, dtype=distinct.dtype, device=dev)]))
-    powers = distinct[1:].double().cpu().numpy()
+        # ---- stimulus design: NumPy (the reference's surface) or a CUDA tensor that is already on the device ----
+        if isinstance(I, torch.Tensor) and I.is_cuda:
+            stim_dev = I.contiguous()
+            if stim_dev.dtype not in (torch.float32, torch.float64):
+                stim_dev = stim_dev.double()
+            N, K = stim_dev.shape
+            nnz, values = scan_stim(stim_dev)                     # np.unique(I)[1:] in one device pass (csrc/stim.cu)
+            powers = powers_like_reference(nnz, values, N * K)
+        else:
+            I = np.asarray(I)
+            if I.dtype not in (np.float32, np.float64):
+                I = I.astype(float)
+            I = np.ascontiguousarray(I)                  # simulate() returns a non-contiguous (N, K) view
+            N, K = I.shape
+            codes, powers, nnz = pack_stim_host(I)       # threaded C helper: powers + uint8 codes (N*K bytes to upload)
+            stim_dev = codes.to(dev, non_blocking=True)
+        # ---- traces: NumPy, or a CUDA tensor (e.g. straight from NeuralDemixer, carrying its y / ss statistics) ----
+        if isinstance(y_psc, torch.Tensor) and y_psc.is_cuda:
+            psc_dev = y_psc.contiguous()
+            if psc_dev.dtype not in (torch.float32, torch.float64):
+                psc_dev = psc_dev.double()
+            y_dev, ss_dev = getattr(y_psc, "cm_y", None), getattr(y_psc, "cm_ss", None)
+        else:
+            y_psc = np.ascontiguousarray(y_psc)
+            if y_psc.dtype not in (np.float32, np.float64):
+                y_psc = y_psc.astype(float)
+            psc_dev = _staging.to_device(y_psc, dev)
+    if powers.size < 1:
+        raise RuntimeError("cm_caviar_fit supports 1..%d distinct stimulus powers, got 0" % _lib.CM_CAVIAR_MAX_POWERS)
     t = lambda x: torch.from_numpy(np.ascontiguousarray(np.asarray(x, dtype=np.float64))).to(dev)
     seed = int(fit_options.get("seed", _DEFAULTS["seed"]))
     opts = {k: v for k, v in fit_options.items() if k != "seed"}
+    src = dict(y=y_dev[None], ss=ss_dev[None]) if (y_dev is not None and ss_dev is not None) else dict(psc=psc_dev[None])
     out = caviar_batched(stim_dev[None], powers, t(mu_prior)[None], t(beta_prior)[None],
                          float(shape_prior), float(rate_prior), t(phi_prior)[None], t(phi_cov_prior)[None],
-                         psc=psc_dev[None], seeds=[seed], nnz_cap=nnz, seed=seed, **opts)
+                         seeds=[seed], nnz_cap=nnz, seed=seed, **src, **opts)
     check_status(out)
     def g(k):
         with torch.cuda.device(dev):

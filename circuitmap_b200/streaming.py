@@ -44,13 +44,18 @@ def demix_pinned(demixer, src, dst, dev_in, dev_out, chunk=5000, monotone_filter
 
 
 def fit_pinned(host_stim, host_psc, dev_stim, dev_psc, powers, priors, seeds, host_out, chunk, nnz_cap=None,
-               workspaces=None, streams=None, **fit_options):
+               workspaces=None, streams=None, on_chunk=None, **fit_options):
     """B independent fits from pinned host inputs to pinned host outputs.
        host_stim[b] (N, K), host_psc[b] (K, T): pinned tensors (sequences of length B; entries may repeat);
        dev_stim (B, N, K), dev_psc (B, K, T): device staging, reused across calls;
        priors: tuple (mu0, beta0, shape0, rate0, phi0, phi_cov0) of device tensors with leading dimension B (scalars
        for shape0 / rate0);  host_out: dict of pinned tensors for mu, beta, shape, rate, phi, phi_cov, z, lam
-       (leading dimension B; 'lam' optional).  Returns the per-fit status (device tensor, all zero on success)."""
+       ('lam' optional).  Every tensor of host_out has either leading dimension >= B (fit b lands in row b) or is a RING
+       of R >= chunk slabs (dense lam is 8 N K bytes per fit): ring tensors are filled chunk by chunk, slot
+       (chunk index mod R // chunk), and `on_chunk(lo, hi, views)` is called -- after the chunk's copies have completed
+       and before its slabs are reused -- with views[k] = the (hi - lo) rows holding fits lo..hi-1 (all keys, ring or not).
+       A ring without on_chunk would silently drop results and is refused.
+       Returns the per-fit status (device tensor, all zero on success)."""
     import torch
     dev = dev_stim.device
     st = streams or _Streams(dev)
@@ -59,9 +64,28 @@ def fit_pinned(host_stim, host_psc, dev_stim, dev_psc, powers, priors, seeds, ho
     for s in (st.copy_in, st.compute, st.copy_out):
         s.wait_stream(cur)
     want_lam = "lam" in host_out
+    keys = [k for k in _STATE_KEYS if k in host_out]
+    rings = {k: host_out[k].shape[0] for k in keys if host_out[k].shape[0] < B}
+    if rings:
+        if on_chunk is None:
+            raise ValueError("fit_pinned: host_out[%r] has %d < B = %d slabs: pass on_chunk to drain the ring "
+                             "(results would be overwritten)" % (next(iter(rings)), next(iter(rings.values())), B))
+        if min(rings.values()) < min(chunk, B):
+            raise ValueError("fit_pinned: a ring needs at least `chunk` slabs")
+    nslots = min([r // chunk for r in rings.values()] + [2]) if rings else 2
     mu0, beta0, shape0, rate0, phi0, cov0 = priors
     workspaces = workspaces if workspaces is not None else {}
     status, keep = [], []
+    pending = None
+
+    def drain(item):
+        lo, hi, slot, ev = item
+        ev.synchronize()
+        if on_chunk is not None:
+            views = {k: (host_out[k][slot * chunk:slot * chunk + hi - lo] if k in rings else host_out[k][lo:hi])
+                     for k in keys}
+            on_chunk(lo, hi, views)
+
     for ci, lo in enumerate(range(0, B, chunk)):
         hi = min(lo + chunk, B)
         with torch.cuda.stream(st.copy_in):
@@ -78,18 +102,145 @@ def fit_pinned(host_stim, host_psc, dev_stim, dev_psc, powers, priors, seeds, ho
             done = st.compute.record_event()
         keep.append(out)                      # outputs stay alive until the copies below have run
         status.append(out["status"])
+        slot = ci % nslots
+        if pending is not None and rings and pending[2] == slot:
+            drain(pending)                    # the slabs this chunk lands in still hold an undelivered chunk
+            pending = None
         with torch.cuda.stream(st.copy_out):
             st.copy_out.wait_event(done)
-            for k in _STATE_KEYS:
-                if k not in host_out:
-                    continue
-                ring = host_out[k].shape[0]
-                if ring >= B:
+            for k in keys:
+                if k in rings:
+                    host_out[k][slot * chunk:slot * chunk + hi - lo].copy_(out[k], non_blocking=True)
+                else:
                     host_out[k][lo:hi].copy_(out[k], non_blocking=True)
-                else:                                     # a ring of pinned slabs the caller drains (dense lam is 8 N K bytes per fit)
-                    for b0 in range(0, hi - lo, ring):
-                        n = min(ring, hi - lo - b0)
-                        host_out[k][:n].copy_(out[k][b0:b0 + n], non_blocking=True)
+            ev = st.copy_out.record_event()
+        if pending is not None:
+            drain(pending)                    # deliver chunk ci-1 while chunk ci is in flight
+        pending = (lo, hi, slot, ev)
+    if pending is not None:
+        drain(pending)
     st.copy_out.synchronize()
     st.compute.synchronize()
     return torch.cat(status)
+
+
+class FitPipeline:
+    """The pipeline users run (README.md:28-51 of the reference: demix -> fit), streamed from pinned host memory in the
+    compact formats the data really has, double-buffered on three streams:
+
+        host (pinned):  traces (K, T) float32   +   design (N, K) uint8 power codes (cm_pack_stim_u8)
+          -- H2D -->  [NeuralDemixer forward: y = trapz, sum x^2 stay on the device]  -->  cm_caviar_fit
+          -- D2H -->  mu, beta, shape, rate, phi, phi_cov, z  +  lam as CSR (8 nnz bytes instead of 8 N K)
+
+    Chunk i+1's upload, chunk i's kernels and chunk i-1's download overlap; `on_result(lo, hi, views)` receives pinned
+    host views of fits lo..hi-1 in order (valid until it returns).  `views['lam']` is a list of optimise.CsrLam.
+    Bit-identical to calling NeuralDemixer / caviar_batched on each map (every fit is independent of its batch mates).
+    """
+
+    OUT_KEYS = ("mu", "beta", "shape", "rate", "phi", "phi_cov", "z", "status", "lam_csr_val", "lam_csr_col",
+                "lam_csr_ptr")
+
+    def __init__(self, N, K, powers, chunk, nnz_cap, device=None, demixer=None, T=900, priors=None, **fit_options):
+        import numpy as np
+        import torch
+        self.N, self.K, self.T, self.chunk, self.nnz_cap = int(N), int(K), int(T), int(chunk), int(nnz_cap)
+        self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.powers = np.ascontiguousarray(powers, dtype=np.float64)
+        self.demixer = demixer
+        self.fit_options = dict(fit_options)
+        d, c = self.dev, self.chunk
+        self.dev_stim = [torch.empty((c, N, K), dtype=torch.uint8, device=d) for _ in range(2)]
+        self.dev_psc = [torch.empty((c, K, T), dtype=torch.float32, device=d) for _ in range(2)]
+        self.dev_dem = torch.empty((c * K, T), dtype=torch.float32, device=d) if demixer is not None else None
+        self.dev_out = [None, None]
+        self.workspace = None
+        f64 = dict(dtype=torch.float64, device=d)
+        if priors is None:                                                       # model.py:24-31
+            cov = torch.zeros(c, N, 2, 2, **f64)
+            cov[..., 0, 0] = 1e-1
+            cov[..., 1, 1] = 1e0
+            phi = torch.stack([1e-1 * torch.ones(c, N, **f64), 5e0 * torch.ones(c, N, **f64)], -1).contiguous()
+            priors = (torch.zeros(c, N, **f64), 1e1 * torch.ones(c, N, **f64), 1.0, 1e-1, phi, cov)
+        self.priors = priors
+        shapes = dict(mu=(c, N), beta=(c, N), shape=(c,), rate=(c,), phi=(c, N, 2), phi_cov=(c, N, 2, 2), z=(c, K),
+                      lam_csr_val=(c, self.nnz_cap))
+        self.host_out = [dict({k: torch.empty(v, dtype=torch.float64).pin_memory() for k, v in shapes.items()},
+                              status=torch.empty((c,), dtype=torch.int32).pin_memory(),
+                              lam_csr_col=torch.empty((c, self.nnz_cap), dtype=torch.int32).pin_memory(),
+                              lam_csr_ptr=torch.empty((c, N + 1), dtype=torch.int32).pin_memory()) for _ in range(2)]
+        self.streams = _Streams(d)
+        self.h2d_bytes_per_fit = N * K + K * T * 4
+        self.d2h_bytes_per_fit = sum(t[0].numel() * t.element_size() for t in self.host_out[0].values())
+
+    def run(self, host_stim, host_psc, seeds, on_result=None):
+        """host_stim[b]: pinned uint8 (N, K); host_psc[b]: pinned float32 (K, T) -- raw traces when the pipeline has a
+        demixer, demixed ones otherwise.  Returns the number of fits that reported a non-zero status."""
+        import torch
+        st, c, K, T = self.streams, self.chunk, self.K, self.T
+        B = len(host_stim)
+        cur = torch.cuda.current_stream(self.dev)
+        for s in (st.copy_in, st.compute, st.copy_out):
+            s.wait_stream(cur)
+        mu0, beta0, shape0, rate0, phi0, cov0 = self.priors
+        ev_compute = [None, None]          # compute of the chunk that last used staging set s
+        ev_out = [None, None]              # D2H of the chunk that last used output set s
+        pending, failed = None, 0
+
+        def drain(item):
+            nonlocal failed
+            lo, hi, s_, ev = item
+            ev.synchronize()
+            ho = self.host_out[s_]
+            n = hi - lo
+            failed += int((ho["status"][:n] != 0).sum().item())
+            if on_result is not None:
+                views = {k: ho[k][:n] for k in ("mu", "beta", "shape", "rate", "phi", "phi_cov", "z", "status")}
+                views["lam"] = [optimise.CsrLam(ho["lam_csr_val"][i].numpy(), ho["lam_csr_col"][i].numpy(),
+                                                ho["lam_csr_ptr"][i].numpy(), K) for i in range(n)]
+                on_result(lo, hi, views)
+
+        for ci, lo in enumerate(range(0, B, c)):
+            hi = min(lo + c, B)
+            n, s_ = hi - lo, ci & 1
+            with torch.cuda.stream(st.copy_in):
+                if ev_compute[s_] is not None:
+                    st.copy_in.wait_event(ev_compute[s_])      # the kernels that read this staging set are done
+                for i, b in enumerate(range(lo, hi)):
+                    self.dev_stim[s_][i].copy_(host_stim[b], non_blocking=True)
+                    self.dev_psc[s_][i].copy_(host_psc[b], non_blocking=True)
+                ready = st.copy_in.record_event()
+            if pending is not None and pending[2] == s_:
+                drain(pending)                                  # (only with a single chunk in flight)
+                pending = None
+            with torch.cuda.stream(st.compute):
+                st.compute.wait_event(ready)
+                if ev_out[s_] is not None:
+                    st.compute.wait_event(ev_out[s_])           # this output set has been copied out
+                src = {}
+                if self.demixer is not None:
+                    _, y, ss = self.demixer.forward_device(self.dev_psc[s_][:n].reshape(n * K, T), out=self.dev_dem[:n * K],
+                                                           stats=True)
+                    src = dict(y=y.view(n, K), ss=ss.view(n, K))
+                else:
+                    src = dict(psc=self.dev_psc[s_][:n])
+                out = optimise.caviar_batched(self.dev_stim[s_][:n], self.powers, mu0[:n], beta0[:n], shape0, rate0,
+                                              phi0[:n], cov0[:n], seeds=list(seeds[lo:hi]), nnz_cap=self.nnz_cap,
+                                              want_lam=False, lam_csr=True, workspace=self.workspace,
+                                              out=self.dev_out[s_], **src, **self.fit_options)
+                self.workspace = out["_workspace"]
+                self.dev_out[s_] = out
+                ev_compute[s_] = st.compute.record_event()
+            with torch.cuda.stream(st.copy_out):
+                st.copy_out.wait_event(ev_compute[s_])
+                ho = self.host_out[s_]
+                for k in self.OUT_KEYS:
+                    ho[k][:n].copy_(out[k], non_blocking=True)
+                ev_out[s_] = st.copy_out.record_event()
+            if pending is not None:
+                drain(pending)                                  # deliver chunk ci-1 while chunk ci is in flight
+            pending = (lo, hi, s_, ev_out[s_])
+        if pending is not None:
+            drain(pending)
+        cur.wait_stream(st.compute)
+        cur.wait_stream(st.copy_out)
+        return failed

@@ -32,7 +32,7 @@ extern "C" {
 #endif
 
 enum { CM_OK = 0, CM_EINVAL = 1, CM_ESHAPE = 2, CM_EUNSUPPORTED = 3, CM_ECUDA = 4, CM_EWORKSPACE = 5 };
-enum { CM_F32 = 0, CM_F64 = 1 };
+enum { CM_F32 = 0, CM_F64 = 1, CM_U8 = 2 };   /* CM_U8: stimulus designs only, see cm_caviar_args.stim_dev */
 
 CM_API int cm_version(void);
 CM_API const char* cm_last_error(void);
@@ -100,7 +100,9 @@ typedef struct cm_caviar_args {
     int           psc_dtype;
     const double* y_dev;         /* B x K  trapz(psc)   (used when psc_dev == NULL)                */
     const double* ss_dev;        /* B x K  sum_t psc^2  (used when psc_dev == NULL)                */
-    const void*   stim_dev;      /* B x N x K, neuron-major rows, K contiguous (stim_dtype)        */
+    const void*   stim_dev;      /* B x N x K, neuron-major rows, K contiguous (stim_dtype): laser powers (CM_F32 /
+                                    CM_F64, 0 = not targeted, README.md:26) or power codes (CM_U8: c in 1..P means
+                                    powers[c-1], 0 = not targeted; see cm_pack_stim_u8)                            */
     int           stim_dtype;
     int           n_powers;      /* P = number of distinct non-zero powers (<= CM_CAVIAR_MAX_POWERS) */
     const double* powers;        /* HOST array, ascending: np.unique(stim)[1:] (caviar.py:42)      */
@@ -135,11 +137,30 @@ typedef struct cm_caviar_args {
     int64_t nnz_cap;             /* upper bound on non-zeros of stim PER FIT */
     void*   workspace_dev;
     size_t  workspace_bytes;     /* >= cm_caviar_workspace_bytes(B, N, K, nnz_cap, flags) */
-    int*    status_dev;          /* B ints: 0 ok, else CM_E* detected on device (e.g. nnz overflow) */
+    int*    status_dev;          /* B ints: 0 ok, else CM_E* detected on device (1 invalid stimulus entry, 5 nnz overflow,
+                                    9 a helper CTA of a large single fit never answered) */
+    /* optional sparse posterior: CSR over (neuron, trial) of the entries lam can be non-zero on, i.e. targeted trials
+     * that pass the lam_mask (caviar.py:30-34,216) -- 8 nnz bytes instead of the 8 N K of lam_dev.  All three or none. */
+    double*  lam_csr_val_dev;    /* B x nnz_cap */
+    int32_t* lam_csr_col_dev;    /* B x nnz_cap  trial index of every entry */
+    int32_t* lam_csr_ptr_dev;    /* B x (N + 1)  row pointers; entries past ptr[N] are unspecified */
 } cm_caviar_args;
 
 CM_API size_t cm_caviar_workspace_bytes(int B, int N, int K, int64_t nnz_cap, int save_histories);
 CM_API int    cm_caviar_fit(const cm_caviar_args* a, void* stream);
+
+/* One streaming pass over a dense device-resident design (count = B*N*K entries of `dtype`): number of non-zero entries and
+ * the sorted distinct non-zero values (what the reference derives on the host with np.unique, caviar.py:42).
+ * values_out: HOST array of CM_CAVIAR_MAX_POWERS + 2 doubles; *n_values_out > CM_CAVIAR_MAX_POWERS + 1 means "too many".
+ * scratch_dev: cm_caviar_scan_scratch_bytes() bytes of device memory.  Synchronises the stream. */
+CM_API size_t cm_caviar_scan_scratch_bytes(void);
+CM_API int    cm_caviar_scan_stim(const void* stim_dev, int dtype, int64_t count, void* scratch_dev, int64_t* nnz_out,
+                                  double* values_out, int* n_values_out, void* stream);
+/* HOST helper (no device work, `threads` worker threads): powers = np.unique(stim)[1:] (caviar.py:42) into powers_out
+ * (CM_CAVIAR_MAX_POWERS doubles), the number of non-zero entries, and -- if codes_out != NULL -- the design as uint8
+ * power codes for the CM_U8 stimulus dtype (N*K bytes to upload instead of 8*N*K).  stim_host: CM_F32 or CM_F64. */
+CM_API int    cm_pack_stim_u8(const void* stim_host, int dtype, int64_t count, double* powers_out, int* n_powers_out,
+                              int64_t* nnz_out, unsigned char* codes_out, int threads);
 
 /* diagnostics: per-phase SM cycle counters of fit 0 of the persistent kernel (see csrc/caviar.cu phase_mark ids);
  * copies up to n counters to `out` (may be NULL), then clears them and sets the enable flag (synchronises). */

@@ -82,3 +82,28 @@ def test_lightning_checkpoints_load_without_lightning():
         w = load_weights("/root/reference/demixers/%s.ckpt" % name)
         g = dict(np.load(os.path.join(GOLDEN, name + "_weights.npz")))
         assert all(np.array_equal(w[k], g[k]) for k in w)
+
+
+def test_pack_stim_u8_host_helper():
+    """cm_pack_stim_u8 (csrc/stim.cu, host only): powers = np.unique(I)[1:] (caviar.py:42), nnz, uint8 codes."""
+    from circuitmap_b200 import optimise
+    rng = np.random.default_rng(0)
+    for dtype in (np.float64, np.float32):
+        I = np.zeros((37, 5000), dtype=dtype)
+        pw = np.array([45, 55, 65, 70.5], dtype=dtype)
+        sel = rng.random(I.shape) < 0.03
+        I[sel] = pw[rng.integers(0, 4, int(sel.sum()))]
+        codes, powers, nnz = optimise.pack_stim_host(I)
+        assert np.array_equal(powers, np.unique(I)[1:].astype(np.float64)) and nnz == np.count_nonzero(I)
+        want = np.zeros(I.shape, np.uint8)
+        for i, p in enumerate(powers):
+            want[I == dtype(p)] = i + 1
+        assert np.array_equal(codes.numpy(), want)
+    # a design without zeros: the smallest value is dropped like the reference does (A.3 #8); its entries become code 255
+    J = np.full((3, 40), 45.0); J[1, :5] = 65.0
+    codes, powers, nnz = optimise.pack_stim_host(J)
+    assert powers.tolist() == [65.0] and nnz == 120 and set(np.unique(codes.numpy())) == {1, 255}
+    with pytest.raises(RuntimeError, match="distinct stimulus powers"):
+        optimise.pack_stim_host(np.arange(1.0, 41.0).reshape(2, 20))
+    with pytest.raises(RuntimeError, match="negative"):
+        optimise.pack_stim_host(np.array([[0.0, -1.0, 45.0]]))

@@ -50,3 +50,92 @@ def test_fit_pinned_equals_batched_call():
     assert int(status.sum().item()) == 0 and status.numel() == B
     for k, v in host_out.items():
         assert np.array_equal(v.numpy(), ref[k].cpu().numpy(), equal_nan=True), k
+
+
+def _maps(B, N, K, H=4):
+    import torch
+    from oracle import simulate as osim
+    sims = [osim.simulate_fast(N=N, K=K, H=H, seed=30 + s) for s in range(B)]
+    f64 = dict(dtype=torch.float64, device="cuda")
+    cov = torch.zeros(B, N, 2, 2, **f64); cov[..., 0, 0] = 0.1; cov[..., 1, 1] = 1.0
+    phi = torch.stack([0.1 * torch.ones(B, N, **f64), 5 * torch.ones(B, N, **f64)], -1).contiguous()
+    pri = (torch.zeros(B, N, **f64), 10 * torch.ones(B, N, **f64), 1.0, 0.1, phi, cov)
+    return sims, pri
+
+
+def test_fit_pinned_ring_smaller_than_batch_delivers_every_fit():
+    """ADVICE r1 / VERDICT weak 5: when host_out['lam'] is a ring of fewer slabs than B, every chunk is handed to the
+    caller's callback before its slabs are reused; a ring without a callback is refused."""
+    import torch
+    from circuitmap_b200 import optimise, streaming
+    B, N, K = 7, 24, 200
+    sims, pri = _maps(B, N, K)
+    hs = [torch.from_numpy(np.ascontiguousarray(s["stim_matrix"])).pin_memory() for s in sims]
+    hp = [torch.from_numpy(np.ascontiguousarray(s["psc"])).pin_memory() for s in sims]
+    stim = torch.stack([h.cuda() for h in hs]).contiguous()
+    psc = torch.stack([h.cuda() for h in hp]).contiguous()
+    powers = np.unique(sims[0]["stim_matrix"])[1:]
+    seeds = list(range(B))
+    ref = optimise.caviar_batched(stim, powers, *pri, psc=psc, seeds=seeds, iters=10, msrmp=0.4)
+    for ring, chunk in ((2, 2), (4, 2), (3, 3)):
+        host_out = {k: torch.empty(ref[k].shape, dtype=ref[k].dtype).pin_memory()
+                    for k in ("mu", "beta", "shape", "rate", "phi", "phi_cov", "z")}
+        host_out["lam"] = torch.empty((ring, N, K), dtype=torch.float64).pin_memory()
+        got = {}
+
+        def on_chunk(lo, hi, views):
+            assert views["lam"].shape[0] == hi - lo and views["mu"].shape[0] == hi - lo
+            for b in range(lo, hi):
+                got[b] = (views["lam"][b - lo].clone(), views["mu"][b - lo].clone())
+
+        dstim, dpsc = torch.empty_like(stim), torch.empty_like(psc)
+        status = streaming.fit_pinned(hs, hp, dstim, dpsc, powers, pri, seeds, host_out, chunk=chunk, on_chunk=on_chunk,
+                                      iters=10, msrmp=0.4)
+        assert int(status.sum().item()) == 0 and sorted(got) == list(range(B))
+        for b in range(B):
+            assert np.array_equal(got[b][0].numpy(), ref["lam"][b].cpu().numpy()), (ring, chunk, b)
+            assert np.array_equal(got[b][1].numpy(), ref["mu"][b].cpu().numpy())
+        with pytest.raises(ValueError, match="on_chunk"):
+            streaming.fit_pinned(hs, hp, dstim, dpsc, powers, pri, seeds, host_out, chunk=chunk, iters=10, msrmp=0.4)
+
+
+@pytest.mark.parametrize("with_demixer", [False, True])
+def test_fit_pipeline_compact_formats_equal_the_batched_call(with_demixer):
+    """FitPipeline: float32 traces + uint8 design codes in pinned memory -> [demix] -> fit -> compact state + CSR lam."""
+    import torch
+    from circuitmap_b200 import NeuralDemixer, optimise, streaming
+    B, N, K = 5, 24, 200
+    sims, pri = _maps(B, N, K)
+    powers = np.unique(sims[0]["stim_matrix"])[1:]
+    seeds = [9, 8, 7, 6, 5]
+    dem = NeuralDemixer(path=os.path.join(GOLDEN, "nwd_ie_ChroME2f_weights.npz"), precision="fp16") if with_demixer else None
+    codes, traces = [], []
+    nnz_cap = 0
+    for s in sims:
+        c, p, nnz = optimise.pack_stim_host(np.ascontiguousarray(s["stim_matrix"]))
+        assert np.array_equal(p, powers)
+        codes.append(c.clone().pin_memory())
+        traces.append(torch.from_numpy(s["psc"].astype(np.float32)).pin_memory())
+        nnz_cap = max(nnz_cap, nnz)
+    # reference: one batched call on the same float32 traces
+    psc32 = torch.stack([t.cuda() for t in traces]).contiguous()
+    stim = torch.stack([torch.from_numpy(np.ascontiguousarray(s["stim_matrix"])).cuda() for s in sims]).contiguous()
+    if with_demixer:
+        _, y, ss = dem.forward_device(psc32.reshape(B * K, 900), stats=True)
+        ref = optimise.caviar_batched(stim, powers, *pri, y=y.view(B, K), ss=ss.view(B, K), seeds=seeds, iters=10, msrmp=0.4)
+    else:
+        ref = optimise.caviar_batched(stim, powers, *pri, psc=psc32, seeds=seeds, iters=10, msrmp=0.4)
+    for chunk in (2, 5):
+        pipe = streaming.FitPipeline(N, K, powers, chunk=chunk, nnz_cap=nnz_cap, demixer=dem, iters=10, msrmp=0.4)
+        got = {}
+
+        def on_result(lo, hi, v):
+            for b in range(lo, hi):
+                got[b] = {k: v[k][b - lo].clone().numpy() for k in ("mu", "beta", "shape", "rate", "phi", "phi_cov", "z")}
+                got[b]["lam"] = v["lam"][b - lo].toarray()
+
+        assert pipe.run(codes, traces, seeds, on_result) == 0 and sorted(got) == list(range(B))
+        for b in range(B):
+            for k in ("mu", "beta", "shape", "rate", "phi", "phi_cov", "z", "lam"):
+                assert np.array_equal(got[b][k], ref[k][b].cpu().numpy(), equal_nan=True), (chunk, b, k)
+        assert pipe.h2d_bytes_per_fit == N * K + K * 900 * 4
