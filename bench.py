@@ -7,7 +7,9 @@
 A step = one pass of the CAVIaR hot path over one batch of B independent synthetic maps of the C3 shape
 (N=1000 neurons, K=10000 trials x 900 samples, 10-target holograms, 3 powers, 50 iterations) per GPU, inputs
 resident in HBM.  Prints ONE JSON line (rank 0).  The NWD path (C2: 20000 traces) is measured in the same run
-and reported under "nwd".
+and reported under "nwd".  Synthetic maps come from the device generator cm_simulate (every fit of a step is a
+distinct map); `e2e` streams them from pinned host memory through circuitmap_b200.streaming.FitPipeline.
+    python bench.py --traffic-probe                          # one fit launch and exit (run under ncu by the own arm)
 """
 import argparse
 import json
@@ -179,6 +181,43 @@ def measured_peaks():
     return 6650.0, 1590.0, 1400.0, "fallback"
 
 
+def measure_traffic(args, B):
+    """DRAM bytes of ONE launch of the persistent fit kernel at this run's batch size, measured now: the own arm re-runs
+    itself as `bench.py --traffic-probe` (one cm_caviar_fit call on B device-generated maps) under
+    `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` and parses the CSV.  Returns (bytes, source) or (None, why)."""
+    import shutil
+    ncu = shutil.which("ncu") or "/usr/local/cuda/bin/ncu"
+    if not os.path.exists(ncu):
+        return None, "ncu not found"
+    cmd = [ncu, "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none", "-k",
+           "regex:caviar_fit_kernel", "-c", "1", "--csv", sys.executable, os.path.abspath(__file__), "--traffic-probe",
+           "--N", str(args.N), "--K", str(args.K), "--H", str(args.H), "--iters", str(args.iters), "--fits-per-gpu", str(B)]
+    try:
+        env = dict(os.environ)
+        for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
+            env.pop(k, None)
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=420, env=env)
+    except Exception as e:                                   # noqa: BLE001
+        return None, "ncu probe failed: %r" % (e,)
+    total, seen = 0.0, 0
+    import csv
+    rows = list(csv.reader(out.stdout.splitlines()))
+    hdr = next((r for r in rows if "Metric Name" in r and "Metric Value" in r), None)
+    if hdr is None:
+        return None, "ncu probe printed no metrics (rc %d): %s" % (out.returncode, (out.stderr or out.stdout)[-300:])
+    iname, iunit, ival = hdr.index("Metric Name"), hdr.index("Metric Unit"), hdr.index("Metric Value")
+    for r in rows:
+        if len(r) == len(hdr) and r[iname] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}.get(r[iunit], None)
+            if mult is None:
+                return None, "unknown ncu unit %r" % r[iunit]
+            total += float(r[ival].replace(",", "")) * mult
+            seen += 1
+    if seen != 2:
+        return None, "ncu probe: expected 2 metric rows, got %d" % seen
+    return total, "ncu dram__bytes_read.sum + dram__bytes_write.sum of one launch, measured in this run"
+
+
 def read_traffic(name, units=None):
     """DRAM bytes per launch from the committed ncu --set full capture (profiles/traffic.json), scaled linearly to
     the number of fits / traces of this launch when the capture used a different batch size."""
@@ -238,7 +277,7 @@ def reference_arm(args, rank):
     line = {"impl": "reference", "metric": "caviar_fits_per_s", "value": fits_per_s, "unit": "fits/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args, None),
+            "config": workload_config(args),
             "iters_per_s": fits_per_s * args.iters,
             "cpu_baseline": {"value": fits_per_s, "unit": "fits/s", "cores": int(torch.get_num_threads()),
                              "host_cores": cores, "kind": "port", "sample": sample,
@@ -249,12 +288,12 @@ def reference_arm(args, rank):
     print(json.dumps(line))
 
 
-def workload_config(args, B):
+def workload_config(args, B=None):
+    """The same dict in both arms (the driver compares them): the unit of work is ONE C3 fit."""
     return {"workload": "C3 compressive ensemble map: N=%d neurons, K=%d trials x 900 samples, H=%d targets, P=3 powers, "
-                        "caviar %d iters%s" % (args.N, args.K, args.H, args.iters,
-                                               "" if B is None else ", %d independent maps per GPU per step" % B),
-            "fits_per_gpu_per_step": B, "distinct_maps": args.maps,
-            "l2_hygiene": "inputs larger than L2 (each fit reads its own %.0f MB of psc+stim)" % ((args.N * args.K * 8 + args.K * 7200) / 1e6),
+                        "caviar %d iters; throughput of independent maps" % (args.N, args.K, args.H, args.iters),
+            "l2_hygiene": "inputs larger than L2 (every fit of a step reads its own map: %.0f MB of traces + design)"
+                          % ((args.N * args.K + args.K * 3600) / 1e6),
             "parallelism": "independent fits sharded over GPUs, no data-path collective"}
 
 
@@ -270,7 +309,7 @@ def main():
     ap.add_argument("--H", type=int, default=10)
     ap.add_argument("--iters", type=int, default=50)
     ap.add_argument("--fits-per-gpu", type=int, default=0, help="B; default = 2 x number of SMs (two fit CTAs per SM)")
-    ap.add_argument("--maps", type=int, default=32, help="distinct synthetic maps (generated in parallel on the host) tiled to B")
+    ap.add_argument("--maps", type=int, default=16, help="distinct maps held in pinned host memory for the e2e leg (tiled to B)")
     ap.add_argument("--nwd-traces", type=int, default=20000)
     ap.add_argument("--ref-iters", type=int, default=8, help="CPU oracle iterations per step (scaled to a full fit)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -278,6 +317,9 @@ def main():
     ap.add_argument("--no-nwd", action="store_true")
     ap.add_argument("--no-c4", action="store_true", help="skip the C4 (1024 maps of N=500, K=5000) secondary measurement")
     ap.add_argument("--no-c5", action="store_true", help="skip the C5 (one map of N=5000, K=100000) secondary measurement")
+    ap.add_argument("--no-single", action="store_true", help="skip the single-fit latency measurement")
+    ap.add_argument("--no-traffic", action="store_true", help="skip the ncu DRAM-traffic probe of the fit kernel")
+    ap.add_argument("--traffic-probe", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -287,15 +329,10 @@ def main():
         reference_arm(args, rank)
         return
 
-    # synthetic inputs first (fork pool on the host cores, before CUDA exists in this process)
-    procs = max(1, (os.cpu_count() or 1) // max(world, 1))
-    gen3 = synth_maps_parallel([(args.N, args.K, args.H, 1000 * rank + i) for i in range(args.maps)], procs)
-    gen4 = None if args.no_c4 else synth_maps_parallel([(500, 5000, args.H, 7000 + 100 * rank + i) for i in range(16)], procs)
-    gen5 = None if (args.no_c5 or rank != 0) else _gen_map_compact((5000, 100000, args.H, 9000))
-
     import torch
     import torch.distributed as dist
-    from circuitmap_b200 import NeuralDemixer, optimise, _lib
+    from circuitmap_b200 import NeuralDemixer, optimise, streaming, _lib
+    from circuitmap_b200.simulation import simulate_batch
     if not torch.cuda.is_available():
         raise SystemExit("bench.py (own arm) needs a CUDA device; there is no CPU fallback")
     torch.cuda.set_device(local_rank)
@@ -319,39 +356,56 @@ def main():
     B = args.fits_per_gpu or 2 * sms
     N, K, H, iters = args.N, args.K, args.H, args.iters
     hbm_peak, bf16_burst, bf16_sust, peak_kind = measured_peaks()
-
-    # ---- synthetic inputs: `maps` distinct maps (seeded per rank), tiled to B fits, pinned on the host ----
-    # `maps` distinct maps per rank, tiled to B fits; the first two also live in pinned host memory for the e2e leg
-    host_stim, host_psc = [], []
-    for i in range(min(2, args.maps)):
-        host_stim.append(torch.from_numpy(dense_stim(gen3[i], N, K)).pin_memory())
-        host_psc.append(torch.from_numpy(gen3[i][3].astype(np.float64)).pin_memory())
-    powers = np.array([45.0, 55.0, 65.0])
-    nnz = int(max(m[0].size for m in gen3))
     f64 = dict(dtype=torch.float64, device=dev)
-    stim = torch.empty((B, N, K), **f64)
-    psc = torch.empty((B, K, 900), **f64)
-    for i in range(args.maps):
-        if i >= B:
-            break
-        stim[i].copy_(torch.from_numpy(dense_stim(gen3[i], N, K)))
-        psc[i].copy_(torch.from_numpy(gen3[i][3]))
-    for b in range(args.maps, B):
-        stim[b].copy_(stim[b % args.maps])
-        psc[b].copy_(psc[b % args.maps])
-    cov = torch.zeros(B, N, 2, 2, **f64)
-    cov[..., 0, 0] = 0.1
-    cov[..., 1, 1] = 1.0
-    phi = torch.stack([0.1 * torch.ones(B, N, **f64), 5 * torch.ones(B, N, **f64)], -1).contiguous()
-    pri = (torch.zeros(B, N, **f64), 10 * torch.ones(B, N, **f64), 1.0, 0.1, phi, cov)
-    seeds = [1 + b + 100000 * rank for b in range(B)]
+    powers = np.array([45.0, 55.0, 65.0])
     opts = dict(iters=iters, msrmp=0.4)
+
+    def default_priors(b, n):
+        cov = torch.zeros(b, n, 2, 2, **f64)
+        cov[..., 0, 0] = 0.1
+        cov[..., 1, 1] = 1.0
+        phi = torch.stack([0.1 * torch.ones(b, n, **f64), 5 * torch.ones(b, n, **f64)], -1).contiguous()
+        return (torch.zeros(b, n, **f64), 10 * torch.ones(b, n, **f64), 1.0, 0.1, phi, cov)
+
+    def gen_maps(count, n, k, seed0, chunk=32):
+        """`count` DISTINCT synthetic maps from the device generator (csrc/simulate.cu, the distributions of
+        circuitmap.simulation.simulate): uint8 power codes (count, n, k) + float32 traces (count, k, 900), resident in HBM."""
+        codes = torch.empty((count, n, k), dtype=torch.uint8, device=dev)
+        traces = torch.empty((count, k, 900), dtype=torch.float32, device=dev)
+        wsim = None
+        for lo in range(0, count, chunk):
+            hi = min(lo + chunk, count)
+            r = simulate_batch([seed0 + i for i in range(lo, hi)], device=dev, workspace=wsim, N=n, trials=k, H=H,
+                               connection_prob=0.1, out=dict(codes=codes[lo:hi], psc=traces[lo:hi]))
+            wsim = r["_workspace"]
+            assert int(r["status"].sum().item()) == 0
+            if r["codes"].data_ptr() != codes[lo:hi].data_ptr():
+                codes[lo:hi].copy_(r["codes"]); traces[lo:hi].copy_(r["psc"])
+        return codes, traces
+
+    if args.traffic_probe:                       # one launch of the timed configuration, for `ncu` (see measure_traffic)
+        codes, traces = gen_maps(B, N, K, 1)
+        out = optimise.caviar_batched(codes, powers, *default_priors(B, N), psc=traces, seeds=list(range(1, B + 1)),
+                                      nnz_cap=K * H, want_lam=False, **opts)
+        torch.cuda.synchronize()
+        return
+
+    # ---- synthetic inputs: B distinct maps per rank, generated on the device (seeded per rank) ----
+    t_gen = time.time()
+    stim, psc = gen_maps(B, N, K, 1 + 100000 * rank)
+    torch.cuda.synchronize()
+    t_gen = time.time() - t_gen
+    nnz = K * H
+    pri = default_priors(B, N)
+    seeds = [1 + b + 100000 * rank for b in range(B)]
     ws = [None]
+    outbuf = [None]
 
     def step():
-        out = optimise.caviar_batched(stim, powers, *pri, psc=psc, seeds=seeds, nnz_cap=nnz, want_lam=True,
-                                      workspace=ws[0], **opts)
+        out = optimise.caviar_batched(stim, powers, *pri, psc=psc, seeds=seeds, nnz_cap=nnz, want_lam=False, lam_csr=True,
+                                      workspace=ws[0], out=outbuf[0], **opts)
         ws[0] = out["_workspace"]
+        outbuf[0] = out
         return out
 
     def sync_all():
@@ -387,62 +441,92 @@ def main():
     algo = algorithmic_bytes_per_fit(N, K, iters) * B
     achieved = algo / (kms / 1e3) / 1e9
     roofline = {"bound": "hbm", "kernel": "caviar_fit_kernel", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved / hbm_peak, "traffic": read_traffic("caviar_fit_kernel", B),
+                "frac": achieved / hbm_peak, "traffic": None,
                 "peak_kind": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback",
-                "kernel_ms_per_launch": kms, "algorithmic_bytes_per_launch": algo, "algorithmic_model": ALGO_NOTE,
+                "kernel_ms_per_launch": kms, "kernel_share_of_step": kms / ms_step,
+                "algorithmic_bytes_per_launch": algo, "algorithmic_model": ALGO_NOTE,
                 "note": "kernel works on a CSR/CSC index of the design (supp(lam) within supp(stim)); achieved is the "
-                        "DENSE algorithmic byte count over time, traffic is what DRAM actually moved"}
+                        "DENSE algorithmic byte count over time, traffic is what DRAM actually moved, dram_frac = traffic / "
+                        "kernel time / peak is the bandwidth the kernel really uses"}
     connected = int((out["mu"][0] != 0).sum().item())
+    nnz_lam = int(out["lam_csr_ptr"][0, -1].item())
 
-    # ---- end-to-end through host buffers: H2D of every fit's psc+stim (pinned), fit, D2H of the full state ----
+    # ---- ONE C3 fit alone on the GPU: the latency north_star sets the roofline target on ----
+    single = None
+    if not args.no_single:
+        pri1 = default_priors(1, N)
+        ws1, o1b, t1 = None, None, []
+        for rep in range(4):
+            torch.cuda.synchronize()
+            q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            q0.record()
+            o1 = optimise.caviar_batched(stim[:1], powers, *pri1, psc=psc[:1], seeds=[seeds[0]], nnz_cap=nnz, want_lam=False,
+                                         lam_csr=True, workspace=ws1, out=o1b, **opts)
+            ws1, o1b = o1["_workspace"], o1
+            k1 = lib.cm_last_main_kernel_ms()
+            q1.record()
+            torch.cuda.synchronize()
+            t1.append((q0.elapsed_time(q1), k1))
+        ms1, k1 = min(t1[1:])
+        algo1 = algorithmic_bytes_per_fit(N, K, iters)
+        single = {"metric": "caviar_single_fit_latency_ms", "value": ms1, "unit": "ms", "higher_is_better": False,
+                  "fits_per_s": 1e3 / ms1, "iters_per_s": iters * 1e3 / ms1, "kernel_ms": k1,
+                  "roofline": {"bound": "hbm", "achieved": algo1 / (ms1 / 1e3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                               "frac": algo1 / (ms1 / 1e3) / 1e9 / hbm_peak, "roofline_time_ms": 1e3 * algo1 / (hbm_peak * 1e9),
+                               "algorithmic_model": ALGO_NOTE},
+                  "note": "one map, inputs resident in HBM (L2-resident working set), whole cm_caviar_fit call incl. prologue"}
+        del o1, o1b, ws1
+
+    # ---- end to end through host buffers (circuitmap_b200.streaming.FitPipeline): pinned float32 traces + uint8 design codes
+    # -> H2D -> [NeuralDemixer -> y / sum-of-squares hand-off] -> cm_caviar_fit -> D2H of the state with lam as CSR ----
     e2e = None
     if not args.no_e2e:
-        slab = max(1, min(B, 16))
-        pin = {k: torch.empty(out[k].shape, dtype=out[k].dtype).pin_memory()
-               for k in ["mu", "beta", "shape", "rate", "phi", "phi_cov", "z"]}
-        pin_lam = torch.empty((slab, N, K), dtype=torch.float64).pin_memory()
-        h2d = B * (N * K * 8 + K * 900 * 8)
-        d2h = sum(v.numel() * 8 for v in pin.values()) + B * N * K * 8
-
-        from circuitmap_b200 import streaming
-        pin["lam"] = pin_lam
-        hs = [host_stim[b % len(host_stim)] for b in range(B)]
-        hp = [host_psc[b % len(host_psc)] for b in range(B)]
-        streams = streaming._Streams(dev)
-        wsp = {}
-
+        npin = max(1, min(B, args.maps))
+        hs_pin = [stim[i].cpu().pin_memory() for i in range(npin)]
+        hp_pin = [psc[i].cpu().pin_memory() for i in range(npin)]
+        hs = [hs_pin[b % npin] for b in range(B)]
+        hp = [hp_pin[b % npin] for b in range(B)]
         e2e_chunk = max(1, sms // 2)
+        dem_e2e = NeuralDemixer(path=os.path.join(GOLD, "nwd_ie_ChroME2f_weights.npz"), device=dev, precision="fp16")
+        res = {}
+        for label, demixer in (("fit", None), ("pipeline", dem_e2e)):
+            pipe = streaming.FitPipeline(N, K, powers, chunk=e2e_chunk, nnz_cap=nnz, device=dev, demixer=demixer, **opts)
+            got = [0]
 
-        def e2e_step():
-            # chunks of half a fit per SM (the step is PCIe-bound: finer chunks shorten the pipeline fill and drain): H2D of chunk i+1, the fit kernels of chunk i and D2H of chunk i-1 overlap
-            st_ = streaming.fit_pinned(hs, hp, stim, psc, powers, pri, seeds, pin, chunk=e2e_chunk, nnz_cap=nnz,
-                                       workspaces=wsp, streams=streams, **opts)
+            def on_result(lo, hi, views, got=got):
+                got[0] += int((views["mu"] != 0).sum().item())      # the host reads every result (connected counts)
+
+            assert pipe.run(hs, hp, seeds, on_result) == 0
+            sync_all()
+            n_e2e = max(1, min(args.steps, 2))
+            t0 = time.time()
+            for _ in range(n_e2e):
+                pipe.run(hs, hp, seeds, on_result)
             torch.cuda.synchronize()
-            return st_
-
-        e2e_step()
-        sync_all()
-        t0 = time.time()
-        n_e2e = max(1, min(args.steps, 2))
-        for _ in range(n_e2e):
-            e2e_step()
-        sync_all()
-        dt = torch.tensor([(time.time() - t0) / n_e2e], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * B / float(dt.item()), "unit": "fits/s", "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * float(dt.item()),
-               "note": "circuitmap_b200.streaming.fit_pinned: fp64 host buffers (pinned; two distinct maps tiled) -> cm_caviar_fit -> full state incl. "
-                       "dense lam back (lam through a ring of %d pinned slabs), copies and kernels overlapped in chunks "
-                       "of %d fits" % (slab, e2e_chunk)}
-        wsp.clear()
+            sync_all()
+            dt = torch.tensor([(time.time() - t0) / n_e2e], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            res[label] = {"value": world * B / float(dt.item()), "unit": "fits/s", "ms_per_step": 1e3 * float(dt.item()),
+                          "h2d_bytes_per_step": B * pipe.h2d_bytes_per_fit, "d2h_bytes_per_step": B * pipe.d2h_bytes_per_fit}
+            del pipe
+            torch.cuda.empty_cache()
+        e2e = dict(res["fit"])
+        e2e["note"] = ("circuitmap_b200.streaming.FitPipeline: pinned host buffers in the formats the data has (float32 traces, uint8 "
+                       "power codes; %d distinct maps tiled to %d fits) -> H2D -> cm_caviar_fit -> D2H of mu, beta, shape, rate, phi, "
+                       "phi_cov, z and lam as CSR, read by the host; upload, kernels and download of consecutive chunks of %d "
+                       "fits overlap" % (npin, B, e2e_chunk))
+        e2e["pipeline_with_demixer"] = dict(res["pipeline"], note="the same with RAW traces in and the fp16 tensor-core "
+                                            "NeuralDemixer in front of the fit (README.md:28-51 of the reference: demix -> fit); "
+                                            "the demixed traces never leave the device, only y = trapz and sum x^2 reach the fit")
+        del hs, hp, hs_pin, hp_pin, dem_e2e
     # ---- the reference-facing call itself: Model(N).fit(psc, stim) with NumPy arrays in and out, one map (rank 0) ----
     if e2e is not None and rank == 0:
         import contextlib
         import io
         from circuitmap_b200 import Model
-        s_np = dense_stim(gen3[0], N, K)
-        p_np = gen3[0][3].astype(np.float64)
+        s_np = (powers[(stim[0].long() - 1).clamp(min=0).cpu().numpy()] * (stim[0].cpu().numpy() > 0)).astype(np.float64)
+        p_np = psc[0].double().cpu().numpy()
         tcall = []
         for _ in range(3):
             mdl = Model(N)
@@ -452,12 +536,24 @@ def main():
                 mdl.fit(p_np, s_np, method="caviar", fit_options=dict(opts, seed=1))
             tcall.append(time.time() - t0)
         e2e["drop_in_call"] = {"fits_per_s": 1.0 / min(tcall), "ms_per_fit": 1e3 * min(tcall),
-                               "note": "Model(N).fit(psc, stim, 'caviar') on pageable float64 NumPy arrays, full state back as NumPy "
-                                       "(one map at a time: latency of the drop-in call, not batch throughput)"}
+                               "note": "Model(N).fit(psc, stim, 'caviar') on pageable float64 NumPy arrays, full state incl. the dense "
+                                       "N x K lam back as NumPy (one map at a time: latency of the drop-in call, not batch throughput)"}
         del s_np, p_np, mdl
     del stim, psc, out
     ws[0] = None
+    outbuf[0] = None
     torch.cuda.empty_cache()
+
+    # ---- measured DRAM traffic of the dominant kernel (rank 0, N=1): a second process under ncu, outside every timed region ----
+    if rank == 0 and world == 1 and not args.no_traffic:
+        tb, src = measure_traffic(args, B)
+        if tb is None:
+            tb, src = read_traffic("caviar_fit_kernel", B), "profiles/traffic.json (round-1 capture, scaled) -- live probe failed: " + src
+        roofline["traffic"] = tb
+        roofline["traffic_source"] = src
+        if tb:
+            roofline["dram_frac"] = tb / (kms / 1e3) / 1e9 / hbm_peak
+            roofline["traffic_per_fit_gb"] = tb / B / 1e9
 
     # ---- C4 (BASELINE.json configs[3]): sweep of 1024 independent maps N=500, K=5000, sharded 1024 / world per GPU ----
     c4 = None
@@ -465,21 +561,9 @@ def main():
         N4, K4, Btot = 500, 5000, 1024
         lo4, hi4 = (rank * Btot) // world, ((rank + 1) * Btot) // world
         B4 = hi4 - lo4
-        nnz4 = int(max(m[0].size for m in gen4))
-        stim4 = torch.empty((B4, N4, K4), **f64)
-        psc4 = torch.empty((B4, K4, 900), dtype=torch.float32, device=dev)
-        nm4 = len(gen4)
-        for i in range(min(nm4, B4)):
-            stim4[i].copy_(torch.from_numpy(dense_stim(gen4[i], N4, K4)))
-            psc4[i].copy_(torch.from_numpy(gen4[i][3]))
-        for b in range(nm4, B4):
-            stim4[b].copy_(stim4[b % nm4])
-            psc4[b].copy_(psc4[b % nm4])
-        cov4 = torch.zeros(B4, N4, 2, 2, **f64)
-        cov4[..., 0, 0] = 0.1
-        cov4[..., 1, 1] = 1.0
-        phi4 = torch.stack([0.1 * torch.ones(B4, N4, **f64), 5 * torch.ones(B4, N4, **f64)], -1).contiguous()
-        pri4 = (torch.zeros(B4, N4, **f64), 10 * torch.ones(B4, N4, **f64), 1.0, 0.1, phi4, cov4)
+        nnz4 = K4 * H
+        stim4, psc4 = gen_maps(B4, N4, K4, 7000000 + lo4, chunk=128)
+        pri4 = default_priors(B4, N4)
         seeds4 = [1 + lo4 + b for b in range(B4)]
         ws4 = None
         for _ in range(2):
@@ -501,8 +585,8 @@ def main():
         algo4 = algorithmic_bytes_per_fit(N4, K4, iters) * B4
         c4 = {"metric": "caviar_fits_per_s", "value": Btot / (float(t4.item()) / 1e3), "unit": "fits/s", "scaling": "strong",
               "config": {"workload": "C4 batched sweep: 1024 independent maps N=500, K=5000, H=%d, %d iters, sharded %d per GPU "
-                                     "(16 distinct maps tiled, distinct seeds; psc fp32, posteriors without the dense lam)"
-                                     % (H, iters, B4)},
+                                     "(all maps distinct, device generator; traces fp32, design as uint8 codes, posteriors "
+                                     "without the dense lam)" % (H, iters, B4)},
               "ms_per_step": float(t4.item()), "connected_in_fit0": int((o4["mu"][0] != 0).sum().item()),
               "roofline": {"bound": "hbm", "kernel": "caviar_fit_kernel", "achieved": algo4 / (k4 / 1e3) / 1e9,
                            "peak": hbm_peak, "unit": "GB/s", "frac": algo4 / (k4 / 1e3) / 1e9 / hbm_peak, "traffic": None,
@@ -511,24 +595,19 @@ def main():
         torch.cuda.empty_cache()
 
     # ---- C5 (BASELINE.json configs[4]): ONE large map N=5000, K=100000 on one GPU (rank 0).  The K-sharded multi-GPU fit
-    # is not built; this is the single-GPU latency of the same map (one persistent fit CTA + panel-GEMM helper CTAs). ----
+    # is not built (measured 2-GPU exchange prototype); this is the single-GPU latency of the same map. ----
     c5 = None
-    if gen5 is not None:
+    if not args.no_c5 and rank == 0:
         N5, K5 = 5000, 100000
-        stim5 = torch.from_numpy(dense_stim(gen5, N5, K5)).to(dev)[None]
-        psc5 = torch.from_numpy(gen5[3]).to(dev)[None]
-        cov5 = torch.zeros(1, N5, 2, 2, **f64)
-        cov5[..., 0, 0] = 0.1
-        cov5[..., 1, 1] = 1.0
-        phi5 = torch.stack([0.1 * torch.ones(1, N5, **f64), 5 * torch.ones(1, N5, **f64)], -1).contiguous()
-        pri5 = (torch.zeros(1, N5, **f64), 10 * torch.ones(1, N5, **f64), 1.0, 0.1, phi5, cov5)
+        stim5, psc5 = gen_maps(1, N5, K5, 9000)
+        pri5 = default_priors(1, N5)
         ws5 = None
         t5 = []
         for rep in range(2):
             torch.cuda.synchronize()
             q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             q0.record()
-            o5 = optimise.caviar_batched(stim5, powers, *pri5, psc=psc5, seeds=[1], nnz_cap=int(gen5[0].size), want_lam=False,
+            o5 = optimise.caviar_batched(stim5, powers, *pri5, psc=psc5, seeds=[1], nnz_cap=K5 * H, want_lam=False,
                                          workspace=ws5, **opts)
             ws5 = o5["_workspace"]
             q1.record()
@@ -539,7 +618,7 @@ def main():
         c5 = {"metric": "caviar_fits_per_s", "value": 1e3 / t5[-1], "unit": "fits/s", "ms_per_fit": t5[-1],
               "iters_per_s": iters * 1e3 / t5[-1],
               "config": {"workload": "C5 large single map: N=5000, K=100000, H=%d, %d iters, ONE B200 (one persistent fit CTA + 15 "
-                                     "panel-GEMM helper CTAs; the K-sharded 8-GPU variant is not built)" % (H, iters)},
+                                     "helper CTAs; the K-sharded 8-GPU variant is not built)" % (H, iters)},
               "connected": int((o5["mu"][0] != 0).sum().item()),
               "roofline": {"bound": "hbm", "achieved": algo5 / (t5[-1] / 1e3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                            "frac": algo5 / (t5[-1] / 1e3) / 1e9 / hbm_peak, "algorithmic_model": ALGO_NOTE}}
@@ -585,7 +664,7 @@ def main():
         x64 = torch.empty((Kt, 900), **f64)
         o64 = torch.empty((Kt, 900), **f64)
 
-        from circuitmap_b200 import streaming as _streaming
+        _streaming = streaming
         nstreams = _streaming._Streams(dev)
 
         def nwd_e2e():
@@ -644,9 +723,12 @@ def main():
     if rank == 0:
         line = {"metric": "caviar_fits_per_s", "value": fits_per_s, "unit": "fits/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic (device generator cm_simulate with circuitmap.simulation's distributions; every fit a distinct map)",
                 "config": workload_config(args, B), "iters_per_s": fits_per_s * iters,
-                "connected_in_fit0": connected, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+                "fits_per_gpu_per_step": B, "data_generation_s": t_gen,
+                "connected_in_fit0": connected, "lam_nnz_in_fit0": nnz_lam, "roofline": roofline, "single_fit": single,
+                "cpu_baseline": cpu, "e2e": e2e,
                 "gpu_launches": int(launches_per_step * args.steps), "clocks": clocks, "nwd": nwd, "c4": c4, "c5": c5}
         print(json.dumps(line))
     if world > 1:

@@ -45,11 +45,21 @@ class CaviarArgs(C.Structure):
                 ("lam_csr_val_dev", C.c_void_p), ("lam_csr_col_dev", C.c_void_p), ("lam_csr_ptr_dev", C.c_void_p)]
 
 
+class SimOptions(C.Structure):
+    _fields_ = [("N", C.c_int), ("K", C.c_int), ("T", C.c_int), ("H", C.c_int), ("n_powers", C.c_int),
+                ("powers", C.c_double * CM_CAVIAR_MAX_POWERS)] + \
+               [(k, C.c_double) for k in ("connection_prob", "frac_strongly_connected", "min_latency", "gamma_beta", "sigma",
+                                          "strong_weight_lower", "strong_weight_upper", "weak_exp_mean", "min_weight",
+                                          "phi_0_lower", "phi_0_upper", "phi_1_lower", "phi_1_upper", "mult_noise_log_var",
+                                          "tau_r_min", "tau_r_max", "tau_delta_min", "tau_delta_max", "gp_scale",
+                                          "gp_lengthscale", "spont_prob", "max_power_min_spike_rate")]
+
+
 # every symbol include/circuitmap_b200.h declares
 EXPORTS = ["cm_version", "cm_last_error", "cm_device_info", "cm_nwd_create", "cm_nwd_destroy", "cm_nwd_forward",
            "cm_nwd_set_precision",
            "cm_caviar_workspace_bytes", "cm_caviar_fit", "cm_caviar_scan_stim", "cm_caviar_scan_scratch_bytes",
-           "cm_pack_stim_u8", "cm_last_launch_count", "cm_last_main_kernel_ms",
+           "cm_pack_stim_u8", "cm_simulate", "cm_simulate_workspace_bytes", "cm_last_launch_count", "cm_last_main_kernel_ms",
            "cm_caviar_debug_phase_cycles", "cm_nwd_debug_cycles", "cm_nwd_mt_debug_cycles", "cm_nwd_mt_debug_dump", "cm_nwd_mt_pack"]
 
 _lib = None
@@ -82,6 +92,10 @@ def load():
     lib.cm_caviar_scan_scratch_bytes.restype = C.c_size_t
     lib.cm_caviar_scan_stim.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.POINTER(C.c_int64),
                                         C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_void_p]
+    lib.cm_simulate_workspace_bytes.restype = C.c_size_t
+    lib.cm_simulate_workspace_bytes.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
+    lib.cm_simulate.argtypes = [C.POINTER(SimOptions), C.c_int, C.POINTER(C.c_uint64), C.c_void_p, C.c_int, C.c_void_p,
+                                C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     lib.cm_pack_stim_u8.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.POINTER(C.c_double), C.POINTER(C.c_int),
                                     C.POINTER(C.c_int64), C.c_void_p, C.c_int]
     _lib = lib

@@ -170,6 +170,47 @@ __device__ __forceinline__ double bits_to_unit_double(uint32_t hi, uint32_t lo) 
 // ------------------------------------------------------------------------------------------------ helpers
 __device__ __forceinline__ double sigmoid_d(double x) { return 1.0 / (1.0 + exp(-x)); }
 
+// 1 / (1 + exp(-x)) for the sweep, whose sequential chain is bound by the dependent-issue latency of this expression
+// (caviar.py:216): exp by argument reduction + a degree-13 polynomial in Estrin form (depth 4 instead of 13), the quotient
+// by the hardware reciprocal seed + three Newton steps instead of the IEEE division sequence.  Error <= 1 ulp, the same
+// class as the library call it replaces (CUDA's exp is not correctly rounded either); arguments beyond +-700 -- where exp
+// overflows or underflows and the reference's result is exactly 0 or 1 -- take the library path, so those exact values
+// (which update_phi's nan_to_num handling depends on) are produced by the same instructions as before.
+__device__ __forceinline__ double sigmoid_fast(double x) {
+    const double t = -x;
+    if (!(fabs(t) <= 700.0)) return 1.0 / (1.0 + exp(t));
+    const double nf = rint(t * 1.4426950408889634);
+    double r = fma(nf, -6.93147180369123816490e-01, t);
+    r = fma(nf, -1.90821492927058770002e-10, r);
+    const double r2 = r * r;
+    const double q0 = fma(r, 1.0, 1.0);
+    const double q1 = fma(r, 1.0 / 6, 0.5);
+    const double q2 = fma(r, 1.0 / 120, 1.0 / 24);
+    const double q3 = fma(r, 1.0 / 5040, 1.0 / 720);
+    const double q4 = fma(r, 1.0 / 362880, 1.0 / 40320);
+    const double q5 = fma(r, 1.0 / 39916800, 1.0 / 3628800);
+    const double q6 = fma(r, 1.0 / 6227020800.0, 1.0 / 479001600);
+    const double r4 = r2 * r2;
+    const double s0 = fma(q1, r2, q0);
+    const double s1 = fma(q3, r2, q2);
+    const double s2 = fma(q5, r2, q4);
+    const double r8 = r4 * r4;
+    const double u0 = fma(s1, r4, s0);
+    const double u1 = fma(q6, r4, s2);
+    const double pe = fma(u1, r8, u0);
+    const double e = pe * __longlong_as_double(((long long)((int)nf + 1023)) << 52);
+    const double d = 1.0 + e;
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    double c = fma(-d, y, 1.0);
+    y = fma(c, y, y);
+    c = fma(-d, y, 1.0);
+    y = fma(c, y, y);
+    c = fma(-d, y, 1.0);
+    y = fma(c, y, y);
+    return y;
+}
+
 // isotonic_regression(sr)[-1] with unit weights: mean of the last pool (pava.py:9-61).
 __device__ __forceinline__ double pava_last(const double* sr, int P) {
     double v[PMAX], w[PMAX];

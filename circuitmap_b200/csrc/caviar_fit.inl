@@ -777,7 +777,7 @@ __device__ __forceinline__ void sweep_row(const RowCtx c, int n, int beg, int le
         const double cj0 = cs[q], cj1 = cs[q + 32];
         const double x0 = chain ? (cj0 - coef * pred[pk0 & 0x7ffffff]) : cj0;
         const double x1 = chain ? (cj1 - coef * pred[pk1 & 0x7ffffff]) : cj1;
-        const double e0 = sigmoid_d(x0), e1 = sigmoid_d(x1);
+        const double e0 = sigmoid_fast(x0), e1 = sigmoid_fast(x1);
         cs[q] = e0; cs[q + 32] = e1;
         const int pw0 = pk0 >> 27, pw1 = pk1 >> 27;
 #pragma unroll
@@ -788,7 +788,7 @@ __device__ __forceinline__ void sweep_row(const RowCtx c, int n, int beg, int le
         const int pk = cp[q];
         const double cj = cs[q];
         const double x = chain ? (cj - coef * pred[pk & 0x7ffffff]) : cj;
-        const double est = sigmoid_d(x);
+        const double est = sigmoid_fast(x);
         cs[q] = est;
         const int pw = pk >> 27;
 #pragma unroll
@@ -885,32 +885,48 @@ __device__ __forceinline__ void sweep_row(const RowCtx c, int n, int beg, int le
 
 constexpr int NSTAGE = 3;
 constexpr int HD = 18;           // header doubles per stage: mu, then 2*PT ints (cntp, nmask)
-constexpr int STAGE_DOUBLES = NSTAGE * (RC + RC + RC / 2 + HD);   // cs, lo, cp (ints), header
+constexpr int TW = 4;            // warps of the chain team (one per SM sub-partition: four fp64 pipes instead of one)
+constexpr int TT = 32 * TW;
+constexpr int EPL = RC / TT;     // staged entries per team thread
+constexpr int STAGE_DOUBLES = NSTAGE * (RC + RC + RC / 2 + TW * HD);   // cs, lo, cp (ints), one header copy per team warp
+__device__ __forceinline__ void team_sync() { asm volatile("bar.sync 1, %0;\n" ::"n"(TT) : "memory"); }
 
-// The sequential part of the sweep: neurons with mu != 0, in update order, by ONE warp.  Rows are prefetched two
-// neurons ahead into shared memory with cp.async so that the chain only waits on shared-memory latency.
+// The sequential part of the sweep: neurons with mu != 0, in update order (caviar.py:196-229; quirk A.3 #3: the in-sweep
+// zeroing of mu is visible to later neurons through the running prediction).  One step per neuron, steps strictly in
+// order, executed by a TEAM of TW warps (one per SM sub-partition):
+//   * every team thread owns the entries q = t, t + TT, ... of the row (a C3 / C4 row has ~100 entries: one sigmoid per
+//     thread), staged two neurons ahead into shared memory with cp.async by the thread that will consume them;
+//   * per-power sums, the sum of squares and the exact-0 / exact-1 counts are reduced inside each warp by shuffles and
+//     across the TW warps through shared memory in fixed warp order (deterministic; the same in both CTA variants);
+//   * every thread takes the accept / reject decision redundantly (spike-rate divisions by lanes 0..P-1, PAVA in
+//     registers), then commits its own entries to lam and to the running prediction in shared memory;
+//   * two named-barrier synchronisations of the team per step (after the partial sums, after the commit).
 template <int PT>
 __device__ __noinline__ void sweep_chain(const Ctx& c, int nchain, double sigma, double thr, double minspk, bool gate, double* pred,
                             double* stage_base) {
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, tw = threadIdx.x >> 5, tt = threadIdx.x;      // the team is warps 0 .. TW-1
+    __shared__ double xch[2][TW][PT + 1];
+    __shared__ int xci[2][TW][2 * PT + 1];
     const RowCtx rc = make_rowctx(c);
     const int* g_colpw = c.colpw; const double* g_cst = c.cst; const double* g_lam = c.lam; const double* g_mu = c.mu;
     const int* g_cntp = c.cntp; const int* g_nmask = c.nmask; const int4* g_chinfo = c.chinfo;
     double* scs = stage_base;                                   // [NSTAGE][RC]
     double* slo = scs + NSTAGE * RC;                            // [NSTAGE][RC]
     int* scp = reinterpret_cast<int*>(slo + NSTAGE * RC);       // [NSTAGE][RC]
-    double* shd = reinterpret_cast<double*>(scp + NSTAGE * RC); // [NSTAGE][HD]: mu, then ints cntp[PT], nmask[PT]
+    double* shd = reinterpret_cast<double*>(scp + NSTAGE * RC); // [NSTAGE][TW][HD]: mu, then ints cntp[PT], nmask[PT]
+    const bool prof = g_phase_enable && blockIdx.x == 0 && tt == 0;
     auto stage = [&](int4 inf, int buf) {
         const int n = inf.x, beg = inf.y, len = inf.z;
         if (len <= RC) {
-            for (int q = lane; q < len; q += 32) {
+            for (int q = tt; q < len; q += TT) {
                 cp_async4(scp + buf * RC + q, g_colpw + beg + q);
                 cp_async8(scs + buf * RC + q, g_cst + beg + q);
                 cp_async8(slo + buf * RC + q, g_lam + beg + q);
             }
         }
-        if (lane == 0) cp_async8(shd + buf * HD, g_mu + n);
-        int* hi = reinterpret_cast<int*>(shd + buf * HD + 1);
+        double* hd = shd + (buf * TW + tw) * HD;
+        if (lane == 0) cp_async8(hd, g_mu + n);
+        int* hi = reinterpret_cast<int*>(hd + 1);
         for (int q = lane; q < 2 * PT; q += 32)
             cp_async4(hi + q, (q < PT) ? (g_cntp + n * PMAX + q) : (g_nmask + n * PMAX + (q - PT)));
         cp_async_commit();
@@ -922,6 +938,8 @@ __device__ __noinline__ void sweep_chain(const Ctx& c, int nchain, double sigma,
     if (nchain > 3) infB = g_chinfo[3];
     int4 cur = nchain > 0 ? g_chinfo[0] : infA, nxt = nchain > 1 ? g_chinfo[1] : infA;
     for (int i = 0; i < nchain; ++i) {
+        long long tp0 = 0;
+        if (prof) tp0 = clock64();
         if (i + 2 < nchain) { stage(infA, (i + 2) % NSTAGE); cp_async_wait<2>(); }
         else if (i + 1 < nchain) cp_async_wait<1>();
         else cp_async_wait<0>();
@@ -929,16 +947,165 @@ __device__ __noinline__ void sweep_chain(const Ctx& c, int nchain, double sigma,
         const int4 after = infA;
         infA = infB;
         if (i + 4 < nchain) infB = g_chinfo[i + 4];
-        const int buf = i % NSTAGE;
+        const int buf = i % NSTAGE, par = i & 1;
         const int n = cur.x, beg = cur.y, len = cur.z;
-        const double mu_n = shd[buf * HD];
-        const int* hi = reinterpret_cast<const int*>(shd + buf * HD + 1);
-        if (len <= RC)
-            sweep_row<PT>(rc, n, beg, len, true, mu_n, hi, hi + PT, scp + buf * RC, scs + buf * RC, slo + buf * RC, sigma,
-                          thr, minspk, gate, pred);
-        else
-            sweep_row<PT>(rc, n, beg, len, true, mu_n, hi, hi + PT, g_colpw + beg, const_cast<double*>(g_cst) + beg,
-                          g_lam + beg, sigma, thr, minspk, gate, pred);
+        const double* hd = shd + (buf * TW + tw) * HD;
+        const double mu_n = hd[0];
+        const int* cntp = reinterpret_cast<const int*>(hd + 1);
+        const int* nmask = cntp + PT;
+        const bool staged = len <= RC;
+        const int* cp = staged ? scp + buf * RC : g_colpw + beg;
+        const double* cs = staged ? scs + buf * RC : g_cst + beg;
+        const double* lo = staged ? slo + buf * RC : g_lam + beg;
+        const double coef = sigma * mu_n;
+        // ---- pass 1: the new posteriors of this thread's entries and their partial statistics ----
+        double accp[PT], se2 = 0.0;
+        int z0[PT], z1[PT];
+#pragma unroll
+        for (int p = 0; p < PT; ++p) { accp[p] = 0.0; z0[p] = 0; z1[p] = 0; }
+        bool rare = false;
+        double ev[EPL];
+        int kv[EPL];
+#pragma unroll
+        for (int j = 0; j < EPL; ++j) {
+            const int q = tt + j * TT;
+            ev[j] = 0.0; kv[j] = -1;
+            if (q < len) {
+                const int pk = cp[q];
+                const int k = pk & 0x7ffffff, pw = pk >> 27;
+                const double e = sigmoid_fast(cs[q] - coef * pred[k]);
+                ev[j] = e; kv[j] = k;
+#pragma unroll
+                for (int p = 0; p < PT; ++p) accp[p] += (pw == p) ? e : 0.0;
+                se2 += e * e;
+                if (e == 0.0 || e == 1.0) {
+                    rare = true;
+#pragma unroll
+                    for (int p = 0; p < PT; ++p) { z0[p] += (pw == p && e == 0.0); z1[p] += (pw == p && e == 1.0); }
+                }
+            }
+        }
+        for (int q = tt + EPL * TT; q < len; q += TT) {          // rows longer than the staging capacity (not at the benchmarked sizes)
+            const int pk = cp[q];
+            const int k = pk & 0x7ffffff, pw = pk >> 27;
+            const double e = sigmoid_fast(cs[q] - coef * pred[k]);
+            const_cast<double*>(g_cst)[beg + q] = e;             // parked in the (global) constant array until the commit
+#pragma unroll
+            for (int p = 0; p < PT; ++p) accp[p] += (pw == p) ? e : 0.0;
+            se2 += e * e;
+            if (e == 0.0 || e == 1.0) {
+                rare = true;
+#pragma unroll
+                for (int p = 0; p < PT; ++p) { z0[p] += (pw == p && e == 0.0); z1[p] += (pw == p && e == 1.0); }
+            }
+        }
+        if (prof) { const long long t = clock64(); g_phase_cycles[20] += t - tp0; tp0 = t; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {                       // P + 1 butterflies interleaved level by level
+            double tmpv[PT];
+#pragma unroll
+            for (int p = 0; p < PT; ++p)
+                if (p < rc.P) tmpv[p] = __shfl_xor_sync(0xffffffffu, accp[p], o);
+            const double t2 = __shfl_xor_sync(0xffffffffu, se2, o);
+#pragma unroll
+            for (int p = 0; p < PT; ++p)
+                if (p < rc.P) accp[p] += tmpv[p];
+            se2 += t2;
+        }
+        const bool wrare = __any_sync(0xffffffffu, rare);
+        if (wrare) {
+#pragma unroll
+            for (int p = 0; p < PT; ++p) { z0[p] = warp_sum(z0[p]); z1[p] = warp_sum(z1[p]); }
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int p = 0; p < PT; ++p) xch[par][tw][p] = accp[p];
+            xch[par][tw][PT] = se2;
+            xci[par][tw][2 * PT] = wrare ? 1 : 0;
+            if (wrare) {
+#pragma unroll
+                for (int p = 0; p < PT; ++p) { xci[par][tw][p] = z0[p]; xci[par][tw][PT + p] = z1[p]; }
+            }
+        }
+        team_sync();
+        // ---- every thread: totals in fixed warp order, decision ----
+        double tot = 0.0;
+        se2 = 0.0;
+        bool anyrare = false;
+#pragma unroll
+        for (int p = 0; p < PT; ++p) accp[p] = 0.0;
+#pragma unroll
+        for (int w = 0; w < TW; ++w) {
+#pragma unroll
+            for (int p = 0; p < PT; ++p)
+                if (p < rc.P) accp[p] += xch[par][w][p];
+            se2 += xch[par][w][PT];
+            anyrare |= xci[par][w][2 * PT] != 0;
+        }
+#pragma unroll
+        for (int p = 0; p < PT; ++p)
+            if (p < rc.P) tot += accp[p];
+        if (prof) { const long long t = clock64(); g_phase_cycles[21] += t - tp0; tp0 = t; }
+        bool ok = true;
+        if (gate) {
+            double mine = 0.0;                                   // spike rate of power p by lane p: one division latency
+            {
+                const int pl = lane < rc.P ? lane : 0;
+                const int cnt = cntp[pl];
+                double num = accp[0];
+#pragma unroll
+                for (int p = 1; p < PT; ++p) num = (pl == p) ? accp[p] : num;
+                mine = num / ((double)cnt + 1e-4 * (cnt == 0 ? 1.0 : 0.0));
+            }
+            double sr[PT];
+#pragma unroll
+            for (int p = 0; p < PT; ++p) sr[p] = __shfl_sync(0xffffffffu, mine, p);
+            ok = (pava_last_reg<PT>(sr, rc.P) >= thr) && (tot >= minspk);
+        }
+        if (prof) { const long long t = clock64(); g_phase_cycles[22] += t - tp0; tp0 = t; }
+        // ---- commit this thread's entries ----
+        const double muok = ok ? mu_n : 0.0;
+        double* lam_row = rc.lam + beg;
+#pragma unroll
+        for (int j = 0; j < EPL; ++j) {
+            const int q = tt + j * TT;
+            if (q < len) {
+                const double nw = ok ? ev[j] : 0.0;
+                const double old = lo[q];
+                lam_row[q] = nw;
+                const int k = kv[j];
+                pred[k] = (pred[k] + muok * nw) - mu_n * old;
+            }
+        }
+        for (int q = tt + EPL * TT; q < len; q += TT) {
+            const double nw = ok ? g_cst[beg + q] : 0.0;
+            const double old = lo[q];
+            const int k = cp[q] & 0x7ffffff;
+            pred[k] = (pred[k] + muok * nw) - mu_n * old;
+            lam_row[q] = nw;                                     // (lo aliases lam_row for unstaged rows: read before write)
+        }
+        if (tt == 0) {
+            int zeros = 0, masked = 0;
+#pragma unroll
+            for (int p = 0; p < PT; ++p)
+                if (p < rc.P) {
+                    int c0 = nmask[p], c1 = 0;
+                    if (anyrare) {
+#pragma unroll
+                        for (int w = 0; w < TW; ++w)
+                            if (xci[par][w][2 * PT]) { c0 += xci[par][w][p]; c1 += xci[par][w][PT + p]; }
+                    }
+                    zeros += c0; masked += nmask[p];
+                    rc.sp[n * PMAX + p] = ok ? accp[p] : 0.0;
+                    rc.n0p[n * PMAX + p] = ok ? c0 : cntp[p];
+                    rc.n1p[n * PMAX + p] = ok ? c1 : 0;
+                }
+            rc.slam[n] = ok ? tot : 0.0;
+            rc.slam2[n] = ok ? se2 : 0.0;
+            rc.rownz[n] = ok ? (len - (zeros - masked)) : 0;
+        }
+        team_sync();                                             // the prediction is consistent before the next neuron reads it
+        if (prof) { const long long t = clock64(); g_phase_cycles[23] += t - tp0; g_phase_cycles[19] += 1; g_phase_cycles[24] += len; }
         cur = nxt;
         nxt = after;
     }
@@ -1159,7 +1326,7 @@ __global__ void __launch_bounds__(NT, (NT == 512) ? 1 : 2) caviar_fit_kernel(con
     c.chinfo = reinterpret_cast<int4*>(base + L.chinfo);
     c.job = reinterpret_cast<int*>(base + L.job);
     c.ct = p.ct;
-    c.role = blockIdx.x - b * p.ct;
+    c.role = p.queue ? 0 : blockIdx.x - b * p.ct;      // queue mode has no helper CTAs: whoever pulls a fit runs it
     c.cscq = reinterpret_cast<double2*>(base + L.cscq);
     c.sortkeys = reinterpret_cast<uint32_t*>(base + L.sortkeys);
     c.keys = reinterpret_cast<uint32_t*>(base + L.keys);
@@ -1329,15 +1496,15 @@ __global__ void __launch_bounds__(NT, (NT == 512) ? 1 : 2) caviar_fit_kernel(con
             const double thr = o.msrmp + sc_spont;
             const bool gate = it > o.delay_spont_est;
             const long long role_t0 = clock64();
-            if (wid == 0) {
+            if (wid < TW) {
                 sweep_chain<PT>(c, nchain, sigma, thr, o.minimum_spike_count, gate, pred, stage_base);
-                if (g_phase_enable && blockIdx.x == 0 && lane == 0) g_phase_cycles[16] += clock64() - role_t0;
+                if (g_phase_enable && blockIdx.x == 0 && threadIdx.x == 0) g_phase_cycles[16] += clock64() - role_t0;
             } else if (wid == NW - 1) {
                 if (it + 1 < iters) rng_iteration(N, rounds, rk0, rk1, keys_nxt, sc_subkeys);
                 if (g_phase_enable && blockIdx.x == 0 && lane == 0) g_phase_cycles[17] += clock64() - role_t0;
             } else {
                 // mu == 0: the row neither reads nor changes the prediction -> order-free, run concurrently
-                for (int m = wid - 1; m < N; m += NW - 2) {
+                for (int m = wid - TW; m < N; m += NW - TW - 1) {
                     const int n = c.order[m];
                     if (c.mu[n] == 0.0 && !c.dcnt[n]) {
                         const int beg = c.row_ptr[n], len = c.row_ptr[n + 1] - beg;
@@ -1345,7 +1512,7 @@ __global__ void __launch_bounds__(NT, (NT == 512) ? 1 : 2) caviar_fit_kernel(con
                                       c.colpw + beg, c.cst + beg, c.lam + beg, sigma, thr, o.minimum_spike_count, gate, pred);
                     }
                 }
-                if (g_phase_enable && blockIdx.x == 0 && wid == 1 && lane == 0) g_phase_cycles[18] += clock64() - role_t0;
+                if (g_phase_enable && blockIdx.x == 0 && wid == TW && lane == 0) g_phase_cycles[18] += clock64() - role_t0;
             }
         }
         __syncthreads();

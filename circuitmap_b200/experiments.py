@@ -6,6 +6,8 @@ with the same trial count is ONE `cm_caviar_fit` call (B fits), so a sweep costs
   downsampling_weights   scripts/run_downsampling_experiments.py:66-91  (trial-count schedule :68-72, subset draw :78,
                          fit options :83, result file :93-97)
   unique_holograms       scripts/generate_loho_cv_slurm_scripts.py:108-112 (leave-one-hologram-out fold enumeration)
+  load_experiment / save_main_results / run_main   scripts/run_circuitmap_main.py:21-63 (NeuroCAAS entry: reader, demix ->
+                         fit, .mat / .npz writers)
   loho_cv_weights        the per-fold worker the reference's SLURM script calls (`run_loho_cv_caviar.py`) is NOT in the
                          reference repository; the fold definition below (drop every trial whose binarised hologram
                          equals the held-out one, fit on the rest) follows the script generator's enumeration.
@@ -131,3 +133,54 @@ def loho_cv_weights(psc_dem, stim_matrix, msrmp, hologram_ids=None, device=None,
             chunk = poss[b0:b0 + max_batch]
             mu[chunk] = _fit_subsets(psc_dev, stim_dev, [train[int(folds[p])] for p in chunk], powers, opts, seed)
     return mu, folds
+
+
+# ------------------------------------------------------------------------------------------------ run_circuitmap_main.py
+def load_experiment(path):
+    """Input reader of scripts/run_circuitmap_main.py:21-32: .mat (scipy loadmat) or .npy / .npz (np.load) holding
+    'psc' (K, T) and 'stimulus_matrix' (N, K); any other extension raises, as the script does."""
+    ext = path[-4:]
+    if ext == ".mat":
+        from scipy.io import loadmat
+        f = loadmat(path)
+    elif ext in (".npy", ".npz"):
+        f = np.load(path)
+    else:
+        raise Exception
+    return f["psc"], f["stimulus_matrix"]
+
+
+def save_main_results(out, data_path, state):
+    """Result writers of scripts/run_circuitmap_main.py:50-63: `<out>/<stem>_cmap.mat` and `<out>/<stem>_cmap.npz`
+    with keys weights = mu, weight_uncertainty = beta, spikes = lam.  Returns both paths."""
+    from pathlib import Path
+    from scipy.io import savemat
+    if out[-1] != "/":
+        out += "/"
+    save_name = out + Path(data_path).stem + "_cmap"
+    payload = {"weights": np.asarray(state["mu"]), "weight_uncertainty": np.asarray(state["beta"]),
+               "spikes": np.asarray(state["lam"])}
+    savemat(save_name + ".mat", payload)
+    np.savez(save_name, **payload)
+    return save_name + ".mat", save_name + ".npz"
+
+
+def run_main(data, config, out, device=None):
+    """scripts/run_circuitmap_main.py as a function: read the experiment, demix with the configured network, fit with the
+    configured msrmp (fit_options {'msrmp': msrmp, 'save_histories': False}), write the .mat and .npz result files.
+    `config` is the yaml path the script takes (keys 'demixer', 'msrmp') or an equivalent dict.  The demixed traces stay
+    on the device between the two steps."""
+    import torch
+    from . import Model, NeuralDemixer
+    if not isinstance(config, dict):
+        import yaml
+        config = yaml.safe_load(open(config))
+    psc, stim_matrix = load_experiment(data)
+    demix = NeuralDemixer(path=config["demixer"], device=device)
+    psc_dev = torch.from_numpy(np.ascontiguousarray(psc, dtype=np.float64)).to(demix.device)
+    psc_dem = demix(psc_dev)                                    # device tensor carrying y / sum-of-squares for the fit
+    msrmp = float(config["msrmp"])
+    N = stim_matrix.shape[0]
+    model = Model(N)
+    model.fit(psc_dem, stim_matrix, method="caviar", fit_options={"msrmp": msrmp, "save_histories": False})
+    return model, save_main_results(out, data, model.state)

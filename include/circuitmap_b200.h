@@ -162,6 +162,36 @@ CM_API int    cm_caviar_scan_stim(const void* stim_dev, int dtype, int64_t count
 CM_API int    cm_pack_stim_u8(const void* stim_host, int dtype, int64_t count, double* powers_out, int* n_powers_out,
                               int64_t* nnz_out, unsigned char* codes_out, int threads);
 
+/* ------------------------------------------------------------------------------------------
+ * Synthetic mapping experiments on the device  (circuitmap/simulation.py:25-215, blockwise design, nreps = 1).
+ * The reference draws from NumPy's unseeded global stream: parity is at the level of the distributions
+ * (tests/test_simulate_gpu.py), not of individual draws.  B maps per call, one seed each.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct cm_sim_options {          /* keyword arguments of simulate(), simulation.py:25-29 (defaults in brackets) */
+    int    N, K, T, H;                   /* neurons [300], trials [1000], samples per trace [900], targets per hologram [10] */
+    int    n_powers;                     /* [3] */
+    double powers[CM_CAVIAR_MAX_POWERS]; /* ascending [45, 55, 65]; each <= 100 (gamma shape 1e4 / power^2 >= 1) */
+    double connection_prob;              /* [0.05] */
+    double frac_strongly_connected;      /* [0.2] */
+    double min_latency, gamma_beta;      /* [160, 15] spike latency = min_latency + Gamma(1e4 / power^2, gamma_beta) */
+    double sigma;                        /* [6e-4] iid noise */
+    double strong_weight_lower, strong_weight_upper, weak_exp_mean, min_weight;          /* [20, 40, 4, 9] */
+    double phi_0_lower, phi_0_upper, phi_1_lower, phi_1_upper;                           /* [0.2, 0.25, 10, 15] */
+    double mult_noise_log_var;           /* [0.01] */
+    double tau_r_min, tau_r_max, tau_delta_min, tau_delta_max;                           /* [25, 60, 75, 250] */
+    double gp_scale, gp_lengthscale;     /* [4e-3, 50] */
+    double spont_prob;                   /* [0.05] */
+    double max_power_min_spike_rate;     /* [0.4] */
+} cm_sim_options;
+
+CM_API size_t cm_simulate_workspace_bytes(int B, int N, int K, int H);
+/* stim_dev: B x N x K laser powers (CM_F32 / CM_F64) or NULL; codes_dev: B x N x K uint8 power codes or NULL (at least one);
+ * psc_dev: B x K x T traces (CM_F32 / CM_F64); weights_dev: B x N ground-truth synaptic weights (may be NULL);
+ * status_dev: B ints (0 ok, CM_EUNSUPPORTED if a neuron has more than 1024 top-power trials); seeds: HOST array of B. */
+CM_API int cm_simulate(const cm_sim_options* o, int B, const uint64_t* seeds, void* stim_dev, int stim_dtype,
+                       unsigned char* codes_dev, void* psc_dev, int psc_dtype, double* weights_dev, int* status_dev,
+                       void* workspace_dev, size_t workspace_bytes, void* stream);
+
 /* diagnostics: per-phase SM cycle counters of fit 0 of the persistent kernel (see csrc/caviar.cu phase_mark ids);
  * copies up to n counters to `out` (may be NULL), then clears them and sets the enable flag (synchronises). */
 CM_API int cm_caviar_debug_phase_cycles(long long* out, int n, int enable);

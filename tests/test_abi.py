@@ -44,9 +44,10 @@ def test_struct_layout_matches_header():
     from circuitmap_b200 import _lib
     with tempfile.TemporaryDirectory() as d:
         src = os.path.join(d, "p.c")
-        open(src, "w").write('#include <stdio.h>\n#include "circuitmap_b200.h"\nint main(){printf("%zu %zu\\n",'
-                             'sizeof(cm_caviar_options),sizeof(cm_caviar_args));return 0;}')
+        open(src, "w").write('#include <stdio.h>\n#include "circuitmap_b200.h"\nint main(){printf("%zu %zu %zu\\n",'
+                             'sizeof(cm_caviar_options),sizeof(cm_caviar_args),sizeof(cm_sim_options));return 0;}')
         exe = os.path.join(d, "p")
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), src, "-o", exe])
-        a, b = map(int, subprocess.check_output([exe]).split())
+        a, b, c = map(int, subprocess.check_output([exe]).split())
     assert ctypes.sizeof(_lib.CaviarOptions) == a and ctypes.sizeof(_lib.CaviarArgs) == b
+    assert ctypes.sizeof(_lib.SimOptions) == c
