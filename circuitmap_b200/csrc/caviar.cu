@@ -37,7 +37,7 @@ struct Layout {
     size_t stride;
     // fp64
     size_t X, PA, PB, lam, cst, y, ss, pred, resid, z, mu, beta, bvec, dvec, wvec, slam, slam2, sp, phibar, phi,
-        phicov, phiz, phicovz, lamhist, lamT, growbuf, cscq;
+        phicov, phiz, phicovz, lamhist, lamT, growbuf, cscq, rcnt;
     // int32 / uint32
     size_t row_ptr, col_ptr, colfill, col_k, csc_row, csc_pos, cntp, n0p, n1p, act, ainv, order, order2, pos, rownz,
         phizok, sortkeys, keys, dcnt, dlist, colpw, nmask, chinfo;
@@ -78,6 +78,7 @@ static Layout make_layout(int N, int K, int64_t nnz, int iters, bool lamhist, in
     L.phicovz = take(n * 4 * 8);
     L.lamhist = take(lamhist ? (size_t)iters * z * 8 : 0);
     L.lamT = take(z * 8);
+    L.rcnt = take(n * PMAX * 8);
     L.row_ptr = take((n + 1) * 4);
     L.col_ptr = take((k + 1) * 4);
     L.colfill = take(k * 4);
@@ -176,9 +177,10 @@ __device__ __forceinline__ double sigmoid_d(double x) { return 1.0 / (1.0 + exp(
 // class as the library call it replaces (CUDA's exp is not correctly rounded either); arguments beyond +-700 -- where exp
 // overflows or underflows and the reference's result is exactly 0 or 1 -- take the library path, so those exact values
 // (which update_phi's nan_to_num handling depends on) are produced by the same instructions as before.
+__device__ __noinline__ double sigmoid_edge(double t) { return 1.0 / (1.0 + exp(t)); }   // out of line: keeps the sweep's loop body small
 __device__ __forceinline__ double sigmoid_fast(double x) {
     const double t = -x;
-    if (!(fabs(t) <= 700.0)) return 1.0 / (1.0 + exp(t));
+    if (!(fabs(t) <= 700.0)) return sigmoid_edge(t);
     const double nf = rint(t * 1.4426950408889634);
     double r = fma(nf, -6.93147180369123816490e-01, t);
     r = fma(nf, -1.90821492927058770002e-10, r);

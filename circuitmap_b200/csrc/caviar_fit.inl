@@ -27,7 +27,7 @@ struct Ctx {
     long long* tlast;   // shared: last phase timestamp (block 0 / thread 0 only)
     int N, K, P, nnz, it;
     double *X, *PA, *PB, *lam, *cst, *y, *ss, *pred, *resid, *z, *mu, *beta, *bvec, *dvec, *wvec, *slam, *slam2, *sp,
-        *phibar, *phi, *phicov, *phiz, *phicovz, *lamhist, *lamT, *growbuf;
+        *phibar, *phi, *phicov, *phiz, *phicovz, *lamhist, *lamT, *growbuf, *rcnt;
     double2* cscq;    // per CSC entry: (active index of the row as int bits, lam) -- rebuilt every a2
     int *row_ptr, *col_ptr, *col_k, *csc_row, *csc_pos, *cntp, *n0p, *n1p, *act, *ainv, *order, *order2, *pos, *rownz,
         *phizok, *dcnt, *dlist, *colpw, *nmask;
@@ -914,7 +914,7 @@ __device__ __noinline__ void sweep_chain(const Ctx& c, int nchain, double sigma,
     double* slo = scs + NSTAGE * RC;                            // [NSTAGE][RC]
     int* scp = reinterpret_cast<int*>(slo + NSTAGE * RC);       // [NSTAGE][RC]
     double* shd = reinterpret_cast<double*>(scp + NSTAGE * RC); // [NSTAGE][TW][HD]: mu, then ints cntp[PT], nmask[PT]
-    const bool prof = g_phase_enable && blockIdx.x == 0 && tt == 0;
+    const bool prof = (g_phase_enable & 64) && blockIdx.x == 0 && tt == 0;     // per-step counters cost ~3k cycles per step: opt-in
     auto stage = [&](int4 inf, int buf) {
         const int n = inf.x, beg = inf.y, len = inf.z;
         if (len <= RC) {
@@ -1106,6 +1106,219 @@ __device__ __noinline__ void sweep_chain(const Ctx& c, int nchain, double sigma,
         }
         team_sync();                                             // the prediction is consistent before the next neuron reads it
         if (prof) { const long long t = clock64(); g_phase_cycles[23] += t - tp0; g_phase_cycles[19] += 1; g_phase_cycles[24] += len; }
+        cur = nxt;
+        nxt = after;
+    }
+}
+
+
+// ---- shared-memory accessors by 32-bit shared address (LDS / STS instead of generic LD / ST on the chain's critical path)
+__device__ __forceinline__ double lds_f64(uint32_t a) { double v; asm volatile("ld.shared.f64 %0, [%1];\n" : "=d"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ int lds_s32(uint32_t a) { int v; asm volatile("ld.shared.s32 %0, [%1];\n" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ void sts_f64(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;\n" ::"r"(a), "d"(v) : "memory"); }
+__device__ __forceinline__ void sts_s32(uint32_t a, int v) { asm volatile("st.shared.s32 [%0], %1;\n" ::"r"(a), "r"(v) : "memory"); }
+
+// isotonic_regression(sr)[-1] for P <= 3 in closed form (pava.py:9-61, unit weights): the pools' sums accumulate in merge
+// order exactly as the stack algorithm does -- (a + b) + c when the first two merged first, a + (b + c) otherwise --
+// and the strict `>` merge tests compare the same quotients (division by 2 is exact; only the final mean of three needs a
+// real division, which `third` supplies: exact IEEE division or a reciprocal multiply, see sweep_chain_fast).
+template <bool EXACT>
+__device__ __forceinline__ double pava3_last(double a, double b, double c, int P) {
+    if (P == 1) return a;
+    if (P == 2) return (a > b) ? 0.5 * (a + b) : b;
+    if (!EXACT) {                                  // straight-line form of the cases below (selects, no branches)
+        const double vab = a + b, vbc = b + c;
+        const double resA = (0.5 * vab > c) ? (vab + c) * (1.0 / 3.0) : c;
+        const double resB = (b > c) ? ((a > 0.5 * vbc) ? (a + vbc) * (1.0 / 3.0) : 0.5 * vbc) : c;
+        return (a > b) ? resA : resB;
+    }
+    if (a > b) {
+        const double v = a + b;
+        if (0.5 * v > c) { const double s = v + c; return EXACT ? s / 3.0 : s * (1.0 / 3.0); }
+        return c;
+    }
+    if (b > c) {
+        const double v = b + c;
+        if (a > 0.5 * v) { const double s = a + v; return EXACT ? s / 3.0 : s * (1.0 / 3.0); }
+        return 0.5 * v;
+    }
+    return c;
+}
+
+// The chain sweep for the common configuration (P <= 3 powers, prediction vector and every chain row staged in shared
+// memory): same team structure as sweep_chain, restructured for the latency of one step --
+// what a single fit is bound by (ncu, profiles/r2c: the general version issues ~900 dependent instructions per step):
+//   * the three per-power sums and the sum of squares are reduced by ONE split butterfly (6 shuffles instead of 20): after
+//     the xor-16 and xor-8 levels every lane carries one of the four values, lanes 0 / 8 / 16 / 24 end up with the totals;
+//   * the exact-0 / exact-1 counts travel as 16-bit fields of two integers through redux.sync (one instruction each);
+//   * the accept / reject gate multiplies by the reciprocal trial counts prepared at init and takes PAVA in closed form;
+//     when the result is within 1e-9 of the threshold -- 1e6 times the rounding error of that shortcut -- the gate is
+//     re-evaluated with the reference's own operations (IEEE divisions), so every decision equals the exact one;
+//   * shared memory is addressed as shared memory (LDS / STS), per-row statistics are stored by eight lanes in parallel.
+__device__ __noinline__ void sweep_chain_fast(const Ctx& c, int nchain, double sigma, double thr, double minspk, bool gate, double* pred,
+                                 double* stage_base) {
+    constexpr int PT = 4;
+    const int lane = threadIdx.x & 31, tw = threadIdx.x >> 5, tt = threadIdx.x;
+    __shared__ __align__(16) double xch[2][TW][4];
+    __shared__ __align__(16) int xci[2][TW][4];
+    const int P = c.P;
+    double* const g_lam = c.lam; double* const g_sp = c.sp; double* const g_slam = c.slam; double* const g_slam2 = c.slam2;
+    int* const g_n0p = c.n0p; int* const g_n1p = c.n1p; int* const g_rownz = c.rownz;
+    const int* g_colpw = c.colpw; const double* g_cst = c.cst; const double* g_mu = c.mu; const double* g_rcnt = c.rcnt;
+    const int* g_cntp = c.cntp; const int* g_nmask = c.nmask; const int4* g_chinfo = c.chinfo;
+    double* scs = stage_base;                                   // [NSTAGE][RC]
+    double* slo = scs + NSTAGE * RC;                            // [NSTAGE][RC]
+    int* scp = reinterpret_cast<int*>(slo + NSTAGE * RC);       // [NSTAGE][RC]
+    double* shd = reinterpret_cast<double*>(scp + NSTAGE * RC); // [NSTAGE][TW][HD]: mu, rcnt[4], then ints cntp[4], nmask[4]
+    const uint32_t a_pred = smem_u32(pred), a_scs = smem_u32(scs), a_slo = smem_u32(slo), a_scp = smem_u32(scp),
+                   a_shd = smem_u32(shd), a_xch = smem_u32(&xch[0][0][0]), a_xci = smem_u32(&xci[0][0][0]);
+    auto stage = [&](int4 inf, int buf) {
+        const int n = inf.x, beg = inf.y, len = inf.z;
+        for (int q = tt; q < len; q += TT) {
+            cp_async4(scp + buf * RC + q, g_colpw + beg + q);
+            cp_async8(scs + buf * RC + q, g_cst + beg + q);
+            cp_async8(slo + buf * RC + q, g_lam + beg + q);
+        }
+        double* hd = shd + (buf * TW + tw) * HD;
+        if (lane == 0) cp_async8(hd, g_mu + n);
+        else if (lane <= PT) cp_async8(hd + lane, g_rcnt + n * PMAX + (lane - 1));
+        else if (lane <= 3 * PT) {
+            int* hi = reinterpret_cast<int*>(hd + 1 + PT);
+            const int q = lane - PT - 1;
+            cp_async4(hi + q, (q < PT) ? (g_cntp + n * PMAX + q) : (g_nmask + n * PMAX + (q - PT)));
+        }
+        cp_async_commit();
+    };
+    int4 infA = make_int4(0, 0, 0, 0), infB = infA;
+    if (nchain > 0) stage(g_chinfo[0], 0);
+    if (nchain > 1) stage(g_chinfo[1], 1);
+    if (nchain > 2) infA = g_chinfo[2];
+    if (nchain > 3) infB = g_chinfo[3];
+    int4 cur = nchain > 0 ? g_chinfo[0] : infA, nxt = nchain > 1 ? g_chinfo[1] : infA;
+    const bool hi16 = (lane & 16) != 0, hi8 = (lane & 8) != 0;
+    for (int i = 0; i < nchain; ++i) {
+        if (i + 2 < nchain) { stage(infA, (i + 2) % NSTAGE); cp_async_wait<2>(); }
+        else if (i + 1 < nchain) cp_async_wait<1>();
+        else cp_async_wait<0>();
+        __syncwarp();
+        const int4 after = infA;
+        infA = infB;
+        if (i + 4 < nchain) infB = g_chinfo[i + 4];
+        const int buf = i % NSTAGE, par = i & 1;
+        const int n = cur.x, beg = cur.y, len = cur.z;
+        const uint32_t a_hd = a_shd + (uint32_t)((buf * TW + tw) * HD) * 8u;
+        const double mu_n = lds_f64(a_hd);
+        const double coef = sigma * mu_n;
+        const uint32_t a_cp = a_scp + (uint32_t)(buf * RC) * 4u, a_cs = a_scs + (uint32_t)(buf * RC) * 8u,
+                       a_lo = a_slo + (uint32_t)(buf * RC) * 8u;
+        // ---- pass 1 ----
+        double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;           // three per-power sums, sum of squares
+        unsigned c0a = 0, c1a = 0, c2 = 0;   // 16-bit fields: #(e==0) of power 0 | 1, #(e==1) of power 0 | 1, #(e==0) | #(e==1) of power 2
+        double ev[EPL];
+        uint32_t ka[EPL];
+#pragma unroll
+        for (int j = 0; j < EPL; ++j) {
+            const int q = tt + j * TT;
+            ev[j] = 0.0; ka[j] = 0;
+            if (j * TT < len && q < len) {                        // first test warp-uniform: rows of <= TT entries run j = 0 only
+                const int pk = lds_s32(a_cp + (uint32_t)q * 4u);
+                const uint32_t kad = a_pred + (uint32_t)(pk & 0x7ffffff) * 8u;
+                const int pw = pk >> 27;
+                const double e = sigmoid_fast(lds_f64(a_cs + (uint32_t)q * 8u) - coef * lds_f64(kad));
+                ev[j] = e; ka[j] = kad;
+                v0 += (pw == 0) ? e : 0.0;
+                v1 += (pw == 1) ? e : 0.0;
+                v2 += (pw == 2) ? e : 0.0;
+                v3 = fma(e, e, v3);
+                const unsigned one = (e == 1.0) ? 1u : 0u, zer = (e == 0.0) ? 1u : 0u;
+                const unsigned sh = (pw == 1) ? 16u : 0u;
+                c0a += (pw < 2) ? (zer << sh) : 0u;
+                c1a += (pw < 2) ? (one << sh) : 0u;
+                c2 += (pw == 2) ? (zer | (one << 16)) : 0u;
+            }
+        }
+        // ---- split butterfly: 4 values, 6 shuffles ----
+        {
+            double a = hi16 ? v2 : v0, b = hi16 ? v3 : v1;
+            const double sa = hi16 ? v0 : v2, sb = hi16 ? v1 : v3;
+            a += __shfl_xor_sync(0xffffffffu, sa, 16);
+            b += __shfl_xor_sync(0xffffffffu, sb, 16);
+            double x = hi8 ? b : a;
+            const double sx = hi8 ? a : b;
+            x += __shfl_xor_sync(0xffffffffu, sx, 8);
+            x += __shfl_xor_sync(0xffffffffu, x, 4);
+            x += __shfl_xor_sync(0xffffffffu, x, 2);
+            x += __shfl_xor_sync(0xffffffffu, x, 1);
+            if ((lane & 7) == 0) sts_f64(a_xch + (uint32_t)(((par * TW + tw) * 4) + (lane >> 3)) * 8u, x);
+        }
+        c0a = __reduce_add_sync(0xffffffffu, c0a);
+        c1a = __reduce_add_sync(0xffffffffu, c1a);
+        c2 = __reduce_add_sync(0xffffffffu, c2);
+        if (lane == 1) sts_s32(a_xci + (uint32_t)((par * TW + tw) * 4) * 4u, (int)c0a);
+        if (lane == 2) sts_s32(a_xci + (uint32_t)((par * TW + tw) * 4 + 1) * 4u, (int)c1a);
+        if (lane == 3) sts_s32(a_xci + (uint32_t)((par * TW + tw) * 4 + 2) * 4u, (int)c2);
+        team_sync();
+        // ---- totals in fixed warp order, gate ----
+        double S0 = 0.0, S1 = 0.0, S2 = 0.0, Q = 0.0;
+#pragma unroll
+        for (int w = 0; w < TW; ++w) {
+            const uint32_t a = a_xch + (uint32_t)((par * TW + w) * 4) * 8u;
+            S0 += lds_f64(a); S1 += lds_f64(a + 8u); S2 += lds_f64(a + 16u); Q += lds_f64(a + 24u);
+        }
+        double tot = S0;
+        if (P > 1) tot += S1;
+        if (P > 2) tot += S2;
+        bool ok = true;
+        if (gate) {
+            const double r0 = lds_f64(a_hd + 8u), r1 = lds_f64(a_hd + 16u), r2 = lds_f64(a_hd + 24u);
+            const double pf = pava3_last<false>(S0 * r0, S1 * r1, S2 * r2, P);
+            ok = pf >= thr;
+            if (!(fabs(pf - thr) > 1e-9)) {                       // the reference's own operations (caviar.py:183, pava.py:42)
+                const int n0 = lds_s32(a_hd + 40u), n1 = lds_s32(a_hd + 44u), n2 = lds_s32(a_hd + 48u);
+                const double e0 = S0 / ((double)n0 + 1e-4 * (n0 == 0 ? 1.0 : 0.0));
+                const double e1 = S1 / ((double)n1 + 1e-4 * (n1 == 0 ? 1.0 : 0.0));
+                const double e2 = S2 / ((double)n2 + 1e-4 * (n2 == 0 ? 1.0 : 0.0));
+                ok = pava3_last<true>(e0, e1, e2, P) >= thr;
+            }
+            ok = ok && (tot >= minspk);
+        }
+        // ---- commit ----
+        const double muok = ok ? mu_n : 0.0;
+#pragma unroll
+        for (int j = 0; j < EPL; ++j) {
+            const int q = tt + j * TT;
+            if (j * TT < len && q < len) {
+                const double nw = ok ? ev[j] : 0.0;
+                const double old = lds_f64(a_lo + (uint32_t)q * 8u);
+                g_lam[beg + q] = nw;
+                sts_f64(ka[j], (lds_f64(ka[j]) + muok * nw) - mu_n * old);
+            }
+        }
+        if (tw == TW - 1 && lane < 8) {
+            // per-row statistics for update_phi / update_sigma (caviar.py:238-244,275-287), branch-free: lanes 0-2 own the
+            // per-power entries, lane 3 the row sum, lane 4 the sum of squares, lane 5 the non-zero count
+            const int4 w0 = *reinterpret_cast<const int4*>(&xci[par][0][0]), w1 = *reinterpret_cast<const int4*>(&xci[par][1][0]);
+            const int4 w2 = *reinterpret_cast<const int4*>(&xci[par][2][0]), w3 = *reinterpret_cast<const int4*>(&xci[par][3][0]);
+            const int c0s = w0.x + w1.x + w2.x + w3.x, c1s = w0.y + w1.y + w2.y + w3.y, cbs = w0.z + w1.z + w2.z + w3.z;
+            const int m0 = lds_s32(a_hd + 56u), m1 = lds_s32(a_hd + 60u), m2 = lds_s32(a_hd + 64u);   // masked trials per power
+            const int z0 = m0 + (c0s & 0xffff), z1 = m1 + (c0s >> 16), z2 = m2 + (cbs & 0xffff);   // exact zeros incl. masked
+            const int pl = lane < 3 ? lane : 0;
+            const int zmine = pl == 0 ? z0 : (pl == 1 ? z1 : z2);
+            const int omine = pl == 0 ? (c1s & 0xffff) : (pl == 1 ? (c1s >> 16) : (cbs >> 16));
+            const int cntmine = lds_s32(a_hd + 40u + 4u * (uint32_t)pl);
+            const int zeros = z0 + (P > 1 ? z1 : 0) + (P > 2 ? z2 : 0), masked = m0 + (P > 1 ? m1 : 0) + (P > 2 ? m2 : 0);
+            double dv = pl == 0 ? S0 : (pl == 1 ? S1 : S2);
+            dv = lane == 3 ? tot : (lane == 4 ? Q : dv);
+            dv = ok ? dv : 0.0;
+            double* dptr = lane < 3 ? g_sp + n * PMAX + pl : (lane == 3 ? g_slam + n : g_slam2 + n);
+            if (lane < P || lane == 3 || lane == 4) *dptr = dv;
+            if (lane < P) {
+                g_n0p[n * PMAX + pl] = ok ? zmine : cntmine;
+                g_n1p[n * PMAX + pl] = ok ? omine : 0;
+            }
+            if (lane == 5) g_rownz[n] = ok ? (len - (zeros - masked)) : 0;
+        }
+        team_sync();                                              // the prediction is consistent before the next neuron reads it
         cur = nxt;
         nxt = after;
     }
@@ -1318,7 +1531,7 @@ __global__ void __launch_bounds__(NT, (NT == 512) ? 1 : 2) caviar_fit_kernel(con
 #define CM_I(name) c.name = reinterpret_cast<int*>(base + L.name)
     CM_D(X); CM_D(PA); CM_D(PB); CM_D(lam); CM_D(cst); CM_D(y); CM_D(ss); CM_D(pred); CM_D(resid); CM_D(z); CM_D(mu);
     CM_D(beta); CM_D(bvec); CM_D(dvec); CM_D(wvec); CM_D(slam); CM_D(slam2); CM_D(sp); CM_D(phibar); CM_D(phi);
-    CM_D(phicov); CM_D(phiz); CM_D(phicovz); CM_D(lamhist); CM_D(lamT); CM_D(growbuf);
+    CM_D(phicov); CM_D(phiz); CM_D(phicovz); CM_D(lamhist); CM_D(lamT); CM_D(growbuf); CM_D(rcnt);
     CM_I(row_ptr); CM_I(col_ptr); CM_I(col_k); CM_I(csc_row); CM_I(csc_pos); CM_I(cntp); CM_I(n0p); CM_I(n1p);
     CM_I(act); CM_I(ainv); CM_I(order); CM_I(order2); CM_I(pos); CM_I(rownz); CM_I(phizok); CM_I(dcnt); CM_I(dlist); CM_I(colpw); CM_I(nmask);
 #undef CM_D
@@ -1383,6 +1596,10 @@ __global__ void __launch_bounds__(NT, (NT == 512) ? 1 : 2) caviar_fit_kernel(con
         c.mu[n] = c.mu0[n]; c.beta[n] = c.beta0[n];
     }
     __syncthreads();
+    for (int i = threadIdx.x; i < N * PMAX; i += NT) {   // reciprocal spike-rate denominators (caviar.py:183) for the fast gate
+        const int cnt = c.cntp[i];
+        c.rcnt[i] = 1.0 / ((double)cnt + 1e-4 * (cnt == 0 ? 1.0 : 0.0));
+    }
     for (int n = threadIdx.x; n < N; n += NT) {       // lam0 = 0.95 [I>0] lam_mask: every indexed entry is unmasked
         const int len = c.row_ptr[n + 1] - c.row_ptr[n];
         c.slam[n] = 0.95 * len; c.slam2[n] = 0.95 * 0.95 * len; c.rownz[n] = len;
@@ -1487,17 +1704,27 @@ __global__ void __launch_bounds__(NT, (NT == 512) ? 1 : 2) caviar_fit_kernel(con
         phase_mark(c, 9);
         // chain = neurons with mu != 0 in update order; (n, row begin, row length) table for the prefetching warp
         const int nchain = block_compact(N, [&](int m) { return c.mu[c.order[m]] != 0.0; }, c.dlist, nullptr, red);
-        for (int i = threadIdx.x; i < nchain; i += NT) {
-            const int n = c.order[c.dlist[i]];
-            c.chinfo[i] = make_int4(n, c.row_ptr[n], c.row_ptr[n + 1] - c.row_ptr[n], 0);
+        if (threadIdx.x == 0) sc_flag = 0;
+        __syncthreads();
+        {
+            int mx = 0;
+            for (int i = threadIdx.x; i < nchain; i += NT) {
+                const int n = c.order[c.dlist[i]];
+                const int len = c.row_ptr[n + 1] - c.row_ptr[n];
+                c.chinfo[i] = make_int4(n, c.row_ptr[n], len, 0);
+                mx = max(mx, len);
+            }
+            if (mx > RC) atomicOr(&sc_flag, 1);            // a chain row exceeds the staging capacity -> general sweep
         }
         __syncthreads();
+        const bool fast_chain = (PT == 4) && P <= 3 && pred_smem && sc_flag == 0;
         {
             const double thr = o.msrmp + sc_spont;
             const bool gate = it > o.delay_spont_est;
             const long long role_t0 = clock64();
             if (wid < TW) {
-                sweep_chain<PT>(c, nchain, sigma, thr, o.minimum_spike_count, gate, pred, stage_base);
+                if (fast_chain) sweep_chain_fast(c, nchain, sigma, thr, o.minimum_spike_count, gate, pred, stage_base);
+                else sweep_chain<PT>(c, nchain, sigma, thr, o.minimum_spike_count, gate, pred, stage_base);
                 if (g_phase_enable && blockIdx.x == 0 && threadIdx.x == 0) g_phase_cycles[16] += clock64() - role_t0;
             } else if (wid == NW - 1) {
                 if (it + 1 < iters) rng_iteration(N, rounds, rk0, rk1, keys_nxt, sc_subkeys);
