@@ -31,6 +31,10 @@ struct Ctx {
     double2* cscq;    // per CSC entry: (active index of the row as int bits, lam) -- rebuilt every a2
     int *row_ptr, *col_ptr, *col_k, *csc_row, *csc_pos, *cntp, *n0p, *n1p, *act, *ainv, *order, *order2, *pos, *rownz,
         *phizok, *dcnt, *dlist, *colpw, *nmask;
+    // The by-trial (CSC) index IN USE: the full one built by the prologue, or -- once most rows have been pruned -- its
+    // restriction to the rows that still carry a non-zero posterior (compact_csc).  lamT / cscq are indexed by it.
+    int *ucol_ptr, *ucsc_row, *ucsc_pos, *ccol_ptr, *ccsc_row, *ccsc_pos, *member;
+    int unnz;
     int4* chinfo;
     uint32_t *sortkeys, *keys;
     unsigned char *pw, *mask, *blocked;
@@ -112,7 +116,7 @@ __device__ int block_compact(int n, F flag, int* out, int* inv, double* red) {
 __device__ __forceinline__ void compute_pred(const Ctx& c, double* dst) {
     for (int k = threadIdx.x; k < c.K; k += NT) {
         double s = 0.0;
-        for (int i = c.col_ptr[k]; i < c.col_ptr[k + 1]; ++i) s += c.mu[c.csc_row[i]] * c.lamT[i];
+        for (int i = c.ucol_ptr[k]; i < c.ucol_ptr[k + 1]; ++i) s += c.mu[c.ucsc_row[i]] * c.lamT[i];
         dst[k] = s;
     }
 }
@@ -187,8 +191,8 @@ __device__ void gram_rows(const Ctx& c, int i0, int nb, double sigma, int part =
                 la = c.lam[j];
                 if (la != 0.0) {
                     const int k = c.col_k[j];
-                    cb = c.col_ptr[k];
-                    len = c.col_ptr[k + 1] - cb;
+                    cb = c.ucol_ptr[k];
+                    len = c.ucol_ptr[k + 1] - cb;
                 }
             }
             int maxlen = len;
@@ -533,11 +537,58 @@ __device__ void helper_loop(const Ctx& c, GemmPipe& gp) {
         } else if (type == 6) {
             a2_mubeta(c, a, ldr, c.role, c.ct);
         } else if (type == 7) {
-            gram_rows(c, a, b, *reinterpret_cast<const double*>(c.job + 8), c.role, c.ct);
+            Ctx h = c;                                           // the by-trial index the fit CTA currently uses
+            if (c.job[5]) { h.ucol_ptr = c.ccol_ptr; h.ucsc_row = c.ccsc_row; h.ucsc_pos = c.ccsc_pos; }
+            h.unnz = c.job[6];
+            gram_rows(h, a, b, *reinterpret_cast<const double*>(c.job + 8), c.role, c.ct);
         }
         __syncthreads();
         if (threadIdx.x == 0) { __threadfence(); red_release_gpu(&c.job[16], 1); }
     }
+}
+
+// Restriction of the by-trial index to the rows with a non-zero posterior (see the call site).  Three block-wide passes
+// over the FULL index: per-trial counts, exclusive scan over the K trials, ordered fill (neuron order within a trial is
+// preserved, so every sum keeps its order).
+__device__ __noinline__ void compact_csc(Ctx& c, double* red) {
+    const int K = c.K, N = c.N;
+    __shared__ int s_carry;
+    int* wsum = reinterpret_cast<int*>(red);                 // NW ints
+    for (int n = threadIdx.x; n < N; n += NT) c.member[n] = c.rownz[n] > 0 ? 1 : 0;
+    if (threadIdx.x == 0) { s_carry = 0; c.ccol_ptr[0] = 0; }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int k0 = 0; k0 < K; k0 += NT) {
+        const int k = k0 + threadIdx.x;
+        int cnt = 0;
+        if (k < K)
+            for (int i = c.col_ptr[k]; i < c.col_ptr[k + 1]; ++i) cnt += c.member[c.csc_row[i]];
+        int inc = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += u;
+        }
+        if (lane == 31) wsum[wid] = inc;
+        __syncthreads();
+        int off = s_carry;
+        for (int w = 0; w < wid; ++w) off += wsum[w];
+        const int start = off + inc - cnt;                   // exclusive prefix of this trial
+        if (k < K) {
+            c.ccol_ptr[k + 1] = off + inc;
+            int o2 = start;
+            for (int i = c.col_ptr[k]; i < c.col_ptr[k + 1]; ++i) {
+                const int r = c.csc_row[i];
+                if (c.member[r]) { c.ccsc_row[o2] = r; c.ccsc_pos[o2] = c.csc_pos[i]; ++o2; }
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == NT - 1) s_carry = off + inc;
+        __syncthreads();
+    }
+    c.ucol_ptr = c.ccol_ptr; c.ucsc_row = c.ccsc_row; c.ucsc_pos = c.ccsc_pos;
+    c.unnz = s_carry;
+    __syncthreads();
 }
 
 __device__ __noinline__ void phase_a2(const Ctx& c, double sigma, int* na_s, GemmPipe& gp) {
@@ -552,8 +603,8 @@ __device__ __noinline__ void phase_a2(const Ctx& c, double sigma, int* na_s, Gem
         if (c.rownz[n] == 0) { c.mu[n] = c.mu0[n]; c.beta[n] = c.beta0[n] * c.beta0[n]; }
     // per CSC entry: (active index of its row, lam) in one 16-byte record for the Gram expansion
 #pragma unroll 8
-    for (int i = threadIdx.x; i < c.nnz; i += NT)
-        c.cscq[i] = make_double2(__longlong_as_double((long long)c.ainv[c.csc_row[i]]), c.lamT[i]);
+    for (int i = threadIdx.x; i < c.unnz; i += NT)
+        c.cscq[i] = make_double2(__longlong_as_double((long long)c.ainv[c.ucsc_row[i]]), c.lamT[i]);
     // per active row: D = sum lam(1-lam), b = sigma * sum lam*y + mu0/beta0^2
     for (int ia = wid; ia < na; ia += NW) {
         const int n = c.act[ia];
@@ -1537,6 +1588,9 @@ __global__ void __launch_bounds__(NT, (NT == 512) ? 1 : 2) caviar_fit_kernel(con
 #undef CM_D
 #undef CM_I
     c.chinfo = reinterpret_cast<int4*>(base + L.chinfo);
+    c.ccol_ptr = reinterpret_cast<int*>(base + L.ccol_ptr); c.ccsc_row = reinterpret_cast<int*>(base + L.ccsc_row);
+    c.ccsc_pos = reinterpret_cast<int*>(base + L.ccsc_pos); c.member = reinterpret_cast<int*>(base + L.member);
+    c.ucol_ptr = c.col_ptr; c.ucsc_row = c.csc_row; c.ucsc_pos = c.csc_pos;
     c.job = reinterpret_cast<int*>(base + L.job);
     c.ct = p.ct;
     c.role = p.queue ? 0 : blockIdx.x - b * p.ct;      // queue mode has no helper CTAs: whoever pulls a fit runs it
@@ -1561,6 +1615,9 @@ __global__ void __launch_bounds__(NT, (NT == 512) ? 1 : 2) caviar_fit_kernel(con
     if (p.status[b] != 0) continue;                   // prologue reported an error for this fit
     if (HELPERS && c.role > 0) { helper_loop(c, gp); return; }
     c.nnz = c.row_ptr[N];
+    c.unnz = c.nnz;
+    for (int n = threadIdx.x; n < N; n += NT) c.member[n] = 1;
+    if (HELPERS && c.ct > 1 && threadIdx.x == 0) { c.job[5] = 0; c.job[6] = c.nnz; }
     const int iters = o.iters;
     const int S = o.num_mc_samples;
     // number of shuffle rounds of jax.random.permutation: ceil(3 ln N / ln(2^32-1))
@@ -1606,7 +1663,7 @@ __global__ void __launch_bounds__(NT, (NT == 512) ? 1 : 2) caviar_fit_kernel(con
     }
     for (int j = threadIdx.x; j < c.nnz; j += NT) c.lam[j] = 0.95;
     __syncthreads();
-    for (int i = threadIdx.x; i < c.nnz; i += NT) c.lamT[i] = c.lam[c.csc_pos[i]];
+    for (int i = threadIdx.x; i < c.unnz; i += NT) c.lamT[i] = c.lam[c.ucsc_pos[i]];
     double sumy = 0.0, ysq = 0.0;
     for (int k = threadIdx.x; k < K; k += NT) { const double v = c.y[k]; sumy += v; ysq += v * v; }
     sumy = block_sum(sumy, red);
@@ -1743,8 +1800,26 @@ __global__ void __launch_bounds__(NT, (NT == 512) ? 1 : 2) caviar_fit_kernel(con
             }
         }
         __syncthreads();
+        // Pruned rows (posterior identically zero) contribute exact zeros to every by-trial pass -- the prediction, the Gram
+        // expansion, the spontaneous-event mask -- so those passes may skip them: once the live rows hold <= 70 % of the
+        // entries of the index in use, it is rebuilt over the live rows only (and again from the full index should a row
+        // outside it come back).  Bitwise neutral: only +-0.0 terms leave the sums.
+        {
+            int alive_entries = 0, outside = 0;
+            for (int n = threadIdx.x; n < N; n += NT)
+                if (c.rownz[n] > 0) {
+                    alive_entries += c.row_ptr[n + 1] - c.row_ptr[n];
+                    outside |= (c.member[n] == 0);
+                }
+            alive_entries = block_sum_int(alive_entries, red);
+            outside = block_sum_int(outside, red);
+            if (!(g_phase_enable & 128) && (outside > 0 || (long long)alive_entries * 10 <= (long long)c.unnz * 7)) {
+                compact_csc(c, red);
+                if (HELPERS && c.ct > 1 && threadIdx.x == 0) { c.job[5] = 1; c.job[6] = c.unnz; }   // helpers switch index too
+            }
+        }
 #pragma unroll 8
-        for (int i = threadIdx.x; i < c.nnz; i += NT) c.lamT[i] = c.lam[c.csc_pos[i]];   // CSC-ordered copy of the new lam
+        for (int i = threadIdx.x; i < c.unnz; i += NT) c.lamT[i] = c.lam[c.ucsc_pos[i]];   // by-trial copy of the new lam
         __syncthreads();
         phase_mark(c, 10);
         // ================= a6: update_sigma (caviar.py:238-244), with a2's mu =================
@@ -1793,7 +1868,7 @@ __global__ void __launch_bounds__(NT, (NT == 512) ? 1 : 2) caviar_fit_kernel(con
         // ================= a8: estimate_spont_act_soft_thresh (caviar.py:146-163, 86-88) =================
         for (int k = threadIdx.x; k < K; k += NT) {
             unsigned char bl = 0;
-            for (int i = c.col_ptr[k]; i < c.col_ptr[k + 1]; ++i) bl |= (c.lamT[i] >= o.spont_orthogonality);
+            for (int i = c.ucol_ptr[k]; i < c.ucol_ptr[k + 1]; ++i) bl |= (c.lamT[i] >= o.spont_orthogonality);
             c.blocked[k] = bl;
         }
         __syncthreads();
