@@ -40,7 +40,7 @@ struct Layout {
         phicov, phiz, phicovz, lamhist, lamT, growbuf, cscq, rcnt;
     // int32 / uint32
     size_t row_ptr, col_ptr, colfill, col_k, csc_row, csc_pos, cntp, n0p, n1p, act, ainv, order, order2, pos, rownz,
-        phizok, sortkeys, keys, dcnt, dlist, colpw, nmask, chinfo, ccol_ptr, ccsc_row, ccsc_pos, member;
+        phizok, sortkeys, keys, dcnt, dlist, colpw, nmask, chinfo, ccol_ptr, ccsc_row, ccsc_pos, member, rowcb;
     // bytes
     size_t pw, mask, blocked;
     size_t job;      // job board of the panel-GEMM helper CTAs (ints)
@@ -106,6 +106,7 @@ static Layout make_layout(int N, int K, int64_t nnz, int iters, bool lamhist, in
     L.ccsc_row = take(z * 4);
     L.ccsc_pos = take(z * 4);
     L.member = take(n * 4);
+    L.rowcb = take(z * 8);
     L.pw = take(z);
     L.mask = take(k);
     L.blocked = take(k);

@@ -34,6 +34,7 @@ struct Ctx {
     // The by-trial (CSC) index IN USE: the full one built by the prologue, or -- once most rows have been pruned -- its
     // restriction to the rows that still carry a non-zero posterior (compact_csc).  lamT / cscq are indexed by it.
     int *ucol_ptr, *ucsc_row, *ucsc_pos, *ccol_ptr, *ccsc_row, *ccsc_pos, *member;
+    int2* rowcb;      // per CSR entry: (begin, length) of its trial's list in the by-trial index in use (Gram expansion)
     int unnz;
     int4* chinfo;
     uint32_t *sortkeys, *keys;
@@ -183,18 +184,15 @@ __device__ void gram_rows(const Ctx& c, int i0, int nb, double sigma, int part =
         for (int q = lane; q <= ia; q += 32) acc[q] = 0.0;
         __syncwarp();
         const int beg = c.row_ptr[n], end = c.row_ptr[n + 1];
+        const int2* __restrict__ rowcb = c.rowcb;
+        double la_n = 0.0;                                   // the next 32 entries are fetched while these are expanded
+        int2 rc_n = make_int2(0, 0);
+        if (beg + lane < end) { la_n = c.lam[beg + lane]; rc_n = rowcb[beg + lane]; }
         for (int jb = beg; jb < end; jb += 32) {
-            const int j = jb + lane;
-            double la = 0.0;
-            int cb = 0, len = 0;
-            if (j < end) {
-                la = c.lam[j];
-                if (la != 0.0) {
-                    const int k = c.col_k[j];
-                    cb = c.ucol_ptr[k];
-                    len = c.ucol_ptr[k + 1] - cb;
-                }
-            }
+            const double la = la_n;
+            const int cb = rc_n.x, len = (la != 0.0) ? rc_n.y : 0;
+            la_n = 0.0; rc_n = make_int2(0, 0);
+            if (jb + 32 + lane < end) { la_n = c.lam[jb + 32 + lane]; rc_n = rowcb[jb + 32 + lane]; }
             int maxlen = len;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, o));
@@ -547,6 +545,17 @@ __device__ void helper_loop(const Ctx& c, GemmPipe& gp) {
     }
 }
 
+// (begin, length) of every CSR entry's trial list in the by-trial index in use: saves the Gram expansion one dependent
+// memory round trip per 32 entries (col_k -> col_ptr); rebuilt whenever that index changes.
+__device__ __forceinline__ void build_rowcb(const Ctx& c) {
+#pragma unroll 4
+    for (int j = threadIdx.x; j < c.nnz; j += NT) {
+        const int k = c.col_k[j];
+        const int cb = c.ucol_ptr[k];
+        c.rowcb[j] = make_int2(cb, c.ucol_ptr[k + 1] - cb);
+    }
+}
+
 // Restriction of the by-trial index to the rows with a non-zero posterior (see the call site).  Three block-wide passes
 // over the FULL index: per-trial counts, exclusive scan over the K trials, ordered fill (neuron order within a trial is
 // preserved, so every sum keeps its order).
@@ -589,6 +598,161 @@ __device__ __noinline__ void compact_csc(Ctx& c, double* red) {
     c.ucol_ptr = c.ccol_ptr; c.ucsc_row = c.ccsc_row; c.ucsc_pos = c.ccsc_pos;
     c.unnz = s_carry;
     __syncthreads();
+    build_rowcb(c);
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------------ a2, small systems
+// block_update_mu (caviar.py:166-172) when the active set is small enough for the whole system to live in shared memory
+// (packed lower triangle: na (na + 1) / 2 doubles -- na <= 222 in the 16-warp variant, 155 in the 8-warp one).  That is
+// the normal state of a fit after its first gated sweep (C3: ~250 -> 100 active rows for 47 of 50 iterations), where the
+// bordered 32-row recursion over global memory spends its time in per-block pipeline fill, barriers and 32 x 32 factor
+// steps rather than in arithmetic.  Here: Gram rows straight into the packed matrix (one warp per row, same deterministic
+// expansion as gram_rows), right-looking Cholesky in place, X = L^-1 in place row by row, then w = X b, mu = X^T w,
+// beta = column sums of squares of X.  No global-memory matrix traffic, no helper jobs.
+__device__ __forceinline__ int tri(int r) { return (r * (r + 1)) >> 1; }
+__device__ __forceinline__ int a2_small_capacity(int smd) {
+    int na = 0;
+    while (tri(na + 1) + (na + 1) + ((NW * (na + 1) + 7) >> 3) + 64 <= smd) ++na;
+    return na;
+}
+__device__ __noinline__ void a2_small(const Ctx& c, double sigma, int na) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    double* Mp = c.sm;                                       // packed lower triangle, row-major: (r, q) at tri(r) + q
+    double* vec = Mp + tri(na);                              // na doubles: current column / row
+    unsigned char* tagbase = reinterpret_cast<unsigned char*>(vec + na);
+    const double2* __restrict__ cscq = c.cscq;
+    // ---- Gram rows (cf. gram_rows) ----
+    for (int ia = wid; ia < na; ia += NW) {
+        const int n = c.act[ia];
+        double* acc = Mp + tri(ia);
+        unsigned char* tags = tagbase + (size_t)wid * na;
+        for (int q = lane; q <= ia; q += 32) acc[q] = 0.0;
+        __syncwarp();
+        const int beg = c.row_ptr[n], end = c.row_ptr[n + 1];
+        for (int jb = beg; jb < end; jb += 32) {
+            const int j = jb + lane;
+            double la = 0.0;
+            int cb = 0, len = 0;
+            if (j < end) {
+                la = c.lam[j];
+                if (la != 0.0) {
+                    const int k = c.col_k[j];
+                    cb = c.ucol_ptr[k];
+                    len = c.ucol_ptr[k + 1] - cb;
+                }
+            }
+            int maxlen = len;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, o));
+            for (int t = 0; t < maxlen; ++t) {
+                int ib = -1;
+                double v = 0.0;
+                if (t < len) {
+                    const double2 rec = cscq[cb + t];
+                    ib = (int)__double_as_longlong(rec.x);
+                    v = la * rec.y;
+                }
+                if (ib > ia) ib = -1;
+                if (ib >= 0) tags[ib] = (unsigned char)lane;
+                __syncwarp();
+                const bool lost = (ib >= 0) && (tags[ib] != (unsigned char)lane);
+                if (!__any_sync(0xffffffffu, lost)) {
+                    if (ib >= 0) acc[ib] += v;                 // all targets distinct
+                } else {                                       // same target hit by several lanes: combine in lane order
+                    const unsigned amask = __ballot_sync(0xffffffffu, ib >= 0);
+                    if (ib >= 0) {
+                        const unsigned grp = __match_any_sync(amask, ib);
+                        const int leader = __ffs(grp) - 1;
+                        unsigned rest = grp & ~(1u << leader);
+                        double ssum = __shfl_sync(amask, v, leader);
+                        while (__any_sync(amask, rest != 0)) {
+                            const int src = rest ? (__ffs(rest) - 1) : lane;
+                            const double ov = __shfl_sync(amask, v, src);
+                            if (rest) { ssum += ov; rest &= rest - 1; }
+                        }
+                        if (lane == leader) acc[ib] += ssum;
+                    }
+                }
+                __syncwarp();
+            }
+        }
+        const double b0 = c.beta0[n];
+        const double dd = c.dvec[ia];
+        for (int q = lane; q <= ia; q += 32) {
+            const double v = acc[q];
+            acc[q] = (q == ia) ? sigma * (dd + v) + 1.0 / (b0 * b0) : sigma * v;
+        }
+    }
+    __syncthreads();
+    phase_mark(c, 1);
+    // ---- Cholesky, right-looking, in place (two barriers per column) ----
+    for (int j = 0; j < na; ++j) {
+        __syncthreads();                                      // the trailing update of column j - 1 is complete
+        const double djj = sqrt(Mp[tri(j) + j]);
+        for (int r = j + threadIdx.x; r < na; r += NT) {
+            if (r == j) vec[j] = djj;                         // (the pivot itself is overwritten after the next barrier)
+            else {
+                const double v = Mp[tri(r) + j] / djj;
+                vec[r] = v;
+                Mp[tri(r) + j] = v;
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) Mp[tri(j) + j] = djj;
+        // trailing update: row r by warp, columns j < q <= r by lanes
+        for (int r = j + 1 + wid; r < na; r += NW) {
+            const double lr = vec[r];
+            double* row = Mp + tri(r);
+            for (int q = j + 1 + lane; q <= r; q += 32) row[q] -= lr * vec[q];
+        }
+    }
+    __syncthreads();
+    phase_mark(c, 3);
+    // ---- X = L^-1 in place, row by row: X[r][q] = -(sum_{t=q}^{r-1} L[r][t] X[t][q]) / L[r][r], X[r][r] = 1 / L[r][r] ----
+    {
+        int tpc = 1;                                         // threads per column (power of two, <= 4)
+        while (tpc < 4 && 2 * tpc * na <= NT) tpc *= 2;
+        const int col = threadIdx.x / tpc, part = threadIdx.x % tpc;
+        for (int r = 0; r < na; ++r) {
+            __syncthreads();
+            for (int t = threadIdx.x; t <= r; t += NT) vec[t] = Mp[tri(r) + t];       // L row r
+            __syncthreads();
+            const double d = vec[r];
+            double sacc = 0.0;
+            if (col < r)
+                for (int t = col + part; t < r; t += tpc) sacc += vec[t] * Mp[tri(t) + col];
+            if (tpc >= 2) sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);              // every lane takes part
+            if (tpc >= 4) sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
+            if (part == 0) {
+                if (col < r) Mp[tri(r) + col] = -sacc / d;
+                else if (col == r) Mp[tri(r) + r] = 1.0 / d;
+            }
+        }
+    }
+    __syncthreads();
+    phase_mark(c, 5);
+    // ---- w = X b ; mu = X^T w ; beta = column sums of squares ----
+    for (int r = threadIdx.x; r < na; r += NT) {
+        double sacc = 0.0;
+        const double* row = Mp + tri(r);
+        for (int q = 0; q <= r; ++q) sacc += row[q] * c.bvec[q];
+        vec[r] = sacc;
+    }
+    __syncthreads();
+    for (int q = threadIdx.x; q < na; q += NT) {
+        double m = 0.0, v = 0.0;
+        for (int r = q; r < na; ++r) {
+            const double x = Mp[tri(r) + q];
+            m += x * vec[r];
+            v += x * x;
+        }
+        const int n = c.act[q];
+        c.mu[n] = m;
+        c.beta[n] = v;
+    }
+    __syncthreads();
+    phase_mark(c, 6);
 }
 
 __device__ __noinline__ void phase_a2(const Ctx& c, double sigma, int* na_s, GemmPipe& gp) {
@@ -624,6 +788,7 @@ __device__ __noinline__ void phase_a2(const Ctx& c, double sigma, int* na_s, Gem
     __syncthreads();
     phase_mark(c, 0);
     if (na == 0) return;
+    if (!(g_phase_enable & 256) && na <= a2_small_capacity(c.smd)) { a2_small(c, sigma, na); return; }
 
     // diagonal block -> its Cholesky factor, and the inverse of that factor (strict upper part zeroed); both live
     // behind the GEMM ring (the Gram conflict tags reuse the same bytes at a different time)
@@ -1511,7 +1676,9 @@ __device__ __noinline__ void newton_rows(const Ctx& c, const double* powers, con
             double rhs = basev + alpha * stp * Jv;
             int bt = 0;
             bool go = (bt < 40) && ((lhs != lhs) || lhs > rhs);
+            int trips = 0;
             while (__any_sync(0xffffffffu, go)) {
+                ++trips;
                 const double stp_try = go ? stp * bbeta : stp;
                 const double lhs_try = nll_quad(s, p0 + stp_try * v0, p1 + stp_try * v1, prior, prec, t);
                 if (go) {
@@ -1524,6 +1691,12 @@ __device__ __noinline__ void newton_rows(const Ctx& c, const double* powers, con
             }
             p0 += stp * v0;
             p1 += stp * v1;
+            if ((g_phase_enable & 1) && blockIdx.x == 0) {       // diagnostics: warp-level loop trips vs backtracks the rows needed
+                const int need = __reduce_add_sync(0xffffffffu, (live && mem == 0) ? bt : 0);
+                if (lane == 0) { atomicAdd((unsigned long long*)&g_phase_cycles[25], (unsigned long long)trips);
+                                 atomicAdd((unsigned long long*)&g_phase_cycles[26], (unsigned long long)need);
+                                 atomicAdd((unsigned long long*)&g_phase_cycles[27], 1ull); }
+            }
         }
         if (live && mem == 0) {
             c.phi[2 * n] = p0; c.phi[2 * n + 1] = p1;
@@ -1590,6 +1763,7 @@ __global__ void __launch_bounds__(NT, (NT == 512) ? 1 : 2) caviar_fit_kernel(con
     c.chinfo = reinterpret_cast<int4*>(base + L.chinfo);
     c.ccol_ptr = reinterpret_cast<int*>(base + L.ccol_ptr); c.ccsc_row = reinterpret_cast<int*>(base + L.ccsc_row);
     c.ccsc_pos = reinterpret_cast<int*>(base + L.ccsc_pos); c.member = reinterpret_cast<int*>(base + L.member);
+    c.rowcb = reinterpret_cast<int2*>(base + L.rowcb);
     c.ucol_ptr = c.col_ptr; c.ucsc_row = c.csc_row; c.ucsc_pos = c.csc_pos;
     c.job = reinterpret_cast<int*>(base + L.job);
     c.ct = p.ct;
@@ -1617,6 +1791,7 @@ __global__ void __launch_bounds__(NT, (NT == 512) ? 1 : 2) caviar_fit_kernel(con
     c.nnz = c.row_ptr[N];
     c.unnz = c.nnz;
     for (int n = threadIdx.x; n < N; n += NT) c.member[n] = 1;
+    build_rowcb(c);
     if (HELPERS && c.ct > 1 && threadIdx.x == 0) { c.job[5] = 0; c.job[6] = c.nnz; }
     const int iters = o.iters;
     const int S = o.num_mc_samples;
