@@ -317,6 +317,8 @@ def main():
     ap.add_argument("--no-nwd", action="store_true")
     ap.add_argument("--no-c4", action="store_true", help="skip the C4 (1024 maps of N=500, K=5000) secondary measurement")
     ap.add_argument("--no-c5", action="store_true", help="skip the C5 (one map of N=5000, K=100000) secondary measurement")
+    ap.add_argument("--e2e-chunk", type=int, default=0, help="fits per chunk of the e2e pipeline (default: a quarter wave)")
+    ap.add_argument("--e2e-depth", type=int, default=0, help="chunks in flight in the e2e pipeline")
     ap.add_argument("--no-single", action="store_true", help="skip the single-fit latency measurement")
     ap.add_argument("--no-traffic", action="store_true", help="skip the ncu DRAM-traffic probe of the fit kernel")
     ap.add_argument("--traffic-probe", action="store_true", help=argparse.SUPPRESS)
@@ -484,13 +486,28 @@ def main():
         npin = max(1, min(B, args.maps))
         hs_pin = [stim[i].cpu().pin_memory() for i in range(npin)]
         hp_pin = [psc[i].cpu().pin_memory() for i in range(npin)]
-        hs = [hs_pin[b % npin] for b in range(B)]
+        hs_coo = [optimise.codes_to_coo(stim[i]) for i in range(npin)]        # the same designs as sparse triples
+        hs = [hs_coo[b % npin] for b in range(B)]
         hp = [hp_pin[b % npin] for b in range(B)]
-        e2e_chunk = max(1, sms // 2)
+        # what this box's host -> device path delivers from pinned memory (a pure copy of the e2e buffers, no kernels)
+        h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        probe = torch.empty((min(B, 64),) + tuple(hp_pin[0].shape), dtype=torch.float32, device=dev)
+        for rep in range(2):
+            torch.cuda.synchronize()
+            h0.record()
+            for i in range(probe.shape[0]):
+                probe[i].copy_(hp[i], non_blocking=True)
+            h1.record()
+            torch.cuda.synchronize()
+        h2d_gbs = probe.numel() * 4 / (h0.elapsed_time(h1) / 1e3) / 1e9
+        del probe
+        # four chunks of half a wave in flight: their fit CTAs share the SMs, the first kernels start after 1/4 of the upload
+        e2e_chunk, e2e_depth = args.e2e_chunk or max(1, sms // 2), args.e2e_depth or 4
         dem_e2e = NeuralDemixer(path=os.path.join(GOLD, "nwd_ie_ChroME2f_weights.npz"), device=dev, precision="fp16")
         res = {}
         for label, demixer in (("fit", None), ("pipeline", dem_e2e)):
-            pipe = streaming.FitPipeline(N, K, powers, chunk=e2e_chunk, nnz_cap=nnz, device=dev, demixer=demixer, **opts)
+            pipe = streaming.FitPipeline(N, K, powers, chunk=e2e_chunk, nnz_cap=nnz, device=dev, demixer=demixer, design="coo",
+                                         depth=e2e_depth, **opts)
             got = [0]
 
             def on_result(lo, hi, views, got=got):
@@ -508,18 +525,21 @@ def main():
             if world > 1:
                 dist.all_reduce(dt, op=dist.ReduceOp.MAX)
             res[label] = {"value": world * B / float(dt.item()), "unit": "fits/s", "ms_per_step": 1e3 * float(dt.item()),
-                          "h2d_bytes_per_step": B * pipe.h2d_bytes_per_fit, "d2h_bytes_per_step": B * pipe.d2h_bytes_per_fit}
+                          "h2d_bytes_per_step": B * pipe.h2d_bytes_per_fit, "d2h_bytes_per_step": B * pipe.d2h_bytes_per_fit,
+                          "h2d_gbs_measured": h2d_gbs,
+                          "h2d_bound_fits_per_s": world * h2d_gbs * 1e9 / pipe.h2d_bytes_per_fit}
             del pipe
             torch.cuda.empty_cache()
         e2e = dict(res["fit"])
-        e2e["note"] = ("circuitmap_b200.streaming.FitPipeline: pinned host buffers in the formats the data has (float32 traces, uint8 "
-                       "power codes; %d distinct maps tiled to %d fits) -> H2D -> cm_caviar_fit -> D2H of mu, beta, shape, rate, phi, "
-                       "phi_cov, z and lam as CSR, read by the host; upload, kernels and download of consecutive chunks of %d "
-                       "fits overlap" % (npin, B, e2e_chunk))
+        e2e["note"] = ("circuitmap_b200.streaming.FitPipeline: pinned host buffers in the formats the data has (float32 traces, the "
+                       "design as sparse (neuron, trial, power code) triples; %d distinct maps tiled to %d fits) -> H2D -> "
+                       "cm_expand_stim_coo -> cm_caviar_fit -> D2H of mu, beta, shape, rate, phi, "
+                       "phi_cov, z and lam as CSR, read by the host; %d chunks of %d fits in flight (upload, kernels and "
+                       "download overlap; the chunks' fit kernels share the SMs)" % (npin, B, e2e_depth, e2e_chunk))
         e2e["pipeline_with_demixer"] = dict(res["pipeline"], note="the same with RAW traces in and the fp16 tensor-core "
                                             "NeuralDemixer in front of the fit (README.md:28-51 of the reference: demix -> fit); "
                                             "the demixed traces never leave the device, only y = trapz and sum x^2 reach the fit")
-        del hs, hp, hs_pin, hp_pin, dem_e2e
+        del hs, hp, hs_pin, hp_pin, hs_coo, dem_e2e
     # ---- the reference-facing call itself: Model(N).fit(psc, stim) with NumPy arrays in and out, one map (rank 0) ----
     if e2e is not None and rank == 0:
         import contextlib

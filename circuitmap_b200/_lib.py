@@ -42,7 +42,8 @@ class CaviarArgs(C.Structure):
                 ("phi_cov_hist_dev", C.c_void_p), ("z_hist_dev", C.c_void_p),
                 ("nnz_cap", C.c_int64), ("workspace_dev", C.c_void_p), ("workspace_bytes", C.c_size_t),
                 ("status_dev", C.c_void_p),
-                ("lam_csr_val_dev", C.c_void_p), ("lam_csr_col_dev", C.c_void_p), ("lam_csr_ptr_dev", C.c_void_p)]
+                ("lam_csr_val_dev", C.c_void_p), ("lam_csr_col_dev", C.c_void_p), ("lam_csr_ptr_dev", C.c_void_p),
+                ("cta_variant", C.c_int)]
 
 
 class SimOptions(C.Structure):
@@ -59,7 +60,7 @@ class SimOptions(C.Structure):
 EXPORTS = ["cm_version", "cm_last_error", "cm_device_info", "cm_nwd_create", "cm_nwd_destroy", "cm_nwd_forward",
            "cm_nwd_set_precision",
            "cm_caviar_workspace_bytes", "cm_caviar_fit", "cm_caviar_scan_stim", "cm_caviar_scan_scratch_bytes",
-           "cm_pack_stim_u8", "cm_simulate", "cm_simulate_workspace_bytes", "cm_last_launch_count", "cm_last_main_kernel_ms",
+           "cm_pack_stim_u8", "cm_expand_stim_coo", "cm_simulate", "cm_simulate_workspace_bytes", "cm_last_launch_count", "cm_last_main_kernel_ms",
            "cm_caviar_debug_phase_cycles", "cm_nwd_debug_cycles", "cm_nwd_mt_debug_cycles", "cm_nwd_mt_debug_dump", "cm_nwd_mt_pack"]
 
 _lib = None
@@ -92,6 +93,8 @@ def load():
     lib.cm_caviar_scan_scratch_bytes.restype = C.c_size_t
     lib.cm_caviar_scan_stim.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.POINTER(C.c_int64),
                                         C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_void_p]
+    lib.cm_expand_stim_coo.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                       C.c_void_p]
     lib.cm_simulate_workspace_bytes.restype = C.c_size_t
     lib.cm_simulate_workspace_bytes.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
     lib.cm_simulate.argtypes = [C.POINTER(SimOptions), C.c_int, C.POINTER(C.c_uint64), C.c_void_p, C.c_int, C.c_void_p,

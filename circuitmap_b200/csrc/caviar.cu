@@ -556,7 +556,9 @@ extern "C" int cm_caviar_debug_phase_cycles(long long* out, int n, int enable) {
 }
 
 // CTA variant of the persistent kernel: 16-warp CTAs (one per SM) unless the batch has at least two fits per SM
-static bool use_small_cta(int B) {
+static bool use_small_cta(int B, int forced) {
+    if (forced == 256) return true;
+    if (forced == 512) return false;
     if (const char* f = getenv("CM_CAVIAR_CTA")) {            // diagnostics: force a variant ("256" / "512")
         if (!strcmp(f, "256")) return true;
         if (!strcmp(f, "512")) return false;
@@ -609,7 +611,8 @@ extern "C" int cm_caviar_fit(const cm_caviar_args* a, void* stream) {
     if (!a->psc_dev && !(a->y_dev && a->ss_dev)) { set_error("cm_caviar_fit: need psc_dev or (y_dev, ss_dev)"); return CM_EINVAL; }
     if (a->opt.iters < 0 || a->opt.num_mc_samples < 1) { set_error("cm_caviar_fit: bad iters/num_mc_samples"); return CM_EINVAL; }
     const bool want_lamhist = a->opt.save_histories && a->lam_hist_dev;
-    const bool small_cta = use_small_cta(a->B);
+    if (a->cta_variant != 0 && a->cta_variant != 256 && a->cta_variant != 512) { set_error("cm_caviar_fit: cta_variant must be 0, 256 or 512"); return CM_EINVAL; }
+    const bool small_cta = use_small_cta(a->B, a->cta_variant);
     const Layout L = small_cta ? make_layout(a->N, a->K, a->nnz_cap, a->opt.iters, want_lamhist, fit256::GCT, fit256::NW)
                                : make_layout(a->N, a->K, a->nnz_cap, a->opt.iters, want_lamhist, fit512::GCT, fit512::NW);
     const size_t need = L.stride * (size_t)a->B + (size_t)a->B * 8 + 512;

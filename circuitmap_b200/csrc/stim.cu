@@ -63,6 +63,18 @@ __global__ void __launch_bounds__(256) scan_stim_kernel(const T* __restrict__ x,
     if ((threadIdx.x & 31) == 0 && nz) atomicAdd(&o->nnz, nz);
 }
 
+// sparse design (COO triples) -> dense uint8 codes on the device: what a compressive design really is (nnz <= K H entries)
+// crosses the bus, the N x K code matrix the index builder streams exists in HBM only
+__global__ void __launch_bounds__(256) expand_coo_kernel(const int* __restrict__ neuron, const int* __restrict__ trial,
+                                                         const unsigned char* __restrict__ code, long long nnz, int N, int K,
+                                                         unsigned char* __restrict__ out, int* status) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nnz) return;
+    const int n = neuron[i], k = trial[i];
+    if (n < 0 || n >= N || k < 0 || k >= K) { if (status) atomicExch(status, CM_EINVAL); return; }
+    out[(size_t)n * K + k] = code[i];
+}
+
 // host side ------------------------------------------------------------------------------------------------------
 template <typename T>
 static void host_distinct(const T* x, long long lo, long long hi, std::vector<double>& vals, std::atomic<int>& too_many,
@@ -195,6 +207,24 @@ extern "C" int cm_caviar_scan_stim(const void* stim_dev, int dtype, int64_t coun
         if (h.slot[i] != stim::EMPTY) { double v; memcpy(&v, &h.slot[i], 8); values_out[n++] = v; }
     std::sort(values_out, values_out + n);
     *n_values_out = h.overflow ? stim::SLOTS + 1 : n;
+    return CM_OK;
+}
+
+extern "C" int cm_expand_stim_coo(const int* neuron_dev, const int* trial_dev, const unsigned char* code_dev, int64_t nnz, int N,
+                                  int K, unsigned char* codes_out_dev, int* status_dev, void* stream) {
+    reset_launch_count();
+    if (!codes_out_dev || N <= 0 || K <= 0 || nnz < 0 || (nnz > 0 && (!neuron_dev || !trial_dev || !code_dev))) {
+        set_error("cm_expand_stim_coo: bad arguments");
+        return CM_EINVAL;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    CM_CUDA_CHECK(cudaMemsetAsync(codes_out_dev, 0, (size_t)N * K, st));
+    if (nnz > 0) {
+        stim::expand_coo_kernel<<<(unsigned)((nnz + 255) / 256), 256, 0, st>>>(neuron_dev, trial_dev, code_dev, nnz, N, K,
+                                                                              codes_out_dev, status_dev);
+        count_launch();
+    }
+    CM_CUDA_CHECK(cudaGetLastError());
     return CM_OK;
 }
 

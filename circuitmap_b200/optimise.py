@@ -106,6 +106,30 @@ def pack_stim_host(I, threads=None):
     return buf[:n].view(I.shape), np.array(powers[:P.value], dtype=np.float64), int(nnz.value)
 
 
+def codes_to_coo(codes):
+    """Dense uint8 design codes (N, K) (host or device tensor) -> pinned host triples (neuron int32, trial int32, code uint8),
+    ordered by neuron then trial.  Set-up helper for the sparse upload of `streaming.FitPipeline(design='coo')`."""
+    import torch
+    idx = torch.nonzero(codes)                       # (nnz, 2), row-major order
+    vals = codes[idx[:, 0], idx[:, 1]]
+    pin = (lambda t: t.cpu().pin_memory()) if torch.cuda.is_available() else (lambda t: t.cpu())
+    return pin(idx[:, 0].to(torch.int32).contiguous()), pin(idx[:, 1].to(torch.int32).contiguous()), pin(vals.contiguous())
+
+
+def expand_coo(neuron_dev, trial_dev, code_dev, N, K, out=None):
+    """Device triples -> dense uint8 code matrix (N, K) on the device (`cm_expand_stim_coo`, csrc/stim.cu)."""
+    import torch
+    lib = _lib.load()
+    dev = code_dev.device
+    if out is None:
+        out = torch.empty((N, K), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream().cuda_stream
+        _lib.check(lib.cm_expand_stim_coo(neuron_dev.data_ptr(), trial_dev.data_ptr(), code_dev.data_ptr(), code_dev.numel(),
+                                          N, K, out.data_ptr(), None, C.c_void_p(stream)), "cm_expand_stim_coo")
+    return out
+
+
 class CsrLam:
     """Sparse posterior of one fit: CSR over (neuron, trial) of the entries `lam` can be non-zero on.  `toarray()`
     gives the dense (N, K) float64 array the reference returns (caviar.py:100)."""
@@ -128,7 +152,7 @@ class CsrLam:
 
 def caviar_batched(stim, powers, mu_prior, beta_prior, shape_prior, rate_prior, phi_prior, phi_cov_prior, psc=None,
                    y=None, ss=None, seeds=None, nnz_cap=None, want_lam=True, lam_csr=False, workspace=None, out=None,
-                   **fit_options):
+                   cta_variant=0, **fit_options):
     """B fits on the current CUDA device.  All array arguments are CUDA tensors:
          stim (B,N,K) f32/f64 laser powers or uint8 power codes (c = powers[c-1], 0 = not targeted);
          psc (B,K,T) f32/f64 or (y, ss) (B,K) f64; priors (B,N[,2[,2]]) f64.
@@ -223,6 +247,7 @@ def caviar_batched(stim, powers, mu_prior, beta_prior, shape_prior, rate_prior, 
     if lam_csr:
         a.lam_csr_val_dev, a.lam_csr_col_dev = out["lam_csr_val"].data_ptr(), out["lam_csr_col"].data_ptr()
         a.lam_csr_ptr_dev = out["lam_csr_ptr"].data_ptr()
+    a.cta_variant = int(cta_variant)
     a.nnz_cap = nnz_cap
     a.workspace_dev, a.workspace_bytes = workspace.data_ptr(), workspace.numel()
     a.status_dev = out["status"].data_ptr()

@@ -126,34 +126,46 @@ def fit_pinned(host_stim, host_psc, dev_stim, dev_psc, powers, priors, seeds, ho
 
 class FitPipeline:
     """The pipeline users run (README.md:28-51 of the reference: demix -> fit), streamed from pinned host memory in the
-    compact formats the data really has, double-buffered on three streams:
+    compact formats the data really has:
 
         host (pinned):  traces (K, T) float32   +   design (N, K) uint8 power codes (cm_pack_stim_u8)
+                                                     or its nnz (neuron, trial, code) triples (design='coo': 9 nnz bytes)
           -- H2D -->  [NeuralDemixer forward: y = trapz, sum x^2 stay on the device]  -->  cm_caviar_fit
           -- D2H -->  mu, beta, shape, rate, phi, phi_cov, z  +  lam as CSR (8 nnz bytes instead of 8 N K)
 
-    Chunk i+1's upload, chunk i's kernels and chunk i-1's download overlap; `on_result(lo, hi, views)` receives pinned
-    host views of fits lo..hi-1 in order (valid until it returns).  `views['lam']` is a list of optimise.CsrLam.
-    Bit-identical to calling NeuralDemixer / caviar_batched on each map (every fit is independent of its batch mates).
+    `depth` chunks are in flight: one upload stream, one download stream and `depth` compute streams whose fit kernels
+    (forced to the two-CTAs-per-SM variant) share the SMs, so the GPU runs a full complement of fits while the next chunk's
+    traces are still on the bus.  `on_result(lo, hi, views)` receives pinned host views of fits lo..hi-1 in order (valid until
+    it returns); `views['lam']` is a list of optimise.CsrLam.  Bit-identical to calling NeuralDemixer / caviar_batched on
+    each map (every fit is independent of its batch mates).
     """
 
     OUT_KEYS = ("mu", "beta", "shape", "rate", "phi", "phi_cov", "z", "status", "lam_csr_val", "lam_csr_col",
                 "lam_csr_ptr")
 
-    def __init__(self, N, K, powers, chunk, nnz_cap, device=None, demixer=None, T=900, priors=None, **fit_options):
+    def __init__(self, N, K, powers, chunk, nnz_cap, device=None, demixer=None, T=900, priors=None, design="codes",
+                 depth=2, **fit_options):
         import numpy as np
         import torch
         self.N, self.K, self.T, self.chunk, self.nnz_cap = int(N), int(K), int(T), int(chunk), int(nnz_cap)
+        self.depth = max(1, int(depth))
         self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.powers = np.ascontiguousarray(powers, dtype=np.float64)
         self.demixer = demixer
+        if design not in ("codes", "coo"):
+            raise ValueError("design must be 'codes' (dense uint8 matrix) or 'coo' (sparse triples)")
+        self.design = design           # 'coo': host_stim[b] = (neuron int32, trial int32, code uint8) pinned triples of length nnz_b
         self.fit_options = dict(fit_options)
-        d, c = self.dev, self.chunk
-        self.dev_stim = [torch.empty((c, N, K), dtype=torch.uint8, device=d) for _ in range(2)]
-        self.dev_psc = [torch.empty((c, K, T), dtype=torch.float32, device=d) for _ in range(2)]
-        self.dev_dem = torch.empty((c * K, T), dtype=torch.float32, device=d) if demixer is not None else None
-        self.dev_out = [None, None]
-        self.workspace = None
+        d, c, D = self.dev, self.chunk, self.depth
+        self.dev_stim = [torch.empty((c, N, K), dtype=torch.uint8, device=d) for _ in range(D)]
+        self.dev_psc = [torch.empty((c, K, T), dtype=torch.float32, device=d) for _ in range(D)]
+        self.dev_dem = [torch.empty((c * K, T), dtype=torch.float32, device=d) if demixer is not None else None for _ in range(D)]
+        if design == "coo":
+            self.dev_coo = [(torch.empty((c, self.nnz_cap), dtype=torch.int32, device=d),
+                             torch.empty((c, self.nnz_cap), dtype=torch.int32, device=d),
+                             torch.empty((c, self.nnz_cap), dtype=torch.uint8, device=d)) for _ in range(D)]
+        self.dev_out = [None] * D
+        self.workspace = [None] * D
         f64 = dict(dtype=torch.float64, device=d)
         if priors is None:                                                       # model.py:24-31
             cov = torch.zeros(c, N, 2, 2, **f64)
@@ -167,24 +179,26 @@ class FitPipeline:
         self.host_out = [dict({k: torch.empty(v, dtype=torch.float64).pin_memory() for k, v in shapes.items()},
                               status=torch.empty((c,), dtype=torch.int32).pin_memory(),
                               lam_csr_col=torch.empty((c, self.nnz_cap), dtype=torch.int32).pin_memory(),
-                              lam_csr_ptr=torch.empty((c, N + 1), dtype=torch.int32).pin_memory()) for _ in range(2)]
-        self.streams = _Streams(d)
-        self.h2d_bytes_per_fit = N * K + K * T * 4
+                              lam_csr_ptr=torch.empty((c, N + 1), dtype=torch.int32).pin_memory()) for _ in range(D)]
+        self.copy_in, self.copy_out = torch.cuda.Stream(device=d), torch.cuda.Stream(device=d)
+        self.compute = [torch.cuda.Stream(device=d) for _ in range(D)]
+        self.h2d_bytes_per_fit = (N * K if design == "codes" else 9 * self.nnz_cap) + K * T * 4
         self.d2h_bytes_per_fit = sum(t[0].numel() * t.element_size() for t in self.host_out[0].values())
 
     def run(self, host_stim, host_psc, seeds, on_result=None):
-        """host_stim[b]: pinned uint8 (N, K); host_psc[b]: pinned float32 (K, T) -- raw traces when the pipeline has a
-        demixer, demixed ones otherwise.  Returns the number of fits that reported a non-zero status."""
+        """host_stim[b]: pinned uint8 (N, K) -- or, with design='coo', pinned triples (neuron, trial, code) of the non-zero
+        entries (optimise.codes_to_coo); host_psc[b]: pinned float32 (K, T) -- raw traces when the pipeline has a demixer,
+        demixed ones otherwise.  Returns the number of fits that reported a non-zero status."""
         import torch
-        st, c, K, T = self.streams, self.chunk, self.K, self.T
+        c, K, T, D = self.chunk, self.K, self.T, self.depth
         B = len(host_stim)
         cur = torch.cuda.current_stream(self.dev)
-        for s in (st.copy_in, st.compute, st.copy_out):
+        for s in [self.copy_in, self.copy_out] + self.compute:
             s.wait_stream(cur)
         mu0, beta0, shape0, rate0, phi0, cov0 = self.priors
-        ev_compute = [None, None]          # compute of the chunk that last used staging set s
-        ev_out = [None, None]              # D2H of the chunk that last used output set s
-        pending, failed = None, 0
+        ev_compute = [None] * D            # compute of the chunk that last used set s
+        ev_out = [None] * D                # D2H of the chunk that last used set s
+        pending, failed = [], 0
 
         def drain(item):
             nonlocal failed
@@ -201,46 +215,58 @@ class FitPipeline:
 
         for ci, lo in enumerate(range(0, B, c)):
             hi = min(lo + c, B)
-            n, s_ = hi - lo, ci & 1
-            with torch.cuda.stream(st.copy_in):
+            n, s_ = hi - lo, ci % D
+            while pending and pending[0][2] == s_:
+                drain(pending.pop(0))                           # the pinned output slabs of this set are handed over first
+            with torch.cuda.stream(self.copy_in):
                 if ev_compute[s_] is not None:
-                    st.copy_in.wait_event(ev_compute[s_])      # the kernels that read this staging set are done
+                    self.copy_in.wait_event(ev_compute[s_])     # the kernels that read this staging set are done
                 for i, b in enumerate(range(lo, hi)):
-                    self.dev_stim[s_][i].copy_(host_stim[b], non_blocking=True)
+                    if self.design == "coo":
+                        hn, ht, hc = host_stim[b]
+                        m = hc.numel()
+                        dn, dt_, dc = self.dev_coo[s_]
+                        dn[i, :m].copy_(hn, non_blocking=True)
+                        dt_[i, :m].copy_(ht, non_blocking=True)
+                        dc[i, :m].copy_(hc, non_blocking=True)
+                    else:
+                        self.dev_stim[s_][i].copy_(host_stim[b], non_blocking=True)
                     self.dev_psc[s_][i].copy_(host_psc[b], non_blocking=True)
-                ready = st.copy_in.record_event()
-            if pending is not None and pending[2] == s_:
-                drain(pending)                                  # (only with a single chunk in flight)
-                pending = None
-            with torch.cuda.stream(st.compute):
-                st.compute.wait_event(ready)
+                ready = self.copy_in.record_event()
+            cs = self.compute[s_]
+            with torch.cuda.stream(cs):
+                cs.wait_event(ready)
                 if ev_out[s_] is not None:
-                    st.compute.wait_event(ev_out[s_])           # this output set has been copied out
-                src = {}
+                    cs.wait_event(ev_out[s_])                   # this output set has been copied out
+                if self.design == "coo":                        # scatter the triples into the dense code matrices (HBM only)
+                    dn, dt_, dc = self.dev_coo[s_]
+                    for i, b in enumerate(range(lo, hi)):
+                        m = host_stim[b][2].numel()
+                        optimise.expand_coo(dn[i, :m], dt_[i, :m], dc[i, :m], self.N, self.K, out=self.dev_stim[s_][i])
                 if self.demixer is not None:
-                    _, y, ss = self.demixer.forward_device(self.dev_psc[s_][:n].reshape(n * K, T), out=self.dev_dem[:n * K],
+                    _, y, ss = self.demixer.forward_device(self.dev_psc[s_][:n].reshape(n * K, T), out=self.dev_dem[s_][:n * K],
                                                            stats=True)
                     src = dict(y=y.view(n, K), ss=ss.view(n, K))
                 else:
                     src = dict(psc=self.dev_psc[s_][:n])
                 out = optimise.caviar_batched(self.dev_stim[s_][:n], self.powers, mu0[:n], beta0[:n], shape0, rate0,
                                               phi0[:n], cov0[:n], seeds=list(seeds[lo:hi]), nnz_cap=self.nnz_cap,
-                                              want_lam=False, lam_csr=True, workspace=self.workspace,
-                                              out=self.dev_out[s_], **src, **self.fit_options)
-                self.workspace = out["_workspace"]
+                                              want_lam=False, lam_csr=True, workspace=self.workspace[s_],
+                                              out=self.dev_out[s_], cta_variant=256 if D > 1 else 0, **src, **self.fit_options)
+                self.workspace[s_] = out["_workspace"]
                 self.dev_out[s_] = out
-                ev_compute[s_] = st.compute.record_event()
-            with torch.cuda.stream(st.copy_out):
-                st.copy_out.wait_event(ev_compute[s_])
+                ev_compute[s_] = cs.record_event()
+            with torch.cuda.stream(self.copy_out):
+                self.copy_out.wait_event(ev_compute[s_])
                 ho = self.host_out[s_]
                 for k in self.OUT_KEYS:
                     ho[k][:n].copy_(out[k], non_blocking=True)
-                ev_out[s_] = st.copy_out.record_event()
-            if pending is not None:
-                drain(pending)                                  # deliver chunk ci-1 while chunk ci is in flight
-            pending = (lo, hi, s_, ev_out[s_])
-        if pending is not None:
-            drain(pending)
-        cur.wait_stream(st.compute)
-        cur.wait_stream(st.copy_out)
+                ev_out[s_] = self.copy_out.record_event()
+            pending.append((lo, hi, s_, ev_out[s_]))
+            while pending and pending[0][3].query():
+                drain(pending.pop(0))                           # deliver whatever has already arrived
+        while pending:
+            drain(pending.pop(0))
+        for s in [self.copy_out] + self.compute:
+            cur.wait_stream(s)
         return failed

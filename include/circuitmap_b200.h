@@ -144,6 +144,10 @@ typedef struct cm_caviar_args {
     double*  lam_csr_val_dev;    /* B x nnz_cap */
     int32_t* lam_csr_col_dev;    /* B x nnz_cap  trial index of every entry */
     int32_t* lam_csr_ptr_dev;    /* B x (N + 1)  row pointers; entries past ptr[N] are unspecified */
+    /* CTA variant of the persistent kernel: 0 = automatic (512-thread CTAs, one per SM, while the batch fits one wave of them;
+     * 256-thread CTAs, two per SM, beyond), 256 / 512 = forced.  Launches that are meant to overlap on the GPU (chunks of a
+     * stream, streaming.FitPipeline) force 256 so that CTAs of two launches share an SM. */
+    int cta_variant;
 } cm_caviar_args;
 
 CM_API size_t cm_caviar_workspace_bytes(int B, int N, int K, int64_t nnz_cap, int save_histories);
@@ -156,6 +160,11 @@ CM_API int    cm_caviar_fit(const cm_caviar_args* a, void* stream);
 CM_API size_t cm_caviar_scan_scratch_bytes(void);
 CM_API int    cm_caviar_scan_stim(const void* stim_dev, int dtype, int64_t count, void* scratch_dev, int64_t* nnz_out,
                                   double* values_out, int* n_values_out, void* stream);
+/* Sparse design -> dense uint8 codes ON THE DEVICE: nnz (neuron, trial, code) triples (device arrays) are scattered into the zeroed
+ * N x K code matrix codes_out_dev that cm_caviar_fit takes as a CM_U8 stimulus.  A compressive design has nnz <= K H entries, so
+ * 9 nnz bytes cross the bus instead of N K.  status_dev (one int, may be NULL) receives CM_EINVAL for an out-of-range index. */
+CM_API int    cm_expand_stim_coo(const int* neuron_dev, const int* trial_dev, const unsigned char* code_dev, int64_t nnz, int N, int K,
+                                 unsigned char* codes_out_dev, int* status_dev, void* stream);
 /* HOST helper (no device work, `threads` worker threads): powers = np.unique(stim)[1:] (caviar.py:42) into powers_out
  * (CM_CAVIAR_MAX_POWERS doubles), the number of non-zero entries, and -- if codes_out != NULL -- the design as uint8
  * power codes for the CM_U8 stimulus dtype (N*K bytes to upload instead of 8*N*K).  stim_host: CM_F32 or CM_F64. */

@@ -122,9 +122,10 @@ def test_fit_pipeline_compact_formats_equal_the_batched_call(with_demixer):
     stim = torch.stack([torch.from_numpy(np.ascontiguousarray(s["stim_matrix"])).cuda() for s in sims]).contiguous()
     if with_demixer:
         _, y, ss = dem.forward_device(psc32.reshape(B * K, 900), stats=True)
-        ref = optimise.caviar_batched(stim, powers, *pri, y=y.view(B, K), ss=ss.view(B, K), seeds=seeds, iters=10, msrmp=0.4)
-    else:
-        ref = optimise.caviar_batched(stim, powers, *pri, psc=psc32, seeds=seeds, iters=10, msrmp=0.4)
+        ref = optimise.caviar_batched(stim, powers, *pri, y=y.view(B, K), ss=ss.view(B, K), seeds=seeds, iters=10, msrmp=0.4,
+                                      cta_variant=256)
+    else:   # (the pipeline's chunks run the two-CTAs-per-SM variant so that they can share the SMs; same variant here)
+        ref = optimise.caviar_batched(stim, powers, *pri, psc=psc32, seeds=seeds, iters=10, msrmp=0.4, cta_variant=256)
     for chunk in (2, 5):
         pipe = streaming.FitPipeline(N, K, powers, chunk=chunk, nnz_cap=nnz_cap, demixer=dem, iters=10, msrmp=0.4)
         got = {}
@@ -139,3 +140,13 @@ def test_fit_pipeline_compact_formats_equal_the_batched_call(with_demixer):
             for k in ("mu", "beta", "shape", "rate", "phi", "phi_cov", "z", "lam"):
                 assert np.array_equal(got[b][k], ref[k][b].cpu().numpy(), equal_nan=True), (chunk, b, k)
         assert pipe.h2d_bytes_per_fit == N * K + K * 900 * 4
+    # the design as sparse triples (9 nnz bytes per fit instead of N K), expanded to the code matrix on the device
+    coo = [optimise.codes_to_coo(c) for c in codes]
+    assert all(t[2].numel() <= nnz_cap for t in coo)
+    pipe = streaming.FitPipeline(N, K, powers, chunk=2, nnz_cap=nnz_cap, demixer=dem, design="coo", depth=3, iters=10, msrmp=0.4)
+    got = {}
+    assert pipe.run(coo, traces, seeds, on_result) == 0 and sorted(got) == list(range(B))
+    for b in range(B):
+        for k in ("mu", "beta", "shape", "rate", "phi", "phi_cov", "z", "lam"):
+            assert np.array_equal(got[b][k], ref[k][b].cpu().numpy(), equal_nan=True), ("coo", b, k)
+    assert pipe.h2d_bytes_per_fit == 9 * nnz_cap + K * 900 * 4
