@@ -1863,23 +1863,52 @@ __global__ void __launch_bounds__(NT, (NT == 512) ? 1 : 2) caviar_fit_kernel(con
         for (int r = 0; r < rounds; ++r) {
             const uint32_t s0 = sc_subkeys[2 * r], s1 = sc_subkeys[2 * r + 1];
             const int h = (N + 1) / 2;
-            for (int q = threadIdx.x; q < h; q += NT) {
-                uint32_t x0 = (uint32_t)q, x1 = (h + q < N) ? (uint32_t)(h + q) : 0u;
-                threefry2x32(s0, s1, x0, x1);
-                c.sortkeys[q] = x0;
-                if (h + q < N) c.sortkeys[h + q] = x1;
-            }
-            __syncthreads();
-            for (int i = threadIdx.x; i < N; i += NT) {
-                const uint32_t ki = c.sortkeys[i];
-                int rank = 0;
-                for (int j = 0; j < N; ++j) {
-                    const uint32_t kj = c.sortkeys[j];
-                    rank += (kj < ki) || (kj == ki && j < i);
+            // stable sort of the current order by fresh 32-bit keys = sort of the unique 64-bit composites (key, position)
+            int npow = 1;
+            while (npow < N) npow <<= 1;
+            if (npow <= c.smd) {                                // bitonic network in shared memory (C3: 1024, C5: 8192 entries)
+                unsigned long long* sk = reinterpret_cast<unsigned long long*>(c.sm);
+                for (int q = threadIdx.x; q < h; q += NT) {
+                    uint32_t x0 = (uint32_t)q, x1 = (h + q < N) ? (uint32_t)(h + q) : 0u;
+                    threefry2x32(s0, s1, x0, x1);
+                    sk[q] = ((unsigned long long)x0 << 32) | (uint32_t)q;
+                    if (h + q < N) sk[h + q] = ((unsigned long long)x1 << 32) | (uint32_t)(h + q);
                 }
-                c.order2[rank] = c.order[i];
+                for (int q = N + threadIdx.x; q < npow; q += NT) sk[q] = ~0ull;
+                __syncthreads();
+                for (int kk = 2; kk <= npow; kk <<= 1)
+                    for (int jj = kk >> 1; jj > 0; jj >>= 1) {
+                        for (int q = threadIdx.x; q < npow; q += NT) {
+                            const int partner = q ^ jj;
+                            if (partner > q) {
+                                const unsigned long long a = sk[q], b = sk[partner];
+                                const bool up = (q & kk) == 0;
+                                if ((a > b) == up) { sk[q] = b; sk[partner] = a; }
+                            }
+                        }
+                        __syncthreads();
+                    }
+                for (int q = threadIdx.x; q < N; q += NT) c.order2[q] = c.order[(int)(sk[q] & 0xffffffffull)];
+                __syncthreads();
+            } else {
+                for (int q = threadIdx.x; q < h; q += NT) {
+                    uint32_t x0 = (uint32_t)q, x1 = (h + q < N) ? (uint32_t)(h + q) : 0u;
+                    threefry2x32(s0, s1, x0, x1);
+                    c.sortkeys[q] = x0;
+                    if (h + q < N) c.sortkeys[h + q] = x1;
+                }
+                __syncthreads();
+                for (int i = threadIdx.x; i < N; i += NT) {
+                    const uint32_t ki = c.sortkeys[i];
+                    int rank = 0;
+                    for (int j = 0; j < N; ++j) {
+                        const uint32_t kj = c.sortkeys[j];
+                        rank += (kj < ki) || (kj == ki && j < i);
+                    }
+                    c.order2[rank] = c.order[i];
+                }
+                __syncthreads();
             }
-            __syncthreads();
             for (int n = threadIdx.x; n < N; n += NT) c.order[n] = c.order2[n];
             __syncthreads();
         }
@@ -2100,10 +2129,13 @@ __global__ void __launch_bounds__(NT, (NT == 512) ? 1 : 2) caviar_fit_kernel(con
         __syncthreads();
         int remaining = nd;
         bool recount = true;
+        int nzz = 0;
         while (remaining > 0) {
-            int nzz = 0;
-            for (int k = threadIdx.x; k < K; k += NT) nzz += (c.z[k] != 0.0);
-            nzz = block_sum_int(nzz, red);
+            if (recount) {                                   // #(z != 0) only changes when a cell is reconnected
+                nzz = 0;
+                for (int k = threadIdx.x; k < K; k += NT) nzz += (c.z[k] != 0.0);
+                nzz = block_sum_int(nzz, red);
+            }
             if (!((double)nzz > o.minimum_spike_count)) break;
             if (recount) {
                 for (int i = wid; i < nd; i += NW) {
