@@ -37,7 +37,7 @@ struct Layout {
     size_t stride;
     // fp64
     size_t X, PA, PB, lam, cst, y, ss, pred, resid, z, mu, beta, bvec, dvec, wvec, slam, slam2, sp, phibar, phi,
-        phicov, phiz, phicovz, lamhist, lamT, growbuf, cscq, rcnt;
+        phicov, phiz, phicovz, lamhist, lamT, growbuf, cscq, rcnt, mce;
     // int32 / uint32
     size_t row_ptr, col_ptr, colfill, col_k, csc_row, csc_pos, cntp, n0p, n1p, act, ainv, order, order2, pos, rownz,
         phizok, sortkeys, keys, dcnt, dlist, colpw, nmask, chinfo, ccol_ptr, ccsc_row, ccsc_pos, member, rowcb;
@@ -79,6 +79,7 @@ static Layout make_layout(int N, int K, int64_t nnz, int iters, bool lamhist, in
     L.lamhist = take(lamhist ? (size_t)iters * z * 8 : 0);
     L.lamT = take(z * 8);
     L.rcnt = take(n * PMAX * 8);
+    L.mce = take(n * PMAX * 8);
     L.row_ptr = take((n + 1) * 4);
     L.col_ptr = take((k + 1) * 4);
     L.colfill = take(k * 4);

@@ -27,7 +27,7 @@ struct Ctx {
     long long* tlast;   // shared: last phase timestamp (block 0 / thread 0 only)
     int N, K, P, nnz, it;
     double *X, *PA, *PB, *lam, *cst, *y, *ss, *pred, *resid, *z, *mu, *beta, *bvec, *dvec, *wvec, *slam, *slam2, *sp,
-        *phibar, *phi, *phicov, *phiz, *phicovz, *lamhist, *lamT, *growbuf, *rcnt;
+        *phibar, *phi, *phicov, *phiz, *phicovz, *lamhist, *lamT, *growbuf, *rcnt, *mce;
     double2* cscq;    // per CSC entry: (active index of the row as int bits, lam) -- rebuilt every a2
     int *row_ptr, *col_ptr, *col_k, *csc_row, *csc_pos, *cntp, *n0p, *n1p, *act, *ainv, *order, *order2, *pos, *rownz,
         *phizok, *dcnt, *dlist, *colpw, *nmask;
@@ -420,9 +420,16 @@ constexpr long long WATCHDOG_CYCLES = 1ll << 36;      // ~35 s at 1.9 GHz for a 
 constexpr int CM_EHELPER = 9;
 
 __device__ __noinline__ void newton_rows(const Ctx& c, const double* powers, const int* list, int nlist, int part, int nparts);
-// Monte-Carlo means of the truncated-normal sigmoid coefficients of every neuron (caviar.py:209-215, App. A.2); one warp
-// per neuron, neurons are independent
-__device__ void mc_means(const Ctx& c, const uint32_t* keys_cur, int S, int part, int nparts) {
+// Monte-Carlo term of update_lam (caviar.py:209-215,233-235) per (neuron, power): mcE = mean_s log(f_s / (1 - f_s)) with
+// f_s = sigmoid(phi0_s I - phi1_s) over the S truncated-normal samples.  log(f / (1 - f)) IS its argument, so the mean
+// collapses to mean(phi0) I - mean(phi1) (App. A.2) -- as long as no sample saturates the float64 sigmoid: 1 - f loses its
+// bits as x grows (the reference's own value is rounding noise of 2^-53 e^x per sample: 2e-4 at x = 28, 1 at x = 36) and
+// from x ~ 36.7 on it is +inf (f rounds to 1).  So the linear form is used when the LARGEST possible argument
+// max(phi0) I - min(phi1) is <= 28 (every reference experiment: powers <= 70 give <= ~23 even with the prior's wide phi),
+// and the reference's own expression is evaluated sample by sample otherwise (large powers / wide phi
+// posteriors).  One warp per neuron; even lanes carry phi0 samples, odd lanes phi1.
+constexpr double MC_LITERAL_X = 28.0;
+__device__ void mc_means(const Ctx& c, const uint32_t* keys_cur, int S, const double* powers, int part, int nparts) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     for (int n = part * NW + wid; n < c.N; n += nparts * NW) {
         if (c.dcnt[n]) continue;
@@ -432,16 +439,63 @@ __device__ void mc_means(const Ctx& c, const uint32_t* keys_cur, int S, int part
         const double mean = c.phi[2 * n + cc];
         const double sd = c.phicov[4 * n + 3 * cc];                // diag(phi_cov): a variance used as sd
         const double cdf0 = normcdf(-mean / sd);
-        double acc = 0.0;
+        double acc = 0.0, ext = -CUDART_INF;                       // ext: max phi0 (even lanes) / max of -phi1 (odd lanes)
         for (int e = lane; e < 2 * S; e += 32) {
             uint32_t x0 = (uint32_t)e, x1 = (uint32_t)(2 * S + e);
             threefry2x32(k0, k1, x0, x1);
             const double u = bits_to_unit_double(x0, x1);
-            acc += normcdfinv(cdf0 + u * (1.0 - cdf0)) * sd + mean;
+            const double smp = normcdfinv(cdf0 + u * (1.0 - cdf0)) * sd + mean;
+            acc += smp;
+            ext = fmax(ext, cc ? -smp : smp);
         }
 #pragma unroll
-        for (int off = 16; off > 1; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+        for (int off = 16; off > 1; off >>= 1) {
+            acc += __shfl_xor_sync(0xffffffffu, acc, off);
+            ext = fmax(ext, __shfl_xor_sync(0xffffffffu, ext, off));
+        }
         if (lane < 2) c.phibar[2 * n + lane] = acc / (double)S;
+        const double pb0 = __shfl_sync(0xffffffffu, acc, 0) / (double)S, pb1 = __shfl_sync(0xffffffffu, acc, 1) / (double)S;
+        const double p0max = __shfl_sync(0xffffffffu, ext, 0), p1min = -__shfl_sync(0xffffffffu, ext, 1);
+        bool lit = false;
+        double pw = 0.0;
+        if (lane < c.P) {
+            pw = powers[lane];
+            lit = !(p0max * pw - p1min <= MC_LITERAL_X);           // also taken for NaN / inf samples, as the reference would propagate them
+            c.mce[n * PMAX + lane] = pb0 * pw - pb1;
+        }
+        unsigned need = __ballot_sync(0xffffffffu, lit);
+        if (need) {                                                // rare: the reference's expression, sample by sample
+            double lacc[PMAX];
+#pragma unroll
+            for (int p = 0; p < PMAX; ++p) lacc[p] = 0.0;
+            for (int e0 = 0; e0 < 2 * S; e0 += 32) {               // uniform trip count: the shuffle below needs the whole warp
+                const int e = e0 + lane;
+                double smp = 0.0;
+                if (e < 2 * S) {
+                    uint32_t x0 = (uint32_t)e, x1 = (uint32_t)(2 * S + e);
+                    threefry2x32(k0, k1, x0, x1);
+                    const double u = bits_to_unit_double(x0, x1);
+                    smp = normcdfinv(cdf0 + u * (1.0 - cdf0)) * sd + mean;
+                }
+                const double other = __shfl_xor_sync(0xffffffffu, smp, 1);     // even lanes: phi1 of the same sample
+                if (cc == 0 && e < 2 * S) {
+#pragma unroll
+                    for (int p = 0; p < PMAX; ++p)
+                        if (need & (1u << p)) {
+                            const double f = sigmoid_d(smp * powers[p] - other);
+                            lacc[p] += log(f / (1.0 - f));
+                        }
+                }
+            }
+#pragma unroll
+            for (int p = 0; p < PMAX; ++p)
+                if (need & (1u << p)) {
+                    double v = lacc[p];
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+                    if (lane == 0) c.mce[n * PMAX + p] = v / (double)S;
+                }
+        }
     }
 }
 
@@ -529,7 +583,7 @@ __device__ void helper_loop(const Ctx& c, GemmPipe& gp) {
         } else if (type == 3) {
             newton_rows(c, powers, c.dlist, a, c.role, c.ct);
         } else if (type == 4) {
-            mc_means(c, c.keys + (size_t)a * 2 * c.N, b, c.role, c.ct);
+            mc_means(c, c.keys + (size_t)a * 2 * c.N, b, powers, c.role, c.ct);
         } else if (type == 5) {
             a2_wvec(c, a, ldr, c.role, c.ct);
         } else if (type == 6) {
@@ -1755,7 +1809,7 @@ __global__ void __launch_bounds__(NT, (NT == 512) ? 1 : 2) caviar_fit_kernel(con
 #define CM_I(name) c.name = reinterpret_cast<int*>(base + L.name)
     CM_D(X); CM_D(PA); CM_D(PB); CM_D(lam); CM_D(cst); CM_D(y); CM_D(ss); CM_D(pred); CM_D(resid); CM_D(z); CM_D(mu);
     CM_D(beta); CM_D(bvec); CM_D(dvec); CM_D(wvec); CM_D(slam); CM_D(slam2); CM_D(sp); CM_D(phibar); CM_D(phi);
-    CM_D(phicov); CM_D(phiz); CM_D(phicovz); CM_D(lamhist); CM_D(lamT); CM_D(growbuf); CM_D(rcnt);
+    CM_D(phicov); CM_D(phiz); CM_D(phicovz); CM_D(lamhist); CM_D(lamT); CM_D(growbuf); CM_D(rcnt); CM_D(mce);
     CM_I(row_ptr); CM_I(col_ptr); CM_I(col_k); CM_I(csc_row); CM_I(csc_pos); CM_I(cntp); CM_I(n0p); CM_I(n1p);
     CM_I(act); CM_I(ainv); CM_I(order); CM_I(order2); CM_I(pos); CM_I(rownz); CM_I(phizok); CM_I(dcnt); CM_I(dlist); CM_I(colpw); CM_I(nmask);
 #undef CM_D
@@ -1940,10 +1994,10 @@ __global__ void __launch_bounds__(NT, (NT == 512) ? 1 : 2) caviar_fit_kernel(con
         // Monte-Carlo means of the truncated-normal sigmoid coefficients (caviar.py:209-215, App. A.2)
         if (HELPERS && c.ct > 1 && N >= 512) {
             post_job(c, 4, it & 1, S, 0);
-            mc_means(c, keys_cur, S, 0, c.ct);
+            mc_means(c, keys_cur, S, sc_powers, 0, c.ct);
             wait_helpers(c);
         } else {
-            mc_means(c, keys_cur, S, 0, 1);
+            mc_means(c, keys_cur, S, sc_powers, 0, 1);
         }
         __syncthreads();
         phase_mark(c, 8);
@@ -1953,12 +2007,11 @@ __global__ void __launch_bounds__(NT, (NT == 512) ? 1 : 2) caviar_fit_kernel(con
         for (int n = wid; n < N; n += NW) {
             if (c.dcnt[n]) continue;
             const double mu_n = c.mu[n], be = c.beta[n];
-            const double pb0 = c.phibar[2 * n], pb1 = c.phibar[2 * n + 1];
             const double cterm = 0.5 * sigma * (mu_n * mu_n + be * be);
+            const double* mce = c.mce + n * PMAX;                // Monte-Carlo term per power (mc_means)
             for (int j = c.row_ptr[n] + lane; j < c.row_ptr[n + 1]; j += 32) {
                 const int k = c.col_k[j];
-                const double pwv = sc_powers[c.pw[j]];
-                c.cst[j] = (pb0 * pwv - pb1 - cterm) + sigma * mu_n * c.y[k] + sigma * mu_n * mu_n * c.lam[j];
+                c.cst[j] = (mce[c.pw[j]] - cterm) + sigma * mu_n * c.y[k] + sigma * mu_n * mu_n * c.lam[j];
             }
         }
         __syncthreads();

@@ -98,6 +98,26 @@ def mc_samples(key, phi_n, phi_cov_n, S):
     return ndtri(c + u * (1 - c)) * sdev + mean
 
 
+MC_LITERAL_X = 28.0
+
+
+def mc_term_per_power(mc, powers):
+    """mean_s log(f_s / (1 - f_s)), f_s = sigmoid(phi0_s I - phi1_s)  (caviar.py:213-215,233-235) for every power I.
+
+    log(f / (1 - f)) is its argument, so the mean is mean(phi0) I - mean(phi1) -- until a sample saturates the float64
+    sigmoid (the reference's value carries rounding noise 2^-53 e^x per sample: 2e-4 at x = 28; x >~ 36.7: +inf).  Reduced
+    form = what the kernel does (csrc/caviar_fit.inl mc_means): linear while the largest possible argument
+    max(phi0) I - min(phi1) <= 28, the reference's expression otherwise."""
+    pb0, pb1 = np.mean(mc[:, 0]), np.mean(mc[:, 1])
+    out = pb0 * powers - pb1
+    xmax = np.max(mc[:, 0]) * powers - np.min(mc[:, 1])
+    for p in np.nonzero(~(xmax <= MC_LITERAL_X))[0]:
+        fn = sigmoid(mc[:, 0] * powers[p] - mc[:, 1])
+        with np.errstate(divide="ignore", invalid="ignore"):
+            out[p] = np.mean(np.log(fn / (1 - fn)))
+    return out
+
+
 def update_lam(y, I, mu, beta, lam, shape, rate, phi, phi_cov, lam_mask, key, S, powers,
                minimum_spike_count, minimax_spk_prob, it, delay_spont_est, form, trace=None):
     """caviar.py:190-231.  Returns (lam, key); in-sweep mu zeroing is discarded (:229-231)."""
@@ -123,11 +143,11 @@ def update_lam(y, I, mu, beta, lam, shape, rate, phi, phi_cov, lam_mask, key, S,
             est = lam_mask * (I[n] > 0) * sigmoid(mcE - 0.5 * arg)
         else:
             idx = np.nonzero(I[n] > 0)[0]
-            pb0, pb1 = np.mean(mc[:, 0]), np.mean(mc[:, 1])
             arg = -2 * sig * y[idx] * mu[n] + 2 * sig * mu[n] * (pred[idx] - mu[n] * lam[n, idx]) \
                 + sig * (mu[n] ** 2 + beta[n] ** 2)
+            mce = mc_term_per_power(mc, powers)
             est = np.zeros(K)
-            est[idx] = lam_mask[idx] * sigmoid(pb0 * I[n, idx] - pb1 - 0.5 * arg)
+            est[idx] = lam_mask[idx] * sigmoid(mce[np.searchsorted(powers, I[n, idx])] - 0.5 * arg)
         srates = eval_spike_rates(I[n], est, powers)
         pv = isotonic_regression(srates)[-1]
         tot = np.sum(est)

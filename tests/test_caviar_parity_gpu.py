@@ -311,3 +311,23 @@ def test_second_device_in_the_same_process():
         res.append((x, out[0]))
     assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
     assert np.array_equal(res[0][1], res[2][1])
+
+
+def test_large_powers_take_the_reference_expression_of_the_monte_carlo_term():
+    """mean_s log(f / (1 - f)) (caviar.py:213-215) saturates for large powers; kernel and reduced oracle then evaluate
+    the reference's own expression instead of the linear shortcut; the literal oracle (the reference's structure) agrees."""
+    from oracle import caviar as oc, simulate as osim
+    sim = osim.simulate_fast(N=24, K=240, H=4, seed=5, powers=(60, 90, 99))
+    stim = np.ascontiguousarray(sim["stim_matrix"])
+    stim[stim == 90] = 160.0
+    stim[stim == 99] = 320.0
+    opts = dict(iters=8, seed=1, msrmp=0.4)
+    pr = oc.default_priors(24)
+    with np.errstate(all="ignore"):
+        lit = oc.caviar(sim["psc"], stim, pr["mu"], pr["beta"], pr["shape"], pr["rate"], pr["phi"], pr["phi_cov"], form="literal", **opts)
+    ref = oracle_fit(sim["psc"], stim, **opts)
+    m = gpu_fit(sim["psc"], stim, **opts)
+    assert np.array_equal(m.state["mu"] != 0, ref[0] != 0) and np.array_equal(m.state["mu"] != 0, lit[0] != 0)
+    for i, nm in enumerate(NAMES):
+        assert close(m.state[nm], ref[i], 1e-6), nm
+        assert close(m.state[nm], lit[i], 1e-5), nm

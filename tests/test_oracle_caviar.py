@@ -83,3 +83,22 @@ def test_simulate_shapes_and_design():
     assert np.all((stim > 0).sum(0) == 10)
     f = osim.simulate_fast(N=40, K=120, H=10, seed=1)
     assert f["stim_matrix"].shape == (40, 120) and np.all((f["stim_matrix"] > 0).sum(0) == 10)
+
+
+def test_literal_equals_reduced_for_large_powers():
+    """for powers >= ~150 the reference's log(f / (1 - f)) Monte-Carlo term saturates (f rounds to 1 -> +inf) and no
+    longer equals the linear form; the reduced form (= the kernel) switches to the reference's expression there."""
+    sim = osim.simulate_fast(N=24, K=240, H=4, seed=5, powers=(60, 90, 99))
+    stim = sim["stim_matrix"].copy()
+    stim[stim == 90] = 160.0                       # the same experiment reported with larger power values
+    stim[stim == 99] = 320.0
+    t1, t2 = {"decisions": []}, {"decisions": []}
+    a = _run(dict(sim, stim_matrix=stim), "literal", t1, iters=8)
+    b = _run(dict(sim, stim_matrix=stim), "reduced", t2, iters=8)
+    assert [(d[2], d[6]) for d in t1["decisions"]] == [(d[2], d[6]) for d in t2["decisions"]]
+    for i in range(8):
+        x, y = np.asarray(a[i], float), np.asarray(b[i], float)
+        assert np.allclose(x, y, rtol=1e-6, atol=1e-9, equal_nan=True), i
+    mc = np.c_[np.full(100, 0.3), np.full(100, 5.0)]
+    out = oc.mc_term_per_power(mc, np.array([50.0, 160.0]))
+    assert np.isclose(out[0], 10.0) and np.isinf(out[1])          # 0.3 * 160 - 5 = 43 > 36.7: f == 1 in float64
