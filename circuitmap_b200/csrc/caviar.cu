@@ -27,6 +27,7 @@ constexpr int MAX_SHUFFLE_ROUNDS = 4;
 constexpr int GK = 16, NST = 4;                                   // panel GEMM: k-chunk, pipeline stages
 constexpr int XD_LD = NB + 4;
 constexpr int ROWPAD = 2 + GK;                                    // slack rows so that whole chunks can be copied
+constexpr int KSEG_MAX = 4;                                       // k segments of a panel GEMM (split-k over the CTAs of a fit)
 
 // The 32-row panels (A block row, Lrow, W) are stored transposed, [column][32 rows], same bit-3 swizzle on odd columns.
 __device__ __forceinline__ size_t pidx(int r, int cc) { return (size_t)cc * NB + (r ^ ((cc & 1) << 3)); }
@@ -36,7 +37,7 @@ __device__ __forceinline__ size_t pidx(int r, int cc) { return (size_t)cc * NB +
 struct Layout {
     size_t stride;
     // fp64
-    size_t X, PA, PB, lam, cst, y, ss, pred, resid, z, mu, beta, bvec, dvec, wvec, slam, slam2, sp, phibar, phi,
+    size_t X, PA, PB, PP, lam, cst, y, ss, pred, resid, z, mu, beta, bvec, dvec, wvec, slam, slam2, sp, phibar, phi,
         phicov, phiz, phicovz, lamhist, lamT, growbuf, cscq, rcnt, mce;
     // int32 / uint32
     size_t row_ptr, col_ptr, colfill, col_k, csc_row, csc_pos, cntp, n0p, n1p, act, ainv, order, order2, pos, rownz,
@@ -54,6 +55,7 @@ static Layout make_layout(int N, int K, int64_t nnz, int iters, bool lamhist, in
     L.X = take(((n + GCT - 1) / GCT) * (size_t)GCT * (n + ROWPAD) * 8);
     L.PA = take((size_t)NB * (n + ROWPAD) * 8);
     L.PB = take((size_t)NB * (n + ROWPAD) * 8);
+    L.PP = take((size_t)KSEG_MAX * NB * (n + ROWPAD) * 8);      // partial panels of the split-k panel GEMMs
     L.growbuf = take((size_t)(NW > NB ? NW : NB) * (n + 2) * 8);     // one row buffer per row of a 32-row block
     L.cscq = take(z * 16);
     L.lam = take(z * 8);
@@ -680,9 +682,9 @@ extern "C" int cm_caviar_fit(const cm_caviar_args* a, void* stream) {
     }
     if (!small_cta && a->N > 256) {
         const int sms = sm_count;
-        int want = 15;
+        int want = a->N >= 2048 ? 47 : 15;                   // large systems have more panel-GEMM jobs (column tiles x k segments)
         if (const char* e = getenv("CM_CAVIAR_HELPERS")) want = atoi(e);
-        want = want < 0 ? 0 : (want > 31 ? 31 : want);
+        want = want < 0 ? 0 : (want > 127 ? 127 : want);
         const int room = sms / a->B - 1;                      // helpers per fit that still leave every CTA resident
         if (want > room) want = room;
         if (want > 0) ct = want + 1;

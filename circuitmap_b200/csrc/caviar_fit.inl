@@ -26,7 +26,7 @@ __device__ __forceinline__ size_t xidx(int kk, int cc, int ldr) {
 struct Ctx {
     long long* tlast;   // shared: last phase timestamp (block 0 / thread 0 only)
     int N, K, P, nnz, it;
-    double *X, *PA, *PB, *lam, *cst, *y, *ss, *pred, *resid, *z, *mu, *beta, *bvec, *dvec, *wvec, *slam, *slam2, *sp,
+    double *X, *PA, *PB, *PP, *lam, *cst, *y, *ss, *pred, *resid, *z, *mu, *beta, *bvec, *dvec, *wvec, *slam, *slam2, *sp,
         *phibar, *phi, *phicov, *phiz, *phicovz, *lamhist, *lamT, *growbuf, *rcnt, *mce;
     double2* cscq;    // per CSC entry: (active index of the row as int bits, lam) -- rebuilt every a2
     int *row_ptr, *col_ptr, *col_k, *csc_row, *csc_pos, *cntp, *n0p, *n1p, *act, *ainv, *order, *order2, *pos, *rownz,
@@ -277,9 +277,17 @@ struct GemmPipe {
 // 32 x GK chunks of IN and GK x 256 chunks of X are streamed through shared memory by cp.async.bulk (issued by warp
 // 0, completion on mbarriers, 4 stages in flight); each warp owns the 32 x 16 slice of the 32 x 256 output tile as
 // 4 x 2 DMMA tiles.  Row strides = 4 (mod 16) doubles keep the fragment loads bank-conflict free.
+// Split-k: the k range of every column tile is cut into `nseg` segments (a function of i0 only, see kseg_for); a job is
+// (tile, segment), jobs part, part + nparts, ... are taken by this CTA; with nseg > 1 a job writes its partial panel to
+// PP[segment] and the caller adds the segments in fixed order (reduce_partials) -- the result does not depend on how many
+// CTAs shared the jobs.
+__device__ __forceinline__ int kseg_for(int i0) {
+    if (!HELPERS) return 1;                        // the 8-warp (batched) variant has no helper CTAs to share segments with
+    return i0 >= 768 ? 4 : (i0 >= 576 ? 3 : (i0 >= 384 ? 2 : 1));
+}
 template <bool UPPER>
 __device__ void panel_gemm(const Ctx& c, int ldr, int i0, int nb, const double* IN, double* OUT, GemmPipe& gp,
-                           int part = 0, int nparts = 1) {
+                           int part = 0, int nparts = 1, int nseg = 1) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int lq = lane >> 2, lr = lane & 3;
     const int sw = (lr & 1) << 3;                 // swizzle term of this lane's k rows (k = 4*ks + lr)
@@ -290,11 +298,17 @@ __device__ void panel_gemm(const Ctx& c, int ldr, int i0, int nb, const double* 
     // the async-proxy bulk copies that reuse the same shared memory
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
     __syncthreads();
-    for (int ct0 = part * GCT; ct0 < i0; ct0 += nparts * GCT) {      // column tiles part, part + nparts, ...
+    const int ntiles = (i0 + GCT - 1) / GCT;
+    for (int job = part; job < ntiles * nseg; job += nparts) {       // jobs (column tile, k segment) part, part + nparts, ...
+        const int tile = job / nseg, seg = job - tile * nseg;
+        const int ct0 = tile * GCT;
         const int tile_end = min(i0, ct0 + GCT);
-        const int kfirst = UPPER ? 0 : ct0;
         const int klast = UPPER ? tile_end : i0;
-        const int nc = (klast - kfirst + GK - 1) / GK;
+        const int nc_all = (klast - (UPPER ? 0 : ct0) + GK - 1) / GK;
+        const int c_lo = (nc_all * seg) / nseg, c_hi = (nc_all * (seg + 1)) / nseg;
+        const int kfirst = (UPPER ? 0 : ct0) + c_lo * GK;             // first k row of this segment
+        const int nc = c_hi - c_lo;
+        double* OUTj = nseg > 1 ? c.PP + (size_t)seg * NB * (c.N + ROWPAD) : OUT;
         const unsigned seq0 = gp.seq;
         const double* Xtile = Xg + (size_t)(ct0 >> GCT_LOG2) * ldr * GCT;
         auto fill = [&](int ci) {                             // warp 0 only: two bulk copies per chunk
@@ -386,8 +400,8 @@ __device__ void panel_gemm(const Ctx& c, int ldr, int i0, int nb, const double* 
 #pragma unroll
                 for (int nt = 0; nt < 2; ++nt) {
                     const int cc = cmin + 8 * nt + 2 * lr;
-                    if (cc < i0) OUT[pidx(r, cc)] = acc[mt][nt][0];
-                    if (cc + 1 < i0) OUT[pidx(r, cc + 1)] = acc[mt][nt][1];
+                    if (cc < i0) OUTj[pidx(r, cc)] = acc[mt][nt][0];
+                    if (cc + 1 < i0) OUTj[pidx(r, cc + 1)] = acc[mt][nt][1];
                 }
             }
         }
@@ -545,12 +559,26 @@ __device__ void wait_helpers(const Ctx& c) {
     __threadfence();
 }
 
+// OUT = sum of the nseg partial panels, segments added in order; columns < i0, all 32 rows of the panel layout
+__device__ void reduce_partials(const Ctx& c, int i0, int nseg, double* OUT) {
+    const size_t stride = (size_t)NB * (c.N + ROWPAD);
+    const int total = i0 * NB;
+    for (int e = threadIdx.x; e < total; e += NT) {
+        double v = c.PP[e];
+        for (int s = 1; s < nseg; ++s) v += c.PP[(size_t)s * stride + e];
+        OUT[e] = v;
+    }
+    __syncthreads();
+}
 template <bool UPPER>
 __device__ void panel_gemm_dist(const Ctx& c, int ldr, int i0, int nb, const double* IN, double* OUT, GemmPipe& gp) {
-    const bool dist = HELPERS && c.ct > 1 && i0 > GCT;           // at least two column tiles
-    if (dist) post_job(c, UPPER ? 1 : 2, i0, nb, 0);  // IN and X are complete (written by this CTA)
-    panel_gemm<UPPER>(c, ldr, i0, nb, IN, OUT, gp, 0, dist ? c.ct : 1);
+    const int nseg = kseg_for(i0);
+    const int njobs = ((i0 + GCT - 1) / GCT) * nseg;
+    const bool dist = HELPERS && c.ct > 1 && njobs > 1;
+    if (dist) post_job(c, UPPER ? 1 : 2, i0, nb, nseg);   // IN and X are complete (written by this CTA)
+    panel_gemm<UPPER>(c, ldr, i0, nb, IN, OUT, gp, 0, dist ? c.ct : 1, nseg);
     if (dist) wait_helpers(c);
+    if (nseg > 1) reduce_partials(c, i0, nseg, OUT);
 }
 
 // Job types: 1 / 2 panel GEMM (upper / lower; a = i0, b = nb), 3 Newton rows of c.dlist (a = rows), 4 Monte-Carlo means
@@ -572,14 +600,14 @@ __device__ void helper_loop(const Ctx& c, GemmPipe& gp) {
             s_job[0] = type; s_job[1] = c.job[2]; s_job[2] = c.job[3]; s_job[3] = c.job[4];
         }
         __syncthreads();
-        const int type = s_job[0], a = s_job[1], b = s_job[2];
+        const int type = s_job[0], a = s_job[1], b = s_job[2], d3 = s_job[3];
         __syncthreads();
         if (type == 0) break;
         ++seen;
         if (type == 1 || type == 2) {
             asm volatile("fence.proxy.async;\n" ::: "memory");      // operands were written through the generic proxy of another SM
-            if (type == 1) panel_gemm<true>(c, ldr, a, b, c.PA, c.PB, gp, c.role, c.ct);
-            else panel_gemm<false>(c, ldr, a, b, c.PB, c.PA, gp, c.role, c.ct);
+            if (type == 1) panel_gemm<true>(c, ldr, a, b, c.PA, c.PB, gp, c.role, c.ct, d3);
+            else panel_gemm<false>(c, ldr, a, b, c.PB, c.PA, gp, c.role, c.ct, d3);
         } else if (type == 3) {
             newton_rows(c, powers, c.dlist, a, c.role, c.ct);
         } else if (type == 4) {
@@ -1807,7 +1835,7 @@ __global__ void __launch_bounds__(NT, (NT == 512) ? 1 : 2) caviar_fit_kernel(con
     c.N = p.N; c.K = p.K; c.P = p.P; c.it = 0;
 #define CM_D(name) c.name = reinterpret_cast<double*>(base + L.name)
 #define CM_I(name) c.name = reinterpret_cast<int*>(base + L.name)
-    CM_D(X); CM_D(PA); CM_D(PB); CM_D(lam); CM_D(cst); CM_D(y); CM_D(ss); CM_D(pred); CM_D(resid); CM_D(z); CM_D(mu);
+    CM_D(X); CM_D(PA); CM_D(PB); CM_D(PP); CM_D(lam); CM_D(cst); CM_D(y); CM_D(ss); CM_D(pred); CM_D(resid); CM_D(z); CM_D(mu);
     CM_D(beta); CM_D(bvec); CM_D(dvec); CM_D(wvec); CM_D(slam); CM_D(slam2); CM_D(sp); CM_D(phibar); CM_D(phi);
     CM_D(phicov); CM_D(phiz); CM_D(phicovz); CM_D(lamhist); CM_D(lamT); CM_D(growbuf); CM_D(rcnt); CM_D(mce);
     CM_I(row_ptr); CM_I(col_ptr); CM_I(col_k); CM_I(csc_row); CM_I(csc_pos); CM_I(cntp); CM_I(n0p); CM_I(n1p);
