@@ -37,7 +37,7 @@ __device__ __forceinline__ size_t pidx(int r, int cc) { return (size_t)cc * NB +
 struct Layout {
     size_t stride;
     // fp64
-    size_t X, PA, PB, PP, lam, cst, y, ss, pred, resid, z, mu, beta, bvec, dvec, wvec, slam, slam2, sp, phibar, phi,
+    size_t X, XI, Dinv, PA, PB, PP, lam, cst, y, ss, pred, resid, z, mu, beta, bvec, dvec, wvec, slam, slam2, sp, phibar, phi,
         phicov, phiz, phicovz, lamhist, lamT, growbuf, cscq, rcnt, mce;
     // int32 / uint32
     size_t row_ptr, col_ptr, colfill, col_k, csc_row, csc_pos, cntp, n0p, n1p, act, ainv, order, order2, pos, rownz,
@@ -52,7 +52,13 @@ static Layout make_layout(int N, int K, int64_t nnz, int iters, bool lamhist, in
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 255) & ~size_t(255); return r; };
     const size_t n = N, k = K, z = (size_t)nnz;
-    L.X = take(((n + GCT - 1) / GCT) * (size_t)GCT * (n + ROWPAD) * 8);
+    const size_t npad = (n + 31) & ~size_t(31);
+    {
+        const size_t tiled = ((n + GCT - 1) / GCT) * (size_t)GCT * (n + ROWPAD) * 8, square = npad * npad * 8;
+        L.X = take(tiled > square ? tiled : square);             // tiled X of the bordered recursion / square A of the tile solve
+    }
+    L.XI = take(GCT == 256 ? npad * npad * 8 : 0);               // inverse factor of the tile solve (16-warp variant only)
+    L.Dinv = take(GCT == 256 ? npad * 32 * 8 : 0);               // inverses of its diagonal tiles
     L.PA = take((size_t)NB * (n + ROWPAD) * 8);
     L.PB = take((size_t)NB * (n + ROWPAD) * 8);
     L.PP = take((size_t)KSEG_MAX * NB * (n + ROWPAD) * 8);      // partial panels of the split-k panel GEMMs

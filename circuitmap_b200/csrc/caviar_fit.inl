@@ -26,7 +26,7 @@ __device__ __forceinline__ size_t xidx(int kk, int cc, int ldr) {
 struct Ctx {
     long long* tlast;   // shared: last phase timestamp (block 0 / thread 0 only)
     int N, K, P, nnz, it;
-    double *X, *PA, *PB, *PP, *lam, *cst, *y, *ss, *pred, *resid, *z, *mu, *beta, *bvec, *dvec, *wvec, *slam, *slam2, *sp,
+    double *X, *XI, *Dinv, *PA, *PB, *PP, *lam, *cst, *y, *ss, *pred, *resid, *z, *mu, *beta, *bvec, *dvec, *wvec, *slam, *slam2, *sp,
         *phibar, *phi, *phicov, *phiz, *phicovz, *lamhist, *lamT, *growbuf, *rcnt, *mce;
     double2* cscq;    // per CSC entry: (active index of the row as int bits, lam) -- rebuilt every a2
     int *row_ptr, *col_ptr, *col_k, *csc_row, *csc_pos, *cntp, *n0p, *n1p, *act, *ainv, *order, *order2, *pos, *rownz,
@@ -581,52 +581,6 @@ __device__ void panel_gemm_dist(const Ctx& c, int ldr, int i0, int nb, const dou
     if (nseg > 1) reduce_partials(c, i0, nseg, OUT);
 }
 
-// Job types: 1 / 2 panel GEMM (upper / lower; a = i0, b = nb), 3 Newton rows of c.dlist (a = rows), 4 Monte-Carlo means
-// (a = key buffer, b = samples), 5 w = X b, 6 mu / beta (a = active rows), 7 Gram rows of a block (a = i0, b = nb, sigma at
-// int offset 8), 0 quit.
-__device__ void helper_loop(const Ctx& c, GemmPipe& gp) {
-    __shared__ int s_job[4];
-    const int ldr = c.N + ROWPAD;
-    const double* powers = reinterpret_cast<const double*>(c.job + 32);
-    int seen = 0;
-    __syncthreads();                                  // mbarriers initialised
-    for (;;) {
-        if (threadIdx.x == 0) {
-            int type = -1;
-            while (type < 0) {
-                if (ld_acquire_gpu(&c.job[0]) != seen) type = c.job[1];
-                else __nanosleep(200);
-            }
-            s_job[0] = type; s_job[1] = c.job[2]; s_job[2] = c.job[3]; s_job[3] = c.job[4];
-        }
-        __syncthreads();
-        const int type = s_job[0], a = s_job[1], b = s_job[2], d3 = s_job[3];
-        __syncthreads();
-        if (type == 0) break;
-        ++seen;
-        if (type == 1 || type == 2) {
-            asm volatile("fence.proxy.async;\n" ::: "memory");      // operands were written through the generic proxy of another SM
-            if (type == 1) panel_gemm<true>(c, ldr, a, b, c.PA, c.PB, gp, c.role, c.ct, d3);
-            else panel_gemm<false>(c, ldr, a, b, c.PB, c.PA, gp, c.role, c.ct, d3);
-        } else if (type == 3) {
-            newton_rows(c, powers, c.dlist, a, c.role, c.ct);
-        } else if (type == 4) {
-            mc_means(c, c.keys + (size_t)a * 2 * c.N, b, powers, c.role, c.ct);
-        } else if (type == 5) {
-            a2_wvec(c, a, ldr, c.role, c.ct);
-        } else if (type == 6) {
-            a2_mubeta(c, a, ldr, c.role, c.ct);
-        } else if (type == 7) {
-            Ctx h = c;                                           // the by-trial index the fit CTA currently uses
-            if (c.job[5]) { h.ucol_ptr = c.ccol_ptr; h.ucsc_row = c.ccsc_row; h.ucsc_pos = c.ccsc_pos; }
-            h.unnz = c.job[6];
-            gram_rows(h, a, b, *reinterpret_cast<const double*>(c.job + 8), c.role, c.ct);
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) { __threadfence(); red_release_gpu(&c.job[16], 1); }
-    }
-}
-
 // (begin, length) of every CSR entry's trial list in the by-trial index in use: saves the Gram expansion one dependent
 // memory round trip per 32 entries (col_k -> col_ptr); rebuilt whenever that index changes.
 __device__ __forceinline__ void build_rowcb(const Ctx& c) {
@@ -837,6 +791,406 @@ __device__ __noinline__ void a2_small(const Ctx& c, double sigma, int na) {
     phase_mark(c, 6);
 }
 
+// ------------------------------------------------------------------------------------------------ a2, tile solve
+// block_update_mu for LARGE active sets in the 16-warp variant (single large fits and their helper CTAs).  The bordered
+// 32-row recursion above is a chain of ~6 dependent phases per 32 rows (Gram job, two panel-GEMM jobs, CTA-wide 32 x 32
+// factor, X update), 20-45 us each whatever the number of CTAs -- a C3 fit spends ~50 ms in ~200 such block steps.  The
+// tile solve keeps the same mathematics (M = L L^T, X = L^-1, mu = X^T X b, beta = colsumsq X) in a form whose parallel
+// width grows with the matrix:
+//   * M (lower triangle) is a plain row-major square of 32 x 32 tiles in global memory (L2-resident), padded to a multiple
+//     of 32 with an identity block; all Gram rows are one job;
+//   * right-looking Cholesky over tile columns kb: the fit CTA factors the diagonal tile (and inverts the factor), then ONE
+//     job scales the panel below it and ONE job applies the rank-32 update to all (nt-kb)(nt-kb-1)/2 trailing tiles, a warp
+//     per tile (DMMA, operands straight from L2);
+//   * X = L^-1 by tile columns: a column is a task of one CTA (its 16 warps split the k range of every tile and add
+//     their partial tiles in fixed order through shared memory), columns are independent;
+//   * every tile is produced by one warp (or one CTA) with a fixed k order, so the result does not depend on how many
+//     CTAs share the jobs (bitwise neutral in the helper count, like the rest).
+struct Tiles { double* A; double* XI; double* Dinv; int lda, nt, na; };
+__device__ __forceinline__ Tiles make_tiles(const Ctx& c, int na) {
+    Tiles t;
+    t.na = na; t.nt = (na + 31) >> 5; t.lda = t.nt * 32; t.A = c.X; t.XI = c.XI; t.Dinv = c.Dinv;
+    return t;
+}
+
+// one warp: acc(32 x 32) += A(32 x 32, row-major) * B^T  [NT: B row-major (n, k)]  or  A * B  [NN: B row-major (k, n)]
+// accumulator layout: acc[mt][nt][e] = C[8 mt + lane / 4][8 nt + 2 (lane % 4) + e]
+template <bool NN>
+__device__ __forceinline__ void tile_mma(double (&acc)[4][4][2], const double* __restrict__ A, int lda,
+                                         const double* __restrict__ B, int ldb) {
+    const int lane = threadIdx.x & 31, lq = lane >> 2, lr = lane & 3;
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) {
+        double a[4], b[4];
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) a[mt] = A[(size_t)(8 * mt + lq) * lda + 4 * ks + lr];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) b[nt] = NN ? B[(size_t)(4 * ks + lr) * ldb + 8 * nt + lq] : B[(size_t)(8 * nt + lq) * ldb + 4 * ks + lr];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt) dmma8x8x4(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
+    }
+}
+__device__ __forceinline__ void tile_zero(double (&acc)[4][4][2]) {
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) { acc[mt][nt][0] = 0.0; acc[mt][nt][1] = 0.0; }
+}
+// C = sgn * acc (+ C if ADD)
+template <bool ADD>
+__device__ __forceinline__ void tile_store(const double (&acc)[4][4][2], double* C, int ldc, double sgn) {
+    const int lane = threadIdx.x & 31, lq = lane >> 2, lr = lane & 3;
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            double2* p = reinterpret_cast<double2*>(C + (size_t)(8 * mt + lq) * ldc + 8 * nt + 2 * lr);
+            double2 v = ADD ? *p : make_double2(0.0, 0.0);
+            v.x += sgn * acc[mt][nt][0]; v.y += sgn * acc[mt][nt][1];
+            *p = v;
+        }
+}
+
+// Gram rows part, part + W, ... of the whole active set (W = warps of all CTAs of the fit) into the square A, incl. the
+// identity padding up to a multiple of 32 (cf. gram_rows: same expansion, same deterministic combination of lanes)
+__device__ void gram_rows_A(const Ctx& c, const Tiles T, double sigma, int part, int nparts) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int cap = GEMM_SMEM_DOUBLES / NW;
+    const int tagcap = ((c.smd - GEMM_SMEM_DOUBLES) * 8) / NW;
+    const double2* __restrict__ cscq = c.cscq;
+    const int2* __restrict__ rowcb = c.rowcb;
+    for (int ia = part * NW + wid; ia < T.lda; ia += nparts * NW) {
+        double* dst = T.A + (size_t)ia * T.lda;
+        if (ia >= T.na) {                                       // identity padding
+            for (int q = lane; q <= ia; q += 32) dst[q] = (q == ia) ? 1.0 : 0.0;
+            continue;
+        }
+        const int n = c.act[ia];
+        double* acc = (ia + 1 <= cap) ? (c.sm + (size_t)wid * cap) : dst;
+        unsigned char* tags = reinterpret_cast<unsigned char*>(c.sm + GEMM_SMEM_DOUBLES) + (size_t)wid * tagcap;
+        const bool use_tags = ia + 1 <= tagcap;
+        for (int q = lane; q <= ia; q += 32) acc[q] = 0.0;
+        __syncwarp();
+        const int beg = c.row_ptr[n], end = c.row_ptr[n + 1];
+        double la_n = 0.0;
+        int2 rc_n = make_int2(0, 0);
+        if (beg + lane < end) { la_n = c.lam[beg + lane]; rc_n = rowcb[beg + lane]; }
+        for (int jb = beg; jb < end; jb += 32) {
+            const double la = la_n;
+            const int cb = rc_n.x, len = (la != 0.0) ? rc_n.y : 0;
+            la_n = 0.0; rc_n = make_int2(0, 0);
+            if (jb + 32 + lane < end) { la_n = c.lam[jb + 32 + lane]; rc_n = rowcb[jb + 32 + lane]; }
+            int maxlen = len;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, o));
+            for (int t0 = 0; t0 < maxlen; t0 += 8) {
+                int ibs[8];
+                double vs[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int t = t0 + u;
+                    int ib = -1;
+                    double lv = 0.0;
+                    if (t < len) {
+                        const double2 rec = cscq[cb + t];
+                        ib = (int)__double_as_longlong(rec.x);
+                        lv = rec.y;
+                    }
+                    if (ib > ia) ib = -1;
+                    ibs[u] = ib;
+                    vs[u] = la * lv;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    if (t0 + u >= maxlen) break;               // warp-uniform
+                    const int ib = ibs[u];
+                    const double v = vs[u];
+                    bool lost = false;
+                    if (use_tags) {
+                        if (ib >= 0) tags[ib] = (unsigned char)lane;
+                        __syncwarp();
+                        lost = (ib >= 0) && (tags[ib] != (unsigned char)lane);
+                    }
+                    if (use_tags && !__any_sync(0xffffffffu, lost)) {
+                        if (ib >= 0) acc[ib] += v;
+                    } else {
+                        const unsigned amask = __ballot_sync(0xffffffffu, ib >= 0);
+                        if (ib >= 0) {
+                            const unsigned grp = __match_any_sync(amask, ib);
+                            const int leader = __ffs(grp) - 1;
+                            unsigned rest = grp & ~(1u << leader);
+                            double ssum = __shfl_sync(amask, v, leader);
+                            while (__any_sync(amask, rest != 0)) {
+                                const int src = rest ? (__ffs(rest) - 1) : lane;
+                                const double ov = __shfl_sync(amask, v, src);
+                                if (rest) { ssum += ov; rest &= rest - 1; }
+                            }
+                            if (lane == leader) acc[ib] += ssum;
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+        const double b0 = c.beta0[n];
+        const double dd = c.dvec[ia];
+        for (int q = lane; q <= ia; q += 32) {
+            const double v = acc[q];
+            dst[q] = (q == ia) ? sigma * (dd + v) + 1.0 / (b0 * b0) : sigma * v;
+        }
+        __syncwarp();
+    }
+}
+
+// panel below diagonal tile kb: A[ib][kb] <- A[ib][kb] * Dinv[kb]^T (= L[ib][kb]); a warp per tile, in place
+__device__ void tiles_trsm(const Tiles T, int kb, int part, int nparts) {
+    const int wid = threadIdx.x >> 5;
+    const double* Di = T.Dinv + (size_t)kb * 1024;
+    for (int ib = kb + 1 + part * NW + wid; ib < T.nt; ib += nparts * NW) {
+        double* C = T.A + (size_t)(32 * ib) * T.lda + 32 * kb;
+        double acc[4][4][2];
+        tile_zero(acc);
+        tile_mma<false>(acc, C, T.lda, Di, 32);
+        __syncwarp();                                           // the whole tile has been read before it is overwritten
+        tile_store<false>(acc, C, T.lda, 1.0);
+    }
+}
+// trailing update after tile column kb: A[ib][jb] -= L[ib][kb] L[jb][kb]^T for kb < jb <= ib; a warp per tile
+__device__ void tiles_update(const Tiles T, int kb, int part, int nparts) {
+    const int wid = threadIdx.x >> 5;
+    const int m = T.nt - kb - 1;
+    const int items = (m * (m + 1)) >> 1;
+    for (int t = part * NW + wid; t < items; t += nparts * NW) {
+        int i = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+        while (((i + 1) * (i + 2)) >> 1 <= t) ++i;
+        while (((i * (i + 1)) >> 1) > t) --i;
+        const int j = t - ((i * (i + 1)) >> 1);
+        const int ib = kb + 1 + i, jb = kb + 1 + j;
+        double acc[4][4][2];
+        tile_zero(acc);
+        tile_mma<false>(acc, T.A + (size_t)(32 * ib) * T.lda + 32 * kb, T.lda, T.A + (size_t)(32 * jb) * T.lda + 32 * kb, T.lda);
+        tile_store<true>(acc, T.A + (size_t)(32 * ib) * T.lda + 32 * jb, T.lda, -1.0);
+    }
+}
+// Cholesky factor of diagonal tile kb and the inverse of that factor (CTA-wide, shared memory), fit CTA only
+__device__ void tiles_potrf(const Ctx& c, const Tiles T, int kb) {
+    double (*Sd)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(c.sm + GEMM_SMEM_DOUBLES);
+    double (*Xd)[XD_LD] = reinterpret_cast<double (*)[XD_LD]>(c.sm + GEMM_SMEM_DOUBLES + NB * (NB + 1));
+    const double* D = T.A + (size_t)(32 * kb) * T.lda + 32 * kb;
+    for (int e = threadIdx.x; e < NB * NB; e += NT) {
+        const int r = e >> 5, q = e & 31;
+        Sd[r][q] = (q <= r) ? D[(size_t)r * T.lda + q] : 0.0;
+    }
+    for (int j = 0; j < NB; ++j) {
+        __syncthreads();
+        const double djj = sqrt(Sd[j][j]);
+        __syncthreads();
+        if (threadIdx.x == 0) Sd[j][j] = djj;
+        if (threadIdx.x > j && threadIdx.x < NB) Sd[threadIdx.x][j] /= djj;
+        __syncthreads();
+        for (int e = threadIdx.x; e < NB * NB; e += NT) {
+            const int r = e >> 5, q = e & 31;
+            if (q > j && q <= r) Sd[r][q] -= Sd[r][j] * Sd[q][j];
+        }
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < NB * XD_LD; e += NT) (&Xd[0][0])[e] = 0.0;
+    __syncthreads();
+    if (threadIdx.x < NB) Xd[threadIdx.x][threadIdx.x] = 1.0 / Sd[threadIdx.x][threadIdx.x];
+    {
+        const int l16 = threadIdx.x & 15;
+        for (int r = 1; r < NB; ++r) {
+            __syncthreads();
+            for (int cc = threadIdx.x >> 4; cc < NB; cc += NT / 16) {
+                double sacc = 0.0;
+                if (cc < r)
+                    for (int t = cc + l16; t < r; t += 16) sacc += Sd[r][t] * Xd[t][cc];
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
+                if (cc < r && l16 == 0) Xd[r][cc] = -sacc / Sd[r][r];
+            }
+        }
+    }
+    __syncthreads();
+    double* Di = T.Dinv + (size_t)kb * 1024;
+    for (int e = threadIdx.x; e < NB * NB; e += NT) Di[e] = Xd[e >> 5][e & 31];
+    __syncthreads();
+}
+// X = L^-1 by tile columns jb = part, part + nparts, ... (a column per CTA): X[jb][jb] = Dinv[jb];
+// X[ib][jb] = -Dinv[ib] * sum_{kb = jb}^{ib - 1} L[ib][kb] X[kb][jb].  The 16 warps split the k range of the sum (warp w
+// takes kb = jb + w, jb + w + NW, ...), their partial tiles are added in warp order through shared memory, then warp w
+// multiplies the 8 x 8 sub-tile w of the product with Dinv[ib].
+__device__ void tiles_inverse(const Ctx& c, const Tiles T, int part, int nparts) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, lq = lane >> 2, lr = lane & 3;
+    double* part_s = c.sm;                                      // [NW][32][32] partial tiles
+    double* sum_s = c.sm + NW * 1024;                           // [32][33] their sum
+    for (int jb = part; jb < T.nt; jb += nparts) {
+        {
+            const double* Di = T.Dinv + (size_t)jb * 1024;
+            double* Xjj = T.XI + (size_t)(32 * jb) * T.lda + 32 * jb;
+            for (int e = threadIdx.x; e < 1024; e += NT) Xjj[(size_t)(e >> 5) * T.lda + (e & 31)] = Di[e];
+        }
+        __syncthreads();
+        for (int ib = jb + 1; ib < T.nt; ++ib) {
+            double acc[4][4][2];
+            tile_zero(acc);
+            for (int kb = jb + wid; kb < ib; kb += NW)
+                tile_mma<true>(acc, T.A + (size_t)(32 * ib) * T.lda + 32 * kb, T.lda, T.XI + (size_t)(32 * kb) * T.lda + 32 * jb, T.lda);
+            double* mine = part_s + wid * 1024;
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) {
+                    mine[(8 * mt + lq) * 32 + 8 * nt + 2 * lr] = acc[mt][nt][0];
+                    mine[(8 * mt + lq) * 32 + 8 * nt + 2 * lr + 1] = acc[mt][nt][1];
+                }
+            __syncthreads();
+            const int nw_used = min(NW, ib - jb);
+            for (int e = threadIdx.x; e < 1024; e += NT) {
+                double v = part_s[e];
+                for (int w = 1; w < nw_used; ++w) v += part_s[w * 1024 + e];
+                sum_s[(e >> 5) * 33 + (e & 31)] = v;
+            }
+            __syncthreads();
+            // X[ib][jb] = -Dinv[ib] (32 x 32, lower) * sum: warp w computes sub-tile (w / 4, w % 4)
+            for (int st = wid; st < 16; st += NW) {
+                const int mt = st >> 2, nt = st & 3;
+                const double* Di = T.Dinv + (size_t)ib * 1024;
+                double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) {
+                    const double a = Di[(8 * mt + lq) * 32 + 4 * ks + lr];
+                    const double b = sum_s[(4 * ks + lr) * 33 + 8 * nt + lq];
+                    dmma8x8x4(d0, d1, a, b);
+                }
+                double* X = T.XI + (size_t)(32 * ib + 8 * mt + lq) * T.lda + 32 * jb + 8 * nt + 2 * lr;
+                X[0] = -d0; X[1] = -d1;
+            }
+            __syncthreads();                                    // X[ib][jb] is read (through L2) by the next rows of this column
+            __threadfence_block();
+        }
+    }
+}
+// w = X b (rows), then mu = X^T w and beta = column sums of squares (columns) on the row-major inverse factor
+__device__ void tiles_wvec(const Ctx& c, const Tiles T, int part, int nparts) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int i = part * NW + wid; i < T.na; i += nparts * NW) {
+        double s = 0.0;
+        const double* row = T.XI + (size_t)i * T.lda;
+        for (int q = lane; q <= i; q += 32) s += row[q] * c.bvec[q];
+        s = warp_sum(s);
+        if (lane == 0) c.wvec[i] = s;
+    }
+}
+__device__ void tiles_mubeta(const Ctx& c, const Tiles T, int part, int nparts) {
+    for (int cc = part * NT + threadIdx.x; cc < T.na; cc += nparts * NT) {
+        double m = 0.0, v = 0.0;
+        for (int i = cc; i < T.na; ++i) {
+            const double x = T.XI[(size_t)i * T.lda + cc];
+            m += x * c.wvec[i];
+            v += x * x;
+        }
+        const int n = c.act[cc];
+        c.mu[n] = m;
+        c.beta[n] = v;
+    }
+}
+// the whole solve, driven by the fit CTA; job types 8..13 are served by helper_loop
+__device__ __noinline__ void a2_tiles(const Ctx& c, double sigma, int na) {
+    const Tiles T = make_tiles(c, na);
+    const bool dist = HELPERS && c.ct > 1;
+    const int np = dist ? c.ct : 1;
+    if (dist) { if (threadIdx.x == 0) *reinterpret_cast<double*>(c.job + 8) = sigma; post_job(c, 8, na, 0, 0); }
+    gram_rows_A(c, T, sigma, 0, np);
+    if (dist) wait_helpers(c); else __syncthreads();
+    phase_mark(c, 1);
+    for (int kb = 0; kb < T.nt; ++kb) {
+        tiles_potrf(c, T, kb);
+        if (kb + 1 < T.nt) {
+            const bool d1 = dist && (T.nt - kb - 1) > NW;       // more panel tiles than this CTA has warps
+            if (d1) post_job(c, 9, na, kb, 0);
+            tiles_trsm(T, kb, 0, d1 ? np : 1);
+            if (d1) wait_helpers(c); else { __threadfence(); __syncthreads(); }
+            const int m = T.nt - kb - 1;
+            const bool d2 = dist && ((m * (m + 1)) >> 1) > NW;
+            if (d2) post_job(c, 10, na, kb, 0);
+            tiles_update(T, kb, 0, d2 ? np : 1);
+            if (d2) wait_helpers(c); else { __threadfence(); __syncthreads(); }
+        }
+    }
+    phase_mark(c, 3);
+    if (dist) post_job(c, 11, na, 0, 0);
+    tiles_inverse(c, T, 0, np);
+    if (dist) wait_helpers(c); else { __threadfence(); __syncthreads(); }
+    phase_mark(c, 5);
+    if (dist) post_job(c, 12, na, 0, 0);
+    tiles_wvec(c, T, 0, np);
+    if (dist) wait_helpers(c); else { __threadfence(); __syncthreads(); }
+    if (dist) post_job(c, 13, na, 0, 0);
+    tiles_mubeta(c, T, 0, np);
+    if (dist) wait_helpers(c); else { __threadfence(); __syncthreads(); }
+    phase_mark(c, 6);
+}
+
+// Job types: 1 / 2 panel GEMM (upper / lower; a = i0, b = nb), 3 Newton rows of c.dlist (a = rows), 4 Monte-Carlo means
+// (a = key buffer, b = samples), 5 w = X b, 6 mu / beta (a = active rows), 7 Gram rows of a block (a = i0, b = nb, sigma at
+// int offset 8), 0 quit.
+__device__ void helper_loop(const Ctx& c, GemmPipe& gp) {
+    __shared__ int s_job[4];
+    const int ldr = c.N + ROWPAD;
+    const double* powers = reinterpret_cast<const double*>(c.job + 32);
+    int seen = 0;
+    __syncthreads();                                  // mbarriers initialised
+    for (;;) {
+        if (threadIdx.x == 0) {
+            int type = -1;
+            while (type < 0) {
+                if (ld_acquire_gpu(&c.job[0]) != seen) type = c.job[1];
+                else __nanosleep(200);
+            }
+            s_job[0] = type; s_job[1] = c.job[2]; s_job[2] = c.job[3]; s_job[3] = c.job[4];
+        }
+        __syncthreads();
+        const int type = s_job[0], a = s_job[1], b = s_job[2], d3 = s_job[3];
+        __syncthreads();
+        if (type == 0) break;
+        ++seen;
+        if (type == 1 || type == 2) {
+            asm volatile("fence.proxy.async;\n" ::: "memory");      // operands were written through the generic proxy of another SM
+            if (type == 1) panel_gemm<true>(c, ldr, a, b, c.PA, c.PB, gp, c.role, c.ct, d3);
+            else panel_gemm<false>(c, ldr, a, b, c.PB, c.PA, gp, c.role, c.ct, d3);
+        } else if (type == 3) {
+            newton_rows(c, powers, c.dlist, a, c.role, c.ct);
+        } else if (type == 4) {
+            mc_means(c, c.keys + (size_t)a * 2 * c.N, b, powers, c.role, c.ct);
+        } else if (type == 5) {
+            a2_wvec(c, a, ldr, c.role, c.ct);
+        } else if (type == 6) {
+            a2_mubeta(c, a, ldr, c.role, c.ct);
+        } else if (type >= 8 && type <= 13) {                    // tile solve (a2_tiles): a = active rows, b = tile column
+            Ctx h = c;
+            if (c.job[5]) { h.ucol_ptr = c.ccol_ptr; h.ucsc_row = c.ccsc_row; h.ucsc_pos = c.ccsc_pos; }
+            h.unnz = c.job[6];
+            const Tiles T = make_tiles(h, a);
+            if (type == 8) gram_rows_A(h, T, *reinterpret_cast<const double*>(c.job + 8), c.role, c.ct);
+            else if (type == 9) tiles_trsm(T, b, c.role, c.ct);
+            else if (type == 10) tiles_update(T, b, c.role, c.ct);
+            else if (type == 11) tiles_inverse(h, T, c.role, c.ct);
+            else if (type == 12) tiles_wvec(h, T, c.role, c.ct);
+            else tiles_mubeta(h, T, c.role, c.ct);
+        } else if (type == 7) {
+            Ctx h = c;                                           // the by-trial index the fit CTA currently uses
+            if (c.job[5]) { h.ucol_ptr = c.ccol_ptr; h.ucsc_row = c.ccsc_row; h.ucsc_pos = c.ccsc_pos; }
+            h.unnz = c.job[6];
+            gram_rows(h, a, b, *reinterpret_cast<const double*>(c.job + 8), c.role, c.ct);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) { __threadfence(); red_release_gpu(&c.job[16], 1); }
+    }
+}
+
 __device__ __noinline__ void phase_a2(const Ctx& c, double sigma, int* na_s, GemmPipe& gp) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int lq = lane >> 2, lr = lane & 3;
@@ -871,6 +1225,7 @@ __device__ __noinline__ void phase_a2(const Ctx& c, double sigma, int* na_s, Gem
     phase_mark(c, 0);
     if (na == 0) return;
     if (!(g_phase_enable & 256) && na <= a2_small_capacity(c.smd)) { a2_small(c, sigma, na); return; }
+    if (HELPERS && !(g_phase_enable & 512)) { a2_tiles(c, sigma, na); return; }
 
     // diagonal block -> its Cholesky factor, and the inverse of that factor (strict upper part zeroed); both live
     // behind the GEMM ring (the Gram conflict tags reuse the same bytes at a different time)
@@ -1835,7 +2190,7 @@ __global__ void __launch_bounds__(NT, (NT == 512) ? 1 : 2) caviar_fit_kernel(con
     c.N = p.N; c.K = p.K; c.P = p.P; c.it = 0;
 #define CM_D(name) c.name = reinterpret_cast<double*>(base + L.name)
 #define CM_I(name) c.name = reinterpret_cast<int*>(base + L.name)
-    CM_D(X); CM_D(PA); CM_D(PB); CM_D(PP); CM_D(lam); CM_D(cst); CM_D(y); CM_D(ss); CM_D(pred); CM_D(resid); CM_D(z); CM_D(mu);
+    CM_D(X); CM_D(XI); CM_D(Dinv); CM_D(PA); CM_D(PB); CM_D(PP); CM_D(lam); CM_D(cst); CM_D(y); CM_D(ss); CM_D(pred); CM_D(resid); CM_D(z); CM_D(mu);
     CM_D(beta); CM_D(bvec); CM_D(dvec); CM_D(wvec); CM_D(slam); CM_D(slam2); CM_D(sp); CM_D(phibar); CM_D(phi);
     CM_D(phicov); CM_D(phiz); CM_D(phicovz); CM_D(lamhist); CM_D(lamT); CM_D(growbuf); CM_D(rcnt); CM_D(mce);
     CM_I(row_ptr); CM_I(col_ptr); CM_I(col_k); CM_I(csc_row); CM_I(csc_pos); CM_I(cntp); CM_I(n0p); CM_I(n1p);
