@@ -974,7 +974,56 @@ __device__ void tiles_update(const Tiles T, int kb, int part, int nparts) {
         tile_store<true>(acc, T.A + (size_t)(32 * ib) * T.lda + 32 * jb, T.lda, -1.0);
     }
 }
-// Cholesky factor of diagonal tile kb and the inverse of that factor (CTA-wide, shared memory), fit CTA only
+
+// Cholesky factor of a 32 x 32 SPD block held in shared memory (Sd, lower triangle) and the inverse of that factor (Xd),
+// by ONE warp with the matrix in REGISTERS: lane r owns row r of the factor (statically indexed after full unrolling),
+// column j is broadcast lane by lane with shuffles; the inverse is a forward substitution per lane (column `lane`) against
+// the factor re-read from shared memory as warp-wide broadcasts, with the reciprocal pivots computed once.  ~10 us per
+// block; the shared-memory versions it replaces (CTA-wide with ~130 block barriers, or one warp looping over aliased
+// read-modify-writes) took 60-75 us -- on the critical path of every 32 rows of every solve.
+__device__ __noinline__ void potrf32_warp(double (*Sd)[NB + 1], double (*Xd)[XD_LD], int nb) {
+    const int lane = threadIdx.x & 31;
+    double a[32];
+#pragma unroll
+    for (int q = 0; q < 32; ++q)
+        a[q] = (lane < nb && q <= lane) ? Sd[lane][q] : ((q == lane) ? 1.0 : 0.0);   // rows >= nb: identity padding
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        const double djj = sqrt(__shfl_sync(0xffffffffu, a[j], j));
+        const double l = (lane == j) ? djj : a[j] / djj;          // lanes < j hold 0 here
+        a[j] = l;
+#pragma unroll
+        for (int q = j + 1; q < 32; ++q) {
+            const double lq = __shfl_sync(0xffffffffu, l, q);      // L[q][j]
+            a[q] = (q <= lane) ? a[q] - l * lq : a[q];
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 32; ++q) Sd[lane][q] = a[q];              // the factor (zeros above the diagonal)
+    __syncwarp();
+    // X = L^-1, column `lane`: x[lane] = 1 / L[lane][lane]; x[r] = -(sum_{t = lane}^{r-1} L[r][t] x[t]) / L[r][r]
+    double x[32];
+    double piv = 1.0;
+#pragma unroll
+    for (int q = 0; q < 32; ++q) piv = (q == lane) ? a[q] : piv;  // own pivot L[lane][lane]
+    const double ipiv = 1.0 / piv;
+#pragma unroll
+    for (int r = 0; r < 32; ++r) {
+        const double ir = __shfl_sync(0xffffffffu, ipiv, r);      // 1 / L[r][r]
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int t = 0; t < r; t += 2) {
+            s0 += Sd[r][t] * ((t >= lane) ? x[t] : 0.0);
+            if (t + 1 < r) s1 += Sd[r][t + 1] * ((t + 1 >= lane) ? x[t + 1] : 0.0);
+        }
+        x[r] = (r == lane) ? ir : ((r > lane) ? -(s0 + s1) * ir : 0.0);
+        Xd[r][lane] = (lane < nb && r < nb) ? x[r] : 0.0;
+    }
+    __syncwarp();
+}
+
+// Cholesky factor of diagonal tile kb and the inverse of that factor (one warp, shared memory), fit CTA only
 __device__ void tiles_potrf(const Ctx& c, const Tiles T, int kb) {
     double (*Sd)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(c.sm + GEMM_SMEM_DOUBLES);
     double (*Xd)[XD_LD] = reinterpret_cast<double (*)[XD_LD]>(c.sm + GEMM_SMEM_DOUBLES + NB * (NB + 1));
@@ -983,36 +1032,8 @@ __device__ void tiles_potrf(const Ctx& c, const Tiles T, int kb) {
         const int r = e >> 5, q = e & 31;
         Sd[r][q] = (q <= r) ? D[(size_t)r * T.lda + q] : 0.0;
     }
-    for (int j = 0; j < NB; ++j) {
-        __syncthreads();
-        const double djj = sqrt(Sd[j][j]);
-        __syncthreads();
-        if (threadIdx.x == 0) Sd[j][j] = djj;
-        if (threadIdx.x > j && threadIdx.x < NB) Sd[threadIdx.x][j] /= djj;
-        __syncthreads();
-        for (int e = threadIdx.x; e < NB * NB; e += NT) {
-            const int r = e >> 5, q = e & 31;
-            if (q > j && q <= r) Sd[r][q] -= Sd[r][j] * Sd[q][j];
-        }
-    }
     __syncthreads();
-    for (int e = threadIdx.x; e < NB * XD_LD; e += NT) (&Xd[0][0])[e] = 0.0;
-    __syncthreads();
-    if (threadIdx.x < NB) Xd[threadIdx.x][threadIdx.x] = 1.0 / Sd[threadIdx.x][threadIdx.x];
-    {
-        const int l16 = threadIdx.x & 15;
-        for (int r = 1; r < NB; ++r) {
-            __syncthreads();
-            for (int cc = threadIdx.x >> 4; cc < NB; cc += NT / 16) {
-                double sacc = 0.0;
-                if (cc < r)
-                    for (int t = cc + l16; t < r; t += 16) sacc += Sd[r][t] * Xd[t][cc];
-#pragma unroll
-                for (int o = 8; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
-                if (cc < r && l16 == 0) Xd[r][cc] = -sacc / Sd[r][r];
-            }
-        }
-    }
+    if (threadIdx.x < 32) potrf32_warp(Sd, Xd, NB);
     __syncthreads();
     double* Di = T.Dinv + (size_t)kb * 1024;
     for (int e = threadIdx.x; e < NB * NB; e += NT) Di[e] = Xd[e >> 5][e & 31];
@@ -1108,19 +1129,21 @@ __device__ __noinline__ void a2_tiles(const Ctx& c, double sigma, int na) {
     phase_mark(c, 1);
     for (int kb = 0; kb < T.nt; ++kb) {
         tiles_potrf(c, T, kb);
+        phase_mark(c, 2);                                       // (diagnostics: 2 = diagonal tiles, 4 = panels, 3 = trailing updates)
         if (kb + 1 < T.nt) {
             const bool d1 = dist && (T.nt - kb - 1) > NW;       // more panel tiles than this CTA has warps
             if (d1) post_job(c, 9, na, kb, 0);
             tiles_trsm(T, kb, 0, d1 ? np : 1);
             if (d1) wait_helpers(c); else { __threadfence(); __syncthreads(); }
+            phase_mark(c, 4);
             const int m = T.nt - kb - 1;
             const bool d2 = dist && ((m * (m + 1)) >> 1) > NW;
             if (d2) post_job(c, 10, na, kb, 0);
             tiles_update(T, kb, 0, d2 ? np : 1);
             if (d2) wait_helpers(c); else { __threadfence(); __syncthreads(); }
+            phase_mark(c, 3);
         }
     }
-    phase_mark(c, 3);
     if (dist) post_job(c, 11, na, 0, 0);
     tiles_inverse(c, T, 0, np);
     if (dist) wait_helpers(c); else { __threadfence(); __syncthreads(); }
@@ -1280,39 +1303,8 @@ __device__ __noinline__ void phase_a2(const Ctx& c, double sigma, int* na_s, Gem
             }
         }
         __syncthreads();
-        // Cholesky of the nb x nb diagonal block with the whole CTA (thread per trailing element), then its inverse by
-        // forward substitution, 16 lanes per column.
-        for (int j = 0; j < nb; ++j) {
-            __syncthreads();
-            const double djj = sqrt(Sd[j][j]);
-            __syncthreads();
-            if (threadIdx.x == 0) Sd[j][j] = djj;
-            if (threadIdx.x > j && threadIdx.x < nb) Sd[threadIdx.x][j] /= djj;
-            __syncthreads();
-            for (int e = threadIdx.x; e < NB * NB; e += NT) {
-                const int r = e >> 5, q = e & 31;
-                if (q > j && q <= r && r < nb) Sd[r][q] -= Sd[r][j] * Sd[q][j];
-            }
-        }
-        __syncthreads();
-        for (int e = threadIdx.x; e < NB * XD_LD; e += NT) (&Xd[0][0])[e] = 0.0;
-        __syncthreads();
-        if (threadIdx.x < nb) Xd[threadIdx.x][threadIdx.x] = 1.0 / Sd[threadIdx.x][threadIdx.x];
-        {
-            const int l16 = threadIdx.x & 15;                              // lane within a 16-lane column group
-            for (int r = 1; r < nb; ++r) {
-                __syncthreads();
-                for (int cc = threadIdx.x >> 4; cc < NB; cc += NT / 16) {  // column (whole 16-lane groups iterate together)
-                    double sacc = 0.0;
-                    if (cc < r) {
-                        for (int t = cc + l16; t < r; t += 16) sacc += Sd[r][t] * Xd[t][cc];
-                    }
-#pragma unroll
-                    for (int o = 8; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
-                    if (cc < r && l16 == 0) Xd[r][cc] = -sacc / Sd[r][r];
-                }
-            }
-        }
+        // Cholesky of the nb x nb diagonal block and the inverse of its factor by one warp (potrf32_warp)
+        if (threadIdx.x < 32) potrf32_warp(Sd, Xd, nb);
         __syncthreads();
         phase_mark(c, 3);
         if (i0 > 0) {
