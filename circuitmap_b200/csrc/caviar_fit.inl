@@ -1800,8 +1800,10 @@ __device__ __forceinline__ double pava3_last(double a, double b, double c, int P
 //     when the result is within 1e-9 of the threshold -- 1e6 times the rounding error of that shortcut -- the gate is
 //     re-evaluated with the reference's own operations (IEEE divisions), so every decision equals the exact one;
 //   * shared memory is addressed as shared memory (LDS / STS), per-row statistics are stored by eight lanes in parallel.
+// PSM: the running prediction lives in shared memory (K doubles fit) -- otherwise in global memory (L2), e.g. C5 with
+// K = 100 000 trials; the value read in pass 1 is kept for the commit either way (nobody else touches the entry in between).
 __device__ __noinline__ void sweep_chain_fast(const Ctx& c, int nchain, double sigma, double thr, double minspk, bool gate, double* pred,
-                                 double* stage_base) {
+                                 double* stage_base, const bool PSM) {
     constexpr int PT = 4;
     const int lane = threadIdx.x & 31, tw = threadIdx.x >> 5, tt = threadIdx.x;
     __shared__ __align__(16) double xch[2][TW][4];
@@ -1815,7 +1817,7 @@ __device__ __noinline__ void sweep_chain_fast(const Ctx& c, int nchain, double s
     double* slo = scs + NSTAGE * RC;                            // [NSTAGE][RC]
     int* scp = reinterpret_cast<int*>(slo + NSTAGE * RC);       // [NSTAGE][RC]
     double* shd = reinterpret_cast<double*>(scp + NSTAGE * RC); // [NSTAGE][TW][HD]: mu, rcnt[4], then ints cntp[4], nmask[4]
-    const uint32_t a_pred = smem_u32(pred), a_scs = smem_u32(scs), a_slo = smem_u32(slo), a_scp = smem_u32(scp),
+    const uint32_t a_pred = PSM ? smem_u32(pred) : 0u, a_scs = smem_u32(scs), a_slo = smem_u32(slo), a_scp = smem_u32(scp),
                    a_shd = smem_u32(shd), a_xch = smem_u32(&xch[0][0][0]), a_xci = smem_u32(&xci[0][0][0]);
     auto stage = [&](int4 inf, int buf) {
         const int n = inf.x, beg = inf.y, len = inf.z;
@@ -1859,18 +1861,20 @@ __device__ __noinline__ void sweep_chain_fast(const Ctx& c, int nchain, double s
         // ---- pass 1 ----
         double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;           // three per-power sums, sum of squares
         unsigned c0a = 0, c1a = 0, c2 = 0;   // 16-bit fields: #(e==0) of power 0 | 1, #(e==1) of power 0 | 1, #(e==0) | #(e==1) of power 2
-        double ev[EPL];
+        double ev[EPL], pv[EPL];
         uint32_t ka[EPL];
 #pragma unroll
         for (int j = 0; j < EPL; ++j) {
             const int q = tt + j * TT;
-            ev[j] = 0.0; ka[j] = 0;
+            ev[j] = 0.0; pv[j] = 0.0; ka[j] = 0;
             if (j * TT < len && q < len) {                        // first test warp-uniform: rows of <= TT entries run j = 0 only
                 const int pk = lds_s32(a_cp + (uint32_t)q * 4u);
-                const uint32_t kad = a_pred + (uint32_t)(pk & 0x7ffffff) * 8u;
+                const uint32_t kk = (uint32_t)(pk & 0x7ffffff);
+                const uint32_t kad = PSM ? a_pred + kk * 8u : kk;
                 const int pw = pk >> 27;
-                const double e = sigmoid_fast(lds_f64(a_cs + (uint32_t)q * 8u) - coef * lds_f64(kad));
-                ev[j] = e; ka[j] = kad;
+                const double pk_pred = PSM ? lds_f64(kad) : pred[kk];
+                const double e = sigmoid_fast(lds_f64(a_cs + (uint32_t)q * 8u) - coef * pk_pred);
+                ev[j] = e; pv[j] = pk_pred; ka[j] = kad;
                 v0 += (pw == 0) ? e : 0.0;
                 v1 += (pw == 1) ? e : 0.0;
                 v2 += (pw == 2) ? e : 0.0;
@@ -1936,7 +1940,8 @@ __device__ __noinline__ void sweep_chain_fast(const Ctx& c, int nchain, double s
                 const double nw = ok ? ev[j] : 0.0;
                 const double old = lds_f64(a_lo + (uint32_t)q * 8u);
                 g_lam[beg + q] = nw;
-                sts_f64(ka[j], (lds_f64(ka[j]) + muok * nw) - mu_n * old);
+                const double np_ = (pv[j] + muok * nw) - mu_n * old;
+                if (PSM) sts_f64(ka[j], np_); else pred[ka[j]] = np_;
             }
         }
         if (tw == TW - 1 && lane < 8) {
@@ -2406,13 +2411,13 @@ __global__ void __launch_bounds__(NT, (NT == 512) ? 1 : 2) caviar_fit_kernel(con
             if (mx > RC) atomicOr(&sc_flag, 1);            // a chain row exceeds the staging capacity -> general sweep
         }
         __syncthreads();
-        const bool fast_chain = (PT == 4) && P <= 3 && pred_smem && sc_flag == 0;
+        const bool fast_chain = (PT == 4) && P <= 3 && sc_flag == 0;
         {
             const double thr = o.msrmp + sc_spont;
             const bool gate = it > o.delay_spont_est;
             const long long role_t0 = clock64();
             if (wid < TW) {
-                if (fast_chain) sweep_chain_fast(c, nchain, sigma, thr, o.minimum_spike_count, gate, pred, stage_base);
+                if (fast_chain) sweep_chain_fast(c, nchain, sigma, thr, o.minimum_spike_count, gate, pred, stage_base, pred_smem);
                 else sweep_chain<PT>(c, nchain, sigma, thr, o.minimum_spike_count, gate, pred, stage_base);
                 if (g_phase_enable && blockIdx.x == 0 && threadIdx.x == 0) g_phase_cycles[16] += clock64() - role_t0;
             } else if (wid == NW - 1) {
