@@ -958,11 +958,11 @@ __device__ void tiles_trsm(const Tiles T, int kb, int part, int nparts) {
     }
 }
 // trailing update after tile column kb: A[ib][jb] -= L[ib][kb] L[jb][kb]^T for kb < jb <= ib; a warp per tile
-__device__ void tiles_update(const Tiles T, int kb, int part, int nparts) {
+__device__ void tiles_update(const Tiles T, int kb, int part, int nparts, int t0 = 0, int t1 = 0x7fffffff) {
     const int wid = threadIdx.x >> 5;
     const int m = T.nt - kb - 1;
-    const int items = (m * (m + 1)) >> 1;
-    for (int t = part * NW + wid; t < items; t += nparts * NW) {
+    const int items = min((m * (m + 1)) >> 1, t1);
+    for (int t = t0 + part * NW + wid; t < items; t += nparts * NW) {
         int i = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
         while (((i + 1) * (i + 2)) >> 1 <= t) ++i;
         while (((i * (i + 1)) >> 1) > t) --i;
@@ -1127,22 +1127,35 @@ __device__ __noinline__ void a2_tiles(const Ctx& c, double sigma, int na) {
     gram_rows_A(c, T, sigma, 0, np);
     if (dist) wait_helpers(c); else __syncthreads();
     phase_mark(c, 1);
-    for (int kb = 0; kb < T.nt; ++kb) {
-        tiles_potrf(c, T, kb);
-        phase_mark(c, 2);                                       // (diagnostics: 2 = diagonal tiles, 4 = panels, 3 = trailing updates)
-        if (kb + 1 < T.nt) {
-            const bool d1 = dist && (T.nt - kb - 1) > NW;       // more panel tiles than this CTA has warps
-            if (d1) post_job(c, 9, na, kb, 0);
-            tiles_trsm(T, kb, 0, d1 ? np : 1);
-            if (d1) wait_helpers(c); else { __threadfence(); __syncthreads(); }
-            phase_mark(c, 4);
-            const int m = T.nt - kb - 1;
-            const bool d2 = dist && ((m * (m + 1)) >> 1) > NW;
-            if (d2) post_job(c, 10, na, kb, 0);
-            tiles_update(T, kb, 0, d2 ? np : 1);
-            if (d2) wait_helpers(c); else { __threadfence(); __syncthreads(); }
+    // Look-ahead: the factor of diagonal tile kb + 1 only needs tile (kb+1, kb+1) of the trailing update of column kb.  With
+    // helpers, the fit CTA applies that one tile itself and factors it while the helpers update all the other tiles.
+    tiles_potrf(c, T, 0);
+    phase_mark(c, 2);                                           // (diagnostics: 2 = diagonal tiles, 4 = panels, 3 = trailing updates)
+    for (int kb = 0; kb + 1 < T.nt; ++kb) {
+        const bool d1 = dist && (T.nt - kb - 1) > NW;           // more panel tiles than this CTA has warps
+        if (d1) post_job(c, 9, na, kb, 0);
+        tiles_trsm(T, kb, 0, d1 ? np : 1);
+        if (d1) wait_helpers(c); else { __threadfence(); __syncthreads(); }
+        phase_mark(c, 4);
+        const int m = T.nt - kb - 1;
+        const bool d2 = dist && ((m * (m + 1)) >> 1) > NW;
+        if (d2) {
+            post_job(c, 10, na, kb, 0);                         // helpers: items 1 .. of the trailing update, shared among them
+            tiles_update(T, kb, 0, 1, 0, 1);                    // fit CTA: item 0 = tile (kb+1, kb+1) ...
+            __threadfence();
+            __syncthreads();
+            tiles_potrf(c, T, kb + 1);                          // ... and its factor, under the helpers' update
+            phase_mark(c, 2);
+            wait_helpers(c);
+        } else {
+            tiles_update(T, kb, 0, 1);
+            __threadfence();
+            __syncthreads();
             phase_mark(c, 3);
+            tiles_potrf(c, T, kb + 1);
+            phase_mark(c, 2);
         }
+        phase_mark(c, 3);
     }
     if (dist) post_job(c, 11, na, 0, 0);
     tiles_inverse(c, T, 0, np);
@@ -1199,7 +1212,7 @@ __device__ void helper_loop(const Ctx& c, GemmPipe& gp) {
             const Tiles T = make_tiles(h, a);
             if (type == 8) gram_rows_A(h, T, *reinterpret_cast<const double*>(c.job + 8), c.role, c.ct);
             else if (type == 9) tiles_trsm(T, b, c.role, c.ct);
-            else if (type == 10) tiles_update(T, b, c.role, c.ct);
+            else if (type == 10) tiles_update(T, b, c.role - 1, c.ct - 1, 1);       // item 0 is the fit CTA's (look-ahead)
             else if (type == 11) tiles_inverse(h, T, c.role, c.ct);
             else if (type == 12) tiles_wvec(h, T, c.role, c.ct);
             else tiles_mubeta(h, T, c.role, c.ct);
