@@ -975,54 +975,6 @@ __device__ void tiles_update(const Tiles T, int kb, int part, int nparts, int t0
     }
 }
 
-// Cholesky factor of a 32 x 32 SPD block held in shared memory (Sd, lower triangle) and the inverse of that factor (Xd),
-// by ONE warp with the matrix in REGISTERS: lane r owns row r of the factor (statically indexed after full unrolling),
-// column j is broadcast lane by lane with shuffles; the inverse is a forward substitution per lane (column `lane`) against
-// the factor re-read from shared memory as warp-wide broadcasts, with the reciprocal pivots computed once.  ~10 us per
-// block; the shared-memory versions it replaces (CTA-wide with ~130 block barriers, or one warp looping over aliased
-// read-modify-writes) took 60-75 us -- on the critical path of every 32 rows of every solve.
-__device__ __noinline__ void potrf32_warp(double (*Sd)[NB + 1], double (*Xd)[XD_LD], int nb) {
-    const int lane = threadIdx.x & 31;
-    double a[32];
-#pragma unroll
-    for (int q = 0; q < 32; ++q)
-        a[q] = (lane < nb && q <= lane) ? Sd[lane][q] : ((q == lane) ? 1.0 : 0.0);   // rows >= nb: identity padding
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-        const double djj = sqrt(__shfl_sync(0xffffffffu, a[j], j));
-        const double l = (lane == j) ? djj : a[j] / djj;          // lanes < j hold 0 here
-        a[j] = l;
-#pragma unroll
-        for (int q = j + 1; q < 32; ++q) {
-            const double lq = __shfl_sync(0xffffffffu, l, q);      // L[q][j]
-            a[q] = (q <= lane) ? a[q] - l * lq : a[q];
-        }
-    }
-    __syncwarp();
-#pragma unroll
-    for (int q = 0; q < 32; ++q) Sd[lane][q] = a[q];              // the factor (zeros above the diagonal)
-    __syncwarp();
-    // X = L^-1, column `lane`: x[lane] = 1 / L[lane][lane]; x[r] = -(sum_{t = lane}^{r-1} L[r][t] x[t]) / L[r][r]
-    double x[32];
-    double piv = 1.0;
-#pragma unroll
-    for (int q = 0; q < 32; ++q) piv = (q == lane) ? a[q] : piv;  // own pivot L[lane][lane]
-    const double ipiv = 1.0 / piv;
-#pragma unroll
-    for (int r = 0; r < 32; ++r) {
-        const double ir = __shfl_sync(0xffffffffu, ipiv, r);      // 1 / L[r][r]
-        double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-        for (int t = 0; t < r; t += 2) {
-            s0 += Sd[r][t] * ((t >= lane) ? x[t] : 0.0);
-            if (t + 1 < r) s1 += Sd[r][t + 1] * ((t + 1 >= lane) ? x[t + 1] : 0.0);
-        }
-        x[r] = (r == lane) ? ir : ((r > lane) ? -(s0 + s1) * ir : 0.0);
-        Xd[r][lane] = (lane < nb && r < nb) ? x[r] : 0.0;
-    }
-    __syncwarp();
-}
-
 // Cholesky factor of diagonal tile kb and the inverse of that factor (one warp, shared memory), fit CTA only
 __device__ void tiles_potrf(const Ctx& c, const Tiles T, int kb) {
     double (*Sd)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(c.sm + GEMM_SMEM_DOUBLES);
