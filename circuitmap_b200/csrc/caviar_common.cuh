@@ -283,49 +283,51 @@ __device__ __forceinline__ double pava_last_reg(const double (&sr)[PT], int P) {
 }
 
 // Cholesky factor of a 32 x 32 SPD block held in shared memory (Sd, lower triangle) and the inverse of that factor (Xd),
-// by ONE warp with the matrix in REGISTERS: lane r owns row r of the factor (statically indexed after full unrolling),
-// column j is broadcast lane by lane with shuffles; the inverse is a forward substitution per lane (column `lane`) against
-// the factor re-read from shared memory as warp-wide broadcasts, with the reciprocal pivots computed once.  ~10 us per
-// block; the shared-memory versions it replaces (CTA-wide with ~130 block barriers, or one warp looping over aliased
-// read-modify-writes) took 60-75 us -- on the critical path of every 32 rows of every solve.
+// by ONE warp with the matrix in REGISTERS: lane r owns row r (statically indexed after full unrolling).
+//   factor, column j: the pivot comes by one shuffle, every lane scales its own entry with rsqrt(pivot), the finished
+//     column goes through 32 doubles of shared memory (rows 0 / 1 of Xd, double-buffered, one __syncwarp per column)
+//     and is read back as broadcasts for the rank-1 update of the remaining columns.  The update runs over the full
+//     row: what it leaves above the diagonal never reaches an entry on or below it and is masked at the store.
+//   inverse, column `lane` of X = L^-1 by column-oriented forward substitution: x[r] = -acc[r] / L[r][r], then
+//     acc[r2] += L[r2][r] x[r] for r2 > r -- independent FMAs against broadcast reads of the factor; x[r] = 0 for
+//     r < lane needs no masking.
+// ~3 k instructions with short dependency chains; the earlier version (each column broadcast lane by lane with 64-bit
+// shuffles, select-masked updates, row-oriented substitution with a chain of r/2 dependent FMAs per row) had ~7 k and
+// sat on the critical path of every 32 rows of every solve.
 static __device__ __noinline__ void potrf32_warp(double (*Sd)[NB + 1], double (*Xd)[XD_LD], int nb) {
     const int lane = threadIdx.x & 31;
     double a[32];
 #pragma unroll
     for (int q = 0; q < 32; ++q)
-        a[q] = (lane < nb && q <= lane) ? Sd[lane][q] : ((q == lane) ? 1.0 : 0.0);   // rows >= nb: identity padding
+        a[q] = (lane < nb) ? ((q <= lane) ? Sd[lane][q] : 0.0) : ((q == lane) ? 1.0 : 0.0);   // rows >= nb: identity padding
+    __syncwarp();
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
-        const double djj = sqrt(__shfl_sync(0xffffffffu, a[j], j));
-        const double l = (lane == j) ? djj : a[j] / djj;          // lanes < j hold 0 here
+        const double ajj = __shfl_sync(0xffffffffu, a[j], j);
+        const double rs = rsqrt(ajj);
+        const double l = (lane == j) ? ajj * rs : a[j] * rs;     // lanes < j: above the diagonal, never used
         a[j] = l;
+        double* cb = &Xd[j & 1][0];
+        cb[lane] = l;
+        __syncwarp();
 #pragma unroll
-        for (int q = j + 1; q < 32; ++q) {
-            const double lq = __shfl_sync(0xffffffffu, l, q);      // L[q][j]
-            a[q] = (q <= lane) ? a[q] - l * lq : a[q];
-        }
+        for (int q = j + 1; q < 32; ++q) a[q] = fma(-l, cb[q], a[q]);
     }
     __syncwarp();
 #pragma unroll
-    for (int q = 0; q < 32; ++q) Sd[lane][q] = a[q];              // the factor (zeros above the diagonal)
+    for (int q = 0; q < 32; ++q) Sd[lane][q] = (q <= lane) ? a[q] : 0.0;     // the factor (zeros above the diagonal)
     __syncwarp();
-    // X = L^-1, column `lane`: x[lane] = 1 / L[lane][lane]; x[r] = -(sum_{t = lane}^{r-1} L[r][t] x[t]) / L[r][r]
-    double x[32];
-    double piv = 1.0;
+    const double ipiv = 1.0 / Sd[lane][lane];
+    double acc[32];
 #pragma unroll
-    for (int q = 0; q < 32; ++q) piv = (q == lane) ? a[q] : piv;  // own pivot L[lane][lane]
-    const double ipiv = 1.0 / piv;
+    for (int q = 0; q < 32; ++q) acc[q] = 0.0;
 #pragma unroll
     for (int r = 0; r < 32; ++r) {
         const double ir = __shfl_sync(0xffffffffu, ipiv, r);      // 1 / L[r][r]
-        double s0 = 0.0, s1 = 0.0;
+        const double xr = (r == lane) ? ir : ((r > lane) ? -acc[r] * ir : 0.0);
+        Xd[r][lane] = (lane < nb && r < nb) ? xr : 0.0;
 #pragma unroll
-        for (int t = 0; t < r; t += 2) {
-            s0 += Sd[r][t] * ((t >= lane) ? x[t] : 0.0);
-            if (t + 1 < r) s1 += Sd[r][t + 1] * ((t + 1 >= lane) ? x[t + 1] : 0.0);
-        }
-        x[r] = (r == lane) ? ir : ((r > lane) ? -(s0 + s1) * ir : 0.0);
-        Xd[r][lane] = (lane < nb && r < nb) ? x[r] : 0.0;
+        for (int r2 = r + 1; r2 < 32; ++r2) acc[r2] = fma(Sd[r2][r], xr, acc[r2]);
     }
     __syncwarp();
 }

@@ -1057,13 +1057,46 @@ __device__ void tiles_wvec(const Ctx& c, const Tiles T, int part, int nparts) {
         if (lane == 0) c.wvec[i] = s;
     }
 }
+// mu = X^T w, beta = column sums of squares of X.  Work items = (tile column of 32 columns, row segment): one warp per
+// item walks the rows of its segment with coalesced 256-byte reads and leaves partial sums in c.PP (free during the tile
+// solve); the fit CTA then adds the segments of every column in ascending order.  The segmentation depends on the
+// number of active rows only, so the result does not depend on the number of CTAs.
+__device__ __forceinline__ int mubeta_seg(int na) {
+    const int nseg = min(56, (na + 255) >> 8);                    // 2 nseg lda doubles must fit c.PP (KSEG_MAX NB (N + ROWPAD))
+    return (((na + nseg - 1) / nseg) + 31) & ~31;                 // rows per segment, a multiple of the tile height
+}
 __device__ void tiles_mubeta(const Ctx& c, const Tiles T, int part, int nparts) {
-    for (int cc = part * NT + threadIdx.x; cc < T.na; cc += nparts * NT) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int seg = mubeta_seg(T.na), nseg = (T.na + seg - 1) / seg;
+    for (int idx = part * NW + wid; idx < T.nt * nseg; idx += nparts * NW) {
+        const int jt = idx / nseg, sg = idx - jt * nseg;
+        if ((sg + 1) * seg <= 32 * jt) continue;                    // segment entirely above the diagonal tile
+        const int cc = 32 * jt + lane;
+        const int ilo = max(sg * seg, 32 * jt), ihi = min((sg + 1) * seg, T.na);
         double m = 0.0, v = 0.0;
-        for (int i = cc; i < T.na; ++i) {
-            const double x = T.XI[(size_t)i * T.lda + cc];
-            m += x * c.wvec[i];
-            v += x * x;
+        const double* col = T.XI + cc;
+        for (int i = ilo; i < ihi; i += 4) {
+            double x[4], w[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const bool ok = i + u < ihi && i + u >= cc;
+                x[u] = ok ? col[(size_t)(i + u) * T.lda] : 0.0;
+                w[u] = (i + u < ihi) ? c.wvec[i + u] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { m += x[u] * w[u]; v += x[u] * x[u]; }
+        }
+        c.PP[(size_t)(2 * sg) * T.lda + cc] = m;
+        c.PP[(size_t)(2 * sg + 1) * T.lda + cc] = v;
+    }
+}
+__device__ void tiles_mubeta_sum(const Ctx& c, const Tiles T) {
+    const int seg = mubeta_seg(T.na), nseg = (T.na + seg - 1) / seg;
+    for (int cc = threadIdx.x; cc < T.na; cc += NT) {
+        double m = 0.0, v = 0.0;
+        for (int sg = (cc & ~31) / seg; sg < nseg; ++sg) {
+            m += c.PP[(size_t)(2 * sg) * T.lda + cc];
+            v += c.PP[(size_t)(2 * sg + 1) * T.lda + cc];
         }
         const int n = c.act[cc];
         c.mu[n] = m;
@@ -1119,12 +1152,86 @@ __device__ __noinline__ void a2_tiles(const Ctx& c, double sigma, int na) {
     if (dist) post_job(c, 13, na, 0, 0);
     tiles_mubeta(c, T, 0, np);
     if (dist) wait_helpers(c); else { __threadfence(); __syncthreads(); }
+    tiles_mubeta_sum(c, T);
+    __syncthreads();
     phase_mark(c, 6);
 }
 
 // Job types: 1 / 2 panel GEMM (upper / lower; a = i0, b = nb), 3 Newton rows of c.dlist (a = rows), 4 Monte-Carlo means
 // (a = key buffer, b = samples), 5 w = X b, 6 mu / beta (a = active rows), 7 Gram rows of a block (a = i0, b = nb, sigma at
 // int offset 8), 0 quit.
+// ---- O(K) / O(nnz) passes of one iteration as helper jobs (single large fits): pure maps over trials, by-trial entries
+// or rows, split into contiguous trial ranges / interleaved rows.  Every output element is computed by one thread (or
+// one warp) exactly as in the single-CTA code, so the fit stays bitwise identical whatever the number of helpers.
+__device__ __forceinline__ int part_lo(int n, int part, int nparts) { return (int)((long long)n * part / nparts); }
+// job 16 (a2 set-up): Gram-expansion records of the by-trial index in use, D and b of the active rows
+__device__ void job_a2_rows(const Ctx& c, double sigma, int na, int part, int nparts) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int i0 = part_lo(c.unnz, part, nparts), i1 = part_lo(c.unnz, part + 1, nparts);
+#pragma unroll 8
+    for (int i = i0 + threadIdx.x; i < i1; i += NT)
+        c.cscq[i] = make_double2(__longlong_as_double((long long)c.ainv[c.ucsc_row[i]]), c.lamT[i]);
+    for (int ia = part * NW + wid; ia < na; ia += nparts * NW) {
+        const int n = c.act[ia];
+        double d = 0.0, by = 0.0;
+        for (int j = c.row_ptr[n] + lane; j < c.row_ptr[n + 1]; j += 32) {
+            const double l = c.lam[j];
+            d += l * (1.0 - l);
+            by += l * c.y[c.col_k[j]];
+        }
+        d = warp_sum(d); by = warp_sum(by);
+        if (lane == 0) {
+            const double b0 = c.beta0[n];
+            c.dvec[ia] = d;
+            c.bvec[ia] = sigma * by + c.mu0[n] / (b0 * b0);
+        }
+    }
+}
+// job 14 (a3 set-up): fresh prediction into c.pred (global) and the per-entry constant part of the sigmoid argument
+__device__ void job_pred_cst(const Ctx& c, double sigma, int part, int nparts) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int k0 = part_lo(c.K, part, nparts), k1 = part_lo(c.K, part + 1, nparts);
+    for (int k = k0 + threadIdx.x; k < k1; k += NT) {
+        double s = 0.0;
+        for (int i = c.ucol_ptr[k]; i < c.ucol_ptr[k + 1]; ++i) s += c.mu[c.ucsc_row[i]] * c.lamT[i];
+        c.pred[k] = s;
+    }
+    for (int n = part * NW + wid; n < c.N; n += nparts * NW) {
+        if (c.dcnt[n]) continue;
+        const double mu_n = c.mu[n], be = c.beta[n];
+        const double cterm = 0.5 * sigma * (mu_n * mu_n + be * be);
+        const double* mce = c.mce + n * PMAX;
+        for (int j = c.row_ptr[n] + lane; j < c.row_ptr[n + 1]; j += 32) {
+            const int k = c.col_k[j];
+            c.cst[j] = (mce[c.pw[j]] - cterm) + sigma * mu_n * c.y[k] + sigma * mu_n * mu_n * c.lam[j];
+        }
+    }
+}
+// job 15 (after the sweep): by-trial copy of the new lam, residual of a6 (caviar.py:238-244) and the
+// spontaneous-event mask of a8 (caviar.py:155) for a contiguous range of trials
+__device__ void job_lamT_resid(const Ctx& c, double spont_orth, int part, int nparts) {
+    const int k0 = part_lo(c.K, part, nparts), k1 = part_lo(c.K, part + 1, nparts);
+    const int i0 = c.ucol_ptr[k0], i1 = c.ucol_ptr[k1];
+#pragma unroll 8
+    for (int i = i0 + threadIdx.x; i < i1; i += NT) c.lamT[i] = c.lam[c.ucsc_pos[i]];
+    __syncthreads();
+    for (int k = k0 + threadIdx.x; k < k1; k += NT) {
+        double s = 0.0;
+        unsigned char bl = 0;
+        for (int i = c.ucol_ptr[k]; i < c.ucol_ptr[k + 1]; ++i) {
+            const double l = c.lamT[i];
+            s += c.mu[c.ucsc_row[i]] * l;
+            bl |= (l >= spont_orth);
+        }
+        c.resid[k] = c.y[k] - s;
+        c.blocked[k] = bl;
+    }
+}
+// the passes above are worth a job hand-off (a few microseconds) from this much work on
+__device__ __forceinline__ bool dist_passes(const Ctx& c) {
+    return HELPERS && c.ct > 1 && !(g_phase_enable & 1024) && (long long)c.K + c.unnz >= 32768;
+}
+
 __device__ void helper_loop(const Ctx& c, GemmPipe& gp) {
     __shared__ int s_job[4];
     const int ldr = c.N + ROWPAD;
@@ -1168,11 +1275,15 @@ __device__ void helper_loop(const Ctx& c, GemmPipe& gp) {
             else if (type == 11) tiles_inverse(h, T, c.role, c.ct);
             else if (type == 12) tiles_wvec(h, T, c.role, c.ct);
             else tiles_mubeta(h, T, c.role, c.ct);
-        } else if (type == 7) {
+        } else if (type == 7 || (type >= 14 && type <= 16)) {
             Ctx h = c;                                           // the by-trial index the fit CTA currently uses
             if (c.job[5]) { h.ucol_ptr = c.ccol_ptr; h.ucsc_row = c.ccsc_row; h.ucsc_pos = c.ccsc_pos; }
             h.unnz = c.job[6];
-            gram_rows(h, a, b, *reinterpret_cast<const double*>(c.job + 8), c.role, c.ct);
+            const double dv = *reinterpret_cast<const double*>(c.job + 8);
+            if (type == 7) gram_rows(h, a, b, dv, c.role, c.ct);
+            else if (type == 14) job_pred_cst(h, dv, c.role, c.ct);
+            else if (type == 15) job_lamT_resid(h, dv, c.role, c.ct);
+            else job_a2_rows(h, dv, a, c.role, c.ct);
         }
         __syncthreads();
         if (threadIdx.x == 0) { __threadfence(); red_release_gpu(&c.job[16], 1); }
@@ -1189,6 +1300,12 @@ __device__ __noinline__ void phase_a2(const Ctx& c, double sigma, int* na_s, Gem
     // inactive rows decouple: mu = mu0, beta = beta0^2 (variance)
     for (int n = threadIdx.x; n < N; n += NT)
         if (c.rownz[n] == 0) { c.mu[n] = c.mu0[n]; c.beta[n] = c.beta0[n] * c.beta0[n]; }
+    if (dist_passes(c)) {
+        if (threadIdx.x == 0) *reinterpret_cast<double*>(c.job + 8) = sigma;
+        post_job(c, 16, na, 0, 0);
+        job_a2_rows(c, sigma, na, 0, c.ct);
+        wait_helpers(c);
+    } else {
     // per CSC entry: (active index of its row, lam) in one 16-byte record for the Gram expansion
 #pragma unroll 8
     for (int i = threadIdx.x; i < c.unnz; i += NT)
@@ -1208,6 +1325,7 @@ __device__ __noinline__ void phase_a2(const Ctx& c, double sigma, int* na_s, Gem
             c.dvec[ia] = d;
             c.bvec[ia] = sigma * by + c.mu0[n] / (b0 * b0);
         }
+    }
     }
     __syncthreads();
     phase_mark(c, 0);
@@ -2346,6 +2464,14 @@ __global__ void __launch_bounds__(NT, (NT == 512) ? 1 : 2) caviar_fit_kernel(con
         }
         __syncthreads();
         phase_mark(c, 8);
+        if (dist_passes(c)) {
+            if (threadIdx.x == 0) *reinterpret_cast<double*>(c.job + 8) = sigma;
+            post_job(c, 14, 0, 0, 0);
+            job_pred_cst(c, sigma, 0, c.ct);
+            wait_helpers(c);
+            if (pred_smem)
+                for (int k = threadIdx.x; k < K; k += NT) pred[k] = c.pred[k];
+        } else {
         compute_pred(c, pred);
         __syncthreads();
         // per-entry constant part of the sigmoid argument
@@ -2358,6 +2484,7 @@ __global__ void __launch_bounds__(NT, (NT == 512) ? 1 : 2) caviar_fit_kernel(con
                 const int k = c.col_k[j];
                 c.cst[j] = (mce[c.pw[j]] - cterm) + sigma * mu_n * c.y[k] + sigma * mu_n * mu_n * c.lam[j];
             }
+        }
         }
         __syncthreads();
         phase_mark(c, 9);
@@ -2420,18 +2547,30 @@ __global__ void __launch_bounds__(NT, (NT == 512) ? 1 : 2) caviar_fit_kernel(con
                 if (HELPERS && c.ct > 1 && threadIdx.x == 0) { c.job[5] = 1; c.job[6] = c.unnz; }   // helpers switch index too
             }
         }
+        // by-trial copy of the new lam; with helpers also the residual of a6 and the spontaneous-event mask of a8
+        const bool dist15 = dist_passes(c);
+        if (dist15) {
+            if (threadIdx.x == 0) *reinterpret_cast<double*>(c.job + 8) = o.spont_orthogonality;
+            post_job(c, 15, 0, 0, 0);
+            job_lamT_resid(c, o.spont_orthogonality, 0, c.ct);
+            wait_helpers(c);
+        } else {
 #pragma unroll 8
-        for (int i = threadIdx.x; i < c.unnz; i += NT) c.lamT[i] = c.lam[c.ucsc_pos[i]];   // by-trial copy of the new lam
+            for (int i = threadIdx.x; i < c.unnz; i += NT) c.lamT[i] = c.lam[c.ucsc_pos[i]];
+        }
         __syncthreads();
         phase_mark(c, 10);
         // ================= a6: update_sigma (caviar.py:238-244), with a2's mu =================
-        compute_pred(c, pred);
-        __syncthreads();
+        if (!dist15) {
+            compute_pred(c, pred);
+            __syncthreads();
+        }
         {
             double s1 = 0.0, s2 = 0.0, s3 = 0.0;
             for (int k = threadIdx.x; k < K; k += NT) {
-                const double r = c.y[k] - pred[k];
-                c.resid[k] = r;
+                double r;
+                if (dist15) r = c.resid[k];
+                else { r = c.y[k] - pred[k]; c.resid[k] = r; }
                 s1 += r * r;
             }
             for (int n = threadIdx.x; n < N; n += NT) {
@@ -2468,11 +2607,12 @@ __global__ void __launch_bounds__(NT, (NT == 512) ? 1 : 2) caviar_fit_kernel(con
         __syncthreads();
         phase_mark(c, 12);
         // ================= a8: estimate_spont_act_soft_thresh (caviar.py:146-163, 86-88) =================
-        for (int k = threadIdx.x; k < K; k += NT) {
-            unsigned char bl = 0;
-            for (int i = c.ucol_ptr[k]; i < c.ucol_ptr[k + 1]; ++i) bl |= (c.lamT[i] >= o.spont_orthogonality);
-            c.blocked[k] = bl;
-        }
+        if (!dist15)
+            for (int k = threadIdx.x; k < K; k += NT) {
+                unsigned char bl = 0;
+                for (int i = c.ucol_ptr[k]; i < c.ucol_ptr[k + 1]; ++i) bl |= (c.lamT[i] >= o.spont_orthogonality);
+                c.blocked[k] = bl;
+            }
         __syncthreads();
         {
             double err = sumy, pen = o.penalty;
