@@ -294,8 +294,14 @@ __device__ __forceinline__ double pava_last_reg(const double (&sr)[PT], int P) {
 // ~3 k instructions with short dependency chains; the earlier version (each column broadcast lane by lane with 64-bit
 // shuffles, select-masked updates, row-oriented substitution with a chain of r/2 dependent FMAs per row) had ~7 k and
 // sat on the critical path of every 32 rows of every solve.
+static __device__ __forceinline__ double potrf_lds(uint32_t a) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];\n" : "=d"(v) : "r"(a) : "memory");
+    return v;
+}
 static __device__ __noinline__ void potrf32_warp(double (*Sd)[NB + 1], double (*Xd)[XD_LD], int nb) {
     const int lane = threadIdx.x & 31;
+    const uint32_t sd_a = (uint32_t)__cvta_generic_to_shared(&Sd[0][0]), xd_a = (uint32_t)__cvta_generic_to_shared(&Xd[0][0]);
     double a[32];
 #pragma unroll
     for (int q = 0; q < 32; ++q)
@@ -311,7 +317,7 @@ static __device__ __noinline__ void potrf32_warp(double (*Sd)[NB + 1], double (*
         cb[lane] = l;
         __syncwarp();
 #pragma unroll
-        for (int q = j + 1; q < 32; ++q) a[q] = fma(-l, cb[q], a[q]);
+        for (int q = j + 1; q < 32; ++q) a[q] = fma(-l, potrf_lds(xd_a + (uint32_t)(((j & 1) * XD_LD + q) * 8)), a[q]);
     }
     __syncwarp();
 #pragma unroll
@@ -327,7 +333,7 @@ static __device__ __noinline__ void potrf32_warp(double (*Sd)[NB + 1], double (*
         const double xr = (r == lane) ? ir : ((r > lane) ? -acc[r] * ir : 0.0);
         Xd[r][lane] = (lane < nb && r < nb) ? xr : 0.0;
 #pragma unroll
-        for (int r2 = r + 1; r2 < 32; ++r2) acc[r2] = fma(Sd[r2][r], xr, acc[r2]);
+        for (int r2 = r + 1; r2 < 32; ++r2) acc[r2] = fma(potrf_lds(sd_a + (uint32_t)((r2 * (NB + 1) + r) * 8)), xr, acc[r2]);
     }
     __syncwarp();
 }
