@@ -517,7 +517,7 @@ def main():
             sync_all()
             # K steps of B fits as ONE continuous stream (what a sweep over many maps is): every step's uploads and
             # downloads are inside the timed region, the pipeline is filled and drained once, not once per step
-            n_e2e = max(1, min(args.steps, 4))
+            n_e2e = max(1, min(args.steps, 8))
             t0 = time.time()
             assert pipe.run(hs * n_e2e, hp * n_e2e, list(seeds) * n_e2e, on_result) == 0
             torch.cuda.synchronize()

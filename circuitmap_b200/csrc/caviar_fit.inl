@@ -581,14 +581,18 @@ __device__ void panel_gemm_dist(const Ctx& c, int ldr, int i0, int nb, const dou
     if (nseg > 1) reduce_partials(c, i0, nseg, OUT);
 }
 
-// (begin, length) of every CSR entry's trial list in the by-trial index in use: saves the Gram expansion one dependent
-// memory round trip per 32 entries (col_k -> col_ptr); rebuilt whenever that index changes.
+// Per CSR entry (n, k): (begin, length) of the part of trial k's list in the by-trial index in use that the Gram
+// expansion of row n needs -- saves it one dependent memory round trip per 32 entries (col_k -> col_ptr).  The lists are
+// sorted by neuron and the active order is the neuron order, so the entries with an active index <= that of row n
+// (the lower triangle) are exactly the list's prefix up to the row's own entry: the length is the own position + 1 and
+// the upper-triangle half of every list is never loaded.  Rebuilt whenever the index in use changes; entries of rows
+// outside it keep stale values and are never read (only active rows are expanded).
 __device__ __forceinline__ void build_rowcb(const Ctx& c) {
 #pragma unroll 4
-    for (int j = threadIdx.x; j < c.nnz; j += NT) {
-        const int k = c.col_k[j];
-        const int cb = c.ucol_ptr[k];
-        c.rowcb[j] = make_int2(cb, c.ucol_ptr[k + 1] - cb);
+    for (int i = threadIdx.x; i < c.unnz; i += NT) {
+        const int j = c.ucsc_pos[i];
+        const int cb = c.ucol_ptr[c.col_k[j]];
+        c.rowcb[j] = make_int2(cb, i - cb + 1);
     }
 }
 
@@ -1160,6 +1164,29 @@ __device__ __noinline__ void a2_tiles(const Ctx& c, double sigma, int na) {
 // Job types: 1 / 2 panel GEMM (upper / lower; a = i0, b = nb), 3 Newton rows of c.dlist (a = rows), 4 Monte-Carlo means
 // (a = key buffer, b = samples), 5 w = X b, 6 mu / beta (a = active rows), 7 Gram rows of a block (a = i0, b = nb, sigma at
 // int offset 8), 0 quit.
+// chinfo[i].w = 1 when chain row i shares a trial with chain row i - 1 (their steps must not overlap), for the two-team
+// chain sweep.  One warp per pair: every entry of row i is looked up in row i - 1 by binary search (the trials of a CSR
+// row are ascending).  Structural test (entries count whatever their posterior is): conservative and cheap.
+__device__ void chain_deps(const Ctx& c, int nchain, int part, int nparts) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int i = 1 + part * NW + wid; i < nchain; i += nparts * NW) {
+        const int4 a = c.chinfo[i - 1], b = c.chinfo[i];
+        const int* ka = c.col_k + a.y;
+        int hit = 0;
+        for (int q = lane; q < b.z; q += 32) {
+            const int k = c.col_k[b.y + q];
+            int lo = 0, hi = a.z;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (ka[mid] < k) lo = mid + 1; else hi = mid;
+            }
+            hit |= (lo < a.z && ka[lo] == k) ? 1 : 0;
+        }
+        hit = __any_sync(0xffffffffu, hit);
+        if (lane == 0) reinterpret_cast<int*>(c.chinfo + i)[3] = hit ? 1 : 0;
+    }
+}
+
 // ---- O(K) / O(nnz) passes of one iteration as helper jobs (single large fits): pure maps over trials, by-trial entries
 // or rows, split into contiguous trial ranges / interleaved rows.  Every output element is computed by one thread (or
 // one warp) exactly as in the single-CTA code, so the fit stays bitwise identical whatever the number of helpers.
@@ -1275,6 +1302,8 @@ __device__ void helper_loop(const Ctx& c, GemmPipe& gp) {
             else if (type == 11) tiles_inverse(h, T, c.role, c.ct);
             else if (type == 12) tiles_wvec(h, T, c.role, c.ct);
             else tiles_mubeta(h, T, c.role, c.ct);
+        } else if (type == 17) {
+            chain_deps(c, a, c.role, c.ct);
         } else if (type == 7 || (type >= 14 && type <= 16)) {
             Ctx h = c;                                           // the by-trial index the fit CTA currently uses
             if (c.job[5]) { h.ucol_ptr = c.ccol_ptr; h.ucsc_row = c.ccsc_row; h.ucsc_pos = c.ccsc_pos; }
@@ -1618,6 +1647,8 @@ constexpr int TT = 32 * TW;
 constexpr int EPL = RC / TT;     // staged entries per team thread
 constexpr int STAGE_DOUBLES = NSTAGE * (RC + RC + RC / 2 + TW * HD);   // cs, lo, cp (ints), one header copy per team warp
 __device__ __forceinline__ void team_sync() { asm volatile("bar.sync 1, %0;\n" ::"n"(TT) : "memory"); }
+__device__ __forceinline__ void team_sync_id(int team) { asm volatile("bar.sync %0, %1;\n" ::"r"(1 + team), "n"(TT) : "memory"); }
+constexpr int CM_ECHAIN = 10;    // status: the two chain teams lost each other (never seen; a bounded wait instead of a hang)
 
 // The sequential part of the sweep: neurons with mu != 0, in update order (caviar.py:196-229; quirk A.3 #3: the in-sweep
 // zeroing of mu is visible to later neurons through the running prediction).  One step per neuron, steps strictly in
@@ -1885,12 +1916,32 @@ __device__ __forceinline__ double pava3_last(double a, double b, double c, int P
 //   * shared memory is addressed as shared memory (LDS / STS), per-row statistics are stored by eight lanes in parallel.
 // PSM: the running prediction lives in shared memory (K doubles fit) -- otherwise in global memory (L2), e.g. C5 with
 // K = 100 000 trials; the value read in pass 1 is kept for the commit either way (nobody else touches the entry in between).
+//
+// TWO TEAMS (16-warp variant): consecutive chain rows that share no trial neither read nor write a common entry of the
+// prediction, so their steps are independent.  Team t takes the steps i = t, t + 2, ...; chinfo[i].w says whether row i
+// shares a trial with row i - 1 (chain_deps).  Before a step the team waits until the other team has finished step
+// i - 3 (always: this bounds the run-ahead, so that only ADJACENT steps ever overlap) and, if the rows are dependent,
+// step i - 1; progress counters in shared memory, st.release.cta by the team leader after the commit barrier,
+// ld.acquire.cta by every waiting lane.  Every entry of the prediction still sees the same updates in the same order:
+// bitwise identical to the one-team sweep.  (A team only ever waits for steps that precede its own, and the team that
+// owns the oldest unfinished step never waits: no deadlock.)
+__device__ __forceinline__ int ld_acquire_cta_s(const int* p) {
+    int v;
+    asm volatile("ld.acquire.cta.shared.s32 %0, [%1];\n" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_cta_s(int* p, int v) {
+    asm volatile("st.release.cta.shared.s32 [%0], %1;\n" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+}
 __device__ __noinline__ void sweep_chain_fast(const Ctx& c, int nchain, double sigma, double thr, double minspk, bool gate, double* pred,
-                                 double* stage_base, const bool PSM) {
+                                 double* stage_base, const bool PSM, const int team, const int nteams, int* done) {
     constexpr int PT = 4;
-    const int lane = threadIdx.x & 31, tw = threadIdx.x >> 5, tt = threadIdx.x;
-    __shared__ __align__(16) double xch[2][TW][4];
-    __shared__ __align__(16) int xci[2][TW][4];
+    const int lane = threadIdx.x & 31, tw = (threadIdx.x >> 5) - team * TW, tt = threadIdx.x - team * TT;
+    __shared__ __align__(16) double xch_s[2][2][TW][4];
+    __shared__ __align__(16) int xci_s[2][2][TW][4];
+    double (*xch)[TW][4] = xch_s[team];
+    int (*xci)[TW][4] = xci_s[team];
+    stage_base += (size_t)team * STAGE_DOUBLES;
     const int P = c.P;
     double* const g_lam = c.lam; double* const g_sp = c.sp; double* const g_slam = c.slam; double* const g_slam2 = c.slam2;
     int* const g_n0p = c.n0p; int* const g_n1p = c.n1p; int* const g_rownz = c.rownz;
@@ -1919,22 +1970,35 @@ __device__ __noinline__ void sweep_chain_fast(const Ctx& c, int nchain, double s
         }
         cp_async_commit();
     };
+    // the team's own steps are i = team + li * nteams, li = 0, 1, ...
+    const int g0 = team, g1 = team + nteams, g2 = team + 2 * nteams, g3 = team + 3 * nteams;
     int4 infA = make_int4(0, 0, 0, 0), infB = infA;
-    if (nchain > 0) stage(g_chinfo[0], 0);
-    if (nchain > 1) stage(g_chinfo[1], 1);
-    if (nchain > 2) infA = g_chinfo[2];
-    if (nchain > 3) infB = g_chinfo[3];
-    int4 cur = nchain > 0 ? g_chinfo[0] : infA, nxt = nchain > 1 ? g_chinfo[1] : infA;
+    if (g0 < nchain) stage(g_chinfo[g0], 0);
+    if (g1 < nchain) stage(g_chinfo[g1], 1);
+    if (g2 < nchain) infA = g_chinfo[g2];
+    if (g3 < nchain) infB = g_chinfo[g3];
+    int4 cur = g0 < nchain ? g_chinfo[g0] : infA, nxt = g1 < nchain ? g_chinfo[g1] : infA;
     const bool hi16 = (lane & 16) != 0, hi8 = (lane & 8) != 0;
-    for (int i = 0; i < nchain; ++i) {
-        if (i + 2 < nchain) { stage(infA, (i + 2) % NSTAGE); cp_async_wait<2>(); }
-        else if (i + 1 < nchain) cp_async_wait<1>();
+    int li = 0;
+    for (int i = team; i < nchain; i += nteams, ++li) {
+        if (i + 2 * nteams < nchain) { stage(infA, (li + 2) % NSTAGE); cp_async_wait<2>(); }
+        else if (i + nteams < nchain) cp_async_wait<1>();
         else cp_async_wait<0>();
         __syncwarp();
         const int4 after = infA;
         infA = infB;
-        if (i + 4 < nchain) infB = g_chinfo[i + 4];
-        const int buf = i % NSTAGE, par = i & 1;
+        if (i + 4 * nteams < nchain) infB = g_chinfo[i + 4 * nteams];
+        const int buf = li % NSTAGE, par = li & 1;
+        if (nteams > 1) {
+            // steps of the other team that must be complete: i - 3 always, i - 1 if this row shares a trial with it
+            const int m = (i + team - 2) >> 1;                   // the other team's local index of step i - 1
+            const int need = cur.w ? m + 1 : m;
+            if (need > 0) {
+                long long spins = 0;
+                while (ld_acquire_cta_s(done + (1 - team)) < need)
+                    if (++spins > (1ll << 28)) { atomicExch(c.status, CM_ECHAIN); break; }
+            }
+        }
         const int n = cur.x, beg = cur.y, len = cur.z;
         const uint32_t a_hd = a_shd + (uint32_t)((buf * TW + tw) * HD) * 8u;
         const double mu_n = lds_f64(a_hd);
@@ -1989,7 +2053,7 @@ __device__ __noinline__ void sweep_chain_fast(const Ctx& c, int nchain, double s
         if (lane == 1) sts_s32(a_xci + (uint32_t)((par * TW + tw) * 4) * 4u, (int)c0a);
         if (lane == 2) sts_s32(a_xci + (uint32_t)((par * TW + tw) * 4 + 1) * 4u, (int)c1a);
         if (lane == 3) sts_s32(a_xci + (uint32_t)((par * TW + tw) * 4 + 2) * 4u, (int)c2);
-        team_sync();
+        team_sync_id(team);
         // ---- totals in fixed warp order, gate ----
         double S0 = 0.0, S1 = 0.0, S2 = 0.0, Q = 0.0;
 #pragma unroll
@@ -2051,7 +2115,8 @@ __device__ __noinline__ void sweep_chain_fast(const Ctx& c, int nchain, double s
             }
             if (lane == 5) g_rownz[n] = ok ? (len - (zeros - masked)) : 0;
         }
-        team_sync();                                              // the prediction is consistent before the next neuron reads it
+        team_sync_id(team);                                       // the prediction is consistent before the next neuron reads it
+        if (nteams > 1 && tt == 0) st_release_cta_s(done + team, li + 1);
         cur = nxt;
         nxt = after;
     }
@@ -2096,134 +2161,150 @@ struct QuadStats {                             // the groups g = m, m+4, ... own
     int ng;
 };
 
+__device__ __forceinline__ double quad_sum_m(double v, unsigned mask) {      // inside a branch taken by whole quads
+    v += __shfl_xor_sync(mask, v, 1);
+    v += __shfl_xor_sync(mask, v, 2);
+    return v;
+}
 __device__ __forceinline__ double quad_sum(double v) {
     v += __shfl_xor_sync(0xffffffffu, v, 1);
     v += __shfl_xor_sync(0xffffffffu, v, 2);
     return v;
 }
 
-// negloglik_with_barrier (caviar.py:312-316) from per-power sufficient statistics; the power groups are spread over
-// the 4 lanes of a quad (one sigmoid + two logs per lane for P <= 3)
-__device__ __forceinline__ double nll_quad(const QuadStats& s, double p0, double p1, const double* prior,
-                                           const double* prec, double t) {
-    double ll = 0.0;
-#pragma unroll
-    for (int i = 0; i < GPL; ++i)
-        if (i < s.ng) {
-            const double f = sigmoid_d(p0 * s.pv[i] - p1);
-            ll += group_loglik(f, s.cnt[i], s.S[i], s.n0[i], s.n1[i]);
-        }
-    ll = quad_sum(ll);
-    const double d0 = p0 - prior[0], d1 = p1 - prior[1];
-    const double quad = 0.5 * (d0 * (prec[0] * d0 + prec[1] * d1) + d1 * (prec[2] * d0 + prec[3] * d1));
-    return -ll - (log(p0) + log(p1)) / t + quad;
-}
-
 // update_phi for the rows list[0..nlist): _laplace_approx (caviar.py:253-308), 10 damped Newton steps from the PRIOR
-// mean, covariance = H^-1 before the last step.  Eight rows per warp (one per quad); every loop is warp-convergent
-// (predicated) so the quad shuffles stay legal while rows need different numbers of backtracking steps.
-// The sigmoids of the gradient pass are reused for the objective at the current point (same inputs, same fp result).
+// mean, covariance = H^-1 before the last step.  One row per quad of lanes (the power groups of a row are spread over
+// its 4 lanes), eight rows in flight per warp -- as a STATE MACHINE: every trip of the warp loop evaluates the objective
+// AND its gradient / Hessian sums at one point per row, the row's current backtracking candidate.  An accepted candidate
+// is the next iterate, and the sums just computed there are that step's gradient pass (same inputs, same operations,
+// same fp result as evaluating them again), so a step costs 1 + #backtracks evaluations instead of 2 + #backtracks; rows
+// advance independently (a warp no longer loops until the slowest of its eight rows has finished EVERY step: the
+// lock-step version spent 5.1 trips per step where the rows needed 1.7) and a quad that finishes a row fetches its next
+// one (rows idx, idx + stride, ... statically per quad: which quad runs a row does not change its result).
 __device__ __noinline__ void newton_rows(const Ctx& c, const double* powers, const int* list, int nlist, int part, int nparts) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int quad = lane >> 2, mem = lane & 3;
     const double t = 10.0, alpha = 0.25, bbeta = 0.5;
-    for (int base = (part * NW + wid) * 8; base < nlist; base += nparts * NW * 8) {      // rows are independent
-        const int idx = base + quad;
-        const bool live = idx < nlist;
-        const int n = live ? list[idx] : list[0];
-        QuadStats s;
-        s.ng = 0;
-        double ctot = 0.0;
-        for (int p = 0; p < c.P; ++p) ctot += (double)c.cntp[n * PMAX + p];
+    const int stride = nparts * NW * 8;
+    int idx = (part * NW + wid) * 8 + quad;                       // next row of this quad
+    bool have = false, first = false;
+    int n = 0, step = 0, bt = 0;
+    QuadStats s;
+    s.ng = 0;
 #pragma unroll
-        for (int i = 0; i < GPL; ++i) {
-            const int g = mem + 4 * i;
-            s.pv[i] = 0.0; s.cnt[i] = 0.0; s.S[i] = 0.0; s.n0[i] = 0.0; s.n1[i] = 0.0;
-            if (g <= c.P) {
-                s.ng = i + 1;
-                if (g == 0) { s.cnt[i] = (double)c.K - ctot; s.n0[i] = s.cnt[i]; }
-                else {
-                    const int p = g - 1;
-                    s.pv[i] = powers[p];
-                    s.cnt[i] = (double)c.cntp[n * PMAX + p];
-                    s.S[i] = c.sp[n * PMAX + p];
-                    s.n0[i] = (double)c.n0p[n * PMAX + p];
-                    s.n1[i] = (double)c.n1p[n * PMAX + p];
-                }
-            }
-        }
-        const double prior[2] = {c.phi0[2 * n], c.phi0[2 * n + 1]};
-        const double* cov0 = c.phicov0 + 4 * n;
-        const double det0 = cov0[0] * cov0[3] - cov0[1] * cov0[2];
-        const double prec[4] = {cov0[3] / det0, -cov0[1] / det0, -cov0[2] / det0, cov0[0] / det0};
-        double p0 = prior[0], p1 = prior[1];
-        double hi[4] = {0, 0, 0, 0};
-        for (int step = 0; step < 10; ++step) {
-            double j1 = 0, j2 = 0, h11 = 0, h12 = 0, h22 = 0, ll = 0;
+    for (int i = 0; i < GPL; ++i) { s.pv[i] = 0.0; s.cnt[i] = 0.0; s.S[i] = 0.0; s.n0[i] = 0.0; s.n1[i] = 0.0; }
+    double prior[2] = {1.0, 1.0}, prec[4] = {0, 0, 0, 0}, hi[4] = {0, 0, 0, 0};
+    double p0 = 1.0, p1 = 1.0, basev = 0.0, v0 = 0.0, v1 = 0.0, Jv = 0.0, stp = 1.0;
+    long long evals_w = 0, evals_r = 0;
+    for (;;) {
+        if (!have && idx < nlist) {                              // fetch the next row: sufficient statistics, prior, precision
+            n = list[idx];
+            idx += stride;
+            double ctot = 0.0;
+            for (int p = 0; p < c.P; ++p) ctot += (double)c.cntp[n * PMAX + p];
+            s.ng = 0;
 #pragma unroll
-            for (int i = 0; i < GPL; ++i)
-                if (i < s.ng) {
-                    const double f = sigmoid_d(p0 * s.pv[i] - p1);
-                    const double r = s.S[i] - s.cnt[i] * f;
-                    const double w = s.cnt[i] * f * (1.0 - f);
-                    j1 -= s.pv[i] * r;
-                    j2 += r;
-                    h11 += s.pv[i] * s.pv[i] * w;
-                    h12 -= s.pv[i] * w;
-                    h22 += w;
-                    ll += group_loglik(f, s.cnt[i], s.S[i], s.n0[i], s.n1[i]);
+            for (int i = 0; i < GPL; ++i) {
+                const int g = mem + 4 * i;
+                s.pv[i] = 0.0; s.cnt[i] = 0.0; s.S[i] = 0.0; s.n0[i] = 0.0; s.n1[i] = 0.0;
+                if (g <= c.P) {
+                    s.ng = i + 1;
+                    if (g == 0) { s.cnt[i] = (double)c.K - ctot; s.n0[i] = s.cnt[i]; }
+                    else {
+                        const int p = g - 1;
+                        s.pv[i] = powers[p];
+                        s.cnt[i] = (double)c.cntp[n * PMAX + p];
+                        s.S[i] = c.sp[n * PMAX + p];
+                        s.n0[i] = (double)c.n0p[n * PMAX + p];
+                        s.n1[i] = (double)c.n1p[n * PMAX + p];
+                    }
                 }
-            j1 = quad_sum(j1); j2 = quad_sum(j2); h11 = quad_sum(h11); h12 = quad_sum(h12); h22 = quad_sum(h22);
-            ll = quad_sum(ll);
-            const double d0 = p0 - prior[0], d1 = p1 - prior[1];
-            const double quadf = 0.5 * (d0 * (prec[0] * d0 + prec[1] * d1) + d1 * (prec[2] * d0 + prec[3] * d1));
-            const double basev = -ll - (log(p0) + log(p1)) / t + quadf;
-            const double J0 = j1 + (prec[0] * d0 + prec[1] * d1) - 1.0 / (t * p0);
-            const double J1 = j2 + (prec[2] * d0 + prec[3] * d1) - 1.0 / (t * p1);
-            const double H00 = h11 + prec[0] + 1.0 / (t * p0 * p0);
-            const double H01 = h12 + prec[1];
-            const double H10 = h12 + prec[2];
-            const double H11 = h22 + prec[3] + 1.0 / (t * p1 * p1);
-            const double det = H00 * H11 - H01 * H10;
-            hi[0] = H11 / det; hi[1] = -H01 / det; hi[2] = -H10 / det; hi[3] = H00 / det;
-            const double v0 = -(hi[0] * J0 + hi[1] * J1), v1 = -(hi[2] * J0 + hi[3] * J1);
-            double stp = 1.0;
-            const double Jv = J0 * v0 + J1 * v1;
-            double lhs = nll_quad(s, p0 + stp * v0, p1 + stp * v1, prior, prec, t);
-            double rhs = basev + alpha * stp * Jv;
-            int bt = 0;
-            bool go = (bt < 40) && ((lhs != lhs) || lhs > rhs);
-            int trips = 0;
-            while (__any_sync(0xffffffffu, go)) {
-                ++trips;
-                const double stp_try = go ? stp * bbeta : stp;
-                const double lhs_try = nll_quad(s, p0 + stp_try * v0, p1 + stp_try * v1, prior, prec, t);
-                if (go) {
-                    ++bt;
-                    stp = stp_try;
-                    lhs = lhs_try;
-                    rhs = basev + alpha * stp * Jv;
-                }
-                go = go && (bt < 40) && ((lhs != lhs) || lhs > rhs);
             }
-            p0 += stp * v0;
-            p1 += stp * v1;
-            if ((g_phase_enable & 1) && blockIdx.x == 0) {       // diagnostics: warp-level loop trips vs backtracks the rows needed
-                const int need = __reduce_add_sync(0xffffffffu, (live && mem == 0) ? bt : 0);
-                if (lane == 0) { atomicAdd((unsigned long long*)&g_phase_cycles[25], (unsigned long long)trips);
-                                 atomicAdd((unsigned long long*)&g_phase_cycles[26], (unsigned long long)need);
-                                 atomicAdd((unsigned long long*)&g_phase_cycles[27], 1ull); }
+            prior[0] = c.phi0[2 * n]; prior[1] = c.phi0[2 * n + 1];
+            const double* cov0 = c.phicov0 + 4 * n;
+            const double det0 = cov0[0] * cov0[3] - cov0[1] * cov0[2];
+            prec[0] = cov0[3] / det0; prec[1] = -cov0[1] / det0; prec[2] = -cov0[2] / det0; prec[3] = cov0[0] / det0;
+            p0 = prior[0]; p1 = prior[1];
+            hi[0] = hi[1] = hi[2] = hi[3] = 0.0;
+            step = 0; bt = 0; stp = 1.0; v0 = 0.0; v1 = 0.0;
+            first = true; have = true;
+        }
+        if (!__any_sync(0xffffffffu, have)) break;
+        // the point this trip evaluates: the iterate itself (first trip of a row) or the current candidate p + stp v
+        const double x0 = first ? p0 : p0 + stp * v0, x1 = first ? p1 : p1 + stp * v1;
+        double j1 = 0, j2 = 0, h11 = 0, h12 = 0, h22 = 0, ll = 0;
+#pragma unroll
+        for (int i = 0; i < GPL; ++i)
+            if (i < s.ng) {
+                const double f = sigmoid_d(x0 * s.pv[i] - x1);
+                const double r = s.S[i] - s.cnt[i] * f;
+                const double w = s.cnt[i] * f * (1.0 - f);
+                j1 -= s.pv[i] * r;
+                j2 += r;
+                h11 += s.pv[i] * s.pv[i] * w;
+                h12 -= s.pv[i] * w;
+                h22 += w;
+                ll += group_loglik(f, s.cnt[i], s.S[i], s.n0[i], s.n1[i]);
+            }
+        ll = quad_sum(ll);
+        const double d0 = x0 - prior[0], d1 = x1 - prior[1];
+        const double quadf = 0.5 * (d0 * (prec[0] * d0 + prec[1] * d1) + d1 * (prec[2] * d0 + prec[3] * d1));
+        // log(x0) + log(x1): even members of the quad take log(x0), odd ones log(x1) -- one logarithm per trip, not two
+        const double lg = log((mem & 1) ? x1 : x0);
+        const double lgo = __shfl_xor_sync(0xffffffffu, lg, 1);
+        const double val = -ll - (((mem & 1) ? lgo : lg) + ((mem & 1) ? lg : lgo)) / t + quadf;
+        ++evals_w;
+        if (have) {
+            ++evals_r;
+            bool accept = first;
+            if (!first) {                                        // Armijo test of the candidate (caviar.py:289-299)
+                const double rhs = basev + alpha * stp * Jv;
+                const bool go = (bt < 40) && ((val != val) || val > rhs);
+                accept = !go;
+                if (go) { ++bt; stp *= bbeta; }
+            }
+            if (accept) {
+                if (!first) { p0 = x0; p1 = x1; ++step; }
+                first = false;
+                if (step == 10) {
+                    if (mem == 0) {
+                        c.phi[2 * n] = p0; c.phi[2 * n + 1] = p1;
+                        for (int q = 0; q < 4; ++q) c.phicov[4 * n + q] = hi[q];
+                        if (c.rownz[n] == 0) {                   // all-zero rows always give the same answer: cache it
+                            c.phiz[2 * n] = p0; c.phiz[2 * n + 1] = p1;
+                            for (int q = 0; q < 4; ++q) c.phicovz[4 * n + q] = hi[q];
+                            c.phizok[n] = 1;
+                        }
+                    }
+                    have = false;
+                } else {                                         // Newton direction at the new iterate
+                    basev = val;
+                    // gradient / Hessian sums over the quad (a whole quad is in this branch or not: `accept` derives
+                    // from quad-uniform values), then three divisions: 1 / p0, 1 / p1, 1 / det
+                    const unsigned qm = 0xFu << (lane & 28);
+                    j1 = quad_sum_m(j1, qm); j2 = quad_sum_m(j2, qm); h11 = quad_sum_m(h11, qm);
+                    h12 = quad_sum_m(h12, qm); h22 = quad_sum_m(h22, qm);
+                    const double rp0 = 1.0 / p0, rp1 = 1.0 / p1, rt = 1.0 / t;
+                    const double J0 = j1 + (prec[0] * d0 + prec[1] * d1) - rt * rp0;
+                    const double J1 = j2 + (prec[2] * d0 + prec[3] * d1) - rt * rp1;
+                    const double H00 = h11 + prec[0] + rt * rp0 * rp0;
+                    const double H01 = h12 + prec[1];
+                    const double H10 = h12 + prec[2];
+                    const double H11 = h22 + prec[3] + rt * rp1 * rp1;
+                    const double rdet = 1.0 / (H00 * H11 - H01 * H10);
+                    hi[0] = H11 * rdet; hi[1] = -H01 * rdet; hi[2] = -H10 * rdet; hi[3] = H00 * rdet;
+                    v0 = -(hi[0] * J0 + hi[1] * J1); v1 = -(hi[2] * J0 + hi[3] * J1);
+                    Jv = J0 * v0 + J1 * v1;
+                    stp = 1.0;
+                    bt = 0;
+                }
             }
         }
-        if (live && mem == 0) {
-            c.phi[2 * n] = p0; c.phi[2 * n + 1] = p1;
-            for (int q = 0; q < 4; ++q) c.phicov[4 * n + q] = hi[q];
-            if (c.rownz[n] == 0) {                       // all-zero rows always give the same answer: cache it
-                c.phiz[2 * n] = p0; c.phiz[2 * n + 1] = p1;
-                for (int q = 0; q < 4; ++q) c.phicovz[4 * n + q] = hi[q];
-                c.phizok[n] = 1;
-            }
-        }
+    }
+    if ((g_phase_enable & 1) && blockIdx.x == 0) {               // diagnostics: warp trips vs evaluations the rows needed
+        const long long need = __reduce_add_sync(0xffffffffu, (unsigned)((mem == 0) ? evals_r : 0));
+        if (lane == 0) { atomicAdd((unsigned long long*)&g_phase_cycles[25], (unsigned long long)evals_w);
+                         atomicAdd((unsigned long long*)&g_phase_cycles[26], (unsigned long long)need); }
     }
 }
 
@@ -2241,6 +2322,7 @@ __global__ void __launch_bounds__(NT, (NT == 512) ? 1 : 2) caviar_fit_kernel(con
     __shared__ __align__(8) uint64_t sc_bar[2 * NST];
 
     __shared__ int sc_b;
+    __shared__ int sc_done[2];         // steps finished by each team of the two-team chain sweep
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     if (threadIdx.x == 0) {
         for (int i = 0; i < NST; ++i) { mbar_init(&sc_bar[i], 1); mbar_init(&sc_bar[NST + i], NW); }
@@ -2504,12 +2586,28 @@ __global__ void __launch_bounds__(NT, (NT == 512) ? 1 : 2) caviar_fit_kernel(con
         }
         __syncthreads();
         const bool fast_chain = (PT == 4) && P <= 3 && sc_flag == 0;
+        // two chain teams (16-warp variant): rows without a common trial overlap, see sweep_chain_fast
+        const bool two_teams = HELPERS && fast_chain && nchain >= 16 && !(g_phase_enable & 2048) &&
+                               (pred_smem ? kpad : 0) + 2 * STAGE_DOUBLES <= c.smd;
+        if (two_teams) {
+            if (threadIdx.x == 0) { sc_done[0] = 0; sc_done[1] = 0; }
+            if (c.ct > 1 && nchain >= 128) {
+                post_job(c, 17, nchain, 0, 0);
+                chain_deps(c, nchain, 0, c.ct);
+                wait_helpers(c);
+            } else {
+                chain_deps(c, nchain, 0, 1);
+                __syncthreads();
+            }
+        }
+        const int nteams = two_teams ? 2 : 1;
         {
             const double thr = o.msrmp + sc_spont;
             const bool gate = it > o.delay_spont_est;
             const long long role_t0 = clock64();
-            if (wid < TW) {
-                if (fast_chain) sweep_chain_fast(c, nchain, sigma, thr, o.minimum_spike_count, gate, pred, stage_base, pred_smem);
+            if (wid < TW * nteams) {
+                if (fast_chain) sweep_chain_fast(c, nchain, sigma, thr, o.minimum_spike_count, gate, pred, stage_base, pred_smem,
+                                                 wid / TW, nteams, sc_done);
                 else sweep_chain<PT>(c, nchain, sigma, thr, o.minimum_spike_count, gate, pred, stage_base);
                 if (g_phase_enable && blockIdx.x == 0 && threadIdx.x == 0) g_phase_cycles[16] += clock64() - role_t0;
             } else if (wid == NW - 1) {
@@ -2517,7 +2615,7 @@ __global__ void __launch_bounds__(NT, (NT == 512) ? 1 : 2) caviar_fit_kernel(con
                 if (g_phase_enable && blockIdx.x == 0 && lane == 0) g_phase_cycles[17] += clock64() - role_t0;
             } else {
                 // mu == 0: the row neither reads nor changes the prediction -> order-free, run concurrently
-                for (int m = wid - TW; m < N; m += NW - TW - 1) {
+                for (int m = wid - TW * nteams; m < N; m += NW - TW * nteams - 1) {
                     const int n = c.order[m];
                     if (c.mu[n] == 0.0 && !c.dcnt[n]) {
                         const int beg = c.row_ptr[n], len = c.row_ptr[n + 1] - beg;
@@ -2525,7 +2623,7 @@ __global__ void __launch_bounds__(NT, (NT == 512) ? 1 : 2) caviar_fit_kernel(con
                                       c.colpw + beg, c.cst + beg, c.lam + beg, sigma, thr, o.minimum_spike_count, gate, pred);
                     }
                 }
-                if (g_phase_enable && blockIdx.x == 0 && wid == TW && lane == 0) g_phase_cycles[18] += clock64() - role_t0;
+                if (g_phase_enable && blockIdx.x == 0 && wid == TW * nteams && lane == 0) g_phase_cycles[18] += clock64() - role_t0;
             }
         }
         __syncthreads();

@@ -266,7 +266,8 @@ def check_status(out):
         b = int(np.nonzero(st)[0][0])
         msg = {1: "stimulus matrix holds a value that is negative, NaN or not among `powers`",
                5: "non-zeros of the stimulus matrix exceed nnz_cap",
-               9: "a helper CTA of the fit never answered; the results are not valid"}.get(int(st[b]), "device error")
+               9: "a helper CTA of the fit never answered; the results are not valid",
+               10: "the two chain teams of the sweep lost each other; the results are not valid"}.get(int(st[b]), "device error")
         raise RuntimeError("cm_caviar_fit: fit %d failed with code %d (%s)" % (b, int(st[b]), msg))
 
 

@@ -53,5 +53,5 @@ print("  chain steps %d, mean row len %.1f; cycles/step: pass1 %.0f reduce %.0f 
     buf[19], buf[24] / max(buf[19], 1), buf[20] / max(buf[19], 1), buf[21] / max(buf[19], 1), buf[22] / max(buf[19], 1), buf[23] / max(buf[19], 1)))
 for i, nm in [(16, "sweep.chain warp"), (17, "sweep.rng warp"), (18, "sweep.inactive warp1")]:
     print("  %-22s %10.3f ms" % (nm, buf[i] / 1.9e6))
-print("  newton: warp-steps %d, backtrack loop trips %d (%.2f per warp-step), backtracks needed by rows %d (%.2f per row-step)" % (
-    buf[27], buf[25], buf[25] / max(buf[27], 1), buf[26], buf[26] / max(8 * buf[27], 1)))
+print("  newton: warp trips (one objective + gradient evaluation per row in flight) %d, evaluations the rows needed %d (%.2f per trip of 8 rows)" % (
+    buf[25], buf[26], buf[26] / max(buf[25], 1)))
