@@ -992,8 +992,45 @@ __device__ void tiles_potrf(const Ctx& c, const Tiles T, int kb) {
     if (threadIdx.x < 32) potrf32_warp(Sd, Xd, NB);
     __syncthreads();
     double* Di = T.Dinv + (size_t)kb * 1024;
-    for (int e = threadIdx.x; e < NB * NB; e += NT) Di[e] = Xd[e >> 5][e & 31];
+    double* Xkk = T.XI + (size_t)(32 * kb) * T.lda + 32 * kb;  // diagonal tile of X = L^-1 (tiles_inv_level starts from these)
+    for (int e = threadIdx.x; e < NB * NB; e += NT) {
+        const double v = Xd[e >> 5][e & 31];
+        Di[e] = v;
+        Xkk[(size_t)(e >> 5) * T.lda + (e & 31)] = v;
+    }
     __syncthreads();
+}
+// X = L^-1 by recursive halving over blocks of tiles, bottom-up: at level s = 1, 2, 4, ... the sibling blocks
+// [lo, mid) and [mid, hi) (lo = 2 s p, mid = lo + s, hi = min(lo + 2 s, nt)) already hold their own inverses X11, X22 and
+//     stage 0:  T[i][j] = sum_{k = j}^{mid - 1} L[i][k] X[k][j]        i in [mid, hi), j in [lo, mid)      (L21 X11)
+//     stage 1:  X[i][j] = - sum_{k = mid}^{i} X[i][k] T[k][j]                                            (- X22 T)
+// fill the block below the diagonal.  Every output tile is one warp job with a fixed k order, all tiles of a stage are
+// independent: log2(nt) levels of two wide jobs each instead of a chain of nt dependent steps per tile column (the
+// column-by-column forward substitution this replaces: 7.5 ms of a C3 fit, 56 ms of a C5 fit).  T[i][j] is kept in the
+// unused upper triangle of the factor's tile matrix, at tile (j, i); every (i, j) belongs to exactly one level.
+__device__ void tiles_inv_level(const Tiles T, int s, int stage, int part, int nparts) {
+    const int wid = threadIdx.x >> 5;
+    const int npairs = (T.nt + 2 * s - 1) / (2 * s);
+    const long long total = (long long)npairs * s * s;
+    for (long long idx = part * NW + wid; idx < total; idx += (long long)nparts * NW) {
+        const int ii = (int)(idx % s);
+        const long long rest = idx / s;
+        const int jj = (int)(rest % s), p = (int)(rest / s);
+        const int lo = 2 * s * p, mid = lo + s;
+        const int i = mid + ii, j = lo + jj;
+        if (i >= T.nt) continue;
+        double acc[4][4][2];
+        tile_zero(acc);
+        if (stage == 0) {
+            for (int k = j; k < mid; ++k)
+                tile_mma<true>(acc, T.A + (size_t)(32 * i) * T.lda + 32 * k, T.lda, T.XI + (size_t)(32 * k) * T.lda + 32 * j, T.lda);
+            tile_store<false>(acc, T.A + (size_t)(32 * j) * T.lda + 32 * i, T.lda, 1.0);
+        } else {
+            for (int k = mid; k <= i; ++k)
+                tile_mma<true>(acc, T.XI + (size_t)(32 * i) * T.lda + 32 * k, T.lda, T.A + (size_t)(32 * j) * T.lda + 32 * k, T.lda);
+            tile_store<false>(acc, T.XI + (size_t)(32 * i) * T.lda + 32 * j, T.lda, -1.0);
+        }
+    }
 }
 // X = L^-1 by tile columns jb = part, part + nparts, ... (a column per CTA): X[jb][jb] = Dinv[jb];
 // X[ib][jb] = -Dinv[ib] * sum_{kb = jb}^{ib - 1} L[ib][kb] X[kb][jb].  The 16 warps split the k range of the sum (warp w
@@ -1146,9 +1183,20 @@ __device__ __noinline__ void a2_tiles(const Ctx& c, double sigma, int na) {
         }
         phase_mark(c, 3);
     }
-    if (dist) post_job(c, 11, na, 0, 0);
-    tiles_inverse(c, T, 0, np);
-    if (dist) wait_helpers(c); else { __threadfence(); __syncthreads(); }
+    if (g_phase_enable & 4096) {                                // diagnostics: the column-by-column forward substitution
+        if (dist) post_job(c, 11, na, 0, -1);
+        tiles_inverse(c, T, 0, np);
+        if (dist) wait_helpers(c); else { __threadfence(); __syncthreads(); }
+    } else {
+        for (int s = 1; s < T.nt; s <<= 1)
+            for (int stage = 0; stage < 2; ++stage) {
+                const long long items = (long long)((T.nt + 2 * s - 1) / (2 * s)) * s * s;
+                const bool d3 = dist && items > NW;
+                if (d3) post_job(c, 11, na, s, stage);
+                tiles_inv_level(T, s, stage, 0, d3 ? np : 1);
+                if (d3) wait_helpers(c); else { __threadfence(); __syncthreads(); }
+            }
+    }
     phase_mark(c, 5);
     if (dist) post_job(c, 12, na, 0, 0);
     tiles_wvec(c, T, 0, np);
@@ -1299,7 +1347,7 @@ __device__ void helper_loop(const Ctx& c, GemmPipe& gp) {
             if (type == 8) gram_rows_A(h, T, *reinterpret_cast<const double*>(c.job + 8), c.role, c.ct);
             else if (type == 9) tiles_trsm(T, b, c.role, c.ct);
             else if (type == 10) tiles_update(T, b, c.role - 1, c.ct - 1, 1);       // item 0 is the fit CTA's (look-ahead)
-            else if (type == 11) tiles_inverse(h, T, c.role, c.ct);
+            else if (type == 11) { if (d3 < 0) tiles_inverse(h, T, c.role, c.ct); else tiles_inv_level(T, b, d3, c.role, c.ct); }
             else if (type == 12) tiles_wvec(h, T, c.role, c.ct);
             else tiles_mubeta(h, T, c.role, c.ct);
         } else if (type == 17) {
