@@ -639,8 +639,8 @@ def main():
         algo5 = algorithmic_bytes_per_fit(N5, K5, iters)
         c5 = {"metric": "caviar_fits_per_s", "value": 1e3 / t5[-1], "unit": "fits/s", "ms_per_fit": t5[-1],
               "iters_per_s": iters * 1e3 / t5[-1],
-              "config": {"workload": "C5 large single map: N=5000, K=100000, H=%d, %d iters, ONE B200 (one persistent fit CTA + 15 "
-                                     "helper CTAs; the K-sharded 8-GPU variant is not built)" % (H, iters)},
+              "config": {"workload": "C5 large single map: N=5000, K=100000, H=%d, %d iters, ONE B200 (one persistent fit CTA + 127 "
+                                     "helper CTAs; the K-sharded 8-GPU variant is not built: DESIGN.md 5)" % (H, iters)},
               "connected": int((o5["mu"][0] != 0).sum().item()),
               "roofline": {"bound": "hbm", "achieved": algo5 / (t5[-1] / 1e3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                            "frac": algo5 / (t5[-1] / 1e3) / 1e9 / hbm_peak, "algorithmic_model": ALGO_NOTE}}

@@ -405,7 +405,7 @@ extern "C" int cm_caviar_fit(const cm_caviar_args* a, void* stream) {
     }
     if (!small_cta && a->N > 256) {
         const int sms = sm_count;
-        int want = a->N >= 2048 ? 127 : 15;                  // large systems: the trailing updates / inverse columns of the tile solve and
+        int want = a->N >= 2048 ? 127 : (a->N >= 768 ? 63 : 15);                  // large systems: the trailing updates / inverse columns of the tile solve and
                                                              // the O(K) passes scale with the CTA count (C5: 47 -> 127 helpers, 628 -> 572 ms)
         if (const char* e = getenv("CM_CAVIAR_HELPERS")) want = atoi(e);
         want = want < 0 ? 0 : (want > 127 ? 127 : want);

@@ -857,6 +857,46 @@ __device__ __forceinline__ void tile_store(const double (&acc)[4][4][2], double*
         }
 }
 
+// Strip form of the same products for jobs with FEW tiles: four consecutive warps share one output tile, warp `strip`
+// computes its rows 8 strip .. 8 strip + 7.  All operands of a 32 x 32 x 32 product (8 + 32 doubles per lane) are loaded
+// before the first DMMA, so a product costs one L2 round trip instead of eight (the full-tile form keeps 32 accumulators
+// per lane and can only prefetch one k step ahead: ~3.3 us per product, latency-bound), and a tile is finished four
+// times sooner.  Every output element accumulates its k steps in the same order as in the full-tile form: bitwise equal.
+template <bool NN>
+__device__ __forceinline__ void tile_mma_strip(double (&acc)[4][2], const double* __restrict__ A, int lda,
+                                               const double* __restrict__ B, int ldb, int strip) {
+    const int lane = threadIdx.x & 31, lq = lane >> 2, lr = lane & 3;
+    double a[8], b[8][4];
+    const double* Ar = A + (size_t)(8 * strip + lq) * lda + lr;
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) a[ks] = Ar[4 * ks];
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) b[ks][nt] = NN ? B[(size_t)(4 * ks + lr) * ldb + 8 * nt + lq] : B[(size_t)(8 * nt + lq) * ldb + 4 * ks + lr];
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) dmma8x8x4(acc[nt][0], acc[nt][1], a[ks], b[ks][nt]);
+}
+__device__ __forceinline__ void strip_zero(double (&acc)[4][2]) {
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) { acc[nt][0] = 0.0; acc[nt][1] = 0.0; }
+}
+template <bool ADD>
+__device__ __forceinline__ void strip_store(const double (&acc)[4][2], double* C, int ldc, double sgn, int strip) {
+    const int lane = threadIdx.x & 31, lq = lane >> 2, lr = lane & 3;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+        double2* p = reinterpret_cast<double2*>(C + (size_t)(8 * strip + lq) * ldc + 8 * nt + 2 * lr);
+        double2 v = ADD ? *p : make_double2(0.0, 0.0);
+        v.x += sgn * acc[nt][0]; v.y += sgn * acc[nt][1];
+        *p = v;
+    }
+}
+// strips when every quad of warps gets at most two tiles of the job
+__device__ __forceinline__ bool use_strips(long long items, int nparts) { return items * 2 <= (long long)nparts * NW; }
+
 // Gram rows part, part + W, ... of the whole active set (W = warps of all CTAs of the fit) into the square A, incl. the
 // identity padding up to a multiple of 32 (cf. gram_rows: same expansion, same deterministic combination of lanes)
 __device__ void gram_rows_A(const Ctx& c, const Tiles T, double sigma, int part, int nparts) {
@@ -952,6 +992,18 @@ __device__ void gram_rows_A(const Ctx& c, const Tiles T, double sigma, int part,
 __device__ void tiles_trsm(const Tiles T, int kb, int part, int nparts) {
     const int wid = threadIdx.x >> 5;
     const double* Di = T.Dinv + (size_t)kb * 1024;
+    if (use_strips(T.nt - kb - 1, nparts)) {
+        const int strip = wid & 3;
+        for (int ib = kb + 1 + ((part * NW + wid) >> 2); ib < T.nt; ib += (nparts * NW) >> 2) {
+            double* C = T.A + (size_t)(32 * ib) * T.lda + 32 * kb;
+            double acc[4][2];
+            strip_zero(acc);
+            tile_mma_strip<false>(acc, C, T.lda, Di, 32, strip);
+            __syncwarp();                                       // the strip has been read before it is overwritten
+            strip_store<false>(acc, C, T.lda, 1.0, strip);
+        }
+        return;
+    }
     for (int ib = kb + 1 + part * NW + wid; ib < T.nt; ib += nparts * NW) {
         double* C = T.A + (size_t)(32 * ib) * T.lda + 32 * kb;
         double acc[4][4][2];
@@ -966,6 +1018,21 @@ __device__ void tiles_update(const Tiles T, int kb, int part, int nparts, int t0
     const int wid = threadIdx.x >> 5;
     const int m = T.nt - kb - 1;
     const int items = min((m * (m + 1)) >> 1, t1);
+    if (use_strips(items - t0, nparts)) {
+        const int strip = wid & 3;
+        for (int t = t0 + ((part * NW + wid) >> 2); t < items; t += (nparts * NW) >> 2) {
+            int i = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+            while (((i + 1) * (i + 2)) >> 1 <= t) ++i;
+            while (((i * (i + 1)) >> 1) > t) --i;
+            const int j = t - ((i * (i + 1)) >> 1);
+            const int ib = kb + 1 + i, jb = kb + 1 + j;
+            double acc[4][2];
+            strip_zero(acc);
+            tile_mma_strip<false>(acc, T.A + (size_t)(32 * ib) * T.lda + 32 * kb, T.lda, T.A + (size_t)(32 * jb) * T.lda + 32 * kb, T.lda, strip);
+            strip_store<true>(acc, T.A + (size_t)(32 * ib) * T.lda + 32 * jb, T.lda, -1.0, strip);
+        }
+        return;
+    }
     for (int t = t0 + part * NW + wid; t < items; t += nparts * NW) {
         int i = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
         while (((i + 1) * (i + 2)) >> 1 <= t) ++i;
@@ -1012,6 +1079,29 @@ __device__ void tiles_inv_level(const Tiles T, int s, int stage, int part, int n
     const int wid = threadIdx.x >> 5;
     const int npairs = (T.nt + 2 * s - 1) / (2 * s);
     const long long total = (long long)npairs * s * s;
+    if (use_strips(total, nparts)) {
+        const int strip = wid & 3;
+        for (long long idx = (part * NW + wid) >> 2; idx < total; idx += (long long)((nparts * NW) >> 2)) {
+            const int ii = (int)(idx % s);
+            const long long rest = idx / s;
+            const int jj = (int)(rest % s), p = (int)(rest / s);
+            const int lo = 2 * s * p, mid = lo + s;
+            const int i = mid + ii, j = lo + jj;
+            if (i >= T.nt) continue;
+            double acc[4][2];
+            strip_zero(acc);
+            if (stage == 0) {
+                for (int k = j; k < mid; ++k)
+                    tile_mma_strip<true>(acc, T.A + (size_t)(32 * i) * T.lda + 32 * k, T.lda, T.XI + (size_t)(32 * k) * T.lda + 32 * j, T.lda, strip);
+                strip_store<false>(acc, T.A + (size_t)(32 * j) * T.lda + 32 * i, T.lda, 1.0, strip);
+            } else {
+                for (int k = mid; k <= i; ++k)
+                    tile_mma_strip<true>(acc, T.XI + (size_t)(32 * i) * T.lda + 32 * k, T.lda, T.A + (size_t)(32 * j) * T.lda + 32 * k, T.lda, strip);
+                strip_store<false>(acc, T.XI + (size_t)(32 * i) * T.lda + 32 * j, T.lda, -1.0, strip);
+            }
+        }
+        return;
+    }
     for (long long idx = part * NW + wid; idx < total; idx += (long long)nparts * NW) {
         const int ii = (int)(idx % s);
         const long long rest = idx / s;
