@@ -114,11 +114,73 @@ __device__ int block_compact(int n, F flag, int* out, int* inv, double* red) {
 }
 
 // fresh prediction pred[k] = sum_n mu[n] lam[n,k] over the (neuron-sorted) column lists
+// sum_i mu[row_i] lam_i over one trial's list, entries added in list order; four entries' loads are issued together
+// (the loop is bound by the latency of its dependent loads -- row index, then mu -- not by arithmetic)
+__device__ __forceinline__ double trial_pred(const Ctx& c, int beg, int end) {
+    double s = 0.0;
+    for (int i = beg; i < end; i += 4) {
+        int r[4];
+        double l[4], m[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const bool ok = i + u < end;
+            r[u] = ok ? c.ucsc_row[i + u] : -1;
+            l[u] = ok ? c.lamT[i + u] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) m[u] = r[u] >= 0 ? c.mu[r[u]] : 0.0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) if (r[u] >= 0) s += m[u] * l[u];
+    }
+    return s;
+}
 __device__ __forceinline__ void compute_pred(const Ctx& c, double* dst) {
-    for (int k = threadIdx.x; k < c.K; k += NT) {
-        double s = 0.0;
-        for (int i = c.ucol_ptr[k]; i < c.ucol_ptr[k + 1]; ++i) s += c.mu[c.ucsc_row[i]] * c.lamT[i];
-        dst[k] = s;
+    for (int k = threadIdx.x; k < c.K; k += NT) dst[k] = trial_pred(c, c.ucol_ptr[k], c.ucol_ptr[k + 1]);
+}
+
+// D = sum lam (1 - lam) and b = sigma sum lam y + mu0 / beta0^2 of active row ia (caviar.py:167-171), one warp.
+// (Four groups of 32 entries per round, as in row_cst below, was measured here and is slower.)
+__device__ __forceinline__ void row_dvec_bvec(const Ctx& c, int ia, double sigma) {
+    const int lane = threadIdx.x & 31;
+    const int n = c.act[ia];
+    double d = 0.0, by = 0.0;
+    for (int j = c.row_ptr[n] + lane; j < c.row_ptr[n + 1]; j += 32) {
+        const double l = c.lam[j];
+        d += l * (1.0 - l);
+        by += l * c.y[c.col_k[j]];
+    }
+    d = warp_sum(d); by = warp_sum(by);
+    if (lane == 0) {
+        const double b0 = c.beta0[n];
+        c.dvec[ia] = d;
+        c.bvec[ia] = sigma * by + c.mu0[n] / (b0 * b0);
+    }
+}
+// One CSR row by one warp, four groups of 32 entries per round so that the dependent gathers (trial index, then y) of
+// a whole ~100-entry row are two round trips instead of eight:
+// per-entry constant part of the sigmoid argument of row n (caviar.py:216-218 with the Monte-Carlo term of mc_means)
+__device__ __forceinline__ void row_cst(const Ctx& c, int n, double sigma) {
+    const int lane = threadIdx.x & 31;
+    const double mu_n = c.mu[n], be = c.beta[n];
+    const double cterm = 0.5 * sigma * (mu_n * mu_n + be * be);
+    const double* mce = c.mce + n * PMAX;                    // Monte-Carlo term per power (mc_means)
+    const int beg = c.row_ptr[n], end = c.row_ptr[n + 1];
+    for (int j0 = beg + lane; j0 < end; j0 += 128) {
+        double l[4], yv[4], mc[4];
+        int k[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int j = j0 + 32 * u;
+            const bool ok = j < end;
+            k[u] = ok ? c.col_k[j] : -1;
+            l[u] = ok ? c.lam[j] : 0.0;
+            mc[u] = ok ? mce[c.pw[j]] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) yv[u] = k[u] >= 0 ? c.y[k[u]] : 0.0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (k[u] >= 0) c.cst[j0 + 32 * u] = (mc[u] - cterm) + sigma * mu_n * yv[u] + sigma * mu_n * mu_n * l[u];
     }
 }
 
@@ -170,6 +232,7 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
 // One warp per row; 32 entries of the row are expanded at once (each lane walks the column list of its own
 // trial, 8 list entries prefetched per round), lanes that hit the same target column in the same step are
 // combined in lane order -> deterministic.
+constexpr int GCH = 8;      // list entries per lane loaded in one round (10 -- a whole list of the 10-target designs -- was measured: slower)
 __device__ void gram_rows(const Ctx& c, int i0, int nb, double sigma, int part = 0, int nparts = 1) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int cap = GEMM_SMEM_DOUBLES / NW;       // row-buffer doubles per warp
@@ -196,11 +259,11 @@ __device__ void gram_rows(const Ctx& c, int i0, int nb, double sigma, int part =
             int maxlen = len;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, o));
-            for (int t0 = 0; t0 < maxlen; t0 += 8) {
-                int ibs[8];
-                double vs[8];
+            for (int t0 = 0; t0 < maxlen; t0 += GCH) {
+                int ibs[GCH];
+                double vs[GCH];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {                  // independent 16-byte loads (memory-level parallelism)
+                for (int u = 0; u < GCH; ++u) {                  // independent 16-byte loads (memory-level parallelism)
                     const int t = t0 + u;
                     int ib = -1;
                     double lv = 0.0;
@@ -214,7 +277,7 @@ __device__ void gram_rows(const Ctx& c, int i0, int nb, double sigma, int part =
                     vs[u] = la * lv;
                 }
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
+                for (int u = 0; u < GCH; ++u) {
                     if (t0 + u >= maxlen) break;               // warp-uniform
                     const int ib = ibs[u];
                     const double v = vs[u];
@@ -929,11 +992,11 @@ __device__ void gram_rows_A(const Ctx& c, const Tiles T, double sigma, int part,
             int maxlen = len;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, o));
-            for (int t0 = 0; t0 < maxlen; t0 += 8) {
-                int ibs[8];
-                double vs[8];
+            for (int t0 = 0; t0 < maxlen; t0 += GCH) {
+                int ibs[GCH];
+                double vs[GCH];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
+                for (int u = 0; u < GCH; ++u) {
                     const int t = t0 + u;
                     int ib = -1;
                     double lv = 0.0;
@@ -947,7 +1010,7 @@ __device__ void gram_rows_A(const Ctx& c, const Tiles T, double sigma, int part,
                     vs[u] = la * lv;
                 }
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
+                for (int u = 0; u < GCH; ++u) {
                     if (t0 + u >= maxlen) break;               // warp-uniform
                     const int ib = ibs[u];
                     const double v = vs[u];
@@ -1336,41 +1399,15 @@ __device__ void job_a2_rows(const Ctx& c, double sigma, int na, int part, int np
 #pragma unroll 8
     for (int i = i0 + threadIdx.x; i < i1; i += NT)
         c.cscq[i] = make_double2(__longlong_as_double((long long)c.ainv[c.ucsc_row[i]]), c.lamT[i]);
-    for (int ia = part * NW + wid; ia < na; ia += nparts * NW) {
-        const int n = c.act[ia];
-        double d = 0.0, by = 0.0;
-        for (int j = c.row_ptr[n] + lane; j < c.row_ptr[n + 1]; j += 32) {
-            const double l = c.lam[j];
-            d += l * (1.0 - l);
-            by += l * c.y[c.col_k[j]];
-        }
-        d = warp_sum(d); by = warp_sum(by);
-        if (lane == 0) {
-            const double b0 = c.beta0[n];
-            c.dvec[ia] = d;
-            c.bvec[ia] = sigma * by + c.mu0[n] / (b0 * b0);
-        }
-    }
+    for (int ia = part * NW + wid; ia < na; ia += nparts * NW) row_dvec_bvec(c, ia, sigma);
 }
 // job 14 (a3 set-up): fresh prediction into c.pred (global) and the per-entry constant part of the sigmoid argument
 __device__ void job_pred_cst(const Ctx& c, double sigma, int part, int nparts) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int k0 = part_lo(c.K, part, nparts), k1 = part_lo(c.K, part + 1, nparts);
-    for (int k = k0 + threadIdx.x; k < k1; k += NT) {
-        double s = 0.0;
-        for (int i = c.ucol_ptr[k]; i < c.ucol_ptr[k + 1]; ++i) s += c.mu[c.ucsc_row[i]] * c.lamT[i];
-        c.pred[k] = s;
-    }
-    for (int n = part * NW + wid; n < c.N; n += nparts * NW) {
-        if (c.dcnt[n]) continue;
-        const double mu_n = c.mu[n], be = c.beta[n];
-        const double cterm = 0.5 * sigma * (mu_n * mu_n + be * be);
-        const double* mce = c.mce + n * PMAX;
-        for (int j = c.row_ptr[n] + lane; j < c.row_ptr[n + 1]; j += 32) {
-            const int k = c.col_k[j];
-            c.cst[j] = (mce[c.pw[j]] - cterm) + sigma * mu_n * c.y[k] + sigma * mu_n * mu_n * c.lam[j];
-        }
-    }
+    for (int k = k0 + threadIdx.x; k < k1; k += NT) c.pred[k] = trial_pred(c, c.ucol_ptr[k], c.ucol_ptr[k + 1]);
+    for (int n = part * NW + wid; n < c.N; n += nparts * NW)
+        if (!c.dcnt[n]) row_cst(c, n, sigma);
 }
 // job 15 (after the sweep): by-trial copy of the new lam, residual of a6 (caviar.py:238-244) and the
 // spontaneous-event mask of a8 (caviar.py:155) for a contiguous range of trials
@@ -1478,21 +1515,7 @@ __device__ __noinline__ void phase_a2(const Ctx& c, double sigma, int* na_s, Gem
     for (int i = threadIdx.x; i < c.unnz; i += NT)
         c.cscq[i] = make_double2(__longlong_as_double((long long)c.ainv[c.ucsc_row[i]]), c.lamT[i]);
     // per active row: D = sum lam(1-lam), b = sigma * sum lam*y + mu0/beta0^2
-    for (int ia = wid; ia < na; ia += NW) {
-        const int n = c.act[ia];
-        double d = 0.0, by = 0.0;
-        for (int j = c.row_ptr[n] + lane; j < c.row_ptr[n + 1]; j += 32) {
-            const double l = c.lam[j];
-            d += l * (1.0 - l);
-            by += l * c.y[c.col_k[j]];
-        }
-        d = warp_sum(d); by = warp_sum(by);
-        if (lane == 0) {
-            const double b0 = c.beta0[n];
-            c.dvec[ia] = d;
-            c.bvec[ia] = sigma * by + c.mu0[n] / (b0 * b0);
-        }
-    }
+    for (int ia = wid; ia < na; ia += NW) row_dvec_bvec(c, ia, sigma);
     }
     __syncthreads();
     phase_mark(c, 0);
@@ -2695,16 +2718,8 @@ __global__ void __launch_bounds__(NT, (NT == 512) ? 1 : 2) caviar_fit_kernel(con
         compute_pred(c, pred);
         __syncthreads();
         // per-entry constant part of the sigmoid argument
-        for (int n = wid; n < N; n += NW) {
-            if (c.dcnt[n]) continue;
-            const double mu_n = c.mu[n], be = c.beta[n];
-            const double cterm = 0.5 * sigma * (mu_n * mu_n + be * be);
-            const double* mce = c.mce + n * PMAX;                // Monte-Carlo term per power (mc_means)
-            for (int j = c.row_ptr[n] + lane; j < c.row_ptr[n + 1]; j += 32) {
-                const int k = c.col_k[j];
-                c.cst[j] = (mce[c.pw[j]] - cterm) + sigma * mu_n * c.y[k] + sigma * mu_n * mu_n * c.lam[j];
-            }
-        }
+        for (int n = wid; n < N; n += NW)
+            if (!c.dcnt[n]) row_cst(c, n, sigma);
         }
         __syncthreads();
         phase_mark(c, 9);

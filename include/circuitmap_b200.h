@@ -138,7 +138,8 @@ typedef struct cm_caviar_args {
     void*   workspace_dev;
     size_t  workspace_bytes;     /* >= cm_caviar_workspace_bytes(B, N, K, nnz_cap, flags) */
     int*    status_dev;          /* B ints: 0 ok, else CM_E* detected on device (1 invalid stimulus entry, 5 nnz overflow,
-                                    9 a helper CTA of a large single fit never answered) */
+                                    9 a helper CTA of a large single fit never answered, 10 the two chain teams of a
+                                    sweep lost each other -- both are bounded waits instead of hangs, never seen in practice) */
     /* optional sparse posterior: CSR over (neuron, trial) of the entries lam can be non-zero on, i.e. targeted trials
      * that pass the lam_mask (caviar.py:30-34,216) -- 8 nnz bytes instead of the 8 N K of lam_dev.  All three or none. */
     double*  lam_csr_val_dev;    /* B x nnz_cap */

@@ -302,6 +302,45 @@ def test_c5_large_single_map_shape():
     assert len(got - truth) <= 5 and len(truth & got) >= 0.7 * len(truth)
 
 
+def test_chain_teams_pass_jobs_and_inverse_variants():
+    """Round-2 rearrangements of a single large fit (csrc/caviar_fit.inl): the second chain team (rows without a common
+    trial overlap, sweep_chain_fast) and the O(K) / O(nnz) pass jobs on the helper CTAs must not change a bit -- every
+    entry of the running prediction sees the same updates in the same order, every map output is computed by one thread
+    as before.  The recursive tile inverse sums in a different order than the column-by-column substitution it
+    replaces: same connected set, values to rounding.  Diagnostics bits 10 / 11 / 12 of cm_caviar_debug_phase_cycles
+    switch the old forms back on."""
+    import torch
+    from oracle import simulate as osim
+    from circuitmap_b200 import optimise, _lib
+    lib = _lib.load()
+    N, K = 700, 6000
+    sim = osim.simulate_fast(N=N, K=K, H=10, seed=77)
+    f64 = dict(dtype=torch.float64, device="cuda")
+    cov = torch.zeros(1, N, 2, 2, **f64); cov[..., 0, 0] = 0.1; cov[..., 1, 1] = 1.0
+    phi = torch.stack([0.1 * torch.ones(1, N, **f64), 5 * torch.ones(1, N, **f64)], -1).contiguous()
+    stim = torch.from_numpy(sim["stim_matrix"][None]).cuda()
+    psc = torch.from_numpy(sim["psc"][None]).cuda()
+    args = (stim, np.unique(sim["stim_matrix"])[1:], torch.zeros(1, N, **f64), 10 * torch.ones(1, N, **f64), 1.0, 0.1, phi, cov)
+    outs = {}
+    try:
+        for name, bits in (("default", 0), ("one_team", 1 << 11), ("no_pass_jobs", 1 << 10), ("column_inverse", 1 << 12)):
+            assert lib.cm_caviar_debug_phase_cycles(None, 0, bits) == 0
+            outs[name] = optimise.caviar_batched(*args, psc=psc, seeds=[3], iters=14, msrmp=0.4)
+            optimise.check_status(outs[name])
+    finally:
+        lib.cm_caviar_debug_phase_cycles(None, 0, 0)
+    ref = outs["default"]
+    assert int((ref["mu"][0] != 0).sum()) > 20
+    for nm in NAMES:
+        assert torch.equal(ref[nm], outs["one_team"][nm]), nm
+        assert torch.equal(ref[nm], outs["no_pass_jobs"][nm]), nm
+    alt = outs["column_inverse"]
+    assert torch.equal(ref["mu"] != 0, alt["mu"] != 0)
+    for nm in NAMES:
+        a, b = ref[nm].double(), alt[nm].double()
+        assert torch.allclose(a, b, rtol=1e-7, atol=1e-9 * float(b.abs().max()), equal_nan=True), nm
+
+
 def test_panel_gemm_helper_ctas_are_bitwise_neutral():
     """A single large fit gets helper CTAs for the column tiles of its panel GEMMs (csrc/caviar_fit.inl,
     panel_gemm_dist).  Every output element is still computed by one warp in the same order: the fit must be bitwise
