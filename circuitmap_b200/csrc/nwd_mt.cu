@@ -166,34 +166,52 @@ __device__ __forceinline__ int ab_unit(const AB b, int cp, int seq, int pp) {
 // ------------------------------------------------------------------------------------------------ MMA issue
 // All MMAs of layer L by one thread.  `abase` / `wbase` are shared-memory byte addresses of the A buffer (plane 0)
 // and of the tap table.  Descriptor start addresses advance in 16-byte units.
+// The issue loop is what paces the tensor pipe when it is not tight (round-2 SASS reading: ~20 instructions with
+// branches and register-to-uniform moves between two UTCHMMA = ~100 cycles per MMA, against 64 for an M = 128, N = 128,
+// K = 16 MMA): only the elected thread runs it, the window loop over `a` carries two running descriptor words, the
+// phase / channel-plane loops are fully unrolled with compile-time offsets, the partial last window row is a
+// compile-time tail and every MMA but the first of a tile takes a constant accumulate flag.
 template <int L, int RL, int CQ0 = 0, int CQ1 = lcfg(L).CIN / 16>
 __device__ __forceinline__ void issue_layer(uint32_t abase, uint32_t wbase, uint32_t tmem, bool leader, uint32_t acc0 = 0) {
     constexpr int PH = lcfg(L).PH, CIN = lcfg(L).CIN, COUT = lcfg(L).COUT, U = lcfg(L).UPAD, V = lc_v(L), N = lc_n(L);
     constexpr int TILES = lc_tiles(L);
     constexpr uint32_t idesc = idesc_f16(N);
     constexpr uint32_t HI_SBO = (128u >> 4) | (1u << 14);                  // high word: SBO = 128 B, descriptor version 1
+    if (!leader) return;
     if constexpr (CIN >= 16) {
         // K steps per window position = pairs of 8-channel planes CQ0 .. CQ1 - 1 (the whole layer by default)
+        constexpr int AFULL = V / PH, TAIL = V % PH;                       // full window rows, phases of the partial one
         const uint32_t a0 = ((abase >> 4) & 0x3FFF) | ((uint32_t)(PH * RL) << 16);      // LBO = plane stride
         const uint32_t b0 = ((wbase >> 4) & 0x3FFF) | ((uint32_t)(U * COUT) << 16);
 #pragma unroll 1
         for (int mt = 0; mt < TILES; ++mt) {
-            uint32_t acc = acc0;
+            const uint32_t td = tmem + mt * N;
+            uint32_t ad = a0 + (uint32_t)(128 * mt), bd = b0;              // descriptors of window row a, phase 0, plane pair 0
+            // window row 0: the first MMA of the tile takes the caller's accumulate flag
+#pragma unroll
+            for (int j = 0; j < (AFULL > 0 ? PH : TAIL); ++j)
+#pragma unroll
+                for (int cq = CQ0; cq < CQ1; ++cq)
+                    umma_f16(td, ad + (uint32_t)((2 * cq * PH + j) * RL), HI_SBO, bd + (uint32_t)((2 * cq * U + j) * COUT), HI_SBO, idesc,
+                             (j == 0 && cq == CQ0) ? acc0 : 1u);
 #pragma unroll 1
-            for (int a = 0; a * PH < V; ++a) {
+            for (int a = 1; a < AFULL; ++a) {
+                ad += 1u;
+                bd += (uint32_t)(PH * COUT);
 #pragma unroll
-                for (int j = 0; j < PH; ++j) {
-                    const int v = a * PH + j;
-                    if (v < V) {
+                for (int j = 0; j < PH; ++j)
 #pragma unroll
-                        for (int cq = CQ0; cq < CQ1; ++cq) {
-                            if (leader)
-                                umma_f16(tmem + mt * N, a0 + (uint32_t)((2 * cq * PH + j) * RL + 128 * mt + a), HI_SBO,
-                                         b0 + (uint32_t)((2 * cq * U + v) * COUT), HI_SBO, idesc, acc);
-                            acc = 1;
-                        }
-                    }
-                }
+                    for (int cq = CQ0; cq < CQ1; ++cq)
+                        umma_f16(td, ad + (uint32_t)((2 * cq * PH + j) * RL), HI_SBO, bd + (uint32_t)((2 * cq * U + j) * COUT), HI_SBO, idesc, 1u);
+            }
+            if constexpr (AFULL > 0 && TAIL > 0) {
+                ad += 1u;
+                bd += (uint32_t)(PH * COUT);
+#pragma unroll
+                for (int j = 0; j < TAIL; ++j)
+#pragma unroll
+                    for (int cq = CQ0; cq < CQ1; ++cq)
+                        umma_f16(td, ad + (uint32_t)((2 * cq * PH + j) * RL), HI_SBO, bd + (uint32_t)((2 * cq * U + j) * COUT), HI_SBO, idesc, 1u);
             }
         }
     } else if constexpr (PH == 1) {                                        // d1: K step = two consecutive units
@@ -203,20 +221,24 @@ __device__ __forceinline__ void issue_layer(uint32_t abase, uint32_t wbase, uint
         for (int mt = 0; mt < TILES; ++mt)
 #pragma unroll
             for (int v = 0; v < V; v += 2)
-                if (leader)
-                    umma_f16(tmem + mt * N, a0 + (uint32_t)(128 * mt + v), HI_SBO, b0 + (uint32_t)(v * COUT), HI_SBO, idesc, v ? 1u : 0u);
+                umma_f16(tmem + mt * N, a0 + (uint32_t)(128 * mt + v), HI_SBO, b0 + (uint32_t)(v * COUT), HI_SBO, idesc, v ? 1u : 0u);
     } else {                                                               // fin: K step = phases j, j + 1
         static_assert(TILES == 1, "single tile");
+        static_assert(V % PH == 0, "whole window rows");
         const uint32_t a0 = ((abase >> 4) & 0x3FFF) | ((uint32_t)RL << 16);
         const uint32_t b0 = ((wbase >> 4) & 0x3FFF) | ((uint32_t)COUT << 16);
-#pragma unroll 1
-        for (int a = 0; a * PH < V; ++a)
+        uint32_t ad = a0, bd = b0;
 #pragma unroll
-            for (int j = 0; j < PH; j += 2) {
-                const int v = a * PH + j;
-                if (v < V && leader)
-                    umma_f16(tmem, a0 + (uint32_t)(j * RL + a), HI_SBO, b0 + (uint32_t)(v * COUT), HI_SBO, idesc, v ? 1u : 0u);
-            }
+        for (int j = 0; j < PH; j += 2)
+            umma_f16(tmem, ad + (uint32_t)(j * RL), HI_SBO, bd + (uint32_t)(j * COUT), HI_SBO, idesc, j ? 1u : 0u);
+#pragma unroll 1
+        for (int a = 1; a < V / PH; ++a) {
+            ad += 1u;
+            bd += (uint32_t)(PH * COUT);
+#pragma unroll
+            for (int j = 0; j < PH; j += 2)
+                umma_f16(tmem, ad + (uint32_t)(j * RL), HI_SBO, bd + (uint32_t)(j * COUT), HI_SBO, idesc, 1u);
+        }
     }
 }
 
