@@ -50,7 +50,7 @@ struct Ctx {
 
 // phase accounting for cm_caviar_debug_phase_cycles (block 0, thread 0; enabled on request only)
 __device__ __forceinline__ void phase_mark(const Ctx& c, int id) {
-    if ((g_phase_enable & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+    if (blockIdx.x == 0 && threadIdx.x == 0 && (g_phase_enable & 1)) {   // one thread reads the switch, not every thread of every CTA
         const long long t = clock64();
         g_phase_cycles[id] += t - *c.tlast;
         *c.tlast = t;
@@ -351,6 +351,7 @@ __device__ __forceinline__ int kseg_for(int i0) {
 template <bool UPPER>
 __device__ void panel_gemm(const Ctx& c, int ldr, int i0, int nb, const double* IN, double* OUT, GemmPipe& gp,
                            int part = 0, int nparts = 1, int nseg = 1) {
+    const int dbg = g_phase_enable;                // diagnostics switches, read once (not once per chunk in the loops below)
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int lq = lane >> 2, lr = lane & 3;
     const int sw = (lr & 1) << 3;                 // swizzle term of this lane's k rows (k = 4*ks + lr)
@@ -382,7 +383,7 @@ __device__ void panel_gemm(const Ctx& c, int ldr, int i0, int nb, const double* 
                 double* As = stage0 + (size_t)st * STAGE_GEMM_DOUBLES;
                 double* Xs = As + GK * NB;
                 const int kk0 = kfirst + ci * GK;
-                if (g_phase_enable & 4) mbar_arrive(&gp.full[st]);          // debug: no copies
+                if (dbg & 4) mbar_arrive(&gp.full[st]);                     // debug: no copies
                 else {
                     mbar_expect_tx(&gp.full[st], (uint32_t)(GK * NB * 8 + GK * GCT * 8));
                     bulk_g2s(As, IN + (size_t)kk0 * NB, GK * NB * 8, &gp.full[st]);
@@ -404,7 +405,7 @@ __device__ void panel_gemm(const Ctx& c, int ldr, int i0, int nb, const double* 
             const int st = g % NST;
             mbar_wait(&gp.full[st], (g / NST) & 1);
             const int kk0 = kfirst + ci * GK;
-            if (cmin < i0 && !(g_phase_enable & 2)) {                       // debug bit 2: no math
+            if (cmin < i0 && !(dbg & 2)) {                                  // debug bit 2: no math
                 const double* ab = stage0 + (size_t)st * STAGE_GEMM_DOUBLES;
                 const double* xb = ab + GK * NB;
                 // interior chunk of the triangle: every (kk, cc) pair of this warp is valid -> no masking at all
@@ -1681,7 +1682,8 @@ __device__ __forceinline__ void sweep_row(const RowCtx c, int n, int beg, int le
                                           const double* lo, double sigma, double thr, double minspk, bool gate,
                                           double* pred) {
     const int lane = threadIdx.x & 31;
-    const bool prof = chain && g_phase_enable && blockIdx.x == 0 && lane == 0;
+    const int dbg = g_phase_enable;                // read once: the stores of the entry loop below could alias it
+    const bool prof = chain && dbg && blockIdx.x == 0 && lane == 0;
     long long tp0 = 0;
     if (prof) tp0 = clock64();
     const double coef = sigma * mu_n;
@@ -1762,7 +1764,7 @@ __device__ __forceinline__ void sweep_row(const RowCtx c, int n, int beg, int le
 #pragma unroll
         for (int p = 0; p < PT; ++p) sr[p] = __shfl_sync(0xffffffffu, mine, p);
         ok = (pava_last_reg<PT>(sr, c.P) >= thr) && (tot >= minspk);
-        if (g_phase_enable & 32) ok = true;          // debug
+        if (dbg & 32) ok = true;          // debug
     }
     if (prof) { const long long t = clock64(); g_phase_cycles[22] += t - tp0; tp0 = t; }
     // second pass: commit the row, update the running prediction
@@ -1772,7 +1774,7 @@ __device__ __forceinline__ void sweep_row(const RowCtx c, int n, int beg, int le
     for (int q = lane; q < len; q += 32) {
         const double nw = ok ? cs[q] : 0.0;
         const double old = lo[q];
-        if (!(g_phase_enable & 16)) lam_row[q] = nw;
+        if (!(dbg & 16)) lam_row[q] = nw;
         if (chain) {
             const int k = cp[q] & 0x7ffffff;
             pred[k] = (pred[k] + muok * nw) - mu_n * old;
@@ -1780,7 +1782,7 @@ __device__ __forceinline__ void sweep_row(const RowCtx c, int n, int beg, int le
         sl2 += nw * nw;
     }
     sl2 = warp_sum(sl2);
-    if (lane == 0 && !(g_phase_enable & 8)) {
+    if (lane == 0 && !(dbg & 8)) {
         int zeros = 0;
 #pragma unroll
         for (int p = 0; p < PT; ++p)
