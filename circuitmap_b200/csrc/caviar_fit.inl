@@ -2343,13 +2343,21 @@ __device__ __forceinline__ double quad_sum(double v) {
 // same fp result as evaluating them again), so a step costs 1 + #backtracks evaluations instead of 2 + #backtracks; rows
 // advance independently (a warp no longer loops until the slowest of its eight rows has finished EVERY step: the
 // lock-step version spent 5.1 trips per step where the rows needed 1.7) and a quad that finishes a row fetches its next
-// one (rows idx, idx + stride, ... statically per quad: which quad runs a row does not change its result).
+// one from the CTA's shared ticket counter (which quad runs a row does not change its result).
 __device__ __noinline__ void newton_rows(const Ctx& c, const double* powers, const int* list, int nlist, int part, int nparts) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int quad = lane >> 2, mem = lane & 3;
     const double t = 10.0, alpha = 0.25, bbeta = 0.5;
-    const int stride = nparts * NW * 8;
-    int idx = (part * NW + wid) * 8 + quad;                       // next row of this quad
+    // Rows are handed out dynamically inside the CTA: positions of the list are dealt to the CTAs of the fit in chunks of
+    // NW * 8, a quad that is free takes the CTA's next position from a shared counter (rows need 10 .. 400 evaluations:
+    // with a static row list per quad the warps ran at 57 - 70 % of their quads on average).
+    constexpr int CH = NW * 8;
+    __shared__ int s_next;
+    __syncthreads();
+    if (threadIdx.x == 0) s_next = 0;
+    __syncthreads();
+    const unsigned qmask = 0xFu << (lane & 28);
+    bool exhausted = false;
     bool have = false, first = false;
     int n = 0, step = 0, bt = 0;
     QuadStats s;
@@ -2360,9 +2368,14 @@ __device__ __noinline__ void newton_rows(const Ctx& c, const double* powers, con
     double p0 = 1.0, p1 = 1.0, basev = 0.0, v0 = 0.0, v1 = 0.0, Jv = 0.0, stp = 1.0;
     long long evals_w = 0, evals_r = 0;
     for (;;) {
-        if (!have && idx < nlist) {                              // fetch the next row: sufficient statistics, prior, precision
+        if (!have && !exhausted) {
+            int tkt = 0;
+            if (mem == 0) tkt = atomicAdd(&s_next, 1);
+            tkt = __shfl_sync(qmask, tkt, lane & 28);
+            const int idx = ((tkt / CH) * nparts + part) * CH + (tkt % CH);
+            if (idx >= nlist) exhausted = true;                   // positions grow with the ticket: nothing left for this CTA
+            else {                                               // fetch the row: sufficient statistics, prior, precision
             n = list[idx];
-            idx += stride;
             double ctot = 0.0;
             for (int p = 0; p < c.P; ++p) ctot += (double)c.cntp[n * PMAX + p];
             s.ng = 0;
@@ -2391,6 +2404,7 @@ __device__ __noinline__ void newton_rows(const Ctx& c, const double* powers, con
             hi[0] = hi[1] = hi[2] = hi[3] = 0.0;
             step = 0; bt = 0; stp = 1.0; v0 = 0.0; v1 = 0.0;
             first = true; have = true;
+            }
         }
         if (!__any_sync(0xffffffffu, have)) break;
         // the point this trip evaluates: the iterate itself (first trip of a row) or the current candidate p + stp v
