@@ -1421,10 +1421,21 @@ __device__ void job_lamT_resid(const Ctx& c, double spont_orth, int part, int np
     for (int k = k0 + threadIdx.x; k < k1; k += NT) {
         double s = 0.0;
         unsigned char bl = 0;
-        for (int i = c.ucol_ptr[k]; i < c.ucol_ptr[k + 1]; ++i) {
-            const double l = c.lamT[i];
-            s += c.mu[c.ucsc_row[i]] * l;
-            bl |= (l >= spont_orth);
+        const int end = c.ucol_ptr[k + 1];
+        for (int i = c.ucol_ptr[k]; i < end; i += 4) {         // four entries' dependent gathers together, sums in list order
+            int r[4];
+            double l[4], m[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const bool ok = i + u < end;
+                r[u] = ok ? c.ucsc_row[i + u] : -1;
+                l[u] = ok ? c.lamT[i + u] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) m[u] = r[u] >= 0 ? c.mu[r[u]] : 0.0;
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (r[u] >= 0) { s += m[u] * l[u]; bl |= (l[u] >= spont_orth); }
         }
         c.resid[k] = c.y[k] - s;
         c.blocked[k] = bl;
@@ -2815,12 +2826,18 @@ __global__ void __launch_bounds__(NT, (NT == 512) ? 1 : 2) caviar_fit_kernel(con
             }
         }
         // by-trial copy of the new lam; with helpers also the residual of a6 and the spontaneous-event mask of a8
-        const bool dist15 = dist_passes(c);
+        // (one fused pass also without helpers: the by-trial lists are walked once instead of three times; bit 10 of the
+        // diagnostics word switches the separate passes back on)
+        const bool dist15 = !(g_phase_enable & 1024);
         if (dist15) {
-            if (threadIdx.x == 0) *reinterpret_cast<double*>(c.job + 8) = o.spont_orthogonality;
-            post_job(c, 15, 0, 0, 0);
-            job_lamT_resid(c, o.spont_orthogonality, 0, c.ct);
-            wait_helpers(c);
+            if (dist_passes(c)) {
+                if (threadIdx.x == 0) *reinterpret_cast<double*>(c.job + 8) = o.spont_orthogonality;
+                post_job(c, 15, 0, 0, 0);
+                job_lamT_resid(c, o.spont_orthogonality, 0, c.ct);
+                wait_helpers(c);
+            } else {
+                job_lamT_resid(c, o.spont_orthogonality, 0, 1);
+            }
         } else {
 #pragma unroll 8
             for (int i = threadIdx.x; i < c.unnz; i += NT) c.lamT[i] = c.lam[c.ucsc_pos[i]];
